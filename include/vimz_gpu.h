@@ -1,0 +1,157 @@
+/* vimz_gpu.h -- C ABI of the B200-native Nova fold kernels (libvimz_gpu.so).
+ *
+ * This is the drop-in boundary for the per-step NIFS fold that zero-savvy/vimz runs through
+ * nova-snark 0.23.0 (hot loop entered at /root/reference/vimz/src/nova_snark_backend/folding.rs:35,
+ * curve cycle selected at /root/reference/vimz/src/nova_snark_backend/mod.rs:19-20).  Each entry
+ * point names the reference interface it replaces; nova-snark itself is an un-vendored dependency
+ * (vimz/Cargo.toml:51, Cargo.lock:3577), so those are crate-relative paths.
+ *
+ * Conventions (identical to the in-memory layout of halo2curves 0.1.0 / pasta_curves 0.5.1):
+ *   - field element  = 32 bytes, 4 x u64 little-endian limbs, MONTGOMERY form with R = 2^256;
+ *   - affine point   = {x, y}, 64 bytes, identity encoded as (0, 0);
+ *   - group element  = Jacobian {X, Y, Z}, 96 bytes, identity Z = 0 (returned as (0, R, 0));
+ *   - every function returns 0 on success, a negative vimz_status otherwise; the message is
+ *     available from vimz_last_error() (thread-local).  No entry point has a CPU fallback.
+ *   - "host" pointers are borrowed for the duration of the call; "_dev" variants take device
+ *     pointers (e.g. torch tensor .data_ptr()) that live on the context's device.
+ *   - one context = one curve on one GPU with its own stream; calls on a context are serialised
+ *     by the caller (nova-snark's prove_step is sequential; use one context per rayon worker).
+ */
+#ifndef VIMZ_GPU_H
+#define VIMZ_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } vimz_fr;                 /* scalar-field element (Montgomery) */
+typedef struct { uint64_t x[4], y[4]; } vimz_affine;       /* base-field affine point */
+typedef struct { uint64_t x[4], y[4], z[4]; } vimz_point;  /* Jacobian group element */
+
+typedef struct vimz_ctx vimz_ctx;     /* curve + device + stream + workspace */
+typedef struct vimz_ck vimz_ck;       /* resident commitment key (window table in HBM) */
+typedef struct vimz_shape vimz_shape; /* resident R1CSShape (CSR A, B, C) */
+typedef struct vimz_acc vimz_acc;     /* resident running relaxed instance/witness */
+
+enum vimz_curve { VIMZ_PALLAS = 0, VIMZ_VESTA = 1, VIMZ_BN254 = 2, VIMZ_GRUMPKIN = 3 };
+
+enum vimz_status {
+  VIMZ_OK = 0,
+  VIMZ_ERR_CUDA = -1,     /* a CUDA runtime call or kernel failed */
+  VIMZ_ERR_ARG = -2,      /* bad argument (null pointer, unknown curve, ...) */
+  VIMZ_ERR_LENGTH = -3,   /* nova-snark's InvalidWitnessLength / ck shorter than the vector */
+  VIMZ_ERR_NO_DEVICE = -4,/* no usable CUDA device: the library never computes on the CPU */
+  VIMZ_ERR_INDEX = -5     /* R1CS entry out of range (nova-snark's InvalidIndex) */
+};
+
+const char* vimz_last_error(void);
+int vimz_version(void);
+int vimz_device_count(void);
+
+/* ---- context -------------------------------------------------------------------------------- */
+/* Replaces the choice of provider made by `type G1/G2` (mod.rs:19-20): one context per curve. */
+int vimz_ctx_create(int curve_id, int device, vimz_ctx** out);
+void vimz_ctx_destroy(vimz_ctx* ctx);
+int vimz_ctx_sync(vimz_ctx* ctx);
+/* Tunables: "msm_window" (c bits, 0 = auto).  Unknown keys -> VIMZ_ERR_ARG. */
+int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value);
+/* The context's CUDA stream (cudaStream_t as void*), so a caller can time on it with events. */
+void* vimz_ctx_stream(vimz_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's "gpu_launches"). */
+uint64_t vimz_ctx_launch_count(vimz_ctx* ctx);
+
+/* ---- commitment key / MSM -------------------------------------------------------------------- */
+/* Replaces CommitmentEngineTrait::setup's product `CommitmentKey{ck: Vec<Affine>}` being read by
+ * every commit ([EXT nova-snark] src/provider/pedersen.rs): the bases are uploaded ONCE and expanded
+ * on the GPU into the window table {2^(c*j) * ck_i} that stays in HBM for all fold steps. */
+int vimz_ck_upload(vimz_ctx* ctx, const vimz_affine* bases, size_t n, vimz_ck** out);
+int vimz_ck_upload_dev(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out);
+void vimz_ck_destroy(vimz_ck* ck);
+size_t vimz_ck_len(const vimz_ck* ck);
+int vimz_ck_window_bits(const vimz_ck* ck);
+int vimz_ck_num_windows(const vimz_ck* ck);
+
+/* Replaces CommitmentEngineTrait::commit(ck, v) == Group::vartime_multiscalar_mul(v, ck[..v.len()])
+ * ([EXT nova-snark] src/provider/pedersen.rs, src/provider/{pasta,bn256_grumpkin,mod}.rs;
+ * C-ABI precedent: pasta-msm `mult_pippenger_pallas`).  n > len(ck) -> VIMZ_ERR_LENGTH. */
+int vimz_msm(vimz_ctx* ctx, const vimz_ck* ck, const vimz_fr* scalars, size_t n, vimz_point* out);
+int vimz_msm_dev(vimz_ctx* ctx, const vimz_ck* ck, const void* d_scalars, size_t n, vimz_point* out);
+/* Point-range shard: sum_{i<n} scalars[i] * ck[first + i] (multi-GPU MSM). */
+int vimz_msm_range_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, vimz_point* out);
+/* Enqueue only: the Jacobian result is written to d_out (96 bytes of device memory) on the context's
+ * stream; no host synchronisation.  Used to time the kernels alone and by the fused step. */
+int vimz_msm_async_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out);
+
+/* Group helpers used on the boundary (all computed on the GPU).
+ * vimz_point_sum: out = sum of k Jacobian points (combining per-GPU MSM shards).
+ * vimz_point_to_affine: canonical affine (x, y) of a Jacobian point, identity -> (0,0)
+ *   (what Commitment::to_coordinates / compress feed to the RO).
+ * vimz_point_scale_add: out = a + r * b  (RelaxedR1CSInstance::fold's comm_W1 + r*comm_W2). */
+int vimz_point_sum(vimz_ctx* ctx, const vimz_point* pts, size_t k, vimz_point* out);
+int vimz_point_to_affine(vimz_ctx* ctx, const vimz_point* p, vimz_affine* out);
+int vimz_point_scale_add(vimz_ctx* ctx, const vimz_point* a, const vimz_fr* r, const vimz_point* b, vimz_point* out);
+
+/* ---- R1CS shape ------------------------------------------------------------------------------ */
+/* Replaces R1CSShape::new ([EXT nova-snark] src/r1cs.rs): COO triples (row, col, val) per matrix in
+ * constraint order, column space z = (W || u || X) of length num_vars + 1 + num_io.  Converted to
+ * CSR once and kept resident. */
+int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_io,
+                      const uint32_t* rowA, const uint32_t* colA, const vimz_fr* valA, size_t nnzA,
+                      const uint32_t* rowB, const uint32_t* colB, const vimz_fr* valB, size_t nnzB,
+                      const uint32_t* rowC, const uint32_t* colC, const vimz_fr* valC, size_t nnzC,
+                      vimz_shape** out);
+void vimz_shape_destroy(vimz_shape* s);
+
+/* Replaces R1CSShape::multiply_vec(z) -> (Az, Bz, Cz).  z_len must equal num_vars + 1 + num_io,
+ * else VIMZ_ERR_LENGTH (nova-snark: NovaError::InvalidWitnessLength). */
+int vimz_multiply_vec(vimz_ctx* ctx, const vimz_shape* s, const vimz_fr* z, size_t z_len,
+                      vimz_fr* Az, vimz_fr* Bz, vimz_fr* Cz);
+
+/* Replaces R1CSShape::commit_T(ck, U1, W1, U2, W2) -> (T, comm_T):
+ *   T = Az1 o Bz2 + Az2 o Bz1 - u1*Cz2 - u2*Cz1 (u2 = 1), comm_T = commit(ck, T).
+ * T_out may be NULL. */
+int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
+                  const vimz_fr* W1, const vimz_fr* u1, const vimz_fr* X1,
+                  const vimz_fr* W2, const vimz_fr* X2,
+                  vimz_fr* T_out, vimz_point* comm_T);
+
+/* Replaces RelaxedR1CSWitness::fold: W = W1 + r*W2 (n), E = E1 + r*T (m). */
+int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r,
+                      const vimz_fr* W1, const vimz_fr* W2, size_t n,
+                      const vimz_fr* E1, const vimz_fr* T, size_t m,
+                      vimz_fr* W_out, vimz_fr* E_out);
+
+/* ---- device-resident fold (the fast path) ---------------------------------------------------- */
+/* The running relaxed witness (W1, E1), instance scalars (u1, X1) and their commitments stay in
+ * HBM between steps; one step = NIFS::prove's data-parallel body ([EXT nova-snark] src/nifs.rs):
+ *   step_begin: upload W2/X2 -> comm_W2 = commit(ck, W2) (the r1cs_instance_and_witness MSM),
+ *               (Az,Bz,Cz)(z1), (Az,Bz,Cz)(z2), T, comm_T = commit(ck, T); returns both commitments.
+ *   [host: RO absorbs comm_T, squeezes r -- untouched Poseidon RO]
+ *   step_end:   W1 += r*W2, E1 += r*T, u1 += r, X1 += r*X2, comm_W1 += r*comm_W2, comm_E1 += r*comm_T.
+ * vimz_acc_init starts from the default (all-zero, u = 0) relaxed instance like
+ * RelaxedR1CSWitness::default / RelaxedR1CSInstance::default; vimz_acc_load starts from given values. */
+int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_acc** out);
+int vimz_acc_load(vimz_acc* acc, const vimz_fr* W, const vimz_fr* E, const vimz_fr* u, const vimz_fr* X,
+                  const vimz_point* comm_W, const vimz_point* comm_E);
+int vimz_acc_step_begin(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);
+int vimz_acc_step_begin_dev(vimz_acc* acc, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);
+int vimz_acc_step_end(vimz_acc* acc, const vimz_fr* r);
+int vimz_acc_download(vimz_acc* acc, vimz_fr* W, vimz_fr* E, vimz_fr* u, vimz_fr* X, vimz_point* comm_W, vimz_point* comm_E);
+/* T of the last step_begin (m elements), for callers that keep nova-snark's (T, comm_T) pair. */
+int vimz_acc_last_T(vimz_acc* acc, vimz_fr* T);
+void vimz_acc_destroy(vimz_acc* acc);
+
+/* ---- test / bench utilities (device-side generators; not part of the reference interface) ---- */
+/* bases[i] = (k0 + i*dk) * G written as n affine points to device memory d_out (64*n bytes). */
+int vimz_gen_bases_dev(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* d_out);
+/* Element-wise Montgomery product out[i] = a[i]*b[i] in the curve's BASE (which=0) or SCALAR (which=1)
+ * field, plus sum/difference: op 0 = mul, 1 = add, 2 = sub.  Exercises fp.cuh directly for the parity tests. */
+int vimz_field_op(vimz_ctx* ctx, int which, int op, const vimz_fr* a, const vimz_fr* b, size_t n, vimz_fr* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIMZ_GPU_H */

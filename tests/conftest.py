@@ -1,0 +1,59 @@
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def coracle():
+    from oracle import c
+    return c()
+
+
+_engines = {}
+
+
+@pytest.fixture(scope="session")
+def engines():
+    """curve name -> vimz_b200.Engine on cuda:0 (created lazily, shared by the session)."""
+    import vimz_b200
+
+    class Lazy(dict):
+        def __missing__(self, name):
+            e = vimz_b200.Engine(name, 0)
+            self[name] = e
+            return e
+
+    d = Lazy()
+    yield d
+    for e in d.values():
+        e.close()
+
+
+def make_bases(curve, n, seed):
+    """n affine points k_i*G with known discrete logs (python big-int oracle)."""
+    from oracle import pyref as P
+    rng = random.Random(seed)
+    G = P.generator(curve)
+    ks = [rng.randrange(1, curve.q) for _ in range(n)]
+    # walk: P_i = P_{i-1} + D keeps this O(n) additions instead of n scalar muls
+    pts = []
+    k0, dk = ks[0], rng.randrange(1, curve.q)
+    cur = P.scalar_mul(curve, k0, G)
+    D = P.scalar_mul(curve, dk, G)
+    logs = []
+    for i in range(n):
+        pts.append(cur)
+        logs.append((k0 + i * dk) % curve.q)
+        cur = P.aff_add(curve, cur, D)
+    return pts, logs

@@ -1,0 +1,52 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/vimz_gpu.h declares, and refuses to
+compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import vimz_b200
+from vimz_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "vimz_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(vimz_[a-z_A-Z0-9]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    names = declared_symbols()
+    assert len(names) >= 30
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/vimz_gpu.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes binding table and header disagree"
+
+
+def test_version_and_error_string():
+    assert _lib.lib.vimz_version() >= 100
+    h = ctypes.c_void_p()
+    rc = _lib.lib.vimz_ctx_create(99, 0, ctypes.byref(h))
+    assert rc == _lib.VIMZ_ERR_ARG and b"curve" in _lib.lib.vimz_last_error()
+
+
+def test_no_cpu_fallback_without_device():
+    if _lib.lib.vimz_device_count() > 0:
+        pytest.skip("a GPU is visible; the refusal path is exercised on the CPU box")
+    with pytest.raises(vimz_b200.VimzError) as ei:
+        vimz_b200.Engine("pallas", 0)
+    assert ei.value.code == _lib.VIMZ_ERR_NO_DEVICE
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, smoke() and bench.py's baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "vimz_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

@@ -1,0 +1,189 @@
+"""CPU-only: pins the oracle itself (oracle/pyref.py and oracle/nova_cpu.c).
+
+The reference holds no golden vector for the fold path (parity unpinned at the
+nova-snark boundary), so the oracle is pinned by (a) number-theoretic facts about the four curves,
+(b) agreement of two independent restatements (Python big-int vs C 4x64 Montgomery), (c) the
+definition-level identities the domain offers, and (d) the committed fixtures in tests/golden/."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyref as P
+from vimz_b200.field import affine_to_mont, ints_to_mont, mont_to_affine, mont_to_ints
+from conftest import make_bases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def is_probable_prime(n, rounds=16):
+    if n < 4:
+        return n in (2, 3)
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    rng = random.Random(7)
+    for _ in range(rounds):
+        a = rng.randrange(2, n - 1)
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+def test_curve_constants(name):
+    c = P.CURVES[name]
+    assert is_probable_prime(c.p) and is_probable_prime(c.q)
+    G = P.generator(c)
+    assert P.on_curve(c, G)
+    assert P.scalar_mul(c, c.q - 1, G) == P.aff_neg(c, G)  # [q]G = O  <=>  [q-1]G = -G
+    assert P.aff_add(c, P.scalar_mul(c, c.q - 1, G), G) is None
+
+
+def test_cycle_structure():
+    assert P.PALLAS.q == P.VESTA.p and P.VESTA.q == P.PALLAS.p
+    assert P.BN254.q == P.GRUMPKIN.p and P.GRUMPKIN.q == P.BN254.p
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+def test_c_field_ops_match_bigint(name, coracle):
+    c = P.CURVES[name]
+    rng = random.Random(11)
+    for which, mod in ((0, c.p), (1, c.q)):
+        a = [rng.randrange(mod) for _ in range(300)] + [0, 1, mod - 1, mod - 1, 0, 1]
+        b = [rng.randrange(mod) for _ in range(300)] + [0, mod - 1, mod - 1, 1, 5, 1]
+        A, B = ints_to_mont(a, mod), ints_to_mont(b, mod)
+        assert mont_to_ints(coracle.field_op(c.curve_id, which, 0, A, B), mod) == [x * y % mod for x, y in zip(a, b)]
+        assert mont_to_ints(coracle.field_op(c.curve_id, which, 1, A, B), mod) == [(x + y) % mod for x, y in zip(a, b)]
+        assert mont_to_ints(coracle.field_op(c.curve_id, which, 2, A, B), mod) == [(x - y) % mod for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+@pytest.mark.parametrize("n", [1, 3, 31, 33, 257])
+def test_msm_three_ways(name, n, coracle):
+    """definition (naive) == restated cpu_best_multiexp (python) == C oracle == closed form via discrete logs."""
+    c = P.CURVES[name]
+    rng = random.Random(n * 31 + c.curve_id)
+    bases, logs = make_bases(c, n, seed=n + c.curve_id)
+    sc = [rng.randrange(c.q) for _ in range(n)]
+    if n >= 3:
+        sc[0], sc[1], sc[2] = 0, 1, c.q - 1
+    expect = P.scalar_mul(c, sum(s * k for s, k in zip(sc, logs)) % c.q, P.generator(c))
+    if n <= 33:
+        assert P.msm_naive(c, sc, bases) == expect
+    assert P.cpu_best_multiexp(c, sc, bases, num_threads=4) == expect
+    Bm, Sm = affine_to_mont(bases, c.p), ints_to_mont(sc, c.q)
+    for nt in (1, 4):
+        got = mont_to_affine(coracle.to_affine(c.curve_id, coracle.msm(c.curve_id, Sm, Bm, nt)), c.p)[0]
+        assert got == expect
+
+
+def test_msm_identity_and_cancellation(coracle):
+    c = P.PALLAS
+    G = P.generator(c)
+    bases = [G, P.aff_neg(c, G), None, G]
+    Bm = affine_to_mont(bases, c.p)
+    # s*G + s*(-G) + 7*O + 0*G = O
+    Sm = ints_to_mont([5, 5, 7, 0], c.q)
+    j = coracle.msm(c.curve_id, Sm, Bm, 1)
+    assert mont_to_affine(coracle.to_affine(c.curve_id, j), c.p)[0] is None
+    # doubling inside a bucket: G + G
+    Sm = ints_to_mont([1, 0, 0, 1], c.q)
+    j = coracle.msm(c.curve_id, Sm, Bm, 1)
+    assert mont_to_affine(coracle.to_affine(c.curve_id, j), c.p)[0] == P.scalar_mul(c, 2, G)
+
+
+@pytest.mark.parametrize("cbits,nwin", [(8, 32), (13, 20), (16, 16), (17, 15)])
+def test_signed_digits(cbits, nwin):
+    rng = random.Random(cbits)
+    q = P.PALLAS.q
+    for s in [0, 1, q - 1, (1 << 254), (1 << 254) - 1, (1 << (cbits - 1)), (1 << (cbits - 1)) + 1] + [rng.randrange(q) for _ in range(200)]:
+        d = P.signed_digits(s, cbits, nwin)
+        assert all(abs(x) <= (1 << (cbits - 1)) for x in d)
+
+
+def _tiny_shape():
+    """x*x = y ; y*x = z ; (z + x + 5)*1 = out   over z = (W=[x,y,z], u, X=[out])  -- the classic cubic."""
+    # columns: 0:x 1:y 2:z 3:u(one) 4:out
+    A = [(0, 0, 1), (1, 1, 1), (2, 2, 1), (2, 0, 1), (2, 3, 5)]
+    B = [(0, 0, 1), (1, 0, 1), (2, 3, 1)]
+    C = [(0, 1, 1), (1, 2, 1), (2, 4, 1)]
+    return P.R1CSShape(3, 3, 1, A, B, C)
+
+
+def test_r1cs_definitions_by_hand():
+    q = P.PALLAS.q
+    S = _tiny_shape()
+    x = 3
+    W, X = [x, x * x, x ** 3], [x ** 3 + x + 5]
+    Az, Bz, Cz = S.multiply_vec(q, W + [1] + X)
+    assert Az == [3, 9, 35] and Bz == [3, 3, 1] and Cz == [9, 27, 35]
+    assert S.is_sat_relaxed(q, W, [0, 0, 0], 1, X)
+    with pytest.raises(ValueError):
+        S.multiply_vec(q, W + [1])
+    # fold two satisfying instances: the folded relaxed instance must satisfy Az o Bz = u Cz + E
+    x2 = 4
+    W2, X2 = [x2, x2 * x2, x2 ** 3], [x2 ** 3 + x2 + 5]
+    T = S.cross_term(q, W, 1, X, W2, X2)
+    # by hand for row 0: Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1 = 3*4 + 4*3 - 16 - 9 = -1
+    assert T[0] == (12 + 12 - 16 - 9) % q
+    r = 0x1234567890ABCDEF
+    Wf, Ef = P.fold_witness(q, W, [0, 0, 0], W2, T, r)
+    Xf = [(a + r * b) % q for a, b in zip(X, X2)]
+    assert S.is_sat_relaxed(q, Wf, Ef, (1 + r) % q, Xf)
+
+
+def test_c_r1cs_matches_python(coracle):
+    c = P.VESTA
+    q = c.q
+    rng = random.Random(5)
+    m, n, io = 40, 30, 2
+    def rand_mat(nnz):
+        return [(rng.randrange(m), rng.randrange(n + 1 + io), rng.choice([1, q - 1, 2, rng.randrange(q)])) for _ in range(nnz)]
+    A, B, Cm = rand_mat(90), rand_mat(70), rand_mat(50)
+    S = P.R1CSShape(m, n, io, A, B, Cm)
+    W1 = [rng.randrange(q) for _ in range(n)]
+    W2 = [rng.randrange(2) for _ in range(n)]
+    X1 = [rng.randrange(q) for _ in range(io)]
+    X2 = [rng.randrange(q) for _ in range(io)]
+    u1 = rng.randrange(q)
+    def pack(M):
+        return (np.array([e[0] for e in M], np.uint32), np.array([e[1] for e in M], np.uint32), ints_to_mont([e[2] for e in M], q))
+    z1 = W1 + [u1] + X1
+    got = coracle.multiply_vec(c.curve_id, m, n, io, pack(A), pack(B), pack(Cm), ints_to_mont(z1, q))
+    exp = S.multiply_vec(q, z1)
+    for g, e in zip(got, exp):
+        assert mont_to_ints(g, q) == e
+    T = coracle.commit_T(c.curve_id, m, n, io, pack(A), pack(B), pack(Cm), ints_to_mont(W1, q), ints_to_mont([u1], q),
+                         ints_to_mont(X1, q), ints_to_mont(W2, q), ints_to_mont(X2, q), ints_to_mont([1], q), nthreads=3)
+    assert mont_to_ints(T, q) == S.cross_term(q, W1, u1, X1, W2, X2)
+    r = rng.randrange(1 << 128)
+    got = coracle.axpy(c.curve_id, ints_to_mont(W1, q), ints_to_mont(W2, q), ints_to_mont([r], q), nthreads=2)
+    assert mont_to_ints(got, q) == [(a + r * b) % q for a, b in zip(W1, W2)]
+    with pytest.raises(ValueError):
+        coracle.multiply_vec(c.curve_id, m, n, io, pack(A), pack(B), pack(Cm), ints_to_mont(z1[:-1], q))
+
+
+def test_golden_fixtures(coracle):
+    """tests/golden/msm_vectors.json was produced by tests/golden/make_golden.py from the python big-int
+    model; the C oracle must reproduce every vector."""
+    with open(os.path.join(GOLDEN, "msm_vectors.json")) as f:
+        data = json.load(f)
+    assert data["vectors"]
+    for v in data["vectors"]:
+        c = P.CURVES[v["curve"]]
+        bases = [None if b is None else (int(b[0], 16), int(b[1], 16)) for b in v["bases"]]
+        sc = [int(s, 16) for s in v["scalars"]]
+        expect = None if v["result"] is None else (int(v["result"][0], 16), int(v["result"][1], 16))
+        j = coracle.msm(c.curve_id, ints_to_mont(sc, c.q), affine_to_mont(bases, c.p), 2)
+        assert mont_to_affine(coracle.to_affine(c.curve_id, j), c.p)[0] == expect

@@ -1,0 +1,198 @@
+// int_peak.cu -- register-only integer-pipe microbenchmark for B200 (sm_100a).
+// Measures, per SM per clock: IMAD (32-bit), IMAD.HI.U32, IMAD.WIDE.U32, carry-chained IMAD.WIDE.U32.X,
+// IADD3.X, an IMAD.WIDE/IADD3 mix, and field multiplications/s of vimz_b200/csrc/fp.cuh.  The result is
+// the denominator of the MSM roofline ("IMAD peak must be measured").
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Ivimz_b200/csrc -o tools/int_peak tools/int_peak.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "fp.cuh"
+using namespace vimz;
+
+#define ITERS 4096
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+__global__ void k_imad(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
+  uint32_t x[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) x[j] = threadIdx.x + j;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
+  }
+  long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= x[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+__global__ void k_imadhi(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
+  uint32_t x[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) x[j] = threadIdx.x + j + 0x80000000u;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
+  }
+  long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= x[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+__global__ void k_wide(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
+  uint64_t x[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) x[j] = threadIdx.x + j;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[j]) : "r"((uint32_t)x[(j + 1) & 7]), "r"(b));
+  }
+  long long t1 = clock64();
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= x[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(s ^ (s >> 32));
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+// carry-chained wide MADs: 2 independent chains of 4 lanes (the fp_mul pattern)
+__global__ void k_widex(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
+  uint32_t x[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = threadIdx.x + j;
+  uint32_t aa = a + threadIdx.x;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      asm volatile(
+          "mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+          "madc.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.cc.u32 %3, %8, %9, %3;\n\t"
+          "madc.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.cc.u32 %5, %8, %9, %5;\n\t"
+          "madc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+          : "+r"(x[8 * h + 0]), "+r"(x[8 * h + 1]), "+r"(x[8 * h + 2]), "+r"(x[8 * h + 3]), "+r"(x[8 * h + 4]),
+            "+r"(x[8 * h + 5]), "+r"(x[8 * h + 6]), "+r"(x[8 * h + 7])
+          : "r"(aa), "r"(b));
+  }
+  long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) s ^= x[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+__global__ void k_iadd3x(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
+  uint32_t x[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = threadIdx.x + j;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      asm volatile(
+          "add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %9;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.cc.u32 %3, %3, %9;\n\t"
+          "addc.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %9;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %9;"
+          : "+r"(x[8 * h + 0]), "+r"(x[8 * h + 1]), "+r"(x[8 * h + 2]), "+r"(x[8 * h + 3]), "+r"(x[8 * h + 4]),
+            "+r"(x[8 * h + 5]), "+r"(x[8 * h + 6]), "+r"(x[8 * h + 7])
+          : "r"(a), "r"(b));
+  }
+  long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) s ^= x[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+// 1:1 mix of IMAD.WIDE and IADD3 (are the FMA-int and ALU pipes issued in parallel?)
+__global__ void k_mix(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
+  uint64_t x[8];
+  uint32_t y[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { x[j] = threadIdx.x + j; y[j] = threadIdx.x * 3 + j; }
+  uint32_t aa = a + threadIdx.x;
+  long long t0 = clock64();
+  for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[j]) : "r"((uint32_t)(x[j] >> 32)), "r"(b));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(y[j]) : "r"(b));
+    }
+  }
+  long long t1 = clock64();
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= x[j] ^ y[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(s ^ (s >> 32));
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+#define MUL_ITERS 512
+template <class F>
+__global__ void k_fpmul(uint32_t* out, const uint32_t* in, long long* cyc) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp<F> x = Fp<F>::load(in + 8 * (tid & 1023)), y = Fp<F>::load(in + 8 * ((tid + 7) & 1023));
+  long long t0 = clock64();
+  for (int i = 0; i < MUL_ITERS; i++) {
+    x = fp_mul(x, y);
+    y = fp_mul(y, x);
+  }
+  long long t1 = clock64();
+  fp_add(x, y).store(out + 8 * tid);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+int main() {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  int sms = prop.multiProcessorCount;
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  const int threads = 256, bps = 4;  // 1024 threads / SM
+  int blocks = sms * bps;
+  uint32_t *out, *in;
+  long long* cyc;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * 32));
+  CK(cudaMalloc(&in, 1024 * 32));
+  CK(cudaMemset(in, 0x11, 1024 * 32));
+  CK(cudaMalloc(&cyc, blocks * sizeof(long long)));
+  long long* hcyc = new long long[blocks];
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  printf("{\"device\": \"%s\", \"sms\": %d, \"max_clock_mhz\": %.0f, \"tests\": [\n", prop.name, sms, clk_khz / 1000.0);
+  auto report = [&](const char* name, double ops_per_thread, float ms, bool last) {
+    cudaMemcpy(hcyc, cyc, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < blocks; i++) avg += hcyc[i];
+    avg /= blocks;
+    double per_sm_clk = ops_per_thread * threads * bps / avg;  // thread-ops / clk / SM (blocks co-resident)
+    double total = ops_per_thread * threads * (double)blocks;
+    printf("  {\"name\": \"%s\", \"ops_per_clk_per_sm\": %.2f, \"Gops_per_s\": %.1f, \"ms\": %.3f, \"eff_clock_mhz\": %.0f}%s\n", name,
+           per_sm_clk, total / (ms * 1e6), ms, avg / (ms * 1e3), last ? "" : ",");
+  };
+#define RUN(NAME, OPS, LAUNCH, LAST)              \
+  do {                                            \
+    for (int w = 0; w < 2; w++) { LAUNCH; }       \
+    cudaEventRecord(e0);                          \
+    LAUNCH;                                       \
+    cudaEventRecord(e1);                          \
+    CK(cudaEventSynchronize(e1));                 \
+    float ms;                                     \
+    cudaEventElapsedTime(&ms, e0, e1);            \
+    report(NAME, OPS, ms, LAST);                  \
+  } while (0)
+  RUN("imad32", 8.0 * ITERS, (k_imad<<<blocks, threads>>>(out, 3, 5, cyc)), false);
+  RUN("imad_hi", 8.0 * ITERS, (k_imadhi<<<blocks, threads>>>(out, 0xfffffff3u, 5, cyc)), false);
+  RUN("imad_wide", 8.0 * ITERS, (k_wide<<<blocks, threads>>>(out, 3, 5, cyc)), false);
+  RUN("imad_wide_x_chain", 8.0 * ITERS, (k_widex<<<blocks, threads>>>(out, 3, 5, cyc)), false);
+  RUN("iadd3_x_chain", 16.0 * ITERS, (k_iadd3x<<<blocks, threads>>>(out, 3, 5, cyc)), false);
+  RUN("mix_wide_plus_iadd(pairs)", 8.0 * ITERS, (k_mix<<<blocks, threads>>>(out, 3, 5, cyc)), false);
+  RUN("fp_mul_pallas_base", 2.0 * MUL_ITERS, (k_fpmul<FieldPallasP><<<blocks, threads>>>(out, in, cyc)), false);
+  RUN("fp_mul_bn254_base", 2.0 * MUL_ITERS, (k_fpmul<FieldBnP><<<blocks, threads>>>(out, in, cyc)), true);
+  printf("]}\n");
+  return 0;
+}

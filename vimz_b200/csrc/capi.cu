@@ -1,0 +1,644 @@
+// capi.cu -- extern "C" entry points of libvimz_gpu.so (declared in include/vimz_gpu.h).
+// Host logic only: argument checks with nova-snark's error behaviour, COO->CSR, window selection,
+// staging copies and the launch sequences of curve_impl.cuh.  There is no CPU compute path: without
+// a CUDA device vimz_ctx_create fails with VIMZ_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "curve_impl.cuh"
+
+namespace vimz {
+thread_local std::string g_last_error;
+const CurveVTable* vtable_pallas();
+const CurveVTable* vtable_vesta();
+const CurveVTable* vtable_bn254();
+const CurveVTable* vtable_grumpkin();
+
+const CurveVTable* curve_vtable(int id) {
+  switch (id) {
+    case VIMZ_PALLAS: return vtable_pallas();
+    case VIMZ_VESTA: return vtable_vesta();
+    case VIMZ_BN254: return vtable_bn254();
+    case VIMZ_GRUMPKIN: return vtable_grumpkin();
+    default: return nullptr;
+  }
+}
+
+// ---- window selection ---------------------------------------------------------------------------
+static int bit_length(const uint32_t v[8]) {
+  for (int i = 7; i >= 0; i--)
+    if (v[i]) return 32 * i + 32 - __builtin_clz(v[i]);
+  return 0;
+}
+// bits [pos, pos+len) of v, len <= 32
+static uint64_t get_bits(const uint32_t v[8], int pos, int len) {
+  uint64_t r = 0;
+  for (int b = 0; b < len; b++) {
+    int p = pos + b;
+    if (p < 256 && ((v[p >> 5] >> (p & 31)) & 1)) r |= 1ull << b;
+  }
+  return r;
+}
+// true iff all bits of v in [0, pos) that are >= bit `from` are zero ... helper: v mod 2^pos < 2^from
+static bool low_part_below(const uint32_t v[8], int pos, int from) {
+  for (int p = from; p < pos; p++)
+    if (p < 256 && ((v[p >> 5] >> (p & 31)) & 1)) return false;
+  return true;
+}
+// Smallest window count for c-bit signed digits such that the top digit never exceeds 2^(c-1)
+// for any scalar in [0, q).
+int msm_num_windows(const uint32_t q[8], int c) {
+  uint32_t qm1[8];
+  memcpy(qm1, q, 32);
+  for (int i = 0; i < 8; i++) {  // q - 1
+    if (qm1[i]-- != 0) break;
+  }
+  int bits = bit_length(qm1);
+  int w = (bits + c - 1) / c;
+  if (w < 1) w = 1;
+  uint64_t M = 1ull << (c - 1);
+  uint64_t top = get_bits(qm1, c * (w - 1), c);
+  bool ok = top < M;
+  if (!ok && top == M && w >= 2) {
+    // top digit can be M only if the lower part is < 2^(c(w-1)-1) for every such scalar: then
+    // window w-2 is < M and produces no carry.
+    ok = low_part_below(qm1, c * (w - 1), c * (w - 1) - 1);
+  }
+  return ok ? w : w + 1;
+}
+
+int msm_pick_window(const uint32_t q[8], size_t n) {
+  int best = 8;
+  double best_cost = 1e300;
+  for (int c = 8; c <= 24; c++) {
+    int w = msm_num_windows(q, c);
+    if (w > MSM_MAX_WINDOWS) continue;
+    if ((double)n * w >= 2147483648.0) continue;  // table index must fit 31 bits
+    // field multiplications: 10 per bucket insertion, ~31 per bucket for the reduction
+    double cost = (double)n * w * 10.0 + 31.0 * (double)(1ull << (c - 1));
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+}  // namespace vimz
+
+using namespace vimz;
+
+#define CHECK_ARG(cond, msg) \
+  do {                       \
+    if (!(cond)) return set_error(VIMZ_ERR_ARG, msg); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+};
+
+extern "C" {
+
+const char* vimz_last_error(void) { return g_last_error.c_str(); }
+int vimz_version(void) { return 100; }
+int vimz_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
+  CHECK_ARG(out != nullptr, "vimz_ctx_create: out is null");
+  *out = nullptr;
+  if (!curve_vtable(curve_id)) return set_error(VIMZ_ERR_ARG, "vimz_ctx_create: unknown curve id");
+  int ndev = vimz_device_count();
+  if (ndev <= 0) return set_error(VIMZ_ERR_NO_DEVICE, "vimz_ctx_create: no CUDA device visible (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return set_error(VIMZ_ERR_ARG, "vimz_ctx_create: device index out of range");
+  VIMZ_CUDA(cudaSetDevice(device));
+  vimz_ctx* ctx = new vimz_ctx();
+  ctx->curve = curve_id;
+  ctx->device = device;
+  VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
+  VIMZ_TRY(ctx->ws.result.reserve(4096));
+  *out = ctx;
+  return VIMZ_OK;
+}
+
+void vimz_ctx_destroy(vimz_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->side);
+  ctx->ws.release();
+  ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
+  ctx->tmp3.release(); ctx->tmp4.release(); ctx->tmp5.release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->side);
+  delete ctx;
+}
+
+int vimz_ctx_sync(vimz_ctx* ctx) {
+  CHECK_ARG(ctx, "vimz_ctx_sync: null ctx");
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
+  return VIMZ_OK;
+}
+
+int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
+  CHECK_ARG(ctx && key, "vimz_ctx_set_option: null argument");
+  if (strcmp(key, "msm_window") == 0) {
+    if (value != 0 && (value < 2 || value > 24)) return set_error(VIMZ_ERR_ARG, "msm_window must be 0 (auto) or in [2, 24]");
+    ctx->opt_window = value;
+    return VIMZ_OK;
+  }
+  return set_error(VIMZ_ERR_ARG, std::string("unknown option: ") + key);
+}
+
+void* vimz_ctx_stream(vimz_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t vimz_ctx_launch_count(vimz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- commitment key --------------------------------------------------------------------------------
+static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out) {
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  int c = ctx->opt_window ? (int)ctx->opt_window : msm_pick_window(vt->scalar_modulus, n);
+  int nwin = msm_num_windows(vt->scalar_modulus, c);
+  if (nwin > MSM_MAX_WINDOWS) return set_error(VIMZ_ERR_ARG, "msm_window too small: more than 32 windows");
+  if ((double)n * nwin >= 2147483648.0) return set_error(VIMZ_ERR_ARG, "commitment key too long for this window size");
+  vimz_ck* ck = new vimz_ck();
+  ck->ctx = ctx;
+  ck->n = n;
+  ck->c = c;
+  ck->nwin = nwin;
+  size_t bytes = std::max<size_t>(n * (size_t)nwin * 64, 64);
+  cudaError_t e = cudaMalloc(&ck->table, bytes);
+  if (e != cudaSuccess) {
+    delete ck;
+    return set_error(VIMZ_ERR_CUDA, std::string("cudaMalloc(window table) failed: ") + cudaGetErrorString(e));
+  }
+  int rc = vt->precompute(ctx, d_bases, n, c, nwin, ck->table);
+  if (rc == VIMZ_OK) {
+    cudaError_t s = cudaStreamSynchronize(ctx->stream);
+    if (s != cudaSuccess) rc = set_error(VIMZ_ERR_CUDA, std::string("window-table expansion failed: ") + cudaGetErrorString(s));
+  }
+  if (rc != VIMZ_OK) {
+    cudaFree(ck->table);
+    delete ck;
+    return rc;
+  }
+  *out = ck;
+  return VIMZ_OK;
+}
+
+int vimz_ck_upload_dev(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out) {
+  CHECK_ARG(ctx && out && (d_bases || n == 0), "vimz_ck_upload_dev: null argument");
+  DeviceGuard g(ctx->device);
+  return ck_build(ctx, d_bases, n, out);
+}
+
+int vimz_ck_upload(vimz_ctx* ctx, const vimz_affine* bases, size_t n, vimz_ck** out) {
+  CHECK_ARG(ctx && out && (bases || n == 0), "vimz_ck_upload: null argument");
+  DeviceGuard g(ctx->device);
+  void* d = nullptr;
+  VIMZ_CUDA(cudaMalloc(&d, std::max<size_t>(n * 64, 64)));
+  cudaError_t e = cudaMemcpyAsync(d, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = e == cudaSuccess ? ck_build(ctx, d, n, out) : set_error(VIMZ_ERR_CUDA, cudaGetErrorString(e));
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  return rc;
+}
+
+void vimz_ck_destroy(vimz_ck* ck) {
+  if (!ck) return;
+  cudaSetDevice(ck->ctx->device);
+  cudaStreamSynchronize(ck->ctx->stream);
+  if (ck->table) cudaFree(ck->table);
+  delete ck;
+}
+size_t vimz_ck_len(const vimz_ck* ck) { return ck ? ck->n : 0; }
+int vimz_ck_window_bits(const vimz_ck* ck) { return ck ? ck->c : 0; }
+int vimz_ck_num_windows(const vimz_ck* ck) { return ck ? ck->nwin : 0; }
+
+// ---- MSM ---------------------------------------------------------------------------------------------
+int vimz_msm_async_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out) {
+  CHECK_ARG(ctx && ck && d_out && (d_scalars || n == 0), "vimz_msm: null argument");
+  CHECK_ARG(ck->ctx == ctx, "vimz_msm: commitment key belongs to another context");
+  if (first + n > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_msm: vector longer than the commitment key");
+  DeviceGuard g(ctx->device);
+  return curve_vtable(ctx->curve)->msm(ctx, ck, first, d_scalars, n, d_out);
+}
+
+static int fetch_points(vimz_ctx* ctx, const void* d_src, void* host_dst, size_t bytes) {
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(host_dst, ctx->pinned, bytes);
+  return VIMZ_OK;
+}
+
+int vimz_msm_range_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, vimz_point* out) {
+  CHECK_ARG(out, "vimz_msm: out is null");
+  VIMZ_TRY(vimz_msm_async_dev(ctx, ck, first, d_scalars, n, ctx ? ctx->ws.result.ptr : nullptr));
+  DeviceGuard g(ctx->device);
+  return fetch_points(ctx, ctx->ws.result.ptr, out, 96);
+}
+
+int vimz_msm_dev(vimz_ctx* ctx, const vimz_ck* ck, const void* d_scalars, size_t n, vimz_point* out) {
+  return vimz_msm_range_dev(ctx, ck, 0, d_scalars, n, out);
+}
+
+int vimz_msm(vimz_ctx* ctx, const vimz_ck* ck, const vimz_fr* scalars, size_t n, vimz_point* out) {
+  CHECK_ARG(ctx && ck && out && (scalars || n == 0), "vimz_msm: null argument");
+  if (n > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_msm: vector longer than the commitment key");
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(ctx->ws.scal.reserve(std::max<size_t>(n * 32, 32)));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->ws.scal.ptr, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return vimz_msm_range_dev(ctx, ck, 0, ctx->ws.scal.ptr, n, out);
+}
+
+// ---- group helpers ---------------------------------------------------------------------------------
+int vimz_point_sum(vimz_ctx* ctx, const vimz_point* pts, size_t k, vimz_point* out) {
+  CHECK_ARG(ctx && out && (pts || k == 0), "vimz_point_sum: null argument");
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(ctx->tmp0.reserve(std::max<size_t>(k * 96, 96) + 96));
+  char* d = ctx->tmp0.as<char>();
+  VIMZ_CUDA(cudaMemcpyAsync(d + 96, pts, k * 96, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_TRY(curve_vtable(ctx->curve)->point_sum(ctx, d + 96, k, d));
+  return fetch_points(ctx, d, out, 96);
+}
+
+int vimz_point_to_affine(vimz_ctx* ctx, const vimz_point* p, vimz_affine* out) {
+  CHECK_ARG(ctx && p && out, "vimz_point_to_affine: null argument");
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(ctx->tmp0.reserve(256));
+  char* d = ctx->tmp0.as<char>();
+  VIMZ_CUDA(cudaMemcpyAsync(d, p, 96, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_TRY(curve_vtable(ctx->curve)->point_to_affine(ctx, d, d + 128));
+  return fetch_points(ctx, d + 128, out, 64);
+}
+
+int vimz_point_scale_add(vimz_ctx* ctx, const vimz_point* a, const vimz_fr* r, const vimz_point* b, vimz_point* out) {
+  CHECK_ARG(ctx && a && r && b && out, "vimz_point_scale_add: null argument");
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(ctx->tmp0.reserve(512));
+  char* d = ctx->tmp0.as<char>();
+  VIMZ_CUDA(cudaMemcpyAsync(d, a, 96, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(d + 96, b, 96, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(d + 192, r, 32, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_TRY(curve_vtable(ctx->curve)->point_scale_add(ctx, ctx->stream, d, d + 192, d + 96, d + 256, 1));
+  return fetch_points(ctx, d + 256, out, 96);
+}
+
+// ---- R1CS shape --------------------------------------------------------------------------------------
+static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row, const uint32_t* col, const vimz_fr* val, size_t nnz,
+                      uint32_t** d_rowptr, uint32_t** d_col, void** d_val) {
+  std::vector<uint32_t> rowptr(m + 1, 0);
+  for (size_t k = 0; k < nnz; k++) {
+    if (row[k] >= m || col[k] >= ncols) return set_error(VIMZ_ERR_INDEX, "vimz_shape_upload: entry out of range (InvalidIndex)");
+    rowptr[row[k] + 1]++;
+  }
+  for (size_t i = 0; i < m; i++) rowptr[i + 1] += rowptr[i];
+  std::vector<uint32_t> cursor(rowptr.begin(), rowptr.end() - 1), ccol(nnz);
+  std::vector<vimz_fr> cval(nnz);
+  for (size_t k = 0; k < nnz; k++) {  // stable: keeps constraint order inside a row
+    uint32_t p = cursor[row[k]]++;
+    ccol[p] = col[k];
+    cval[p] = val[k];
+  }
+  VIMZ_CUDA(cudaMalloc(d_rowptr, (m + 1) * 4));
+  VIMZ_CUDA(cudaMalloc(d_col, std::max<size_t>(nnz * 4, 4)));
+  VIMZ_CUDA(cudaMalloc(d_val, std::max<size_t>(nnz * 32, 32)));
+  VIMZ_CUDA(cudaMemcpyAsync(*d_rowptr, rowptr.data(), (m + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(*d_col, ccol.data(), nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(*d_val, cval.data(), nnz * 32, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIMZ_OK;
+}
+
+void vimz_shape_destroy(vimz_shape* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int k = 0; k < 3; k++) {
+    if (s->rowptr[k]) cudaFree(s->rowptr[k]);
+    if (s->col[k]) cudaFree(s->col[k]);
+    if (s->val[k]) cudaFree(s->val[k]);
+  }
+  delete s;
+}
+
+int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_io,
+                      const uint32_t* rowA, const uint32_t* colA, const vimz_fr* valA, size_t nnzA,
+                      const uint32_t* rowB, const uint32_t* colB, const vimz_fr* valB, size_t nnzB,
+                      const uint32_t* rowC, const uint32_t* colC, const vimz_fr* valC, size_t nnzC,
+                      vimz_shape** out) {
+  CHECK_ARG(ctx && out, "vimz_shape_upload: null argument");
+  CHECK_ARG((nnzA == 0 || (rowA && colA && valA)) && (nnzB == 0 || (rowB && colB && valB)) && (nnzC == 0 || (rowC && colC && valC)),
+            "vimz_shape_upload: null matrix arrays");
+  CHECK_ARG(num_cons < (1ull << 31) && num_vars + num_io + 1 < (1ull << 31), "vimz_shape_upload: shape too large");
+  DeviceGuard g(ctx->device);
+  vimz_shape* s = new vimz_shape();
+  s->ctx = ctx;
+  s->m = num_cons;
+  s->n = num_vars;
+  s->io = num_io;
+  size_t ncols = num_vars + 1 + num_io;
+  const uint32_t* rows[3] = {rowA, rowB, rowC};
+  const uint32_t* cols[3] = {colA, colB, colC};
+  const vimz_fr* vals[3] = {valA, valB, valC};
+  size_t nnz[3] = {nnzA, nnzB, nnzC};
+  for (int k = 0; k < 3; k++) {
+    s->nnz[k] = nnz[k];
+    int rc = coo_to_csr(ctx, num_cons, ncols, rows[k], cols[k], vals[k], nnz[k], &s->rowptr[k], &s->col[k], &s->val[k]);
+    if (rc != VIMZ_OK) {
+      vimz_shape_destroy(s);
+      return rc;
+    }
+  }
+  *out = s;
+  return VIMZ_OK;
+}
+
+int vimz_multiply_vec(vimz_ctx* ctx, const vimz_shape* s, const vimz_fr* z, size_t z_len, vimz_fr* Az, vimz_fr* Bz, vimz_fr* Cz) {
+  CHECK_ARG(ctx && s && z && Az && Bz && Cz, "vimz_multiply_vec: null argument");
+  if (z_len != s->n + 1 + s->io) return set_error(VIMZ_ERR_LENGTH, "vimz_multiply_vec: z.len() != num_io + num_vars + 1 (InvalidWitnessLength)");
+  DeviceGuard g(ctx->device);
+  size_t mb = std::max<size_t>(s->m * 32, 32);
+  VIMZ_TRY(ctx->tmp0.reserve(z_len * 32));
+  VIMZ_TRY(ctx->tmp1.reserve(mb));
+  VIMZ_TRY(ctx->tmp2.reserve(mb));
+  VIMZ_TRY(ctx->tmp3.reserve(mb));
+  char* dz = ctx->tmp0.as<char>();
+  VIMZ_CUDA(cudaMemcpyAsync(dz, z, z_len * 32, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_TRY(curve_vtable(ctx->curve)->spmv3(ctx, s, dz, dz + s->n * 32, ctx->tmp1.ptr, ctx->tmp2.ptr, ctx->tmp3.ptr));
+  VIMZ_CUDA(cudaMemcpyAsync(Az, ctx->tmp1.ptr, s->m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(Bz, ctx->tmp2.ptr, s->m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(Cz, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIMZ_OK;
+}
+
+int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
+                  const vimz_fr* W1, const vimz_fr* u1, const vimz_fr* X1,
+                  const vimz_fr* W2, const vimz_fr* X2, vimz_fr* T_out, vimz_point* comm_T) {
+  CHECK_ARG(ctx && s && ck && u1 && comm_T && (W1 || s->n == 0) && (W2 || s->n == 0) && ((X1 && X2) || s->io == 0),
+            "vimz_commit_T: null argument");
+  if (s->m > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_commit_T: commitment key shorter than num_cons");
+  DeviceGuard g(ctx->device);
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  size_t nb = std::max<size_t>(s->n * 32, 32), tb = (1 + s->io) * 32;
+  VIMZ_TRY(ctx->tmp0.reserve(nb));
+  VIMZ_TRY(ctx->tmp1.reserve(nb));
+  VIMZ_TRY(ctx->tmp2.reserve(2 * tb));
+  VIMZ_TRY(ctx->tmp3.reserve(std::max<size_t>(s->m * 32, 32)));
+  char* t1 = ctx->tmp2.as<char>();
+  char* t2 = t1 + tb;
+  cudaStream_t st = ctx->stream;
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp0.ptr, W1, s->n * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp1.ptr, W2, s->n * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(t1, u1, 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(t2, vt->scalar_one_mont, 32, cudaMemcpyHostToDevice, st));
+  if (s->io) {
+    VIMZ_CUDA(cudaMemcpyAsync(t1 + 32, X1, s->io * 32, cudaMemcpyHostToDevice, st));
+    VIMZ_CUDA(cudaMemcpyAsync(t2 + 32, X2, s->io * 32, cudaMemcpyHostToDevice, st));
+  }
+  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr));
+  if (T_out) VIMZ_CUDA(cudaMemcpyAsync(T_out, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, st));
+  VIMZ_TRY(vt->msm(ctx, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr));
+  return fetch_points(ctx, ctx->ws.result.ptr, comm_T, 96);
+}
+
+int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r, const vimz_fr* W1, const vimz_fr* W2, size_t n,
+                      const vimz_fr* E1, const vimz_fr* T, size_t m, vimz_fr* W_out, vimz_fr* E_out) {
+  CHECK_ARG(ctx && r && (n == 0 || (W1 && W2 && W_out)) && (m == 0 || (E1 && T && E_out)), "vimz_fold_witness: null argument");
+  DeviceGuard g(ctx->device);
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  cudaStream_t st = ctx->stream;
+  VIMZ_TRY(ctx->tmp0.reserve(std::max<size_t>(n * 32, 32)));
+  VIMZ_TRY(ctx->tmp1.reserve(std::max<size_t>(n * 32, 32)));
+  VIMZ_TRY(ctx->tmp2.reserve(std::max<size_t>(m * 32, 32)));
+  VIMZ_TRY(ctx->tmp3.reserve(std::max<size_t>(m * 32, 32)));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp0.ptr, W1, n * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp1.ptr, W2, n * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp2.ptr, E1, m * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp3.ptr, T, m * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_TRY(vt->axpy(ctx, ctx->tmp0.ptr, ctx->tmp1.ptr, r, n, ctx->tmp0.ptr));
+  VIMZ_TRY(vt->axpy(ctx, ctx->tmp2.ptr, ctx->tmp3.ptr, r, m, ctx->tmp2.ptr));
+  VIMZ_CUDA(cudaMemcpyAsync(W_out, ctx->tmp0.ptr, n * 32, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaMemcpyAsync(E_out, ctx->tmp2.ptr, m * 32, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  return VIMZ_OK;
+}
+
+// ---- device-resident running instance --------------------------------------------------------------
+void vimz_acc_destroy(vimz_acc* a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  cudaStreamSynchronize(a->ctx->stream);
+  cudaStreamSynchronize(a->ctx->side);
+  void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (a->ev_main) cudaEventDestroy(a->ev_main);
+  for (int k = 0; k < 2; k++)
+    if (a->ev_side[k]) cudaEventDestroy(a->ev_side[k]);
+  delete a;
+}
+
+int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_acc** out) {
+  CHECK_ARG(ctx && s && ck && out, "vimz_acc_init: null argument");
+  CHECK_ARG(s->ctx == ctx && ck->ctx == ctx, "vimz_acc_init: shape / key belong to another context");
+  if (ck->n < s->m || ck->n < s->n) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_init: commitment key shorter than the shape");
+  DeviceGuard g(ctx->device);
+  vimz_acc* a = new vimz_acc();
+  a->ctx = ctx;
+  a->shape = s;
+  a->ck = ck;
+  size_t nb = std::max<size_t>(s->n * 32, 32), mb = std::max<size_t>(s->m * 32, 32), tb = (1 + s->io) * 32;
+  cudaError_t e = cudaSuccess;
+  auto alloc0 = [&](void** p, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, ctx->stream);
+  };
+  alloc0(&a->W1, nb); alloc0(&a->W2, nb); alloc0(&a->E1, mb); alloc0(&a->T, mb);
+  alloc0(&a->tail1, tb); alloc0(&a->tail2, tb); alloc0(&a->comms, 6 * 96 + 2 * 32);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_main, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_side[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_side[1], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    vimz_acc_destroy(a);
+    return set_error(VIMZ_ERR_CUDA, std::string("vimz_acc_init: ") + cudaGetErrorString(e));
+  }
+  *out = a;
+  return VIMZ_OK;
+}
+
+// main stream waits for the commitment folds still running on the side stream
+static int acc_wait_side(vimz_acc* a) {
+  for (int k = 0; k < 2; k++)
+    if (a->side_pending[k]) {
+      VIMZ_CUDA(cudaStreamWaitEvent(a->ctx->stream, a->ev_side[k], 0));
+      a->side_pending[k] = false;
+    }
+  return VIMZ_OK;
+}
+
+int vimz_acc_load(vimz_acc* a, const vimz_fr* W, const vimz_fr* E, const vimz_fr* u, const vimz_fr* X,
+                  const vimz_point* comm_W, const vimz_point* comm_E) {
+  CHECK_ARG(a && u && comm_W && comm_E && (W || a->shape->n == 0) && (E || a->shape->m == 0) && (X || a->shape->io == 0),
+            "vimz_acc_load: null argument");
+  vimz_ctx* ctx = a->ctx;
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(acc_wait_side(a));
+  cudaStream_t st = ctx->stream;
+  const vimz_shape* s = a->shape;
+  VIMZ_CUDA(cudaMemcpyAsync(a->W1, W, s->n * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(a->E1, E, s->m * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(a->tail1, u, 32, cudaMemcpyHostToDevice, st));
+  if (s->io) VIMZ_CUDA(cudaMemcpyAsync((char*)a->tail1 + 32, X, s->io * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(a->comms, comm_W, 96, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync((char*)a->comms + 96, comm_E, 96, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  return VIMZ_OK;
+}
+
+static int acc_step_begin_common(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
+  vimz_ctx* ctx = a->ctx;
+  const vimz_shape* s = a->shape;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  cudaStream_t st = ctx->stream;
+  // comm_W2 / comm_T alternate between two slot pairs so the side-stream fold of the previous
+  // step can still read its inputs; the pair used two steps ago must be free again.
+  a->parity ^= 1;
+  if (a->side_pending[a->parity]) {
+    VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_side[a->parity], 0));
+    a->side_pending[a->parity] = false;
+  }
+  char* comms = (char*)a->comms;
+  char* fresh = comms + (2 + 2 * a->parity) * 96;
+  // tail2 = (1, X2)
+  uint8_t* stage = (uint8_t*)ctx->pinned + 1024;
+  memcpy(stage, vt->scalar_one_mont, 32);
+  if (s->io) memcpy(stage + 32, X2, s->io * 32);
+  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  // comm_W2 = commit(ck, W2)            (r1cs_instance_and_witness)
+  VIMZ_TRY(vt->msm(ctx, a->ck, 0, d_W2, s->n, fresh));
+  // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
+  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, d_W2, a->tail2, a->T));
+  VIMZ_TRY(vt->msm(ctx, a->ck, 0, a->T, s->m, fresh + 96));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  memcpy(comm_W2, ctx->pinned, 96);
+  memcpy(comm_T, (char*)ctx->pinned + 96, 96);
+  return VIMZ_OK;
+}
+
+int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
+  CHECK_ARG(a && comm_W2 && comm_T && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin: null argument");
+  DeviceGuard g(a->ctx->device);
+  size_t io = a->shape->io;
+  if (1024 + (1 + io) * 32 > 4096) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
+  VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  return acc_step_begin_common(a, a->W2, X2, comm_W2, comm_T);
+}
+
+int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
+  CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
+  DeviceGuard g(a->ctx->device);
+  size_t io = a->shape->io;
+  if (1024 + (1 + io) * 32 > 4096) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
+  // keep W2 resident for step_end
+  VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
+  return acc_step_begin_common(a, a->W2, X2, comm_W2, comm_T);
+}
+
+int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
+  CHECK_ARG(a && r, "vimz_acc_step_end: null argument");
+  vimz_ctx* ctx = a->ctx;
+  DeviceGuard g(ctx->device);
+  const vimz_shape* s = a->shape;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  cudaStream_t st = ctx->stream;
+  char* comms = (char*)a->comms;
+  char* fresh = comms + (2 + 2 * a->parity) * 96;
+  char* d_r = comms + 6 * 96 + 32 * a->parity;
+  // r goes to the device once for the commitment folds (side stream) ...
+  uint8_t* stage = (uint8_t*)ctx->pinned + 2048 + 32 * a->parity;
+  memcpy(stage, r, 32);
+  VIMZ_CUDA(cudaMemcpyAsync(d_r, stage, 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaEventRecord(a->ev_main, st));
+  // ... and by value into the witness folds: W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2)
+  VIMZ_TRY(vt->axpy(ctx, a->W1, a->W2, r, s->n, a->W1));
+  VIMZ_TRY(vt->axpy(ctx, a->E1, a->T, r, s->m, a->E1));
+  VIMZ_TRY(vt->axpy(ctx, a->tail1, a->tail2, r, 1 + s->io, a->tail1));
+  // comm_W1 += r*comm_W2 ; comm_E1 += r*comm_T : two 128-bit scalar multiplications, latency-bound,
+  // so they run on the side stream and overlap the next step's MSMs.
+  VIMZ_CUDA(cudaStreamWaitEvent(ctx->side, a->ev_main, 0));
+  VIMZ_TRY(vt->point_scale_add(ctx, ctx->side, comms, d_r, fresh, comms, 2));
+  VIMZ_CUDA(cudaEventRecord(a->ev_side[a->parity], ctx->side));
+  a->side_pending[a->parity] = true;
+  return VIMZ_OK;
+}
+
+int vimz_acc_download(vimz_acc* a, vimz_fr* W, vimz_fr* E, vimz_fr* u, vimz_fr* X, vimz_point* comm_W, vimz_point* comm_E) {
+  CHECK_ARG(a, "vimz_acc_download: null argument");
+  vimz_ctx* ctx = a->ctx;
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(acc_wait_side(a));
+  cudaStream_t st = ctx->stream;
+  const vimz_shape* s = a->shape;
+  if (W) VIMZ_CUDA(cudaMemcpyAsync(W, a->W1, s->n * 32, cudaMemcpyDeviceToHost, st));
+  if (E) VIMZ_CUDA(cudaMemcpyAsync(E, a->E1, s->m * 32, cudaMemcpyDeviceToHost, st));
+  if (u) VIMZ_CUDA(cudaMemcpyAsync(u, a->tail1, 32, cudaMemcpyDeviceToHost, st));
+  if (X && s->io) VIMZ_CUDA(cudaMemcpyAsync(X, (char*)a->tail1 + 32, s->io * 32, cudaMemcpyDeviceToHost, st));
+  if (comm_W) VIMZ_CUDA(cudaMemcpyAsync(comm_W, a->comms, 96, cudaMemcpyDeviceToHost, st));
+  if (comm_E) VIMZ_CUDA(cudaMemcpyAsync(comm_E, (char*)a->comms + 96, 96, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  return VIMZ_OK;
+}
+
+int vimz_acc_last_T(vimz_acc* a, vimz_fr* T) {
+  CHECK_ARG(a && (T || a->shape->m == 0), "vimz_acc_last_T: null argument");
+  DeviceGuard g(a->ctx->device);
+  VIMZ_CUDA(cudaMemcpyAsync(T, a->T, a->shape->m * 32, cudaMemcpyDeviceToHost, a->ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(a->ctx->stream));
+  return VIMZ_OK;
+}
+
+// ---- test / bench utilities --------------------------------------------------------------------------
+int vimz_gen_bases_dev(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* d_out) {
+  CHECK_ARG(ctx && (d_out || n == 0), "vimz_gen_bases_dev: null argument");
+  DeviceGuard g(ctx->device);
+  VIMZ_TRY(curve_vtable(ctx->curve)->gen_bases(ctx, k0, dk, n, d_out));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIMZ_OK;
+}
+
+int vimz_field_op(vimz_ctx* ctx, int which, int op, const vimz_fr* a, const vimz_fr* b, size_t n, vimz_fr* out) {
+  CHECK_ARG(ctx && (n == 0 || (a && b && out)) && which >= 0 && which <= 1 && op >= 0 && op <= 2, "vimz_field_op: bad argument");
+  DeviceGuard g(ctx->device);
+  size_t bytes = std::max<size_t>(n * 32, 32);
+  VIMZ_TRY(ctx->tmp0.reserve(bytes));
+  VIMZ_TRY(ctx->tmp1.reserve(bytes));
+  VIMZ_TRY(ctx->tmp2.reserve(bytes));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp0.ptr, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->tmp1.ptr, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  VIMZ_TRY(curve_vtable(ctx->curve)->field_op(ctx, which, op, ctx->tmp0.ptr, ctx->tmp1.ptr, n, ctx->tmp2.ptr));
+  VIMZ_CUDA(cudaMemcpyAsync(out, ctx->tmp2.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIMZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// common.cuh -- context, error handling and device buffers shared by the kernels' host drivers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/vimz_gpu.h"
+
+namespace vimz {
+
+extern thread_local std::string g_last_error;
+
+inline int set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define VIMZ_CUDA(expr)                                                                            \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _buf[512];                                                                              \
+      snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ::vimz::set_error(VIMZ_ERR_CUDA, _buf);                                               \
+    }                                                                                              \
+  } while (0)
+
+#define VIMZ_TRY(expr)             \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != VIMZ_OK) return _rc; \
+  } while (0)
+
+// Grow-only device buffer (no per-call cudaMalloc on the hot path).
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return VIMZ_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    VIMZ_CUDA(cudaMalloc(&ptr, want));
+    cap = want;
+    return VIMZ_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+}  // namespace vimz
+
+// MSM scratch: everything Pippenger needs besides the resident table.
+struct MsmWorkspace {
+  vimz::DevBuf counts;     // [M]   entries per bucket
+  vimz::DevBuf offsets;    // [M+1] exclusive prefix of counts
+  vimz::DevBuf cursor;     // [M]   scatter cursors
+  vimz::DevBuf blocksums;  // scan scratch
+  vimz::DevBuf sorted;     // [E]   table index | sign<<31, grouped by bucket
+  vimz::DevBuf order;      // [M]   bucket ids, largest first
+  vimz::DevBuf cls;        // class histogram / starts / cursors + big-bucket bookkeeping
+  vimz::DevBuf biglist;    // big bucket ids, task starts
+  vimz::DevBuf partials;   // XYZZ partial sums of big-bucket tasks
+  vimz::DevBuf buckets;    // [M] XYZZ
+  vimz::DevBuf chunkA;     // [T] XYZZ chunk sums
+  vimz::DevBuf chunkL;     // [T] XYZZ chunk weighted sums
+  vimz::DevBuf bitsums;    // [(nb+1) * G] XYZZ
+  vimz::DevBuf scal;       // staged scalars (host-pointer entry points)
+  vimz::DevBuf result;     // Jacobian results (device)
+  void release() {
+    counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release();
+    order.release(); cls.release(); biglist.release(); partials.release(); buckets.release();
+    chunkA.release(); chunkL.release(); bitsums.release(); scal.release(); result.release();
+  }
+};
+
+struct vimz_ctx {
+  int curve = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // instance-fold scalar multiplications overlap the next step here
+  int sm_count = 148;
+  long opt_window = 0;  // 0 = auto
+  uint64_t launches = 0;
+  MsmWorkspace ws;
+  vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points
+  void* pinned = nullptr;                      // small pinned staging block for results
+};
+
+struct vimz_ck {
+  vimz_ctx* ctx = nullptr;
+  size_t n = 0;
+  int c = 0;          // window bits
+  int nwin = 0;       // windows
+  void* table = nullptr;  // [nwin][n] affine points, row j = 2^(c*j) * base
+};
+
+struct vimz_shape {
+  vimz_ctx* ctx = nullptr;
+  size_t m = 0, n = 0, io = 0;
+  size_t nnz[3] = {0, 0, 0};
+  uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};  // [m+1]
+  uint32_t* col[3] = {nullptr, nullptr, nullptr};     // [nnz]
+  void* val[3] = {nullptr, nullptr, nullptr};         // [nnz] Montgomery scalars
+};
+
+struct vimz_acc {
+  vimz_ctx* ctx = nullptr;
+  const vimz_shape* shape = nullptr;
+  const vimz_ck* ck = nullptr;
+  void *W1 = nullptr, *E1 = nullptr, *W2 = nullptr, *T = nullptr;
+  void *tail1 = nullptr, *tail2 = nullptr;  // [1+io]: (u, X)
+  // Jacobian points comm_W1, comm_E1, then two alternating (comm_W2, comm_T) pairs, then two r slots
+  void* comms = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr};
+  bool side_pending[2] = {false, false};
+  int parity = 0;
+};

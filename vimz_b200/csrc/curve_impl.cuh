@@ -1,0 +1,237 @@
+// curve_impl.cuh -- host-side launch sequences, templated on the curve; each curve_<name>.cu
+// instantiates one CurveVTable so the four curves compile in parallel translation units.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include "common.cuh"
+#include "msm.cuh"
+#include "r1cs.cuh"
+
+namespace vimz {
+
+struct CurveVTable {
+  int id;
+  const char* name;
+  uint32_t scalar_modulus[8];
+  uint32_t scalar_one_mont[8];
+  int (*precompute)(vimz_ctx*, const void* d_bases, size_t n, int c, int nwin, void* table);
+  int (*msm)(vimz_ctx*, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out);
+  int (*point_sum)(vimz_ctx*, const void* d_pts, size_t k, void* d_out);
+  int (*point_to_affine)(vimz_ctx*, const void* d_pt, void* d_out);
+  int (*point_scale_add)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count);
+  int (*gen_bases)(vimz_ctx*, uint64_t k0, uint64_t dk, size_t n, void* d_out);
+  int (*spmv3)(vimz_ctx*, const vimz_shape*, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz);
+  int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T);
+  int (*axpy)(vimz_ctx*, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out);
+  int (*field_op)(vimz_ctx*, int which, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
+};
+
+const CurveVTable* curve_vtable(int curve_id);
+
+#define VIMZ_LAUNCH_CHECK(ctx)                 \
+  do {                                         \
+    (ctx)->launches++;                         \
+    VIMZ_CUDA(cudaGetLastError());             \
+  } while (0)
+
+inline uint32_t ceil_div(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+template <class C>
+int impl_precompute(vimz_ctx* ctx, const void* d_bases, size_t n, int c, int nwin, void* table) {
+  if (n == 0) return VIMZ_OK;
+  k_precompute<C><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(d_bases, (uint32_t)n, c, nwin, table);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+
+template <class C>
+int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out) {
+  cudaStream_t st = ctx->stream;
+  MsmWorkspace& ws = ctx->ws;
+  const int c = ck->c, nwin = ck->nwin;
+  const uint32_t M = 1u << (c - 1);
+  const size_t E = std::max<size_t>(n * (size_t)nwin, 1);
+  const int K = (int)std::min<uint32_t>(MSM_REDUCE_K, M);
+  int logK = 0;
+  while ((1 << logK) < K) logK++;
+  const uint32_t T = M / K;
+  int nb = 0;
+  while ((1u << nb) < T) nb++;
+  const int G = MSM_REDUCE_G;
+
+  // bucket-size classes: buckets above `cap` entries are split into block tasks
+  size_t lambda = E / M;
+  uint32_t cap = (uint32_t)std::min<size_t>(std::max<size_t>(4 * lambda, 256), MSM_MAX_CLASSES - 1);
+  uint32_t maxbig = (uint32_t)(E / cap + 2);
+  size_t maxtasks = E / MSM_BIG_CHUNK + maxbig + 1;
+  const uint32_t NC = MSM_MAX_CLASSES;
+
+  VIMZ_TRY(ws.counts.reserve((size_t)M * 4));
+  VIMZ_TRY(ws.offsets.reserve(((size_t)M + 1) * 4));
+  VIMZ_TRY(ws.cursor.reserve((size_t)M * 4));
+  uint32_t scan_blocks = ceil_div(M, SCAN_THREADS * SCAN_ITEMS);
+  VIMZ_TRY(ws.blocksums.reserve(((size_t)scan_blocks + 2) * 4));
+  VIMZ_TRY(ws.sorted.reserve(E * 4));
+  VIMZ_TRY(ws.order.reserve((size_t)M * 4));
+  VIMZ_TRY(ws.cls.reserve(((size_t)3 * NC + 8) * 4));
+  VIMZ_TRY(ws.biglist.reserve(((size_t)2 * maxbig + 2) * 4));
+  VIMZ_TRY(ws.partials.reserve(maxtasks * 128));
+  VIMZ_TRY(ws.buckets.reserve((size_t)M * 128));
+  VIMZ_TRY(ws.chunkA.reserve((size_t)T * 128));
+  VIMZ_TRY(ws.chunkL.reserve((size_t)T * 128));
+  VIMZ_TRY(ws.bitsums.reserve((size_t)(nb + 1) * G * 128));
+
+  uint32_t* counts = ws.counts.as<uint32_t>();
+  uint32_t* offsets = ws.offsets.as<uint32_t>();
+  uint32_t* cursor = ws.cursor.as<uint32_t>();
+  uint32_t* blocksums = ws.blocksums.as<uint32_t>();
+  uint32_t* sorted = ws.sorted.as<uint32_t>();
+  uint32_t* order = ws.order.as<uint32_t>();
+  MsmSchedule sc;
+  sc.hist = ws.cls.as<uint32_t>();
+  sc.cstart = sc.hist + NC;
+  sc.ccursor = sc.hist + 2 * NC;
+  sc.ctrl = sc.hist + 3 * NC;
+  sc.biglist = ws.biglist.as<uint32_t>();
+  sc.taskstart = sc.biglist + maxbig;
+  sc.cap = cap;
+  sc.maxbig = maxbig;
+
+  VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
+  VIMZ_CUDA(cudaMemsetAsync(sc.hist, 0, ((size_t)3 * NC + 8) * 4, st));
+
+  const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
+  if (n > 0) {
+    k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
+    VIMZ_LAUNCH_CHECK(ctx);
+  }
+  k_scan_blocksum<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_scan_top<<<1, 1024, 0, st>>>(blocksums, scan_blocks, blocksums + scan_blocks + 1);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_scan_apply<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums, offsets, cursor);
+  VIMZ_LAUNCH_CHECK(ctx);
+  if (n > 0) {
+    k_msm_scatter<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin,
+                                              (uint32_t)ck->n, (uint32_t)first, cursor, sorted);
+    VIMZ_LAUNCH_CHECK(ctx);
+  }
+  const int grid_m = (int)std::min<size_t>(ceil_div(M, 256), (size_t)ctx->sm_count * 8);
+  k_sched_hist<<<grid_m, 256, (cap + 1) * 4, st>>>(counts, M, sc);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_sched_scan<<<1, 1024, 0, st>>>(counts, sc);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_sched_scatter<<<grid_m, 256, 0, st>>>(counts, M, sc, order);
+  VIMZ_LAUNCH_CHECK(ctx);
+
+  k_msm_accumulate<C><<<ceil_div(M, 128), 128, 0, st>>>(order, counts, offsets, sorted, ck->table, M, sc.ctrl, ws.buckets.ptr);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_msm_accumulate_big<C><<<ctx->sm_count * 4, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_msm_big_combine<C><<<32, 128, 0, st>>>(sc, ws.partials.ptr, ws.buckets.ptr);
+  VIMZ_LAUNCH_CHECK(ctx);
+
+  k_reduce_chunks<C><<<ceil_div(T, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_reduce_bits<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, ws.bitsums.ptr);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_reduce_final<C><<<1, 32 * (nb + 1), 0, st>>>(ws.bitsums.ptr, nb, G, logK, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+
+template <class C>
+int impl_point_sum(vimz_ctx* ctx, const void* d_pts, size_t k, void* d_out) {
+  k_point_sum<C><<<1, 32, 0, ctx->stream>>>(d_pts, (uint32_t)k, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_point_to_affine(vimz_ctx* ctx, const void* d_pt, void* d_out) {
+  k_point_to_affine<C><<<1, 32, 0, ctx->stream>>>(d_pt, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_point_scale_add(vimz_ctx* ctx, cudaStream_t st, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count) {
+  // one thread per block so independent scalar multiplications land on different SMs
+  k_point_scale_add<C><<<count, 1, 0, st>>>(d_a, d_r, d_b, d_out, count);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_gen_bases(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* d_out) {
+  if (n == 0) return VIMZ_OK;
+  k_gen_bases<C><<<ceil_div(ceil_div(n, GEN_RUN), 128), 128, 0, ctx->stream>>>(k0, dk, (uint32_t)n, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+
+inline CsrView csr_view(const vimz_shape* s, int k) {
+  CsrView v;
+  v.rowptr = s->rowptr[k];
+  v.col = s->col[k];
+  v.val = s->val[k];
+  return v;
+}
+
+template <class C>
+int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz) {
+  if (s->m == 0) return VIMZ_OK;
+  k_spmv3<typename C::Fs><<<dim3(ceil_div(s->m, 256), 3), 256, 0, ctx->stream>>>(
+      csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W, d_tail, d_Az, d_Bz, d_Cz);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T) {
+  if (s->m == 0) return VIMZ_OK;
+  k_cross_term<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(
+      csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_axpy(vimz_ctx* ctx, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out) {
+  if (len == 0) return VIMZ_OK;
+  Fp<typename C::Fs> rr;
+  memcpy(rr.v, r, 32);
+  int grid = (int)std::min<size_t>(ceil_div(len, 256), (size_t)ctx->sm_count * 16);
+  k_axpy<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(d_a, d_b, rr, len, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_field_op(vimz_ctx* ctx, int which, int op, const void* d_a, const void* d_b, size_t n, void* d_out) {
+  if (n == 0) return VIMZ_OK;
+  if (which == 0)
+    k_field_op<typename C::Fb><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(op, d_a, d_b, n, d_out);
+  else
+    k_field_op<typename C::Fs><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(op, d_a, d_b, n, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+
+template <class C>
+CurveVTable make_vtable(const char* name) {
+  CurveVTable t;
+  t.id = C::ID;
+  t.name = name;
+  for (int i = 0; i < 8; i++) {
+    t.scalar_modulus[i] = C::Fs::p(i);
+    t.scalar_one_mont[i] = C::Fs::one(i);
+  }
+  t.precompute = &impl_precompute<C>;
+  t.msm = &impl_msm<C>;
+  t.point_sum = &impl_point_sum<C>;
+  t.point_to_affine = &impl_point_to_affine<C>;
+  t.point_scale_add = &impl_point_scale_add<C>;
+  t.gen_bases = &impl_gen_bases<C>;
+  t.spmv3 = &impl_spmv3<C>;
+  t.cross_term = &impl_cross_term<C>;
+  t.axpy = &impl_axpy<C>;
+  t.field_op = &impl_field_op<C>;
+  return t;
+}
+
+}  // namespace vimz

@@ -1,0 +1,591 @@
+// msm.cuh -- Pippenger MSM over a resident window table, sm_100a.
+//
+// Replaces CommitmentEngine::commit -> Group::vartime_multiscalar_mul ([EXT nova-snark 0.23.0]
+// src/provider/pedersen.rs, src/provider/mod.rs `cpu_best_multiexp`; pasta-msm for Pallas/Vesta),
+// i.e. SURVEY.md rows a9/a10/a13.  Same group element, different schedule:
+//
+//   * The commitment key is fixed for the whole proof, so at upload we expand it ONCE into
+//     table[j][i] = 2^(c*j) * ck_i (affine, 64 B).  A scalar s_i = sum_j d_ij 2^(c*j) with signed
+//     digits then contributes d_ij * table[j][i]: every window shares ONE set of M = 2^(c-1)
+//     buckets, there is no per-window bucket reduction and no final doubling chain.
+//   * digits (k_count) -> counting sort by bucket (scan + k_scatter) -> bucket sums
+//     (k_accumulate: one thread per bucket, buckets ordered by size so a warp's lanes run the same
+//     trip count; oversized buckets are split into block tasks) -> sum_k (k+1) * B_k
+//     (k_reduce_chunks / k_reduce_bits / k_reduce_final).
+//   * All arithmetic is exact; the result is the unique group element sum_i s_i * ck_i.
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace vimz {
+
+constexpr int MSM_REDUCE_K = 8;       // buckets per thread in the first reduction level
+constexpr int MSM_REDUCE_G = 16;      // blocks per masked sum in the second level
+constexpr int MSM_BIG_CHUNK = 2048;   // entries per block task for oversized buckets
+constexpr int MSM_MAX_CLASSES = 4096; // bucket-size classes for the size ordering
+constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
+
+// ---- signed-digit recoding -------------------------------------------------------------------
+// raw scalar (canonical, NOT Montgomery) -> digits d_j in [-2^(c-1), 2^(c-1)], j < nwin.
+// f(j, magnitude, negative) is called for every non-zero digit.
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, int nwin, Fn f) {
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1);
+  uint32_t carry = 0;
+  for (int j = 0; j < nwin; j++) {
+    int pos = j * c;
+    int limb = pos >> 5, off = pos & 31;
+    uint64_t lo = 0;
+    // dynamic limb index resolved with selects (registers cannot be indexed)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k == limb) lo |= (uint64_t)s[k];
+      if (k == limb + 1) lo |= (uint64_t)s[k] << 32;
+    }
+    uint32_t d = (uint32_t)((lo >> off) & mask) + carry;
+    carry = 0;
+    bool neg = false;
+    if (d > half && j != nwin - 1) {
+      d = (1u << c) - d;
+      neg = true;
+      carry = 1;
+    }
+    if (d != 0) f(j, d, neg);
+  }
+}
+
+template <class C>
+__global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
+                            uint32_t* __restrict__ counts) {
+  using Fs = Fp<typename C::Fs>;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
+    for_each_digit(s.v, c, nwin, [&](int, uint32_t mag, bool) { atomicAdd(&counts[mag - 1], 1u); });
+  }
+}
+
+template <class C>
+__global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
+                              uint32_t table_stride, uint32_t first,
+                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  using Fs = Fp<typename C::Fs>;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
+    for_each_digit(s.v, c, nwin, [&](int j, uint32_t mag, bool neg) {
+      uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
+      sorted[pos] = ((uint32_t)j * table_stride + first + i) | (neg ? 0x80000000u : 0u);
+    });
+  }
+}
+
+// ---- exclusive scan over the bucket counts (3 small kernels) --------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;  // per thread -> 2048 per block
+
+static __global__ void k_scan_blocksum(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ blocksums) {
+  __shared__ uint32_t sh[SCAN_THREADS / 32];
+  uint32_t base = blockIdx.x * SCAN_THREADS * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    uint32_t idx = base + k * SCAN_THREADS + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; w++) t += sh[w];
+    blocksums[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of blocksums in place (nblocks <= 65536)
+static __global__ void k_scan_top(uint32_t* __restrict__ blocksums, uint32_t nblocks, uint32_t* __restrict__ total) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblocks; base += 1024) {
+    uint32_t idx = base + threadIdx.x;
+    uint32_t v = idx < nblocks ? blocksums[idx] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint32_t incl = sh[threadIdx.x];
+    if (idx < nblocks) blocksums[idx] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// per block: exclusive scan + block prefix; writes offsets[] and a copy into cursor[]
+static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ blocksums,
+                             uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t sh[SCAN_THREADS];
+  uint32_t base = blockIdx.x * SCAN_THREADS * SCAN_ITEMS + threadIdx.x * SCAN_ITEMS;  // blocked arrangement
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+    uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = blocksums[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) {
+      offsets[base + k] = run;
+      cursor[base + k] = run;
+    }
+    run += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) offsets[n] = run;
+}
+
+// ---- bucket schedule: order buckets by size (largest first), split oversized ones ------------
+// cls layout (uint32): [0, NC) histogram, [NC, 2NC) class start, [2NC, 3NC) class cursor,
+// then ctrl: [3NC+0] nbig, [3NC+1] ntasks, [3NC+2] task counter, [3NC+3] big-combine counter.
+struct MsmSchedule {
+  uint32_t* hist;
+  uint32_t* cstart;
+  uint32_t* ccursor;
+  uint32_t* ctrl;
+  uint32_t* biglist;    // [maxbig] bucket ids
+  uint32_t* taskstart;  // [maxbig + 1]
+  uint32_t cap;         // buckets with count > cap are "big"
+  uint32_t maxbig;
+};
+
+static __global__ void k_sched_hist(const uint32_t* __restrict__ counts, uint32_t M, MsmSchedule sc) {
+  extern __shared__ uint32_t sh_hist[];  // cap + 1
+  for (uint32_t k = threadIdx.x; k <= sc.cap; k += blockDim.x) sh_hist[k] = 0;
+  __syncthreads();
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < M; b += gridDim.x * blockDim.x) {
+    uint32_t cnt = counts[b];
+    if (cnt > sc.cap) {
+      uint32_t e = atomicAdd(&sc.ctrl[0], 1u);
+      if (e < sc.maxbig) sc.biglist[e] = b;
+    } else {
+      atomicAdd(&sh_hist[cnt], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k <= sc.cap; k += blockDim.x)
+    if (sh_hist[k]) atomicAdd(&sc.hist[k], sh_hist[k]);
+}
+
+// single block: class starts (descending size) and big-bucket task starts
+static __global__ void k_sched_scan(const uint32_t* __restrict__ counts, MsmSchedule sc) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  // classes in descending order: position p <-> class cap - p
+  uint32_t nc = sc.cap + 1;
+  for (uint32_t base = 0; base < nc; base += 1024) {
+    uint32_t p = base + threadIdx.x;
+    uint32_t v = p < nc ? sc.hist[sc.cap - p] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint32_t incl = sh[threadIdx.x];
+    if (p < nc) {
+      sc.cstart[sc.cap - p] = carry + incl - v;
+      sc.ccursor[sc.cap - p] = carry + incl - v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  // big buckets: tasks of MSM_BIG_CHUNK entries
+  uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nbig; base += 1024) {
+    uint32_t e = base + threadIdx.x;
+    uint32_t v = e < nbig ? (counts[sc.biglist[e]] + MSM_BIG_CHUNK - 1) / MSM_BIG_CHUNK : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint32_t incl = sh[threadIdx.x];
+    if (e < nbig) sc.taskstart[e] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sc.taskstart[nbig] = carry;
+    sc.ctrl[1] = carry;
+  }
+}
+
+static __global__ void k_sched_scatter(const uint32_t* __restrict__ counts, uint32_t M, MsmSchedule sc, uint32_t* __restrict__ order) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < M; b += gridDim.x * blockDim.x) {
+    uint32_t cnt = counts[b];
+    if (cnt <= sc.cap) {
+      uint32_t pos = atomicAdd(&sc.ccursor[cnt], 1u);
+      order[pos] = b;
+    }
+  }
+}
+
+// ---- bucket accumulation ----------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
+                                                        const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
+                                                        const void* __restrict__ table, uint32_t M, const uint32_t* __restrict__ ctrl,
+                                                        void* __restrict__ buckets) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nsmall = M - min(ctrl[0], M);
+  if (j >= nsmall) return;
+  uint32_t b = order[j];
+  uint32_t cnt = counts[b];
+  const uint32_t* ent = sorted + offsets[b];
+  Xyzz<C> acc = Xyzz<C>::identity();
+  if (cnt > 0) {
+    uint32_t e = ent[0];
+    Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
+    for (uint32_t k = 0; k < cnt; k++) {
+      Affine<C> cur = p;
+      bool neg = (e >> 31) != 0;
+      if (k + 1 < cnt) {  // prefetch the next base while this madd runs
+        e = ent[k + 1];
+        p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
+      }
+      xyzz_madd<C>(acc, cur, neg);
+    }
+  }
+  acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+}
+
+// shared-memory tree reduction of one XYZZ value per thread; result valid in thread 0
+template <class C, int THREADS>
+__device__ __forceinline__ void block_reduce_xyzz(Xyzz<C>& acc, uint32_t* smem /* THREADS*32 words */) {
+  uint32_t* mine = smem + threadIdx.x * 32;
+  acc.store(mine);
+  __syncthreads();
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      Xyzz<C> other = Xyzz<C>::load(smem + (threadIdx.x + s) * 32);
+      xyzz_add<C>(acc, other);
+      acc.store(mine);
+    }
+    __syncthreads();
+  }
+}
+
+template <class C>
+__device__ __forceinline__ Xyzz<C> warp_reduce_xyzz(Xyzz<C> acc) {
+  for (int o = 16; o > 0; o >>= 1) {
+    Xyzz<C> other;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      other.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], o);
+      other.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], o);
+      other.zz.v[k] = __shfl_down_sync(0xffffffffu, acc.zz.v[k], o);
+      other.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], o);
+    }
+    xyzz_add<C>(acc, other);
+  }
+  return acc;
+}
+
+// persistent blocks pull (big bucket, chunk) tasks; each writes one XYZZ partial
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                            const uint32_t* __restrict__ sorted, const void* __restrict__ table,
+                                                            MsmSchedule sc, void* __restrict__ partials) {
+  __shared__ __align__(16) uint32_t smem[128 * 32];
+  __shared__ uint32_t s_task;
+  uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
+  uint32_t ntasks = sc.ctrl[1];
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(&sc.ctrl[2], 1u);
+    __syncthreads();
+    uint32_t task = s_task;
+    if (task >= ntasks) break;
+    // find e with taskstart[e] <= task < taskstart[e+1]
+    uint32_t lo = 0, hi = nbig;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (sc.taskstart[mid] <= task) lo = mid; else hi = mid;
+    }
+    uint32_t b = sc.biglist[lo];
+    uint32_t chunk = task - sc.taskstart[lo];
+    uint32_t cnt = counts[b];
+    uint32_t beg = chunk * MSM_BIG_CHUNK, end = min(cnt, beg + MSM_BIG_CHUNK);
+    const uint32_t* ent = sorted + offsets[b];
+    Xyzz<C> acc = Xyzz<C>::identity();
+    for (uint32_t k = beg + threadIdx.x; k < end; k += 128) {
+      uint32_t e = ent[k];
+      Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
+      xyzz_madd<C>(acc, p, (e >> 31) != 0);
+    }
+    block_reduce_xyzz<C, 128>(acc, smem);
+    if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(partials) + (size_t)task * 128);
+    __syncthreads();
+  }
+}
+
+// one warp per big bucket: sum its task partials into the bucket
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_big_combine(MsmSchedule sc, const void* __restrict__ partials, void* __restrict__ buckets) {
+  uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t e = warp; e < nbig; e += nwarps) {
+    uint32_t t0 = sc.taskstart[e], t1 = sc.taskstart[e + 1];
+    Xyzz<C> acc = Xyzz<C>::identity();
+    for (uint32_t t = t0 + lane; t < t1; t += 32) {
+      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + (size_t)t * 128);
+      xyzz_add<C>(acc, p);
+    }
+    acc = warp_reduce_xyzz<C>(acc);
+    if (lane == 0) acc.store(reinterpret_cast<char*>(buckets) + (size_t)sc.biglist[e] * 128);
+  }
+}
+
+// ---- bucket reduction: sum_{k=0}^{M-1} (k+1) * B_k ------------------------------------------
+// level 1: thread t owns K consecutive buckets [tK, tK+K): A_t = sum B, L_t = sum (j+1) * B_{tK+j}
+template <class C>
+__global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets, uint32_t T, int K,
+                                                       void* __restrict__ chunkA, void* __restrict__ chunkL) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Xyzz<C> running = Xyzz<C>::identity(), acc = Xyzz<C>::identity();
+  const char* base = reinterpret_cast<const char*>(buckets) + (size_t)t * K * 128;
+  for (int j = K - 1; j >= 0; j--) {
+    Xyzz<C> b = Xyzz<C>::load(base + (size_t)j * 128);
+    xyzz_add<C>(running, b);
+    xyzz_add<C>(acc, running);
+  }
+  running.store(reinterpret_cast<char*>(chunkA) + (size_t)t * 128);
+  acc.store(reinterpret_cast<char*>(chunkL) + (size_t)t * 128);
+}
+
+// level 2: sum id s = blockIdx.y: s < nb -> sum of A_t over t with bit s set; s == nb -> sum of L_t.
+template <class C>
+__global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb,
+                                                     void* __restrict__ bitsums) {
+  __shared__ __align__(16) uint32_t smem[128 * 32];
+  int s = blockIdx.y;
+  Xyzz<C> acc = Xyzz<C>::identity();
+  if (s == nb) {
+    for (uint32_t t = blockIdx.x * 128 + threadIdx.x; t < T; t += gridDim.x * 128) {
+      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(chunkL) + (size_t)t * 128);
+      xyzz_add<C>(acc, p);
+    }
+  } else {
+    // enumerate exactly the indices with bit s set so every lane is busy
+    uint32_t half = T >> 1, lowmask = (1u << s) - 1;
+    for (uint32_t u = blockIdx.x * 128 + threadIdx.x; u < half; u += gridDim.x * 128) {
+      uint32_t t = ((u & ~lowmask) << 1) | (1u << s) | (u & lowmask);
+      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(chunkA) + (size_t)t * 128);
+      xyzz_add<C>(acc, p);
+    }
+  }
+  block_reduce_xyzz<C, 128>(acc, smem);
+  if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * gridDim.x + blockIdx.x) * 128);
+}
+
+// level 3: one block, warp s sums the G partials of sum s; thread 0 then evaluates
+//   result = S_L + K * sum_b 2^b * S_b     and writes it as a Jacobian point.
+template <class C>
+__global__ void __launch_bounds__(768) k_reduce_final(const void* __restrict__ bitsums, int nb, int G, int logK, void* __restrict__ out_jac) {
+  __shared__ __align__(16) uint32_t sums[32 * 32];  // up to 32 sums
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp <= nb) {
+    Xyzz<C> acc = Xyzz<C>::identity();
+    for (int g = lane; g < G; g += 32) {
+      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)warp * G + g) * 128);
+      xyzz_add<C>(acc, p);
+    }
+    acc = warp_reduce_xyzz<C>(acc);
+    if (lane == 0) acc.store(sums + warp * 32);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Xyzz<C> r = Xyzz<C>::identity();
+    for (int b = nb - 1; b >= 0; b--) {
+      r = xyzz_dbl<C>(r);
+      Xyzz<C> sb = Xyzz<C>::load(sums + b * 32);
+      xyzz_add<C>(r, sb);
+    }
+    for (int k = 0; k < logK; k++) r = xyzz_dbl<C>(r);
+    Xyzz<C> sl = Xyzz<C>::load(sums + nb * 32);
+    xyzz_add<C>(r, sl);
+    Fp<typename C::Fb> X, Y, Z;
+    xyzz_to_jacobian<C>(r, X, Y, Z);
+    char* o = reinterpret_cast<char*>(out_jac);
+    X.store(o); Y.store(o + 32); Z.store(o + 64);
+  }
+}
+
+// ---- window-table expansion (once per commitment key) ---------------------------------------
+// thread i: table[j][i] = 2^(c*j) * base_i for j < nwin, normalised to affine with one inversion.
+template <class C>
+__global__ void __launch_bounds__(128) k_precompute(const void* __restrict__ bases, uint32_t n, int c, int nwin, void* __restrict__ table) {
+  using F = Fp<typename C::Fb>;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<C> p = Affine<C>::load(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
+  p.store(reinterpret_cast<char*>(table) + (size_t)i * 64);
+  if (nwin <= 1) return;
+  Affine<C> zero;
+  zero.x = F::zero(); zero.y = F::zero();
+  if (p.is_identity()) {
+    for (int j = 1; j < nwin; j++) zero.store(reinterpret_cast<char*>(table) + ((size_t)j * n + i) * 64);
+    return;
+  }
+  Xyzz<C> pts[MSM_MAX_WINDOWS];
+  F prefix[MSM_MAX_WINDOWS];
+  Xyzz<C> cur = Xyzz<C>::from_affine(p);
+  F run = F::one();
+  for (int j = 1; j < nwin; j++) {
+    for (int k = 0; k < c; k++) cur = xyzz_dbl<C>(cur);
+    pts[j] = cur;          // prime-order group: never the identity
+    prefix[j] = run;       // product of zzz_1 .. zzz_{j-1}
+    run = fp_mul(run, cur.zzz);
+  }
+  F inv = fp_inv(run);
+  for (int j = nwin - 1; j >= 1; j--) {
+    F zi = fp_mul(inv, prefix[j]);      // 1 / zzz_j
+    inv = fp_mul(inv, pts[j].zzz);
+    F zzi = fp_sqr(fp_mul(pts[j].zz, zi));  // 1 / zz_j
+    Affine<C> a;
+    a.x = fp_mul(pts[j].x, zzi);
+    a.y = fp_mul(pts[j].y, zi);
+    a.store(reinterpret_cast<char*>(table) + ((size_t)j * n + i) * 64);
+  }
+}
+
+// ---- small single-thread group kernels ---------------------------------------------------------
+template <class C>
+__global__ void k_point_sum(const void* __restrict__ pts, uint32_t k, void* __restrict__ out) {
+  using F = Fp<typename C::Fb>;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Xyzz<C> acc = Xyzz<C>::identity();
+  for (uint32_t i = 0; i < k; i++) {
+    const char* p = reinterpret_cast<const char*>(pts) + (size_t)i * 96;
+    Xyzz<C> q = xyzz_from_jacobian<C>(F::load(p), F::load(p + 32), F::load(p + 64));
+    xyzz_add<C>(acc, q);
+  }
+  F X, Y, Z;
+  xyzz_to_jacobian<C>(acc, X, Y, Z);
+  char* o = reinterpret_cast<char*>(out);
+  X.store(o); Y.store(o + 32); Z.store(o + 64);
+}
+
+template <class C>
+__global__ void k_point_to_affine(const void* __restrict__ pt, void* __restrict__ out) {
+  using F = Fp<typename C::Fb>;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const char* p = reinterpret_cast<const char*>(pt);
+  Xyzz<C> q = xyzz_from_jacobian<C>(F::load(p), F::load(p + 32), F::load(p + 64));
+  Affine<C> a = xyzz_to_affine<C>(q);
+  a.store(out);
+}
+
+// out[t] = a[t] + r * b[t] for `count` independent pairs (one thread each); r is a Montgomery scalar.
+template <class C>
+__global__ void k_point_scale_add(const void* __restrict__ a, const void* __restrict__ r_mont, const void* __restrict__ b,
+                                  void* __restrict__ out, int count) {
+  using F = Fp<typename C::Fb>;
+  using Fs = Fp<typename C::Fs>;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  Fs r = fp_from_mont(Fs::load(r_mont));
+  const char* pb = reinterpret_cast<const char*>(b) + (size_t)t * 96;
+  const char* pa = reinterpret_cast<const char*>(a) + (size_t)t * 96;
+  Xyzz<C> base = xyzz_from_jacobian<C>(F::load(pb), F::load(pb + 32), F::load(pb + 64));
+  Xyzz<C> acc = Xyzz<C>::identity();
+  int top = 255;
+  while (top >= 0 && !((r.v[top >> 5] >> (top & 31)) & 1)) top--;
+  for (int bit = top; bit >= 0; bit--) {
+    acc = xyzz_dbl<C>(acc);
+    if ((r.v[bit >> 5] >> (bit & 31)) & 1) xyzz_add<C>(acc, base);
+  }
+  Xyzz<C> pa_x = xyzz_from_jacobian<C>(F::load(pa), F::load(pa + 32), F::load(pa + 64));
+  xyzz_add<C>(acc, pa_x);
+  F X, Y, Z;
+  xyzz_to_jacobian<C>(acc, X, Y, Z);
+  char* o = reinterpret_cast<char*>(out) + (size_t)t * 96;
+  X.store(o); Y.store(o + 32); Z.store(o + 64);
+}
+
+// bases[i] = (k0 + i*dk) * G ; each thread walks a run of GEN_RUN consecutive multiples.
+constexpr int GEN_RUN = 16;
+template <class C>
+__global__ void __launch_bounds__(128) k_gen_bases(uint64_t k0, uint64_t dk, uint32_t n, void* __restrict__ out) {
+  using F = Fp<typename C::Fb>;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i0 = t * GEN_RUN;
+  if (i0 >= n) return;
+  Affine<C> g;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { g.x.v[k] = C::gx_mont(k); g.y.v[k] = C::gy_mont(k); }
+  auto smul = [&](uint64_t s) {
+    Xyzz<C> acc = Xyzz<C>::identity();
+    for (int bit = 63; bit >= 0; bit--) {
+      acc = xyzz_dbl<C>(acc);
+      if ((s >> bit) & 1) xyzz_madd<C>(acc, g, false);
+    }
+    return acc;
+  };
+  Xyzz<C> step = smul(dk);
+  Xyzz<C> cur = smul(k0 + (uint64_t)i0 * dk);
+  Xyzz<C> pts[GEN_RUN];
+  F prefix[GEN_RUN];
+  F run = F::one();
+  int cnt = min((uint32_t)GEN_RUN, n - i0);
+  for (int j = 0; j < cnt; j++) {
+    pts[j] = cur;
+    prefix[j] = run;
+    if (!cur.is_identity()) run = fp_mul(run, cur.zzz);
+    xyzz_add<C>(cur, step);
+  }
+  F inv = fp_inv(run);
+  for (int j = cnt - 1; j >= 0; j--) {
+    Affine<C> a;
+    if (pts[j].is_identity()) {
+      a.x = F::zero(); a.y = F::zero();
+    } else {
+      F zi = fp_mul(inv, prefix[j]);
+      inv = fp_mul(inv, pts[j].zzz);
+      F zzi = fp_sqr(fp_mul(pts[j].zz, zi));
+      a.x = fp_mul(pts[j].x, zzi);
+      a.y = fp_mul(pts[j].y, zi);
+    }
+    a.store(reinterpret_cast<char*>(out) + (size_t)(i0 + j) * 64);
+  }
+}
+
+}  // namespace vimz
