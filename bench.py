@@ -1,0 +1,456 @@
+#!/usr/bin/env python3
+"""bench.py -- Nova fold steps/s (HD grayscale step circuit) and Pallas MSM Mpts/s on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of nova-snark's path (oracle/)
+
+One "step" = the data-parallel body of RecursiveSNARK::prove_step for one image row
+(/root/reference/vimz/src/nova_snark_backend/folding.rs:35 -> [EXT nova-snark] NIFS::prove):
+  primary curve (Pallas, grayscale_step_HD shape m=130 864 n=128 307):
+      comm_W2 = commit(ck, W2); T = cross-term(A,B,C; z1, z2); comm_T = commit(ck, T); r = RO(comm_T);
+      W1 += r W2; E1 += r T; (u, X) += r (1, X2); comm_W1 += r comm_W2; comm_E1 += r comm_T
+  secondary curve (Vesta, ~10.5k-row shape): the same.
+Witness generation, bellperson synthesis and the Poseidon RO are untouched host code in the reference
+and are not part of the step (a SHAKE-256 stand-in derives r).  Inputs are synthetic (vimz_b200/synthetic.py):
+the real .r1cs / witnesses cannot be produced in this image.
+
+N > 1: one process per GPU, each rank folds an independent transformation (weak scaling, no data-path
+collective -- SURVEY.md section 8e "replicas"); the MSM sweep additionally shards one MSM by point range
+and combines the per-rank partial sums with an NCCL all-gather.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0xB200
+K0, DK = 77, 1234577           # bases (K0 + i*DK) * G
+NUM_WITNESSES = 4              # distinct fresh witnesses cycled through the steps
+IMAD_PER_MODMUL = 272          # 8-limb CIOS: 2*8^2 + 8 products x 2 IMAD
+MODMUL_PER_MADD = 10           # XYZZ mixed add 8M + 2S
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "imad_tops": 148 * 64 * 1.965e9 / 1e12,
+             "imad_src": "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (SURVEY.md section 8d)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            peaks["hbm_src"] = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    p = os.path.join(ROOT, "profiles", "int_peak.json")
+    if os.path.exists(p):
+        try:
+            tests = {t["name"]: t for t in json.load(open(p))["tests"]}
+            peaks["imad_tops"] = float(tests["imad32"]["Gops_per_s"]) / 1e3
+            peaks["imad_src"] = "measured IMAD32 rate, tools/int_peak.cu (profiles/int_peak.json)"
+        except Exception:
+            pass
+    return peaks
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampler for the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self._stop_evt = threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def challenge_from(comm_T_bytes: bytes, step: int) -> int:
+    """Stand-in for the Poseidon RO squeeze: 128-bit r from the commitment bytes."""
+    return int.from_bytes(hashlib.shake_256(comm_T_bytes + step.to_bytes(4, "little")).digest(16), "little")
+
+
+def build_problem(curve_name: str, circuit: str, seed: int):
+    """Host-side synthetic shape + NUM_WITNESSES satisfying witnesses (Montgomery arrays)."""
+    from vimz_b200 import synthetic as S
+    from vimz_b200.field import CURVES, ints_to_mont
+    cv = CURVES[curve_name]
+    sh = S.synthetic_shape(cv, circuit, seed=seed)
+    wits = []
+    for k in range(NUM_WITNESSES):
+        Wi, Xi = S.synthetic_witness(sh, seed + 1000 + k)
+        wits.append((ints_to_mont(Wi, cv.scalar_modulus), ints_to_mont(Xi, cv.scalar_modulus)))
+    return cv, sh, wits
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of nova-snark's path (oracle/), all host cores
+# ------------------------------------------------------------------------------------------------
+class CpuFold:
+    def __init__(self, curve_name, circuit, seed, threads):
+        from oracle import c as oracle_c
+        from vimz_b200.field import affine_to_mont, ints_to_mont
+        self.o = oracle_c()
+        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.cid = self.cv.curve_id
+        self.threads = threads
+        gens = {"pallas": (self.cv.base_modulus - 1, 2), "vesta": (self.cv.base_modulus - 1, 2), "bn254": (1, 2),
+                "grumpkin": (1, 17631683881184975370165255887551781615748388533673675138860)}
+        g = affine_to_mont([gens[curve_name]], self.cv.base_modulus)[0]
+        nck = max(self.sh.num_cons, self.sh.num_vars)
+        self.bases = self.o.gen_bases(self.cid, g, K0, DK, nck)
+        q = self.cv.scalar_modulus
+        self.one = ints_to_mont([1], q)
+        m, n, io = self.sh.num_cons, self.sh.num_vars, self.sh.num_io
+        self.W1 = np.zeros((n, 4), np.uint64); self.E1 = np.zeros((m, 4), np.uint64)
+        self.u1 = np.zeros((1, 4), np.uint64); self.X1 = np.zeros((io, 4), np.uint64)
+        self.cW = np.zeros(12, np.uint64); self.cE = np.zeros(12, np.uint64)
+        self.q = q
+
+    def step(self, k: int):
+        from vimz_b200.field import ints_to_mont
+        o, cid, sh, t = self.o, self.cid, self.sh, self.threads
+        W2, X2 = self.wits[k % NUM_WITNESSES]
+        comm_W2 = o.msm(cid, W2, self.bases, t)
+        T = o.commit_T(cid, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, self.W1, self.u1, self.X1, W2, X2, self.one, nthreads=t)
+        comm_T = o.msm(cid, T, self.bases, t)
+        r = ints_to_mont([challenge_from(comm_T.tobytes(), k)], self.q)
+        self.W1 = o.axpy(cid, self.W1, W2, r, t)
+        self.E1 = o.axpy(cid, self.E1, T, r, t)
+        tail = o.axpy(cid, np.concatenate([self.u1, self.X1]), np.concatenate([self.one, X2]), r, 1)
+        self.u1, self.X1 = tail[:1], tail[1:]
+        self.cW = o.point_scale_add(cid, self.cW, r, comm_W2)
+        self.cE = o.point_scale_add(cid, self.cE, r, comm_T)
+
+
+def run_cpu_steps(steps: int, warmup: int, threads: int):
+    prim = CpuFold("pallas", "grayscale", SEED, threads)
+    sec = CpuFold("vesta", "secondary", SEED + 1, threads)
+    for k in range(warmup):
+        sec.step(k); prim.step(k)
+    t0 = time.perf_counter()
+    for k in range(warmup, warmup + steps):
+        sec.step(k); prim.step(k)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "grayscale_step_HD fold step: primary Pallas relaxed-R1CS m=130864 n=128307 nnz=713556 (ck 2^17 points) + secondary Vesta m=n=10500; "
+                       "synthetic satisfying witnesses (86% 0/1), SHAKE-256 stand-in for the RO",
+           "curve_cycle": "pallas/vesta", "l2": "inputs rotate over 4 distinct witnesses; MSM window table (134 MB) + buckets exceed nothing special -- see DESIGN.md"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 8))          # bounded sample: a CPU step is ~0.3-1 s
+    warmup = max(1, min(args.warmup, 2))
+    sps, dt = run_cpu_steps(steps, warmup, threads)
+    line = {"metric": "nova_fold_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)",
+            "data": "synthetic", "impl": "reference",
+            "config": workload_config({"note": "CPU restatement of nova-snark 0.23.0 (oracle/nova_cpu.c): the Rust crate cannot be built here (no cargo/rustc)"}),
+            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": f"{steps} full grayscale_HD fold steps (primary+secondary) after {warmup} warm-up"},
+            "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class GpuFold:
+    def __init__(self, curve_name, circuit, seed, device, torch):
+        import vimz_b200
+        from vimz_b200 import CommitmentKey, FoldAccumulator, R1CSShape
+        self.torch = torch
+        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.eng = vimz_b200.Engine(curve_name, device)
+        sh = self.sh
+        self.shape = R1CSShape(self.eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
+        nck = max(sh.num_cons, sh.num_vars)
+        nck = 1 << (nck - 1).bit_length()
+        d_bases = torch.empty(nck * 8, dtype=torch.int64, device=f"cuda:{device}")
+        vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(self.eng._h, K0, DK, nck, d_bases.data_ptr()))
+        self.ck = CommitmentKey.from_device(self.eng, d_bases.data_ptr(), nck)
+        del d_bases
+        self.acc = FoldAccumulator(self.shape, self.ck)
+        # resident copies (for `value`) and pinned host copies (for `e2e`) of the fresh witnesses
+        self.dev_W = [torch.from_numpy(w.view(np.int64)).to(f"cuda:{device}") for w, _ in self.wits]
+        self.pin_W = []
+        for w, _ in self.wits:
+            t = torch.from_numpy(w.view(np.int64).copy()).pin_memory()
+            self.pin_W.append(t)
+        self.q = self.cv.scalar_modulus
+
+    def step(self, k: int, resident: bool):
+        from vimz_b200.field import ints_to_mont
+        i = k % NUM_WITNESSES
+        X2 = self.wits[i][1]
+        if resident:
+            cw, ct = self.acc.step_begin_dev(self.dev_W[i].data_ptr(), X2)
+        else:
+            cw, ct = self.acc.step_begin(self.pin_W[i].numpy().view(np.uint64), X2)
+        r = ints_to_mont([challenge_from(ct.tobytes(), k)], self.q)
+        self.acc.step_end(r)
+
+    def h2d_bytes(self):
+        return (self.sh.num_vars + self.sh.num_io + 1 + 1) * 32
+
+    def cross_term_bytes(self):
+        sh = self.sh
+        return sh.nnz * 36 + sh.num_cons * 32 + 3 * (sh.num_cons + 1) * 4 + 2 * (sh.num_vars + 1 + sh.num_io) * 32
+
+
+def timed_region(torch, engines, fn, steps, dist):
+    """barrier + sync; CUDA events on the primary context's stream around `steps` calls of fn; max over ranks."""
+    stream = torch.cuda.ExternalStream(engines[0].stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for e in engines:
+        e.sync()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        fn(k)
+    for e in engines:
+        e.sync()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = float(t[0]), float(t[1]) / 1e3
+    return ms, wall
+
+
+def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
+    """Pallas MSM over 2^log2n resident points, uniform full-width scalars resident in HBM.  world > 1: point-range
+    shards, per-rank partial sums all-gathered over NCCL and added on the GPU."""
+    import vimz_b200
+    from vimz_b200 import CommitmentEngine, CommitmentKey
+    from vimz_b200 import synthetic as S
+    eng = vimz_b200.Engine("pallas", device)
+    n = 1 << log2n
+    per = n // world
+    first = rank * per
+    d_bases = torch.empty(per * 8, dtype=torch.int64, device=f"cuda:{device}")
+    vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, K0 + first * DK, DK, per, d_bases.data_ptr()))
+    ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), per)
+    del d_bases
+    sc = [torch.from_numpy(S.uniform_scalars_mont(per, eng.curve.scalar_modulus, SEED + 7 * rank + j).view(np.int64)).to(f"cuda:{device}")
+          for j in range(2)]
+    d_out = torch.zeros(12, dtype=torch.int64, device=f"cuda:{device}")
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def one(j):
+        CommitmentEngine.commit_async_dev(ck, sc[j % 2].data_ptr(), per, d_out.data_ptr())
+        if world > 1:
+            eng.sync()
+            parts = [torch.empty_like(d_out) for _ in range(world)]
+            dist.all_gather(parts, d_out)
+            pts = torch.stack(parts).cpu().numpy().view(np.uint64)
+            return eng.point_sum(pts)
+        return None
+
+    for j in range(3):
+        one(j)
+    eng.sync()
+    eng.set_option("profile", 1)
+    eng.profile(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for j in range(iters):
+        one(j)
+    eng.sync()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1), wall_ms if world > 1 else 0.0)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    prof = eng.profile(reset=True)
+    eng.set_option("profile", 0)
+    acc_ms, acc_calls = prof["msm_accumulate"]
+    entries = prof["msm_entries"][1]
+    res = {"log2_points": log2n, "mpts_per_s": n * iters / ms / 1e3, "ms_per_msm": ms / iters, "window_bits": ck.window_bits,
+           "windows": ck.num_windows, "scalars": "uniform 255-bit", "sharding": f"point-range x{world}" if world > 1 else "none"}
+    if acc_ms > 0:
+        imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
+        res["accumulate_ms"] = acc_ms / max(acc_calls, 1)
+        res["sort_ms"] = prof["msm_sort"][0] / max(prof["msm_sort"][1], 1)
+        res["reduce_ms"] = prof["msm_reduce"][0] / max(prof["msm_reduce"][1], 1)
+        res["accumulate_timad_per_s"] = imad / (acc_ms * 1e-3) / 1e12
+        res["accumulate_frac_of_imad_peak"] = res["accumulate_timad_per_s"] / peaks["imad_tops"]
+        res["whole_msm_timad_per_s"] = (n * iters * ck.num_windows * MODMUL_PER_MADD * IMAD_PER_MODMUL) / (ms * 1e-3) / 1e12 / world * world
+    ck.close()
+    eng.close()
+    return res
+
+
+def main_gpu(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as d
+        d.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist = d
+    peaks = load_peaks()
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # each rank folds its own transformation (different witnesses), same circuit
+    prim = GpuFold("pallas", "grayscale", SEED + 100 * rank, local_rank, torch)
+    sec = GpuFold("vesta", "secondary", SEED + 100 * rank + 1, local_rank, torch)
+    engines = [prim.eng, sec.eng]
+
+    def step_resident(k):
+        sec.step(k, True); prim.step(k, True)
+
+    def step_e2e(k):
+        sec.step(k, False); prim.step(k, False)
+
+    for k in range(warmup):
+        step_resident(k)
+    for k in range(2):
+        step_e2e(k)
+    for e in engines:
+        e.set_option("profile", 1)
+        e.profile(reset=True)
+    launches0 = sum(e.launch_count for e in engines)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, wall = timed_region(torch, engines, lambda k: step_resident(warmup + k), steps, dist)
+    clocks = sampler.stop()
+    launches = sum(e.launch_count for e in engines) - launches0
+    prof = prim.eng.profile(reset=True)
+    prof_sec = sec.eng.profile(reset=True)
+    for e in engines:
+        e.set_option("profile", 0)
+    ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(warmup + steps + k), steps, dist)
+
+    value = world * steps / (ms * 1e-3)
+    e2e_value = world * steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel (primary-curve bucket accumulation)
+    acc_ms, acc_calls = prof["msm_accumulate"]
+    entries = prof["msm_entries"][1]
+    imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
+    achieved = imad / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    roofline = {"kernel": "k_msm_accumulate<Pallas> (+ big-bucket tasks)", "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
+                "unit": "TIMAD/s", "frac": (achieved / peaks["imad_tops"]) if achieved else None, "traffic": None,
+                "peak_source": peaks["imad_src"],
+                "algorithmic": f"{entries} bucket insertions x {MODMUL_PER_MADD} modmul x {IMAD_PER_MODMUL} IMAD over {acc_calls} launches",
+                "share_of_step": acc_ms / ms if ms > 0 else None,
+                "note": "integer-multiply bound, not hbm/tensor: nothing on this path is a dense contraction (BASELINE.json north_star)"}
+    ct_ms, ct_calls = prof["cross_term"]
+    ct_bytes = prim.cross_term_bytes()
+    ct_gbs = ct_bytes * ct_calls / (ct_ms * 1e-3) / 1e9 if ct_ms > 0 else None
+    roofline_hbm = {"kernel": "k_cross_term<VestaP> (6 mat-vecs + T fused)", "bound": "hbm", "achieved": ct_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": (ct_gbs / peaks["hbm_gbs"]) if ct_gbs else None, "traffic": None, "peak_source": peaks["hbm_src"],
+                    "algorithmic": f"{ct_bytes} B per launch = nnz*36 + m*32 + 3(m+1)*4 + 2(n+3)*32"}
+    phases = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof.items() if k != "msm_entries"}
+    phases_sec = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof_sec.items() if k != "msm_entries"}
+
+    # Pallas MSM throughput (second half of the metric)
+    msm = []
+    for lg in args.msm_log2:
+        msm.append(msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sps, dt = run_cpu_steps(3, 1, threads)
+        cpu_baseline = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+                        "sample": f"3 full grayscale_HD fold steps (primary+secondary) of oracle/nova_cpu.c after 1 warm-up, {dt:.1f} s"}
+
+    if rank == 0:
+        bad = [r for r in clocks["reasons"] if r != "sw_power_cap"]
+        line = {"metric": "nova_fold_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
+                "config": workload_config({"parallelism": f"replicas x{world} (one transformation per GPU)", "msm_window_bits": prim.ck.window_bits,
+                                           "msm_windows": prim.ck.num_windows}),
+                "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
+                        "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_e2e / steps},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
+                "clocks": clocks, "clock_verdict": "rejected: " + ",".join(bad) if bad else "ok",
+                "phases_primary": phases, "phases_secondary": phases_sec,
+                "wall_ms_per_step": wall * 1e3 / steps,
+                "msm": msm, "published_reference": "README-derived >= 2.99 steps/s end-to-end on a Ryzen 9 (BASELINE.md section 1), other hardware"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--msm-log2", type=int, nargs="*", default=[20])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        main_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,7 @@ class COracle:
         L.oracle_cross_term.argtypes = [i32, sz] + [vp] * 8 + [i32]
         L.oracle_axpy.argtypes = [i32, sz, vp, vp, vp, vp, i32]
         L.oracle_field_op.argtypes = [i32, i32, i32, vp, vp, sz, vp]
+        L.oracle_gen_bases.argtypes = [i32, vp, C.c_uint64, C.c_uint64, sz, vp]
 
     @staticmethod
     def _p(a):
@@ -102,6 +103,13 @@ class COracle:
         b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
         out = np.zeros_like(a)
         assert self.lib.oracle_field_op(curve_id, which, op, self._p(a), self._p(b), a.shape[0], self._p(out)) == 0
+        return out
+
+    def gen_bases(self, curve_id, g_aff_mont, k0, dk, n):
+        """(k0 + i*dk) * G for i < n as (n, 8) affine Montgomery rows."""
+        g = np.ascontiguousarray(g_aff_mont, dtype=np.uint64).reshape(8)
+        out = np.zeros((n, 8), dtype=np.uint64)
+        assert self.lib.oracle_gen_bases(curve_id, self._p(g), k0, dk, n, self._p(out)) == 0
         return out
 
     def commit_T(self, curve_id, m, num_vars, num_io, A, B, Cm, W1, u1, X1, W2, X2, one_mont, nthreads=1):

@@ -519,3 +519,48 @@ int oracle_field_op(int curve_id, int which, int op, const uint64_t* a, const ui
   }
   return 0;
 }
+
+/* bases[i] = (k0 + i*dk) * G as affine Montgomery points (same family as vimz_gen_bases_dev), with one
+ * batched inversion.  gx/gy: generator in Montgomery form. */
+int oracle_gen_bases(int curve_id, const uint64_t* g_aff, uint64_t k0, uint64_t dk, size_t n, uint64_t* out_aff) {
+  if (curve_id < 0 || curve_id > 3) return -2;
+  oracle_init();
+  const field_t* F = &CURVES[curve_id].fb;
+  aff g;
+  memcpy(&g, g_aff, 64);
+  jac G, step, cur;
+  G.x = g.x; G.y = g.y; G.z = F->one;
+  jac_set_identity(F, &step);
+  jac_set_identity(F, &cur);
+  for (int i = 63; i >= 0; i--) {
+    jac_double(F, &step, &step);
+    if ((dk >> i) & 1) jac_add(F, &step, &step, &G);
+    jac_double(F, &cur, &cur);
+    if ((k0 >> i) & 1) jac_add(F, &cur, &cur, &G);
+  }
+  jac* pts = (jac*)malloc((n ? n : 1) * sizeof(jac));
+  fe* prefix = (fe*)malloc((n ? n : 1) * sizeof(fe));
+  fe run = F->one;
+  for (size_t i = 0; i < n; i++) {
+    pts[i] = cur;
+    prefix[i] = run;
+    if (!fe_is_zero(&cur.z)) f_mul(F, &run, &run, &cur.z);
+    jac_add(F, &cur, &cur, &step);
+  }
+  fe inv;
+  f_inv(F, &inv, &run);
+  aff* out = (aff*)out_aff;
+  for (size_t i = n; i-- > 0;) {
+    if (fe_is_zero(&pts[i].z)) { memset(&out[i], 0, sizeof(aff)); continue; }
+    fe zi, zi2, zi3;
+    f_mul(F, &zi, &inv, &prefix[i]);
+    f_mul(F, &inv, &inv, &pts[i].z);
+    f_sqr(F, &zi2, &zi);
+    f_mul(F, &zi3, &zi2, &zi);
+    f_mul(F, &out[i].x, &pts[i].x, &zi2);
+    f_mul(F, &out[i].y, &pts[i].y, &zi3);
+  }
+  free(pts);
+  free(prefix);
+  return 0;
+}

@@ -54,6 +54,7 @@ def _load() -> C.CDLL:
         "vimz_ctx_destroy": (None, [vp]),
         "vimz_ctx_sync": (i32, [vp]),
         "vimz_ctx_set_option": (i32, [vp, C.c_char_p, C.c_long]),
+        "vimz_ctx_profile": (i32, [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), i32]),
         "vimz_ctx_stream": (vp, [vp]),
         "vimz_ctx_launch_count": (u64, [vp]),
         "vimz_ck_upload": (i32, [vp, vp, sz, pp]),

@@ -144,6 +144,10 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
   ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
   ctx->tmp3.release(); ctx->tmp4.release(); ctx->tmp5.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (ProfSpan& sp : ctx->prof.open) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
+  for (uint32_t* slot : ctx->prof.entry_slots) cudaFreeHost(slot);
+  for (uint32_t* slot : ctx->prof.entry_pool) cudaFreeHost(slot);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->side);
   delete ctx;
@@ -163,7 +167,52 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     ctx->opt_window = value;
     return VIMZ_OK;
   }
+  if (strcmp(key, "profile") == 0) {
+    ctx->prof.on = value != 0;
+    return VIMZ_OK;
+  }
   return set_error(VIMZ_ERR_ARG, std::string("unknown option: ") + key);
+}
+
+static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_reduce", "cross_term", "axpy", "spmv"};
+
+int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset) {
+  CHECK_ARG(ctx && name, "vimz_ctx_profile: null argument");
+  DeviceGuard g(ctx->device);
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  Profiler& p = ctx->prof;
+  for (ProfSpan& s : p.open) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+      p.ms[s.timer] += t;
+      p.calls[s.timer]++;
+    }
+    p.pool.push_back(s.a);
+    p.pool.push_back(s.b);
+  }
+  p.open.clear();
+  for (uint32_t* slot : p.entry_slots) {
+    p.msm_entries += *slot;
+    p.entry_pool.push_back(slot);
+  }
+  p.entry_slots.clear();
+  int rc = VIMZ_ERR_ARG;
+  if (strcmp(name, "msm_entries") == 0) {
+    if (ms) *ms = 0;
+    if (calls) *calls = p.msm_entries;
+    rc = VIMZ_OK;
+  }
+  for (int k = 0; k < PROF_COUNT && rc != VIMZ_OK; k++)
+    if (strcmp(name, PROF_NAMES[k]) == 0) {
+      if (ms) *ms = p.ms[k];
+      if (calls) *calls = p.calls[k];
+      rc = VIMZ_OK;
+    }
+  if (reset) {
+    for (int k = 0; k < PROF_COUNT; k++) { p.ms[k] = 0; p.calls[k] = 0; }
+    p.msm_entries = 0;
+  }
+  return rc == VIMZ_OK ? rc : set_error(VIMZ_ERR_ARG, std::string("unknown profile timer: ") + name);
 }
 
 void* vimz_ctx_stream(vimz_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -81,6 +81,21 @@ struct MsmWorkspace {
   }
 };
 
+// Optional per-phase device timers (vimz_ctx_set_option("profile", 1)): event pairs are recorded on the
+// context stream around a phase and resolved when vimz_ctx_profile() is called.
+enum ProfTimer { PROF_MSM_SORT = 0, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_CROSS_TERM, PROF_AXPY, PROF_SPMV, PROF_COUNT };
+struct ProfSpan { cudaEvent_t a, b; int timer; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfSpan> open;          // recorded, not yet resolved
+  std::vector<cudaEvent_t> pool;       // reusable events
+  double ms[PROF_COUNT] = {0};
+  uint64_t calls[PROF_COUNT] = {0};
+  uint64_t msm_entries = 0;            // bucket insertions (non-zero digits) seen by profiled MSMs
+  std::vector<uint32_t*> entry_slots;  // pinned words receiving each MSM's entry total
+  std::vector<uint32_t*> entry_pool;
+};
+
 struct vimz_ctx {
   int curve = 0;
   int device = 0;
@@ -92,7 +107,32 @@ struct vimz_ctx {
   MsmWorkspace ws;
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points
   void* pinned = nullptr;                      // small pinned staging block for results
+  Profiler prof;
 };
+
+namespace vimz {
+struct ProfScope {
+  vimz_ctx* ctx;
+  ProfSpan span;
+  bool active;
+  ProfScope(vimz_ctx* c, int timer) : ctx(c), active(c->prof.on) {
+    if (!active) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!ctx->prof.pool.empty()) { e = ctx->prof.pool.back(); ctx->prof.pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    span.a = get(); span.b = get(); span.timer = timer;
+    cudaEventRecord(span.a, ctx->stream);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    cudaEventRecord(span.b, ctx->stream);
+    ctx->prof.open.push_back(span);
+  }
+};
+}  // namespace vimz
 
 struct vimz_ck {
   vimz_ctx* ctx = nullptr;

@@ -101,6 +101,8 @@ int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scala
   VIMZ_CUDA(cudaMemsetAsync(sc.hist, 0, ((size_t)3 * NC + 8) * 4, st));
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
+  {
+  ProfScope prof_sort(ctx, PROF_MSM_SORT);
   if (n > 0) {
     k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
     VIMZ_LAUNCH_CHECK(ctx);
@@ -123,14 +125,24 @@ int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scala
   VIMZ_LAUNCH_CHECK(ctx);
   k_sched_scatter<<<grid_m, 256, 0, st>>>(counts, M, sc, order);
   VIMZ_LAUNCH_CHECK(ctx);
-
+  }
+  if (ctx->prof.on) {  // total bucket insertions of this MSM = offsets[M]
+    uint32_t* slot;
+    if (!ctx->prof.entry_pool.empty()) { slot = ctx->prof.entry_pool.back(); ctx->prof.entry_pool.pop_back(); }
+    else VIMZ_CUDA(cudaMallocHost(&slot, 4));
+    VIMZ_CUDA(cudaMemcpyAsync(slot, offsets + M, 4, cudaMemcpyDeviceToHost, st));
+    ctx->prof.entry_slots.push_back(slot);
+  }
+  {
+  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE);
   k_msm_accumulate<C><<<ceil_div(M, 128), 128, 0, st>>>(order, counts, offsets, sorted, ck->table, M, sc.ctrl, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_msm_accumulate_big<C><<<ctx->sm_count * 4, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_msm_big_combine<C><<<32, 128, 0, st>>>(sc, ws.partials.ptr, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-
+  }
+  ProfScope prof_red(ctx, PROF_MSM_REDUCE);
   k_reduce_chunks<C><<<ceil_div(T, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_reduce_bits<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, ws.bitsums.ptr);
@@ -178,6 +190,7 @@ inline CsrView csr_view(const vimz_shape* s, int k) {
 template <class C>
 int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz) {
   if (s->m == 0) return VIMZ_OK;
+  ProfScope prof(ctx, PROF_SPMV);
   k_spmv3<typename C::Fs><<<dim3(ceil_div(s->m, 256), 3), 256, 0, ctx->stream>>>(
       csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W, d_tail, d_Az, d_Bz, d_Cz);
   VIMZ_LAUNCH_CHECK(ctx);
@@ -186,6 +199,7 @@ int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* 
 template <class C>
 int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T) {
   if (s->m == 0) return VIMZ_OK;
+  ProfScope prof(ctx, PROF_CROSS_TERM);
   k_cross_term<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(
       csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
   VIMZ_LAUNCH_CHECK(ctx);
@@ -197,6 +211,7 @@ int impl_axpy(vimz_ctx* ctx, const void* d_a, const void* d_b, const vimz_fr* r,
   Fp<typename C::Fs> rr;
   memcpy(rr.v, r, 32);
   int grid = (int)std::min<size_t>(ceil_div(len, 256), (size_t)ctx->sm_count * 16);
+  ProfScope prof(ctx, PROF_AXPY);
   k_axpy<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(d_a, d_b, rr, len, d_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
