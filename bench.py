@@ -36,7 +36,8 @@ sys.path.insert(0, ROOT)
 
 SEED = 0xB200
 K0, DK = 77, 1234577           # bases (K0 + i*DK) * G
-NUM_WITNESSES = 4              # distinct fresh witnesses cycled through the steps
+NUM_WITNESSES = 32             # distinct fresh witnesses (one image row each) cycled through the steps
+PREFOLD = 32                   # untimed folds before measuring, so W1/E1 are full-width and well mixed like mid-proof
 IMAD_PER_MODMUL = 272          # 8-limb CIOS: 2*8^2 + 8 products x 2 IMAD
 MODMUL_PER_MADD = 10           # XYZZ mixed add 8M + 2S
 
@@ -170,7 +171,8 @@ def run_cpu_steps(steps: int, warmup: int, threads: int):
 def workload_config(extra=None):
     cfg = {"workload": "grayscale_step_HD fold step: primary Pallas relaxed-R1CS m=130864 n=128307 nnz=713556 (ck 2^17 points) + secondary Vesta m=n=10500; "
                        "synthetic satisfying witnesses (86% 0/1), SHAKE-256 stand-in for the RO",
-           "curve_cycle": "pallas/vesta", "l2": "inputs rotate over 4 distinct witnesses; MSM window table (134 MB) + buckets exceed nothing special -- see DESIGN.md"}
+           "curve_cycle": "pallas/vesta", "l2": "no explicit flush: a step touches the 126 MB window table + 26 MB CSR + 21 MB of vectors/buckets (> 126 MB L2) and every step "
+                 "folds a different witness (32 distinct rows cycled)"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -359,8 +361,10 @@ def main_gpu(args, rank, world, local_rank):
     def step_e2e(k):
         sec.step(k, False); prim.step(k, False)
 
-    for k in range(warmup):
+    for k in range(PREFOLD):          # untimed: mix the running instance
         step_resident(k)
+    for k in range(warmup):
+        step_resident(PREFOLD + k)
     for k in range(2):
         step_e2e(k)
     for e in engines:
@@ -369,14 +373,14 @@ def main_gpu(args, rank, world, local_rank):
     launches0 = sum(e.launch_count for e in engines)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, wall = timed_region(torch, engines, lambda k: step_resident(warmup + k), steps, dist)
+    ms, wall = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + k), steps, dist)
     clocks = sampler.stop()
     launches = sum(e.launch_count for e in engines) - launches0
     prof = prim.eng.profile(reset=True)
     prof_sec = sec.eng.profile(reset=True)
     for e in engines:
         e.set_option("profile", 0)
-    ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(warmup + steps + k), steps, dist)
+    ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
 
     value = world * steps / (ms * 1e-3)
     e2e_value = world * steps / (ms_e2e * 1e-3)

@@ -128,6 +128,7 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
   ctx->device = device;
   VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
   VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
   VIMZ_TRY(ctx->ws.result.reserve(4096));
@@ -140,7 +141,9 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->side);
+  cudaStreamSynchronize(ctx->aux);
   ctx->ws.release();
+  ctx->ws_aux.release();
   ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
   ctx->tmp3.release(); ctx->tmp4.release(); ctx->tmp5.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -150,6 +153,7 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
   for (uint32_t* slot : ctx->prof.entry_pool) cudaFreeHost(slot);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->side);
+  cudaStreamDestroy(ctx->aux);
   delete ctx;
 }
 
@@ -157,6 +161,7 @@ int vimz_ctx_sync(vimz_ctx* ctx) {
   CHECK_ARG(ctx, "vimz_ctx_sync: null ctx");
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
   return VIMZ_OK;
 }
 
@@ -180,6 +185,7 @@ int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* call
   CHECK_ARG(ctx && name, "vimz_ctx_profile: null argument");
   DeviceGuard g(ctx->device);
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
   Profiler& p = ctx->prof;
   for (ProfSpan& s : p.open) {
     float t = 0;
@@ -285,7 +291,7 @@ int vimz_msm_async_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const voi
   CHECK_ARG(ck->ctx == ctx, "vimz_msm: commitment key belongs to another context");
   if (first + n > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_msm: vector longer than the commitment key");
   DeviceGuard g(ctx->device);
-  return curve_vtable(ctx->curve)->msm(ctx, ck, first, d_scalars, n, d_out);
+  return curve_vtable(ctx->curve)->msm(ctx, 0, ck, first, d_scalars, n, d_out);
 }
 
 static int fetch_points(vimz_ctx* ctx, const void* d_src, void* host_dst, size_t bytes) {
@@ -350,12 +356,13 @@ int vimz_point_scale_add(vimz_ctx* ctx, const vimz_point* a, const vimz_fr* r, c
 
 // ---- R1CS shape --------------------------------------------------------------------------------------
 static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row, const uint32_t* col, const vimz_fr* val, size_t nnz,
-                      uint32_t** d_rowptr, uint32_t** d_col, void** d_val) {
+                      uint32_t** d_rowptr, uint32_t** d_col, void** d_val, std::vector<uint32_t>& row_nnz) {
   std::vector<uint32_t> rowptr(m + 1, 0);
   for (size_t k = 0; k < nnz; k++) {
     if (row[k] >= m || col[k] >= ncols) return set_error(VIMZ_ERR_INDEX, "vimz_shape_upload: entry out of range (InvalidIndex)");
     rowptr[row[k] + 1]++;
   }
+  for (size_t i = 0; i < m; i++) row_nnz[i] += rowptr[i + 1];
   for (size_t i = 0; i < m; i++) rowptr[i + 1] += rowptr[i];
   std::vector<uint32_t> cursor(rowptr.begin(), rowptr.end() - 1), ccol(nnz);
   std::vector<vimz_fr> cval(nnz);
@@ -383,6 +390,7 @@ void vimz_shape_destroy(vimz_shape* s) {
     if (s->col[k]) cudaFree(s->col[k]);
     if (s->val[k]) cudaFree(s->val[k]);
   }
+  if (s->long_rows) cudaFree(s->long_rows);
   delete s;
 }
 
@@ -406,12 +414,26 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   const uint32_t* cols[3] = {colA, colB, colC};
   const vimz_fr* vals[3] = {valA, valB, valC};
   size_t nnz[3] = {nnzA, nnzB, nnzC};
+  std::vector<uint32_t> row_nnz(num_cons, 0);
   for (int k = 0; k < 3; k++) {
     s->nnz[k] = nnz[k];
-    int rc = coo_to_csr(ctx, num_cons, ncols, rows[k], cols[k], vals[k], nnz[k], &s->rowptr[k], &s->col[k], &s->val[k]);
+    int rc = coo_to_csr(ctx, num_cons, ncols, rows[k], cols[k], vals[k], nnz[k], &s->rowptr[k], &s->col[k], &s->val[k], row_nnz);
     if (rc != VIMZ_OK) {
       vimz_shape_destroy(s);
       return rc;
+    }
+  }
+  // rows too long for one thread get a warp each in the cross-term kernel
+  std::vector<uint32_t> long_rows;
+  for (size_t i = 0; i < num_cons; i++)
+    if (row_nnz[i] > R1CS_LONG_ROW) long_rows.push_back((uint32_t)i);
+  s->n_long = long_rows.size();
+  if (s->n_long) {
+    cudaError_t e = cudaMalloc(&s->long_rows, s->n_long * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(s->long_rows, long_rows.data(), s->n_long * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      vimz_shape_destroy(s);
+      return set_error(VIMZ_ERR_CUDA, std::string("vimz_shape_upload: ") + cudaGetErrorString(e));
     }
   }
   *out = s;
@@ -463,7 +485,7 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
   }
   VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr));
   if (T_out) VIMZ_CUDA(cudaMemcpyAsync(T_out, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, st));
-  VIMZ_TRY(vt->msm(ctx, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr));
+  VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr));
   return fetch_points(ctx, ctx->ws.result.ptr, comm_T, 96);
 }
 
@@ -495,10 +517,13 @@ void vimz_acc_destroy(vimz_acc* a) {
   cudaSetDevice(a->ctx->device);
   cudaStreamSynchronize(a->ctx->stream);
   cudaStreamSynchronize(a->ctx->side);
+  cudaStreamSynchronize(a->ctx->aux);
   void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (a->ev_main) cudaEventDestroy(a->ev_main);
+  if (a->ev_w2) cudaEventDestroy(a->ev_w2);
+  if (a->ev_aux) cudaEventDestroy(a->ev_aux);
   for (int k = 0; k < 2; k++)
     if (a->ev_side[k]) cudaEventDestroy(a->ev_side[k]);
   delete a;
@@ -523,6 +548,8 @@ int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_ac
   alloc0(&a->W1, nb); alloc0(&a->W2, nb); alloc0(&a->E1, mb); alloc0(&a->T, mb);
   alloc0(&a->tail1, tb); alloc0(&a->tail2, tb); alloc0(&a->comms, 6 * 96 + 2 * 32);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_main, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_w2, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_aux, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_side[0], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_side[1], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -582,11 +609,16 @@ static int acc_step_begin_common(vimz_acc* a, const void* d_W2, const vimz_fr* X
   memcpy(stage, vt->scalar_one_mont, 32);
   if (s->io) memcpy(stage + 32, X2, s->io * 32);
   VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
-  // comm_W2 = commit(ck, W2)            (r1cs_instance_and_witness)
-  VIMZ_TRY(vt->msm(ctx, a->ck, 0, d_W2, s->n, fresh));
+  // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) -- independent of T, so it runs on the aux
+  // stream with its own workspace while the main stream does the cross term and commit(T).
+  VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
+  VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
+  VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, d_W2, s->n, fresh));
+  VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
   // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, d_W2, a->tail2, a->T));
-  VIMZ_TRY(vt->msm(ctx, a->ck, 0, a->T, s->m, fresh + 96));
+  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96));
+  VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   VIMZ_CUDA(cudaStreamSynchronize(st));
   memcpy(comm_W2, ctx->pinned, 96);

@@ -72,12 +72,13 @@ struct MsmWorkspace {
   vimz::DevBuf chunkA;     // [T] XYZZ chunk sums
   vimz::DevBuf chunkL;     // [T] XYZZ chunk weighted sums
   vimz::DevBuf bitsums;    // [(nb+1) * G] XYZZ
+  vimz::DevBuf scaled;     // [nb+1] XYZZ
   vimz::DevBuf scal;       // staged scalars (host-pointer entry points)
   vimz::DevBuf result;     // Jacobian results (device)
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release();
     order.release(); cls.release(); biglist.release(); partials.release(); buckets.release();
-    chunkA.release(); chunkL.release(); bitsums.release(); scal.release(); result.release();
+    chunkA.release(); chunkL.release(); bitsums.release(); scaled.release(); scal.release(); result.release();
   }
 };
 
@@ -101,10 +102,11 @@ struct vimz_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // instance-fold scalar multiplications overlap the next step here
+  cudaStream_t aux = nullptr;   // second MSM lane: commit(W2) runs beside cross-term + commit(T)
   int sm_count = 148;
   long opt_window = 0;  // 0 = auto
   uint64_t launches = 0;
-  MsmWorkspace ws;
+  MsmWorkspace ws, ws_aux;
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points
   void* pinned = nullptr;                      // small pinned staging block for results
   Profiler prof;
@@ -115,7 +117,8 @@ struct ProfScope {
   vimz_ctx* ctx;
   ProfSpan span;
   bool active;
-  ProfScope(vimz_ctx* c, int timer) : ctx(c), active(c->prof.on) {
+  cudaStream_t st;
+  ProfScope(vimz_ctx* c, int timer, cudaStream_t stream) : ctx(c), active(c->prof.on), st(stream) {
     if (!active) return;
     auto get = [&]() {
       cudaEvent_t e;
@@ -124,11 +127,11 @@ struct ProfScope {
       return e;
     };
     span.a = get(); span.b = get(); span.timer = timer;
-    cudaEventRecord(span.a, ctx->stream);
+    cudaEventRecord(span.a, st);
   }
   ~ProfScope() {
     if (!active) return;
-    cudaEventRecord(span.b, ctx->stream);
+    cudaEventRecord(span.b, st);
     ctx->prof.open.push_back(span);
   }
 };
@@ -149,6 +152,8 @@ struct vimz_shape {
   uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};  // [m+1]
   uint32_t* col[3] = {nullptr, nullptr, nullptr};     // [nnz]
   void* val[3] = {nullptr, nullptr, nullptr};         // [nnz] Montgomery scalars
+  uint32_t* long_rows = nullptr;                      // rows with > R1CS_LONG_ROW non-zeros over A+B+C
+  size_t n_long = 0;
 };
 
 struct vimz_acc {
@@ -159,7 +164,7 @@ struct vimz_acc {
   void *tail1 = nullptr, *tail2 = nullptr;  // [1+io]: (u, X)
   // Jacobian points comm_W1, comm_E1, then two alternating (comm_W2, comm_T) pairs, then two r slots
   void* comms = nullptr;
-  cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr}, ev_w2 = nullptr, ev_aux = nullptr;
   bool side_pending[2] = {false, false};
   int parity = 0;
 };

@@ -15,7 +15,8 @@ struct CurveVTable {
   uint32_t scalar_modulus[8];
   uint32_t scalar_one_mont[8];
   int (*precompute)(vimz_ctx*, const void* d_bases, size_t n, int c, int nwin, void* table);
-  int (*msm)(vimz_ctx*, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out);
+  // lane 0 = context stream + main workspace, lane 1 = aux stream + second workspace (runs concurrently)
+  int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out);
   int (*point_sum)(vimz_ctx*, const void* d_pts, size_t k, void* d_out);
   int (*point_to_affine)(vimz_ctx*, const void* d_pt, void* d_out);
   int (*point_scale_add)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count);
@@ -45,19 +46,20 @@ int impl_precompute(vimz_ctx* ctx, const void* d_bases, size_t n, int c, int nwi
 }
 
 template <class C>
-int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out) {
-  cudaStream_t st = ctx->stream;
-  MsmWorkspace& ws = ctx->ws;
+int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out) {
+  cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
+  MsmWorkspace& ws = lane == 0 ? ctx->ws : ctx->ws_aux;
   const int c = ck->c, nwin = ck->nwin;
   const uint32_t M = 1u << (c - 1);
   const size_t E = std::max<size_t>(n * (size_t)nwin, 1);
-  const int K = (int)std::min<uint32_t>(MSM_REDUCE_K, M);
+  // reduction geometry: chunks of K buckets (deeper chunks only when there are many buckets)
+  const int K = (int)std::min<uint32_t>(M >= (1u << 18) ? 8 : 4, M);
   int logK = 0;
   while ((1 << logK) < K) logK++;
   const uint32_t T = M / K;
   int nb = 0;
   while ((1u << nb) < T) nb++;
-  const int G = MSM_REDUCE_G;
+  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 128), 1), 64);
 
   // bucket-size classes: buckets above `cap` entries are split into block tasks
   size_t lambda = E / M;
@@ -80,6 +82,7 @@ int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scala
   VIMZ_TRY(ws.chunkA.reserve((size_t)T * 128));
   VIMZ_TRY(ws.chunkL.reserve((size_t)T * 128));
   VIMZ_TRY(ws.bitsums.reserve((size_t)(nb + 1) * G * 128));
+  VIMZ_TRY(ws.scaled.reserve((size_t)(nb + 1) * 128));
 
   uint32_t* counts = ws.counts.as<uint32_t>();
   uint32_t* offsets = ws.offsets.as<uint32_t>();
@@ -102,7 +105,7 @@ int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scala
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
   {
-  ProfScope prof_sort(ctx, PROF_MSM_SORT);
+  ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
   if (n > 0) {
     k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
     VIMZ_LAUNCH_CHECK(ctx);
@@ -134,20 +137,22 @@ int impl_msm(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scala
     ctx->prof.entry_slots.push_back(slot);
   }
   {
-  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE);
+  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
   k_msm_accumulate<C><<<ceil_div(M, 128), 128, 0, st>>>(order, counts, offsets, sorted, ck->table, M, sc.ctrl, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-  k_msm_accumulate_big<C><<<ctx->sm_count * 4, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr);
+  k_msm_accumulate_big<C><<<ctx->sm_count * 2, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_msm_big_combine<C><<<32, 128, 0, st>>>(sc, ws.partials.ptr, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   }
-  ProfScope prof_red(ctx, PROF_MSM_REDUCE);
+  ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);
   k_reduce_chunks<C><<<ceil_div(T, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_reduce_bits<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, ws.bitsums.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-  k_reduce_final<C><<<1, 32 * (nb + 1), 0, st>>>(ws.bitsums.ptr, nb, G, logK, d_out);
+  k_reduce_scale<C><<<nb + 1, 32, 0, st>>>(ws.bitsums.ptr, nb, G, logK, ws.scaled.ptr);
+  VIMZ_LAUNCH_CHECK(ctx);
+  k_reduce_out<C><<<1, 32, 0, st>>>(ws.scaled.ptr, nb + 1, d_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -190,7 +195,7 @@ inline CsrView csr_view(const vimz_shape* s, int k) {
 template <class C>
 int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz) {
   if (s->m == 0) return VIMZ_OK;
-  ProfScope prof(ctx, PROF_SPMV);
+  ProfScope prof(ctx, PROF_SPMV, ctx->stream);
   k_spmv3<typename C::Fs><<<dim3(ceil_div(s->m, 256), 3), 256, 0, ctx->stream>>>(
       csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W, d_tail, d_Az, d_Bz, d_Cz);
   VIMZ_LAUNCH_CHECK(ctx);
@@ -199,10 +204,15 @@ int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* 
 template <class C>
 int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T) {
   if (s->m == 0) return VIMZ_OK;
-  ProfScope prof(ctx, PROF_CROSS_TERM);
+  ProfScope prof(ctx, PROF_CROSS_TERM, ctx->stream);
   k_cross_term<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(
       csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
   VIMZ_LAUNCH_CHECK(ctx);
+  if (s->n_long) {
+    k_cross_term_long<typename C::Fs><<<ceil_div(s->n_long * 32, 128), 128, 0, ctx->stream>>>(
+        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->long_rows, (uint32_t)s->n_long, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
+    VIMZ_LAUNCH_CHECK(ctx);
+  }
   return VIMZ_OK;
 }
 template <class C>
@@ -211,7 +221,7 @@ int impl_axpy(vimz_ctx* ctx, const void* d_a, const void* d_b, const vimz_fr* r,
   Fp<typename C::Fs> rr;
   memcpy(rr.v, r, 32);
   int grid = (int)std::min<size_t>(ceil_div(len, 256), (size_t)ctx->sm_count * 16);
-  ProfScope prof(ctx, PROF_AXPY);
+  ProfScope prof(ctx, PROF_AXPY, ctx->stream);
   k_axpy<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(d_a, d_b, rr, len, d_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;

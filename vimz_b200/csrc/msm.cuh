@@ -11,7 +11,7 @@
 //   * digits (k_count) -> counting sort by bucket (scan + k_scatter) -> bucket sums
 //     (k_accumulate: one thread per bucket, buckets ordered by size so a warp's lanes run the same
 //     trip count; oversized buckets are split into block tasks) -> sum_k (k+1) * B_k
-//     (k_reduce_chunks / k_reduce_bits / k_reduce_final).
+//     (k_reduce_chunks / k_reduce_bits / k_reduce_scale / k_reduce_out).
 //   * All arithmetic is exact; the result is the unique group element sum_i s_i * ck_i.
 #pragma once
 #include "common.cuh"
@@ -19,9 +19,7 @@
 
 namespace vimz {
 
-constexpr int MSM_REDUCE_K = 8;       // buckets per thread in the first reduction level
-constexpr int MSM_REDUCE_G = 16;      // blocks per masked sum in the second level
-constexpr int MSM_BIG_CHUNK = 2048;   // entries per block task for oversized buckets
+constexpr int MSM_BIG_CHUNK = 256;    // entries per warp task for oversized buckets
 constexpr int MSM_MAX_CLASSES = 4096; // bucket-size classes for the size ordering
 constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
 
@@ -286,51 +284,58 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restri
   acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
 }
 
-// shared-memory tree reduction of one XYZZ value per thread; result valid in thread 0
-template <class C, int THREADS>
-__device__ __forceinline__ void block_reduce_xyzz(Xyzz<C>& acc, uint32_t* smem /* THREADS*32 words */) {
-  uint32_t* mine = smem + threadIdx.x * 32;
-  acc.store(mine);
-  __syncthreads();
-  for (int s = THREADS / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) {
-      Xyzz<C> other = Xyzz<C>::load(smem + (threadIdx.x + s) * 32);
-      xyzz_add<C>(acc, other);
-      acc.store(mine);
-    }
-    __syncthreads();
+template <class C>
+__device__ __forceinline__ Xyzz<C> shfl_down_xyzz(const Xyzz<C>& acc, int o) {
+  Xyzz<C> other;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    other.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], o);
+    other.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], o);
+    other.zz.v[k] = __shfl_down_sync(0xffffffffu, acc.zz.v[k], o);
+    other.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], o);
   }
+  return other;
 }
 
+// register-only warp tree (5 levels); result valid in lane 0
 template <class C>
 __device__ __forceinline__ Xyzz<C> warp_reduce_xyzz(Xyzz<C> acc) {
   for (int o = 16; o > 0; o >>= 1) {
-    Xyzz<C> other;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      other.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], o);
-      other.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], o);
-      other.zz.v[k] = __shfl_down_sync(0xffffffffu, acc.zz.v[k], o);
-      other.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], o);
-    }
+    Xyzz<C> other = shfl_down_xyzz<C>(acc, o);
     xyzz_add<C>(acc, other);
   }
   return acc;
 }
 
-// persistent blocks pull (big bucket, chunk) tasks; each writes one XYZZ partial
+// block of 128 threads: warp trees, then the 4 warp leaders are combined by warp 0; result valid in thread 0
+template <class C>
+__device__ __forceinline__ void block_reduce_xyzz_128(Xyzz<C>& acc, uint32_t* smem /* 4*32 words */) {
+  acc = warp_reduce_xyzz<C>(acc);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) acc.store(smem + warp * 32);
+  __syncthreads();
+  if (warp == 0) {
+    acc = lane < 4 ? Xyzz<C>::load(smem + lane * 32) : Xyzz<C>::identity();
+    for (int o = 2; o > 0; o >>= 1) {
+      Xyzz<C> other = shfl_down_xyzz<C>(acc, o);
+      xyzz_add<C>(acc, other);
+    }
+  }
+  __syncthreads();
+}
+
+// persistent warps pull (big bucket, chunk) tasks of MSM_BIG_CHUNK entries; each writes one XYZZ partial
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                             const uint32_t* __restrict__ sorted, const void* __restrict__ table,
                                                             MsmSchedule sc, void* __restrict__ partials) {
-  __shared__ __align__(16) uint32_t smem[128 * 32];
-  __shared__ uint32_t s_task;
   uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
   uint32_t ntasks = sc.ctrl[1];
+  uint32_t lane = threadIdx.x & 31;
   for (;;) {
-    if (threadIdx.x == 0) s_task = atomicAdd(&sc.ctrl[2], 1u);
-    __syncthreads();
-    uint32_t task = s_task;
+    uint32_t task = 0;
+    if (lane == 0) task = atomicAdd(&sc.ctrl[2], 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= ntasks) break;
     // find e with taskstart[e] <= task < taskstart[e+1]
     uint32_t lo = 0, hi = nbig;
@@ -344,14 +349,13 @@ __global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __re
     uint32_t beg = chunk * MSM_BIG_CHUNK, end = min(cnt, beg + MSM_BIG_CHUNK);
     const uint32_t* ent = sorted + offsets[b];
     Xyzz<C> acc = Xyzz<C>::identity();
-    for (uint32_t k = beg + threadIdx.x; k < end; k += 128) {
+    for (uint32_t k = beg + lane; k < end; k += 32) {
       uint32_t e = ent[k];
       Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
       xyzz_madd<C>(acc, p, (e >> 31) != 0);
     }
-    block_reduce_xyzz<C, 128>(acc, smem);
-    if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(partials) + (size_t)task * 128);
-    __syncthreads();
+    acc = warp_reduce_xyzz<C>(acc);
+    if (lane == 0) acc.store(reinterpret_cast<char*>(partials) + (size_t)task * 128);
   }
 }
 
@@ -374,7 +378,13 @@ __global__ void __launch_bounds__(128) k_msm_big_combine(MsmSchedule sc, const v
 }
 
 // ---- bucket reduction: sum_{k=0}^{M-1} (k+1) * B_k ------------------------------------------
-// level 1: thread t owns K consecutive buckets [tK, tK+K): A_t = sum B, L_t = sum (j+1) * B_{tK+j}
+// Every EC addition executed by a lone warp costs ~4 us, so the reduction is organised for DEPTH:
+//   level 1 (k_reduce_chunks): thread t owns K consecutive buckets: A_t = sum B, L_t = sum (j+1) B_{tK+j}   [2K adds deep]
+//   level 2 (k_reduce_bits):   sum = S_L + K * sum_t t*A_t = S_L + sum_b 2^(b+logK) S_b with the plain sums
+//                              S_b = sum_{t: bit b set} A_t, S_L = sum L_t                                  [trees]
+//   level 3 (k_reduce_scale):  one warp per sum folds its G block partials, lane 0 applies the 2^(b+logK)
+//                              doublings -- all sums in parallel instead of a serial Horner chain
+//   level 4 (k_reduce_out):    one warp adds the <= 32 scaled sums and writes the Jacobian result.
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets, uint32_t T, int K,
                                                        void* __restrict__ chunkA, void* __restrict__ chunkL) {
@@ -391,11 +401,11 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
   acc.store(reinterpret_cast<char*>(chunkL) + (size_t)t * 128);
 }
 
-// level 2: sum id s = blockIdx.y: s < nb -> sum of A_t over t with bit s set; s == nb -> sum of L_t.
+// sum id s = blockIdx.y: s < nb -> sum of A_t over t with bit s set; s == nb -> sum of L_t.
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb,
                                                      void* __restrict__ bitsums) {
-  __shared__ __align__(16) uint32_t smem[128 * 32];
+  __shared__ __align__(16) uint32_t smem[4 * 32];
   int s = blockIdx.y;
   Xyzz<C> acc = Xyzz<C>::identity();
   if (s == nb) {
@@ -412,38 +422,36 @@ __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ ch
       xyzz_add<C>(acc, p);
     }
   }
-  block_reduce_xyzz<C, 128>(acc, smem);
+  block_reduce_xyzz_128<C>(acc, smem);
   if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * gridDim.x + blockIdx.x) * 128);
 }
 
-// level 3: one block, warp s sums the G partials of sum s; thread 0 then evaluates
-//   result = S_L + K * sum_b 2^b * S_b     and writes it as a Jacobian point.
+// one warp (block) per sum s: fold the G block partials, then scale by 2^(s+logK) (s < nb) -> scaled[s]
 template <class C>
-__global__ void __launch_bounds__(768) k_reduce_final(const void* __restrict__ bitsums, int nb, int G, int logK, void* __restrict__ out_jac) {
-  __shared__ __align__(16) uint32_t sums[32 * 32];  // up to 32 sums
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp <= nb) {
-    Xyzz<C> acc = Xyzz<C>::identity();
-    for (int g = lane; g < G; g += 32) {
-      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)warp * G + g) * 128);
-      xyzz_add<C>(acc, p);
-    }
-    acc = warp_reduce_xyzz<C>(acc);
-    if (lane == 0) acc.store(sums + warp * 32);
+__global__ void __launch_bounds__(32) k_reduce_scale(const void* __restrict__ bitsums, int nb, int G, int logK, void* __restrict__ scaled) {
+  int s = blockIdx.x, lane = threadIdx.x;
+  Xyzz<C> acc = Xyzz<C>::identity();
+  for (int g = lane; g < G; g += 32) {
+    Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128);
+    xyzz_add<C>(acc, p);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Xyzz<C> r = Xyzz<C>::identity();
-    for (int b = nb - 1; b >= 0; b--) {
-      r = xyzz_dbl<C>(r);
-      Xyzz<C> sb = Xyzz<C>::load(sums + b * 32);
-      xyzz_add<C>(r, sb);
-    }
-    for (int k = 0; k < logK; k++) r = xyzz_dbl<C>(r);
-    Xyzz<C> sl = Xyzz<C>::load(sums + nb * 32);
-    xyzz_add<C>(r, sl);
+  acc = warp_reduce_xyzz<C>(acc);
+  if (lane == 0) {
+    if (s < nb)
+      for (int k = 0; k < s + logK; k++) acc = xyzz_dbl<C>(acc);
+    acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
+  }
+}
+
+// one warp: add the nsums (<= 32) scaled sums, convert to Jacobian
+template <class C>
+__global__ void __launch_bounds__(32) k_reduce_out(const void* __restrict__ scaled, int nsums, void* __restrict__ out_jac) {
+  int lane = threadIdx.x;
+  Xyzz<C> acc = lane < nsums ? Xyzz<C>::load(reinterpret_cast<const char*>(scaled) + (size_t)lane * 128) : Xyzz<C>::identity();
+  acc = warp_reduce_xyzz<C>(acc);
+  if (lane == 0) {
     Fp<typename C::Fb> X, Y, Z;
-    xyzz_to_jacobian<C>(r, X, Y, Z);
+    xyzz_to_jacobian<C>(acc, X, Y, Z);
     char* o = reinterpret_cast<char*>(out_jac);
     X.store(o); Y.store(o + 32); Z.store(o + 64);
   }

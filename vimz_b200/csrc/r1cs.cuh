@@ -41,26 +41,52 @@ __global__ void __launch_bounds__(256) k_spmv3(CsrView A, CsrView B, CsrView Cm,
   for (uint32_t k = beg; k < end; k++) {
     Fp<F> v = Fp<F>::load_nc(reinterpret_cast<const char*>(M.val) + (size_t)k * 32);
     Fp<F> z = load_z<F>(W, tail, n, __ldg(M.col + k));
-    acc = fp_add(acc, fp_mul(v, z));
+    acc = fp_add(acc, coeff_mul(v, z));
   }
   acc.store(reinterpret_cast<char*>(out) + (size_t)row * 32);
 }
 
+constexpr uint32_t R1CS_LONG_ROW = 32;  // rows with more non-zeros (A+B+C) get a whole warp
+
+// v * z with the two overwhelmingly common coefficients (1 and -1: bit / copy / C rows) short-cut
 template <class F>
-VIMZ_DI void row_dot2(const CsrView& M, uint32_t row, uint32_t n, const void* __restrict__ W1, const void* __restrict__ t1,
+VIMZ_DI Fp<F> coeff_mul(const Fp<F>& v, const Fp<F>& z) {
+  bool is_one = true, is_m1 = true;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    is_one &= v.v[i] == F::one(i);
+    // -1 in Montgomery form = p - R mod p
+  }
+  if (is_one) return z;
+  Fp<F> m1 = fp_neg(Fp<F>::one());
+  is_m1 = (v == m1);
+  if (is_m1) return fp_neg(z);
+  return fp_mul(v, z);
+}
+
+template <class F>
+VIMZ_DI void row_dot2(const CsrView& M, uint32_t beg, uint32_t end, uint32_t stride, uint32_t n,
+                      const void* __restrict__ W1, const void* __restrict__ t1,
                       const void* __restrict__ W2, const void* __restrict__ t2, Fp<F>& d1, Fp<F>& d2) {
   d1 = Fp<F>::zero();
   d2 = Fp<F>::zero();
-  uint32_t beg = M.rowptr[row], end = M.rowptr[row + 1];
-  for (uint32_t k = beg; k < end; k++) {
+  for (uint32_t k = beg; k < end; k += stride) {
     Fp<F> v = Fp<F>::load_nc(reinterpret_cast<const char*>(M.val) + (size_t)k * 32);
     uint32_t c = __ldg(M.col + k);
-    d1 = fp_add(d1, fp_mul(v, load_z<F>(W1, t1, n, c)));
-    d2 = fp_add(d2, fp_mul(v, load_z<F>(W2, t2, n, c)));
+    d1 = fp_add(d1, coeff_mul(v, load_z<F>(W1, t1, n, c)));
+    d2 = fp_add(d2, coeff_mul(v, load_z<F>(W2, t2, n, c)));
   }
 }
 
-// T[i] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1   (u2 = 1; u1 = tail1[0])
+template <class F>
+VIMZ_DI Fp<F> cross_term_row(const Fp<F>& a1, const Fp<F>& a2, const Fp<F>& b1, const Fp<F>& b2, const Fp<F>& c1, const Fp<F>& c2,
+                             const Fp<F>& u1) {
+  Fp<F> t = fp_add(fp_mul(a1, b2), fp_mul(a2, b1));
+  t = fp_sub(t, fp_mul(u1, c2));
+  return fp_sub(t, c1);
+}
+
+// T[i] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1   (u2 = 1; u1 = tail1[0]).  One thread per short row.
 template <class F>
 __global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrView Cm, uint32_t m, uint32_t n,
                                                     const void* __restrict__ W1, const void* __restrict__ tail1,
@@ -68,15 +94,46 @@ __global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrVie
                                                     void* __restrict__ T) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= m) return;
+  uint32_t ab = A.rowptr[row], ae = A.rowptr[row + 1], bb = B.rowptr[row], be = B.rowptr[row + 1];
+  uint32_t cb = Cm.rowptr[row], ce = Cm.rowptr[row + 1];
+  if ((ae - ab) + (be - bb) + (ce - cb) > R1CS_LONG_ROW) return;  // k_cross_term_long owns this row
   Fp<F> a1, a2, b1, b2, c1, c2;
-  row_dot2<F>(A, row, n, W1, tail1, W2, tail2, a1, a2);
-  row_dot2<F>(B, row, n, W1, tail1, W2, tail2, b1, b2);
-  row_dot2<F>(Cm, row, n, W1, tail1, W2, tail2, c1, c2);
-  Fp<F> u1 = Fp<F>::load(tail1);
-  Fp<F> t = fp_add(fp_mul(a1, b2), fp_mul(a2, b1));
-  t = fp_sub(t, fp_mul(u1, c2));
-  t = fp_sub(t, c1);
-  t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+  row_dot2<F>(A, ab, ae, 1, n, W1, tail1, W2, tail2, a1, a2);
+  row_dot2<F>(B, bb, be, 1, n, W1, tail1, W2, tail2, b1, b2);
+  row_dot2<F>(Cm, cb, ce, 1, n, W1, tail1, W2, tail2, c1, c2);
+  cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1)).store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+}
+
+template <class F>
+VIMZ_DI Fp<F> warp_sum_fp(Fp<F> v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    Fp<F> other;
+#pragma unroll
+    for (int k = 0; k < 8; k++) other.v[k] = __shfl_down_sync(0xffffffffu, v.v[k], o);
+    v = fp_add(v, other);
+  }
+  return v;
+}
+
+// One warp per long row (e.g. the 240-term Num2Bits packing rows): lanes stride the non-zeros.
+template <class F>
+__global__ void __launch_bounds__(128) k_cross_term_long(CsrView A, CsrView B, CsrView Cm, const uint32_t* __restrict__ long_rows,
+                                                         uint32_t n_long, uint32_t n,
+                                                         const void* __restrict__ W1, const void* __restrict__ tail1,
+                                                         const void* __restrict__ W2, const void* __restrict__ tail2,
+                                                         void* __restrict__ T) {
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_long) return;
+  uint32_t row = long_rows[w];
+  Fp<F> a1, a2, b1, b2, c1, c2;
+  row_dot2<F>(A, A.rowptr[row] + lane, A.rowptr[row + 1], 32, n, W1, tail1, W2, tail2, a1, a2);
+  row_dot2<F>(B, B.rowptr[row] + lane, B.rowptr[row + 1], 32, n, W1, tail1, W2, tail2, b1, b2);
+  row_dot2<F>(Cm, Cm.rowptr[row] + lane, Cm.rowptr[row + 1], 32, n, W1, tail1, W2, tail2, c1, c2);
+  a1 = warp_sum_fp(a1); a2 = warp_sum_fp(a2);
+  b1 = warp_sum_fp(b1); b2 = warp_sum_fp(b2);
+  c1 = warp_sum_fp(c1); c2 = warp_sum_fp(c2);
+  if (lane == 0)
+    cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1)).store(reinterpret_cast<char*>(T) + (size_t)row * 32);
 }
 
 // out[i] = a[i] + r * b[i]
