@@ -205,6 +205,9 @@ class GpuFold:
         self.torch = torch
         self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
         self.eng = vimz_b200.Engine(curve_name, device)
+        win = os.environ.get("VIMZ_WINDOW_" + curve_name.upper())
+        if win:
+            self.eng.set_option("msm_window", int(win))
         sh = self.sh
         self.shape = R1CSShape(self.eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
         nck = max(sh.num_cons, sh.num_vars)

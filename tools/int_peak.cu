@@ -174,16 +174,24 @@ int main() {
     printf("  {\"name\": \"%s\", \"ops_per_clk_per_sm\": %.2f, \"Gops_per_s\": %.1f, \"ms\": %.3f, \"eff_clock_mhz\": %.0f}%s\n", name,
            per_sm_clk, total / (ms * 1e6), ms, avg / (ms * 1e3), last ? "" : ",");
   };
+// warm up for ~150 ms so the SM clock has ramped, then time 20 back-to-back launches
 #define RUN(NAME, OPS, LAUNCH, LAST)              \
   do {                                            \
-    for (int w = 0; w < 2; w++) { LAUNCH; }       \
     cudaEventRecord(e0);                          \
-    LAUNCH;                                       \
+    float wms = 0;                                \
+    while (wms < 150.f) {                         \
+      for (int w = 0; w < 10; w++) { LAUNCH; }    \
+      cudaEventRecord(e1);                        \
+      CK(cudaEventSynchronize(e1));               \
+      cudaEventElapsedTime(&wms, e0, e1);         \
+    }                                             \
+    cudaEventRecord(e0);                          \
+    for (int w = 0; w < 20; w++) { LAUNCH; }      \
     cudaEventRecord(e1);                          \
     CK(cudaEventSynchronize(e1));                 \
     float ms;                                     \
     cudaEventElapsedTime(&ms, e0, e1);            \
-    report(NAME, OPS, ms, LAST);                  \
+    report(NAME, OPS, ms / 20.f, LAST);           \
   } while (0)
   RUN("imad32", 8.0 * ITERS, (k_imad<<<blocks, threads>>>(out, 3, 5, cyc)), false);
   RUN("imad_hi", 8.0 * ITERS, (k_imadhi<<<blocks, threads>>>(out, 0xfffffff3u, 5, cyc)), false);

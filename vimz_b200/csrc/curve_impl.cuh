@@ -59,12 +59,16 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   const uint32_t T = M / K;
   int nb = 0;
   while ((1u << nb) < T) nb++;
-  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 128), 1), 64);
+  // second level: ~4 chunk sums per thread keeps the trees shallow without flooding the SMs with idle lanes
+  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 128 * 4), 1), 32);
 
   // bucket-size classes: buckets above `cap` entries are split into block tasks
+  // A thread walks its bucket serially at ~3.5 us per insertion, the whole chip retires ~7 insertions/ns:
+  // chains longer than the throughput-bound time of the kernel (E * 4e-5 insertions) only add latency.
   size_t lambda = E / M;
-  uint32_t cap = (uint32_t)std::min<size_t>(std::max<size_t>(4 * lambda, 256), MSM_MAX_CLASSES - 1);
-  uint32_t maxbig = (uint32_t)(E / cap + 2);
+  size_t chain = std::max<size_t>(2 * lambda + 16, (size_t)(E * 4e-5));
+  uint32_t cap = (uint32_t)std::min<size_t>(std::max<size_t>(chain, 32), MSM_MAX_CLASSES - 1);  // upper bound; device refines
+  uint32_t maxbig = (uint32_t)(E / 24 + 2);
   size_t maxtasks = E / MSM_BIG_CHUNK + maxbig + 1;
   const uint32_t NC = MSM_MAX_CLASSES;
 
@@ -91,6 +95,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   uint32_t* sorted = ws.sorted.as<uint32_t>();
   uint32_t* order = ws.order.as<uint32_t>();
   MsmSchedule sc;
+  sc.total = offsets + M;
+  sc.M = M;
   sc.hist = ws.cls.as<uint32_t>();
   sc.cstart = sc.hist + NC;
   sc.ccursor = sc.hist + 2 * NC;
@@ -140,9 +146,9 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
   k_msm_accumulate<C><<<ceil_div(M, 128), 128, 0, st>>>(order, counts, offsets, sorted, ck->table, M, sc.ctrl, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-  k_msm_accumulate_big<C><<<ctx->sm_count * 2, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr);
+  k_msm_accumulate_big<C><<<ctx->sm_count * 2, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-  k_msm_big_combine<C><<<32, 128, 0, st>>>(sc, ws.partials.ptr, ws.buckets.ptr);
+  k_msm_big_combine<C><<<64, 128, 0, st>>>(sc, ws.partials.ptr, ws.buckets.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   }
   ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);

@@ -69,47 +69,80 @@ struct Xyzz {
   }
 };
 
+// Multiplication policy.  The throughput kernel (bucket accumulation) inlines every field multiplication
+// so ptxas can interleave independent products; the latency-bound kernels (bucket reduction trees,
+// scalar multiplications, table expansion) instead CALL one shared copy: their warps run alone, and with
+// ~3 KB per inlined product an EC addition is ~45 KB of straight-line code that never fits the
+// instruction caches (measured: 10 us per addition inlined vs ~3 us called).
+template <class F>
+struct FpPair { Fp<F> a, b; };
+template <class F>
+__device__ __noinline__ Fp<F> fp_mul_call(Fp<F> a, Fp<F> b) { return fp_mul(a, b); }
+// two independent products in one call: a lone warp is bound by the dependent-issue latency of one
+// Montgomery chain, two interleaved chains nearly halve the time per product
+template <class F>
+__device__ __noinline__ FpPair<F> fp_mul2_call(Fp<F> a1, Fp<F> b1, Fp<F> a2, Fp<F> b2) {
+  FpPair<F> r;
+  fp_mul2(r.a, a1, b1, r.b, a2, b2);
+  return r;
+}
+struct MulInline {
+  template <class F> static VIMZ_DI Fp<F> mul(const Fp<F>& a, const Fp<F>& b) { return fp_mul(a, b); }
+  template <class F> static VIMZ_DI void mul2(Fp<F>& r1, const Fp<F>& a1, const Fp<F>& b1, Fp<F>& r2, const Fp<F>& a2, const Fp<F>& b2) {
+    r1 = fp_mul(a1, b1);
+    r2 = fp_mul(a2, b2);
+  }
+};
+struct MulCall {
+  template <class F> static VIMZ_DI Fp<F> mul(const Fp<F>& a, const Fp<F>& b) { return fp_mul_call<F>(a, b); }
+  template <class F> static VIMZ_DI void mul2(Fp<F>& r1, const Fp<F>& a1, const Fp<F>& b1, Fp<F>& r2, const Fp<F>& a2, const Fp<F>& b2) {
+    FpPair<F> r = fp_mul2_call<F>(a1, b1, a2, b2);
+    r1 = r.a;
+    r2 = r.b;
+  }
+};
+
 // 2 * (affine point) -> XYZZ   ("mdbl-2008-s-1", a = 0)
-template <class C>
+template <class C, class M = MulInline>
 VIMZ_DI Xyzz<C> xyzz_dbl_affine(const Affine<C>& p) {
   using F = Fp<typename C::Fb>;
   Xyzz<C> r;
   if (p.y.is_zero()) return Xyzz<C>::identity();  // identity (0,0); no finite point has y = 0 on these curves
   F u = fp_dbl(p.y);
-  F v = fp_sqr(u);
-  F w = fp_mul(u, v);
-  F s = fp_mul(p.x, v);
-  F xx = fp_sqr(p.x);
+  F v, xx, w, s, mm, wy;
+  M::mul2(v, u, u, xx, p.x, p.x);
+  M::mul2(w, u, v, s, p.x, v);
   F m = fp_add(fp_dbl(xx), xx);
-  r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-  r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+  M::mul2(mm, m, m, wy, w, p.y);
+  r.x = fp_sub(mm, fp_dbl(s));
+  r.y = fp_sub(M::mul(m, fp_sub(s, r.x)), wy);
   r.zz = v;
   r.zzz = w;
   return r;
 }
 
 // 2 * XYZZ ("dbl-2008-s-1", a = 0)
-template <class C>
+template <class C, class M = MulInline>
 VIMZ_DI Xyzz<C> xyzz_dbl(const Xyzz<C>& p) {
   using F = Fp<typename C::Fb>;
   if (p.is_identity() || p.y.is_zero()) return Xyzz<C>::identity();
   Xyzz<C> r;
   F u = fp_dbl(p.y);
-  F v = fp_sqr(u);
-  F w = fp_mul(u, v);
-  F s = fp_mul(p.x, v);
-  F xx = fp_sqr(p.x);
+  F v, xx, w, s, mm, wy, t;
+  M::mul2(v, u, u, xx, p.x, p.x);
+  M::mul2(w, u, v, s, p.x, v);
   F m = fp_add(fp_dbl(xx), xx);
-  r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-  r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
-  r.zz = fp_mul(v, p.zz);
-  r.zzz = fp_mul(w, p.zzz);
+  M::mul2(mm, m, m, wy, w, p.y);
+  r.x = fp_sub(mm, fp_dbl(s));
+  M::mul2(t, m, fp_sub(s, r.x), r.zz, v, p.zz);
+  r.y = fp_sub(t, wy);
+  r.zzz = M::mul(w, p.zzz);
   return r;
 }
 
 // acc += (neg ? -q : q), q affine  ("madd-2008-s", 8M + 2S).  All exceptional cases are handled
 // (acc = identity, q = identity, q = +-acc) so results are exact for any input, including repeated bases.
-template <class C>
+template <class C, class M = MulInline>
 VIMZ_DI void xyzz_madd(Xyzz<C>& acc, const Affine<C>& q, bool neg) {
   using F = Fp<typename C::Fb>;
   if (q.is_identity()) return;
@@ -118,96 +151,105 @@ VIMZ_DI void xyzz_madd(Xyzz<C>& acc, const Affine<C>& q, bool neg) {
     acc.x = q.x; acc.y = qy; acc.zz = F::one(); acc.zzz = F::one();
     return;
   }
-  F u2 = fp_mul(q.x, acc.zz);
-  F s2 = fp_mul(qy, acc.zzz);
+  F u2, s2;
+  M::mul2(u2, q.x, acc.zz, s2, qy, acc.zzz);
   F p = fp_sub(u2, acc.x);
   F r = fp_sub(s2, acc.y);
   if (p.is_zero()) {
     if (r.is_zero()) {
       Affine<C> t;
       t.x = q.x; t.y = qy;
-      acc = xyzz_dbl_affine<C>(t);
+      acc = xyzz_dbl_affine<C, M>(t);
     } else {
       acc = Xyzz<C>::identity();
     }
     return;
   }
-  F pp = fp_sqr(p);
-  F ppp = fp_mul(p, pp);
-  F qq = fp_mul(acc.x, pp);
-  F x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-  F y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(acc.y, ppp));
+  F pp, rr, ppp, qq, t1, t2;
+  M::mul2(pp, p, p, rr, r, r);
+  M::mul2(ppp, p, pp, qq, acc.x, pp);
+  F x3 = fp_sub(fp_sub(rr, ppp), fp_dbl(qq));
+  M::mul2(t1, r, fp_sub(qq, x3), t2, acc.y, ppp);
   acc.x = x3;
-  acc.y = y3;
-  acc.zz = fp_mul(acc.zz, pp);
-  acc.zzz = fp_mul(acc.zzz, ppp);
+  acc.y = fp_sub(t1, t2);
+  M::mul2(acc.zz, acc.zz, pp, acc.zzz, acc.zzz, ppp);
 }
 
 // acc += q, both XYZZ ("add-2008-s", 12M + 2S)
-template <class C>
+template <class C, class M = MulInline>
 VIMZ_DI void xyzz_add(Xyzz<C>& acc, const Xyzz<C>& q) {
   using F = Fp<typename C::Fb>;
   if (q.is_identity()) return;
   if (acc.is_identity()) { acc = q; return; }
-  F u1 = fp_mul(acc.x, q.zz);
-  F u2 = fp_mul(q.x, acc.zz);
-  F s1 = fp_mul(acc.y, q.zzz);
-  F s2 = fp_mul(q.y, acc.zzz);
+  F u1, u2, s1, s2;
+  M::mul2(u1, acc.x, q.zz, u2, q.x, acc.zz);
+  M::mul2(s1, acc.y, q.zzz, s2, q.y, acc.zzz);
   F p = fp_sub(u2, u1);
   F r = fp_sub(s2, s1);
   if (p.is_zero()) {
-    if (r.is_zero()) acc = xyzz_dbl<C>(acc);
+    if (r.is_zero()) acc = xyzz_dbl<C, M>(acc);
     else acc = Xyzz<C>::identity();
     return;
   }
-  F pp = fp_sqr(p);
-  F ppp = fp_mul(p, pp);
-  F qq = fp_mul(u1, pp);
-  F x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-  F y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(s1, ppp));
+  F pp, rr, ppp, qq, zzq, zzzq, t1, t2;
+  M::mul2(pp, p, p, rr, r, r);
+  M::mul2(zzq, acc.zz, q.zz, zzzq, acc.zzz, q.zzz);
+  M::mul2(ppp, p, pp, qq, u1, pp);
+  F x3 = fp_sub(fp_sub(rr, ppp), fp_dbl(qq));
+  M::mul2(t1, r, fp_sub(qq, x3), t2, s1, ppp);
   acc.x = x3;
-  acc.y = y3;
-  acc.zz = fp_mul(fp_mul(acc.zz, q.zz), pp);
-  acc.zzz = fp_mul(fp_mul(acc.zzz, q.zzz), ppp);
+  acc.y = fp_sub(t1, t2);
+  M::mul2(acc.zz, zzq, pp, acc.zzz, zzzq, ppp);
 }
 
 // XYZZ -> Jacobian without inversion: Z = ZZ*ZZZ  =>  Z^2 = ZZ^5, Z^3 = ZZZ^5 (using ZZ^3 = ZZZ^2),
 // so X_j = X*ZZ^4, Y_j = Y*ZZZ^4.  Identity -> (0, 1, 0) like halo2curves.
-template <class C>
+template <class C, class M = MulInline>
 VIMZ_DI void xyzz_to_jacobian(const Xyzz<C>& p, Fp<typename C::Fb>& X, Fp<typename C::Fb>& Y, Fp<typename C::Fb>& Z) {
   using F = Fp<typename C::Fb>;
   if (p.is_identity()) {
     X = F::zero(); Y = F::one(); Z = F::zero();
     return;
   }
-  F zz2 = fp_sqr(p.zz), zzz2 = fp_sqr(p.zzz);
-  X = fp_mul(p.x, fp_sqr(zz2));
-  Y = fp_mul(p.y, fp_sqr(zzz2));
-  Z = fp_mul(p.zz, p.zzz);
+  F zz2 = M::mul(p.zz, p.zz), zzz2 = M::mul(p.zzz, p.zzz);
+  X = M::mul(p.x, M::mul(zz2, zz2));
+  Y = M::mul(p.y, M::mul(zzz2, zzz2));
+  Z = M::mul(p.zz, p.zzz);
 }
 
 // XYZZ -> canonical affine (one inversion; identity -> (0,0)).
 template <class C>
 __device__ __noinline__ Affine<C> xyzz_to_affine(const Xyzz<C>& p) {
   using F = Fp<typename C::Fb>;
+  using M = MulCall;
   Affine<C> a;
   if (p.is_identity()) { a.x = F::zero(); a.y = F::zero(); return a; }
   F zi = fp_inv(p.zzz);              // 1/ZZZ
-  F zzi = fp_sqr(fp_mul(p.zz, zi));  // (ZZ/ZZZ)^2 = ZZ^2/ZZ^3 = 1/ZZ
-  a.x = fp_mul(p.x, zzi);
-  a.y = fp_mul(p.y, zi);
+  F t = M::mul(p.zz, zi);
+  F zzi = M::mul(t, t);              // (ZZ/ZZZ)^2 = ZZ^2/ZZ^3 = 1/ZZ
+  a.x = M::mul(p.x, zzi);
+  a.y = M::mul(p.y, zi);
   return a;
 }
 
 // Jacobian {X,Y,Z} (Z may be anything, identity Z = 0) -> XYZZ (ZZ = Z^2, ZZZ = Z^3).
-template <class C>
+template <class C, class M = MulInline>
 VIMZ_DI Xyzz<C> xyzz_from_jacobian(const Fp<typename C::Fb>& X, const Fp<typename C::Fb>& Y, const Fp<typename C::Fb>& Z) {
   Xyzz<C> r;
   if (Z.is_zero()) return Xyzz<C>::identity();
   r.x = X; r.y = Y;
-  r.zz = fp_sqr(Z);
-  r.zzz = fp_mul(r.zz, Z);
+  r.zz = M::mul(Z, Z);
+  r.zzz = M::mul(r.zz, Z);
   return r;
 }
+
+// Group operations for the latency-bound kernels: formulas inlined, every field product a call to the one
+// shared fp_mul_call (operands by value, in registers), ~10 KB per addition instead of ~45 KB.
+template <class C>
+VIMZ_DI void xyzz_add_call(Xyzz<C>& acc, const Xyzz<C>& q) { xyzz_add<C, MulCall>(acc, q); }
+template <class C>
+VIMZ_DI void xyzz_dbl_call(Xyzz<C>& p) { p = xyzz_dbl<C, MulCall>(p); }
+template <class C>
+VIMZ_DI void xyzz_madd_call(Xyzz<C>& acc, const Affine<C>& q, bool neg) { xyzz_madd<C, MulCall>(acc, q, neg); }
 
 }  // namespace vimz

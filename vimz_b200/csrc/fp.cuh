@@ -189,6 +189,29 @@ VIMZ_DI Fp<F> fp_cneg(const Fp<F>& a, bool neg) {
 template <class F>
 VIMZ_DI Fp<F> fp_dbl(const Fp<F>& a) { return fp_add(a, a); }
 
+// a > (p-1)/2 for a canonical (non-Montgomery) value a: the "negative half" of the field
+template <class F>
+VIMZ_DI bool fp_gt_half(const Fp<F>& a) {
+  uint32_t borrow = 0;
+  // (p-1)/2 - a  borrows  <=>  a > (p-1)/2
+  uint32_t t;
+  asm("sub.cc.u32 %0, %2, %10;\n\t"
+      "subc.cc.u32 %0, %3, %11;\n\t"
+      "subc.cc.u32 %0, %4, %12;\n\t"
+      "subc.cc.u32 %0, %5, %13;\n\t"
+      "subc.cc.u32 %0, %6, %14;\n\t"
+      "subc.cc.u32 %0, %7, %15;\n\t"
+      "subc.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %0, %9, %17;\n\t"
+      "subc.u32 %1, 0, 0;"
+      : "=&r"(t), "=&r"(borrow)
+      : "r"((F::p(0) >> 1) | (F::p(1) << 31)), "r"((F::p(1) >> 1) | (F::p(2) << 31)), "r"((F::p(2) >> 1) | (F::p(3) << 31)),
+        "r"((F::p(3) >> 1) | (F::p(4) << 31)), "r"((F::p(4) >> 1) | (F::p(5) << 31)), "r"((F::p(5) >> 1) | (F::p(6) << 31)),
+        "r"((F::p(6) >> 1) | (F::p(7) << 31)), "r"(F::p(7) >> 1),
+        "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+  return borrow != 0;
+}
+
 // ---- Montgomery multiplication ----------------------------------------------------------------
 // One row: acc += a * bi ; m = acc[0] * INV ; acc += m * p ; acc >>= 32, with the accumulator split
 // into an even-aligned (ev) and an odd-aligned (od) set of 64-bit lanes.  The 32-bit right shift
@@ -310,6 +333,53 @@ VIMZ_DI Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
   return r;
 }
 
+// Two independent products with their Montgomery rows interleaved in program order, so a lone warp has
+// two carry chains in flight instead of one (used by the latency-bound kernels through fp_mul2_call).
+template <class F>
+VIMZ_DI void fp_mul2(Fp<F>& r1, const Fp<F>& a1, const Fp<F>& b1, Fp<F>& r2, const Fp<F>& a2, const Fp<F>& b2) {
+  uint32_t e1[8], o1[8], e2[8], o2[8];
+  mont_row<F, true>(e1, o1, a1.v, b1.v[0]);
+  mont_row<F, true>(e2, o2, a2.v, b2.v[0]);
+  mont_row<F, false>(o1, e1, a1.v, b1.v[1]);
+  mont_row<F, false>(o2, e2, a2.v, b2.v[1]);
+  mont_row<F, false>(e1, o1, a1.v, b1.v[2]);
+  mont_row<F, false>(e2, o2, a2.v, b2.v[2]);
+  mont_row<F, false>(o1, e1, a1.v, b1.v[3]);
+  mont_row<F, false>(o2, e2, a2.v, b2.v[3]);
+  mont_row<F, false>(e1, o1, a1.v, b1.v[4]);
+  mont_row<F, false>(e2, o2, a2.v, b2.v[4]);
+  mont_row<F, false>(o1, e1, a1.v, b1.v[5]);
+  mont_row<F, false>(o2, e2, a2.v, b2.v[5]);
+  mont_row<F, false>(e1, o1, a1.v, b1.v[6]);
+  mont_row<F, false>(e2, o2, a2.v, b2.v[6]);
+  mont_row<F, false>(o1, e1, a1.v, b1.v[7]);
+  mont_row<F, false>(o2, e2, a2.v, b2.v[7]);
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(e1[0]), "+r"(e1[1]), "+r"(e1[2]), "+r"(e1[3]), "+r"(e1[4]), "+r"(e1[5]), "+r"(e1[6]), "+r"(e1[7])
+      : "r"(o1[1]), "r"(o1[2]), "r"(o1[3]), "r"(o1[4]), "r"(o1[5]), "r"(o1[6]), "r"(o1[7]));
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(e2[0]), "+r"(e2[1]), "+r"(e2[2]), "+r"(e2[3]), "+r"(e2[4]), "+r"(e2[5]), "+r"(e2[6]), "+r"(e2[7])
+      : "r"(o2[1]), "r"(o2[2]), "r"(o2[3]), "r"(o2[4]), "r"(o2[5]), "r"(o2[6]), "r"(o2[7]));
+#pragma unroll
+  for (int i = 0; i < 8; i++) { r1.v[i] = e1[i]; r2.v[i] = e2[i]; }
+  fp_final_sub(r1);
+  fp_final_sub(r2);
+}
+
 template <class F>
 VIMZ_DI Fp<F> fp_sqr(const Fp<F>& a) { return fp_mul(a, a); }
 
@@ -322,7 +392,10 @@ VIMZ_DI Fp<F> fp_from_mont(const Fp<F>& a) {
 template <class F>
 VIMZ_DI Fp<F> fp_to_mont(const Fp<F>& a) { return fp_mul(a, Fp<F>::r2()); }
 
-// a^(p-2): only used by the one-thread affine normalisation, never on the hot loop.
+template <class F>
+__device__ __noinline__ Fp<F> fp_mul_noinline(Fp<F> a, Fp<F> b) { return fp_mul(a, b); }
+
+// a^(p-2): only used by affine normalisation (one inversion per thread), never on the hot loop.
 template <class F>
 __device__ __noinline__ Fp<F> fp_inv(const Fp<F>& a) {
   Fp<F> r = Fp<F>::one();
@@ -334,8 +407,8 @@ __device__ __noinline__ Fp<F> fp_inv(const Fp<F>& a) {
       case 1: w = F::pm2(1); break; default: break;
     }
     for (int bit = 31; bit >= 0; bit--) {
-      r = fp_sqr(r);
-      if ((w >> bit) & 1) r = fp_mul(r, a);
+      r = fp_mul_noinline<F>(r, r);
+      if ((w >> bit) & 1) r = fp_mul_noinline<F>(r, a);
     }
   }
   return r;

@@ -59,6 +59,7 @@ __global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, in
   using Fs = Fp<typename C::Fs>;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
+    if (fp_gt_half(s)) s = fp_neg(s);  // s*P = (q-s)*(-P): digits of the smaller magnitude
     for_each_digit(s.v, c, nwin, [&](int, uint32_t mag, bool) { atomicAdd(&counts[mag - 1], 1u); });
   }
 }
@@ -70,9 +71,14 @@ __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t n, 
   using Fs = Fp<typename C::Fs>;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
+    // Nova's running vectors are dominated by values of small magnitude modulo q (sums of 128-bit
+    // challenges and their negatives): recode q - s with the point negated, so a "negative small" scalar
+    // costs as few bucket insertions as a positive one instead of all windows.
+    bool flip = fp_gt_half(s);
+    if (flip) s = fp_neg(s);
     for_each_digit(s.v, c, nwin, [&](int j, uint32_t mag, bool neg) {
       uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
-      sorted[pos] = ((uint32_t)j * table_stride + first + i) | (neg ? 0x80000000u : 0u);
+      sorted[pos] = ((uint32_t)j * table_stride + first + i) | ((neg != flip) ? 0x80000000u : 0u);
     });
   }
 }
@@ -160,8 +166,13 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
 
 // ---- bucket schedule: order buckets by size (largest first), split oversized ones ------------
 // cls layout (uint32): [0, NC) histogram, [NC, 2NC) class start, [2NC, 3NC) class cursor,
-// then ctrl: [3NC+0] nbig, [3NC+1] ntasks, [3NC+2] task counter, [3NC+3] big-combine counter.
+// then ctrl: [3NC+0] nbig, [3NC+1] ntasks, [3NC+2] task counter.
+// The split threshold is decided on the device from the ACTUAL number of insertions E = offsets[M]
+// (zeros and short scalars make it much smaller than n * windows): buckets above
+// max(24, 2E/M + 8, 4e-5 E) entries are cut into warp tasks so no thread walks a long chain alone.
 struct MsmSchedule {
+  const uint32_t* total;  // &offsets[M]
+  uint32_t M;
   uint32_t* hist;
   uint32_t* cstart;
   uint32_t* ccursor;
@@ -172,13 +183,22 @@ struct MsmSchedule {
   uint32_t maxbig;
 };
 
+__device__ __forceinline__ uint32_t sched_cap(const MsmSchedule& sc) {
+  uint32_t e = *sc.total;
+  // a chain of k insertions costs ~3.5 us * k; the whole kernel needs ~e * 1.4e-4 us at full throughput,
+  // so chains up to e * 4e-5 are free, and never split below twice the mean bucket
+  uint32_t free_chain = (uint32_t)((uint64_t)e * 41u >> 20);
+  return min(sc.cap, max(max(24u, free_chain), 2u * (e / sc.M) + 8u));
+}
+
 static __global__ void k_sched_hist(const uint32_t* __restrict__ counts, uint32_t M, MsmSchedule sc) {
   extern __shared__ uint32_t sh_hist[];  // cap + 1
   for (uint32_t k = threadIdx.x; k <= sc.cap; k += blockDim.x) sh_hist[k] = 0;
   __syncthreads();
+  const uint32_t cap = sched_cap(sc);
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < M; b += gridDim.x * blockDim.x) {
     uint32_t cnt = counts[b];
-    if (cnt > sc.cap) {
+    if (cnt > cap) {
       uint32_t e = atomicAdd(&sc.ctrl[0], 1u);
       if (e < sc.maxbig) sc.biglist[e] = b;
     } else {
@@ -246,9 +266,10 @@ static __global__ void k_sched_scan(const uint32_t* __restrict__ counts, MsmSche
 }
 
 static __global__ void k_sched_scatter(const uint32_t* __restrict__ counts, uint32_t M, MsmSchedule sc, uint32_t* __restrict__ order) {
+  const uint32_t cap = sched_cap(sc);
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < M; b += gridDim.x * blockDim.x) {
     uint32_t cnt = counts[b];
-    if (cnt <= sc.cap) {
+    if (cnt <= cap) {
       uint32_t pos = atomicAdd(&sc.ccursor[cnt], 1u);
       order[pos] = b;
     }
@@ -257,7 +278,7 @@ static __global__ void k_sched_scatter(const uint32_t* __restrict__ counts, uint
 
 // ---- bucket accumulation ----------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
+__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
                                                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
                                                         const void* __restrict__ table, uint32_t M, const uint32_t* __restrict__ ctrl,
                                                         void* __restrict__ buckets) {
@@ -284,14 +305,18 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restri
   acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
 }
 
+// value of lane (lane + o); lanes whose partner is out of range get the identity (NOT their own value:
+// acc + acc would send them down the doubling path and the whole warp would pay for it)
 template <class C>
-__device__ __forceinline__ Xyzz<C> shfl_down_xyzz(const Xyzz<C>& acc, int o) {
+__device__ __forceinline__ Xyzz<C> shfl_down_xyzz(const Xyzz<C>& acc, int o, int width = 32) {
   Xyzz<C> other;
+  bool valid = (int)(threadIdx.x & 31) + o < width;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     other.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], o);
     other.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], o);
-    other.zz.v[k] = __shfl_down_sync(0xffffffffu, acc.zz.v[k], o);
+    uint32_t zz = __shfl_down_sync(0xffffffffu, acc.zz.v[k], o);
+    other.zz.v[k] = valid ? zz : 0u;
     other.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], o);
   }
   return other;
@@ -302,7 +327,7 @@ template <class C>
 __device__ __forceinline__ Xyzz<C> warp_reduce_xyzz(Xyzz<C> acc) {
   for (int o = 16; o > 0; o >>= 1) {
     Xyzz<C> other = shfl_down_xyzz<C>(acc, o);
-    xyzz_add<C>(acc, other);
+    xyzz_add_call<C>(acc, other);
   }
   return acc;
 }
@@ -317,8 +342,8 @@ __device__ __forceinline__ void block_reduce_xyzz_128(Xyzz<C>& acc, uint32_t* sm
   if (warp == 0) {
     acc = lane < 4 ? Xyzz<C>::load(smem + lane * 32) : Xyzz<C>::identity();
     for (int o = 2; o > 0; o >>= 1) {
-      Xyzz<C> other = shfl_down_xyzz<C>(acc, o);
-      xyzz_add<C>(acc, other);
+      Xyzz<C> other = shfl_down_xyzz<C>(acc, o, 2 * o);
+      xyzz_add_call<C>(acc, other);
     }
   }
   __syncthreads();
@@ -328,7 +353,7 @@ __device__ __forceinline__ void block_reduce_xyzz_128(Xyzz<C>& acc, uint32_t* sm
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                             const uint32_t* __restrict__ sorted, const void* __restrict__ table,
-                                                            MsmSchedule sc, void* __restrict__ partials) {
+                                                            MsmSchedule sc, void* __restrict__ partials, void* __restrict__ buckets) {
   uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
   uint32_t ntasks = sc.ctrl[1];
   uint32_t lane = threadIdx.x & 31;
@@ -352,28 +377,30 @@ __global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __re
     for (uint32_t k = beg + lane; k < end; k += 32) {
       uint32_t e = ent[k];
       Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
-      xyzz_madd<C>(acc, p, (e >> 31) != 0);
+      xyzz_madd_call<C>(acc, p, (e >> 31) != 0);
     }
     acc = warp_reduce_xyzz<C>(acc);
-    if (lane == 0) acc.store(reinterpret_cast<char*>(partials) + (size_t)task * 128);
+    // a bucket that fits one task is finished here; otherwise k_msm_big_combine adds the partials
+    bool single = sc.taskstart[lo + 1] - sc.taskstart[lo] == 1;
+    if (lane == 0) acc.store(single ? reinterpret_cast<char*>(buckets) + (size_t)b * 128 : reinterpret_cast<char*>(partials) + (size_t)task * 128);
   }
 }
 
-// one warp per big bucket: sum its task partials into the bucket
+// one 128-thread block per big bucket: sum its task partials into the bucket
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_big_combine(MsmSchedule sc, const void* __restrict__ partials, void* __restrict__ buckets) {
+  __shared__ __align__(16) uint32_t smem[4 * 32];
   uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
-  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t e = warp; e < nbig; e += nwarps) {
+  for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
     uint32_t t0 = sc.taskstart[e], t1 = sc.taskstart[e + 1];
+    if (t1 - t0 <= 1) continue;  // written directly by its only task (block-uniform branch)
     Xyzz<C> acc = Xyzz<C>::identity();
-    for (uint32_t t = t0 + lane; t < t1; t += 32) {
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += 128) {
       Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + (size_t)t * 128);
-      xyzz_add<C>(acc, p);
+      xyzz_add_call<C>(acc, p);
     }
-    acc = warp_reduce_xyzz<C>(acc);
-    if (lane == 0) acc.store(reinterpret_cast<char*>(buckets) + (size_t)sc.biglist[e] * 128);
+    block_reduce_xyzz_128<C>(acc, smem);
+    if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(buckets) + (size_t)sc.biglist[e] * 128);
   }
 }
 
@@ -394,8 +421,8 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
   const char* base = reinterpret_cast<const char*>(buckets) + (size_t)t * K * 128;
   for (int j = K - 1; j >= 0; j--) {
     Xyzz<C> b = Xyzz<C>::load(base + (size_t)j * 128);
-    xyzz_add<C>(running, b);
-    xyzz_add<C>(acc, running);
+    xyzz_add_call<C>(running, b);
+    xyzz_add_call<C>(acc, running);
   }
   running.store(reinterpret_cast<char*>(chunkA) + (size_t)t * 128);
   acc.store(reinterpret_cast<char*>(chunkL) + (size_t)t * 128);
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ ch
   if (s == nb) {
     for (uint32_t t = blockIdx.x * 128 + threadIdx.x; t < T; t += gridDim.x * 128) {
       Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(chunkL) + (size_t)t * 128);
-      xyzz_add<C>(acc, p);
+      xyzz_add_call<C>(acc, p);
     }
   } else {
     // enumerate exactly the indices with bit s set so every lane is busy
@@ -419,7 +446,7 @@ __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ ch
     for (uint32_t u = blockIdx.x * 128 + threadIdx.x; u < half; u += gridDim.x * 128) {
       uint32_t t = ((u & ~lowmask) << 1) | (1u << s) | (u & lowmask);
       Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(chunkA) + (size_t)t * 128);
-      xyzz_add<C>(acc, p);
+      xyzz_add_call<C>(acc, p);
     }
   }
   block_reduce_xyzz_128<C>(acc, smem);
@@ -433,12 +460,12 @@ __global__ void __launch_bounds__(32) k_reduce_scale(const void* __restrict__ bi
   Xyzz<C> acc = Xyzz<C>::identity();
   for (int g = lane; g < G; g += 32) {
     Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128);
-    xyzz_add<C>(acc, p);
+    xyzz_add_call<C>(acc, p);
   }
   acc = warp_reduce_xyzz<C>(acc);
   if (lane == 0) {
     if (s < nb)
-      for (int k = 0; k < s + logK; k++) acc = xyzz_dbl<C>(acc);
+      for (int k = 0; k < s + logK; k++) xyzz_dbl_call<C>(acc);
     acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
   }
 }
@@ -451,7 +478,7 @@ __global__ void __launch_bounds__(32) k_reduce_out(const void* __restrict__ scal
   acc = warp_reduce_xyzz<C>(acc);
   if (lane == 0) {
     Fp<typename C::Fb> X, Y, Z;
-    xyzz_to_jacobian<C>(acc, X, Y, Z);
+    xyzz_to_jacobian<C, MulCall>(acc, X, Y, Z);
     char* o = reinterpret_cast<char*>(out_jac);
     X.store(o); Y.store(o + 32); Z.store(o + 64);
   }
@@ -503,11 +530,11 @@ __global__ void k_point_sum(const void* __restrict__ pts, uint32_t k, void* __re
   Xyzz<C> acc = Xyzz<C>::identity();
   for (uint32_t i = 0; i < k; i++) {
     const char* p = reinterpret_cast<const char*>(pts) + (size_t)i * 96;
-    Xyzz<C> q = xyzz_from_jacobian<C>(F::load(p), F::load(p + 32), F::load(p + 64));
-    xyzz_add<C>(acc, q);
+    Xyzz<C> q = xyzz_from_jacobian<C, MulCall>(F::load(p), F::load(p + 32), F::load(p + 64));
+    xyzz_add_call<C>(acc, q);
   }
   F X, Y, Z;
-  xyzz_to_jacobian<C>(acc, X, Y, Z);
+  xyzz_to_jacobian<C, MulCall>(acc, X, Y, Z);
   char* o = reinterpret_cast<char*>(out);
   X.store(o); Y.store(o + 32); Z.store(o + 64);
 }
@@ -517,7 +544,7 @@ __global__ void k_point_to_affine(const void* __restrict__ pt, void* __restrict_
   using F = Fp<typename C::Fb>;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const char* p = reinterpret_cast<const char*>(pt);
-  Xyzz<C> q = xyzz_from_jacobian<C>(F::load(p), F::load(p + 32), F::load(p + 64));
+  Xyzz<C> q = xyzz_from_jacobian<C, MulCall>(F::load(p), F::load(p + 32), F::load(p + 64));
   Affine<C> a = xyzz_to_affine<C>(q);
   a.store(out);
 }
@@ -533,18 +560,18 @@ __global__ void k_point_scale_add(const void* __restrict__ a, const void* __rest
   Fs r = fp_from_mont(Fs::load(r_mont));
   const char* pb = reinterpret_cast<const char*>(b) + (size_t)t * 96;
   const char* pa = reinterpret_cast<const char*>(a) + (size_t)t * 96;
-  Xyzz<C> base = xyzz_from_jacobian<C>(F::load(pb), F::load(pb + 32), F::load(pb + 64));
+  Xyzz<C> base = xyzz_from_jacobian<C, MulCall>(F::load(pb), F::load(pb + 32), F::load(pb + 64));
   Xyzz<C> acc = Xyzz<C>::identity();
   int top = 255;
   while (top >= 0 && !((r.v[top >> 5] >> (top & 31)) & 1)) top--;
   for (int bit = top; bit >= 0; bit--) {
-    acc = xyzz_dbl<C>(acc);
-    if ((r.v[bit >> 5] >> (bit & 31)) & 1) xyzz_add<C>(acc, base);
+    xyzz_dbl_call<C>(acc);
+    if ((r.v[bit >> 5] >> (bit & 31)) & 1) xyzz_add_call<C>(acc, base);
   }
-  Xyzz<C> pa_x = xyzz_from_jacobian<C>(F::load(pa), F::load(pa + 32), F::load(pa + 64));
-  xyzz_add<C>(acc, pa_x);
+  Xyzz<C> pa_x = xyzz_from_jacobian<C, MulCall>(F::load(pa), F::load(pa + 32), F::load(pa + 64));
+  xyzz_add_call<C>(acc, pa_x);
   F X, Y, Z;
-  xyzz_to_jacobian<C>(acc, X, Y, Z);
+  xyzz_to_jacobian<C, MulCall>(acc, X, Y, Z);
   char* o = reinterpret_cast<char*>(out) + (size_t)t * 96;
   X.store(o); Y.store(o + 32); Z.store(o + 64);
 }
@@ -563,8 +590,8 @@ __global__ void __launch_bounds__(128) k_gen_bases(uint64_t k0, uint64_t dk, uin
   auto smul = [&](uint64_t s) {
     Xyzz<C> acc = Xyzz<C>::identity();
     for (int bit = 63; bit >= 0; bit--) {
-      acc = xyzz_dbl<C>(acc);
-      if ((s >> bit) & 1) xyzz_madd<C>(acc, g, false);
+      xyzz_dbl_call<C>(acc);
+      if ((s >> bit) & 1) xyzz_madd_call<C>(acc, g, false);
     }
     return acc;
   };
@@ -578,7 +605,7 @@ __global__ void __launch_bounds__(128) k_gen_bases(uint64_t k0, uint64_t dk, uin
     pts[j] = cur;
     prefix[j] = run;
     if (!cur.is_identity()) run = fp_mul(run, cur.zzz);
-    xyzz_add<C>(cur, step);
+    xyzz_add_call<C>(cur, step);
   }
   F inv = fp_inv(run);
   for (int j = cnt - 1; j >= 0; j--) {
