@@ -9,7 +9,7 @@
 #include "fp.cuh"
 using namespace vimz;
 
-#define ITERS 4096
+#define ITERS 65536
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 
 __global__ void k_imad(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
@@ -130,7 +130,7 @@ __global__ void k_mix(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(s ^ (s >> 32));
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
-#define MUL_ITERS 512
+#define MUL_ITERS 4096
 template <class F>
 __global__ void k_fpmul(uint32_t* out, const uint32_t* in, long long* cyc) {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,18 +180,18 @@ int main() {
     cudaEventRecord(e0);                          \
     float wms = 0;                                \
     while (wms < 150.f) {                         \
-      for (int w = 0; w < 10; w++) { LAUNCH; }    \
+      for (int w = 0; w < 2; w++) { LAUNCH; }    \
       cudaEventRecord(e1);                        \
       CK(cudaEventSynchronize(e1));               \
       cudaEventElapsedTime(&wms, e0, e1);         \
     }                                             \
     cudaEventRecord(e0);                          \
-    for (int w = 0; w < 20; w++) { LAUNCH; }      \
+    for (int w = 0; w < 5; w++) { LAUNCH; }       \
     cudaEventRecord(e1);                          \
     CK(cudaEventSynchronize(e1));                 \
     float ms;                                     \
     cudaEventElapsedTime(&ms, e0, e1);            \
-    report(NAME, OPS, ms / 20.f, LAST);           \
+    report(NAME, OPS, ms / 5.f, LAST);           \
   } while (0)
   RUN("imad32", 8.0 * ITERS, (k_imad<<<blocks, threads>>>(out, 3, 5, cyc)), false);
   RUN("imad_hi", 8.0 * ITERS, (k_imadhi<<<blocks, threads>>>(out, 0xfffffff3u, 5, cyc)), false);

@@ -176,6 +176,10 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     ctx->prof.on = value != 0;
     return VIMZ_OK;
   }
+  if (strcmp(key, "graph") == 0) {
+    ctx->opt_graph = value != 0;
+    return VIMZ_OK;
+  }
   return set_error(VIMZ_ERR_ARG, std::string("unknown option: ") + key);
 }
 
@@ -521,6 +525,8 @@ void vimz_acc_destroy(vimz_acc* a) {
   void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  for (int k = 0; k < 2; k++)
+    if (a->graph[k]) cudaGraphExecDestroy(a->graph[k]);
   if (a->ev_main) cudaEventDestroy(a->ev_main);
   if (a->ev_w2) cudaEventDestroy(a->ev_w2);
   if (a->ev_aux) cudaEventDestroy(a->ev_aux);
@@ -590,7 +596,29 @@ int vimz_acc_load(vimz_acc* a, const vimz_fr* W, const vimz_fr* E, const vimz_fr
   return VIMZ_OK;
 }
 
-static int acc_step_begin_common(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
+// The stream work of step_begin after W2 is resident: everything here has fixed addresses, so it can be captured.
+static int enqueue_step_begin(vimz_acc* a, char* fresh) {
+  vimz_ctx* ctx = a->ctx;
+  const vimz_shape* s = a->shape;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  cudaStream_t st = ctx->stream;
+  uint8_t* stage = (uint8_t*)ctx->pinned + 1024;
+  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) -- independent of T, so it runs on the aux
+  // stream with its own workspace while the main stream does the cross term and commit(T).
+  VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
+  VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
+  VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, a->W2, s->n, fresh));
+  VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
+  // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
+  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T));
+  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96));
+  VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
+  VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
+  return VIMZ_OK;
+}
+
+static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   vimz_ctx* ctx = a->ctx;
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
@@ -598,28 +626,53 @@ static int acc_step_begin_common(vimz_acc* a, const void* d_W2, const vimz_fr* X
   // comm_W2 / comm_T alternate between two slot pairs so the side-stream fold of the previous
   // step can still read its inputs; the pair used two steps ago must be free again.
   a->parity ^= 1;
-  if (a->side_pending[a->parity]) {
-    VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_side[a->parity], 0));
-    a->side_pending[a->parity] = false;
+  const int p = a->parity;
+  if (a->side_pending[p]) {
+    VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_side[p], 0));
+    a->side_pending[p] = false;
   }
-  char* comms = (char*)a->comms;
-  char* fresh = comms + (2 + 2 * a->parity) * 96;
-  // tail2 = (1, X2)
+  char* fresh = (char*)a->comms + (2 + 2 * p) * 96;
+  // tail2 = (1, X2) staged in pinned memory (read by the copy when it executes)
   uint8_t* stage = (uint8_t*)ctx->pinned + 1024;
   memcpy(stage, vt->scalar_one_mont, 32);
   if (s->io) memcpy(stage + 32, X2, s->io * 32);
-  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
-  // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) -- independent of T, so it runs on the aux
-  // stream with its own workspace while the main stream does the cross term and commit(T).
-  VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
-  VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
-  VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, d_W2, s->n, fresh));
-  VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
-  // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
-  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, d_W2, a->tail2, a->T));
-  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96));
-  VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
-  VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
+
+  bool use_graph = ctx->opt_graph && !ctx->prof.on && a->warm[p];
+  if (use_graph && a->graph[p] && a->graph_epoch[p] != alloc_epoch()) {  // a workspace moved: rebuild
+    cudaGraphExecDestroy(a->graph[p]);
+    a->graph[p] = nullptr;
+    use_graph = false;  // one eager run re-validates the buffers first
+  }
+  if (use_graph) {
+    if (!a->graph[p]) {
+      uint64_t l0 = ctx->launches, e0 = alloc_epoch();
+      VIMZ_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      int rc = enqueue_step_begin(a, fresh);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc != VIMZ_OK || e != cudaSuccess || alloc_epoch() != e0) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        ctx->opt_graph = false;  // fall back to stream launches for good
+        if (rc == VIMZ_OK) rc = enqueue_step_begin(a, fresh);
+        if (rc != VIMZ_OK) return rc;
+      } else {
+        a->graph_launches[p] = ctx->launches - l0;
+        ctx->launches = l0;
+        e = cudaGraphInstantiate(&a->graph[p], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return set_error(VIMZ_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        a->graph_epoch[p] = e0;
+      }
+    }
+    if (a->graph[p]) {
+      VIMZ_CUDA(cudaGraphLaunch(a->graph[p], st));
+      ctx->launches += a->graph_launches[p];
+    }
+  } else {
+    VIMZ_TRY(enqueue_step_begin(a, fresh));
+    a->warm[p] = true;
+  }
   VIMZ_CUDA(cudaStreamSynchronize(st));
   memcpy(comm_W2, ctx->pinned, 96);
   memcpy(comm_T, (char*)ctx->pinned + 96, 96);
@@ -632,7 +685,7 @@ int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_
   size_t io = a->shape->io;
   if (1024 + (1 + io) * 32 > 4096) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
-  return acc_step_begin_common(a, a->W2, X2, comm_W2, comm_T);
+  return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
 int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
@@ -642,7 +695,7 @@ int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vi
   if (1024 + (1 + io) * 32 > 4096) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   // keep W2 resident for step_end
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
-  return acc_step_begin_common(a, a->W2, X2, comm_W2, comm_T);
+  return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
 int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {

@@ -32,6 +32,12 @@ inline int set_error(int code, const std::string& msg) {
     if (_rc != VIMZ_OK) return _rc; \
   } while (0)
 
+// Bumped whenever a DevBuf is (re)allocated: captured CUDA graphs hold raw pointers and are rebuilt when it moves.
+inline uint64_t& alloc_epoch() {
+  static uint64_t e = 0;
+  return e;
+}
+
 // Grow-only device buffer (no per-call cudaMalloc on the hot path).
 struct DevBuf {
   void* ptr = nullptr;
@@ -44,6 +50,7 @@ struct DevBuf {
     size_t want = bytes + bytes / 8 + 256;
     VIMZ_CUDA(cudaMalloc(&ptr, want));
     cap = want;
+    alloc_epoch()++;
     return VIMZ_OK;
   }
   void release() {
@@ -105,6 +112,7 @@ struct vimz_ctx {
   cudaStream_t aux = nullptr;   // second MSM lane: commit(W2) runs beside cross-term + commit(T)
   int sm_count = 148;
   long opt_window = 0;  // 0 = auto
+  bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points
@@ -167,4 +175,10 @@ struct vimz_acc {
   cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr}, ev_w2 = nullptr, ev_aux = nullptr;
   bool side_pending[2] = {false, false};
   int parity = 0;
+  // step_begin's launch sequence (cross term + both MSMs, ~35 kernels on two streams) captured once per
+  // parity slot and replayed: the step is latency-bound and stream launches cost more than the small kernels
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  uint64_t graph_epoch[2] = {0, 0};
+  uint64_t graph_launches[2] = {0, 0};
+  bool warm[2] = {false, false};
 };

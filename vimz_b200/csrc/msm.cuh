@@ -325,6 +325,7 @@ __device__ __forceinline__ Xyzz<C> shfl_down_xyzz(const Xyzz<C>& acc, int o, int
 // register-only warp tree (5 levels); result valid in lane 0
 template <class C>
 __device__ __forceinline__ Xyzz<C> warp_reduce_xyzz(Xyzz<C> acc) {
+#pragma unroll 1  // one copy of the addition: these warps run alone and are instruction-fetch bound
   for (int o = 16; o > 0; o >>= 1) {
     Xyzz<C> other = shfl_down_xyzz<C>(acc, o);
     xyzz_add_call<C>(acc, other);
@@ -341,6 +342,7 @@ __device__ __forceinline__ void block_reduce_xyzz_128(Xyzz<C>& acc, uint32_t* sm
   __syncthreads();
   if (warp == 0) {
     acc = lane < 4 ? Xyzz<C>::load(smem + lane * 32) : Xyzz<C>::identity();
+#pragma unroll 1
     for (int o = 2; o > 0; o >>= 1) {
       Xyzz<C> other = shfl_down_xyzz<C>(acc, o, 2 * o);
       xyzz_add_call<C>(acc, other);
@@ -419,6 +421,7 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
   if (t >= T) return;
   Xyzz<C> running = Xyzz<C>::identity(), acc = Xyzz<C>::identity();
   const char* base = reinterpret_cast<const char*>(buckets) + (size_t)t * K * 128;
+#pragma unroll 1
   for (int j = K - 1; j >= 0; j--) {
     Xyzz<C> b = Xyzz<C>::load(base + (size_t)j * 128);
     xyzz_add_call<C>(running, b);
@@ -435,19 +438,15 @@ __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ ch
   __shared__ __align__(16) uint32_t smem[4 * 32];
   int s = blockIdx.y;
   Xyzz<C> acc = Xyzz<C>::identity();
-  if (s == nb) {
-    for (uint32_t t = blockIdx.x * 128 + threadIdx.x; t < T; t += gridDim.x * 128) {
-      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(chunkL) + (size_t)t * 128);
-      xyzz_add_call<C>(acc, p);
-    }
-  } else {
-    // enumerate exactly the indices with bit s set so every lane is busy
-    uint32_t half = T >> 1, lowmask = (1u << s) - 1;
-    for (uint32_t u = blockIdx.x * 128 + threadIdx.x; u < half; u += gridDim.x * 128) {
-      uint32_t t = ((u & ~lowmask) << 1) | (1u << s) | (u & lowmask);
-      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(chunkA) + (size_t)t * 128);
-      xyzz_add_call<C>(acc, p);
-    }
+  // s < nb: enumerate exactly the indices with bit s set so every lane is busy; s == nb: all of chunkL
+  const bool plain = (s == nb);
+  const uint32_t count = plain ? T : (T >> 1), lowmask = plain ? 0u : ((1u << s) - 1);
+  const char* src = reinterpret_cast<const char*>(plain ? chunkL : chunkA);
+#pragma unroll 1
+  for (uint32_t u = blockIdx.x * 128 + threadIdx.x; u < count; u += gridDim.x * 128) {
+    uint32_t t = plain ? u : (((u & ~lowmask) << 1) | (1u << s) | (u & lowmask));
+    Xyzz<C> p = Xyzz<C>::load(src + (size_t)t * 128);
+    xyzz_add_call<C>(acc, p);
   }
   block_reduce_xyzz_128<C>(acc, smem);
   if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * gridDim.x + blockIdx.x) * 128);
@@ -458,6 +457,7 @@ template <class C>
 __global__ void __launch_bounds__(32) k_reduce_scale(const void* __restrict__ bitsums, int nb, int G, int logK, void* __restrict__ scaled) {
   int s = blockIdx.x, lane = threadIdx.x;
   Xyzz<C> acc = Xyzz<C>::identity();
+#pragma unroll 1
   for (int g = lane; g < G; g += 32) {
     Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128);
     xyzz_add_call<C>(acc, p);
@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(32) k_reduce_scale(const void* __restrict__ bi
   acc = warp_reduce_xyzz<C>(acc);
   if (lane == 0) {
     if (s < nb)
+#pragma unroll 1
       for (int k = 0; k < s + logK; k++) xyzz_dbl_call<C>(acc);
     acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
   }
