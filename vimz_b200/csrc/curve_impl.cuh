@@ -59,8 +59,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   const uint32_t T = M / K;
   int nb = 0;
   while ((1u << nb) < T) nb++;
-  // second level: ~4 chunk sums per thread keeps the trees shallow without flooding the SMs with idle lanes
-  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 128 * 4), 1), 32);
+  // second level: 32 quads per block, ~8 chunk sums per quad keeps the trees shallow without flooding the SMs
+  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 8), 1), 32);
 
   // bucket-size classes: buckets above `cap` entries are split into block tasks
   // A thread walks its bucket serially at ~3.5 us per insertion, the whole chip retires ~7 insertions/ns:
@@ -152,7 +152,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   VIMZ_LAUNCH_CHECK(ctx);
   }
   ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);
-  k_reduce_chunks<C><<<ceil_div(T, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
+  k_reduce_chunks<C><<<ceil_div((size_t)T * 4, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_reduce_bits<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, ws.bitsums.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
@@ -177,8 +177,8 @@ int impl_point_to_affine(vimz_ctx* ctx, const void* d_pt, void* d_out) {
 }
 template <class C>
 int impl_point_scale_add(vimz_ctx* ctx, cudaStream_t st, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count) {
-  // one thread per block so independent scalar multiplications land on different SMs
-  k_point_scale_add<C><<<count, 1, 0, st>>>(d_a, d_r, d_b, d_out, count);
+  if (count > 8) return set_error(VIMZ_ERR_ARG, "point_scale_add: at most 8 pairs per call");
+  k_point_scale_add<C><<<1, 32, 0, st>>>(d_a, d_r, d_b, d_out, count);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }

@@ -16,6 +16,7 @@
 #pragma once
 #include "common.cuh"
 #include "ec.cuh"
+#include "ecq.cuh"
 
 namespace vimz {
 
@@ -381,54 +382,81 @@ __global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __re
       Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
       xyzz_madd_call<C>(acc, p, (e >> 31) != 0);
     }
-    acc = warp_reduce_xyzz<C>(acc);
+    // 32 per-lane sums -> one point: each quad first folds its own four lanes' points, then a quad tree
+    QPoint<C> qa = QPoint<C>::identity();
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) qa = q_add<C>(qa, q_from_lane<C>(acc, j));
+    qa = q_warp_reduce<C>(qa);
     // a bucket that fits one task is finished here; otherwise k_msm_big_combine adds the partials
     bool single = sc.taskstart[lo + 1] - sc.taskstart[lo] == 1;
-    if (lane == 0) acc.store(single ? reinterpret_cast<char*>(buckets) + (size_t)b * 128 : reinterpret_cast<char*>(partials) + (size_t)task * 128);
+    if (lane < 4) qa.store(single ? reinterpret_cast<char*>(buckets) + (size_t)b * 128 : reinterpret_cast<char*>(partials) + (size_t)task * 128);
   }
 }
 
-// one 128-thread block per big bucket: sum its task partials into the bucket
+// 32 quads of a 128-thread block each hold one point: warp trees, then warp 0 folds the four warp results.
+// Result valid in quad 0 of warp 0 (threads 0..3).  smem: 4 XYZZ records.
+template <class C>
+__device__ __forceinline__ QPoint<C> q_block_reduce_128(QPoint<C> acc, uint32_t* smem) {
+  acc = q_warp_reduce<C>(acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) acc.store(smem + warp * 32);
+  __syncthreads();
+  if (warp == 0) {  // warp-uniform: all 32 lanes run the cooperative tree; quads >= 4 contribute the identity
+    acc = lane < 16 ? QPoint<C>::load(smem + (lane >> 2) * 32) : QPoint<C>::identity();
+    acc = q_warp_reduce<C>(acc);
+  }
+  __syncthreads();
+  return acc;
+}
+
+// one 128-thread block per big bucket: its task partials are summed by 32 cooperating quads
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_big_combine(MsmSchedule sc, const void* __restrict__ partials, void* __restrict__ buckets) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
   uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
+  const uint32_t quad = threadIdx.x >> 2;
   for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
     uint32_t t0 = sc.taskstart[e], t1 = sc.taskstart[e + 1];
     if (t1 - t0 <= 1) continue;  // written directly by its only task (block-uniform branch)
-    Xyzz<C> acc = Xyzz<C>::identity();
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += 128) {
-      Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + (size_t)t * 128);
-      xyzz_add_call<C>(acc, p);
+    QPoint<C> acc = QPoint<C>::identity();
+    uint32_t iters = (t1 - t0 + 31) / 32;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; it++) {  // warp-uniform trip count: every lane joins the shuffles
+      uint32_t t = t0 + it * 32 + quad;
+      QPoint<C> p = t < t1 ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + (size_t)t * 128) : QPoint<C>::identity();
+      acc = q_add<C>(acc, p);
     }
-    block_reduce_xyzz_128<C>(acc, smem);
-    if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(buckets) + (size_t)sc.biglist[e] * 128);
+    acc = q_block_reduce_128<C>(acc, smem);
+    if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)sc.biglist[e] * 128);
   }
 }
 
 // ---- bucket reduction: sum_{k=0}^{M-1} (k+1) * B_k ------------------------------------------
-// Every EC addition executed by a lone warp costs ~4 us, so the reduction is organised for DEPTH:
-//   level 1 (k_reduce_chunks): thread t owns K consecutive buckets: A_t = sum B, L_t = sum (j+1) B_{tK+j}   [2K adds deep]
+// Every step below is a chain of EC additions executed by warps that run alone, so it is organised for
+// DEPTH and every addition is done by a quad of lanes (ecq.cuh):
+//   level 1 (k_reduce_chunks): quad t owns K consecutive buckets: A_t = sum B, L_t = sum (j+1) B_{tK+j}   [2K adds deep]
 //   level 2 (k_reduce_bits):   sum = S_L + K * sum_t t*A_t = S_L + sum_b 2^(b+logK) S_b with the plain sums
 //                              S_b = sum_{t: bit b set} A_t, S_L = sum L_t                                  [trees]
-//   level 3 (k_reduce_scale):  one warp per sum folds its G block partials, lane 0 applies the 2^(b+logK)
+//   level 3 (k_reduce_scale):  one warp per sum folds its G block partials, then applies the 2^(b+logK)
 //                              doublings -- all sums in parallel instead of a serial Horner chain
 //   level 4 (k_reduce_out):    one warp adds the <= 32 scaled sums and writes the Jacobian result.
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets, uint32_t T, int K,
                                                        void* __restrict__ chunkA, void* __restrict__ chunkL) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  Xyzz<C> running = Xyzz<C>::identity(), acc = Xyzz<C>::identity();
-  const char* base = reinterpret_cast<const char*>(buckets) + (size_t)t * K * 128;
+  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool valid = t < T;  // whole quads are valid or not; invalid quads still run the shuffles
+  QPoint<C> running = QPoint<C>::identity(), acc = QPoint<C>::identity();
+  const char* base = reinterpret_cast<const char*>(buckets) + (size_t)(valid ? t : 0) * K * 128;
 #pragma unroll 1
   for (int j = K - 1; j >= 0; j--) {
-    Xyzz<C> b = Xyzz<C>::load(base + (size_t)j * 128);
-    xyzz_add_call<C>(running, b);
-    xyzz_add_call<C>(acc, running);
+    QPoint<C> b = valid ? QPoint<C>::load(base + (size_t)j * 128) : QPoint<C>::identity();
+    running = q_add<C>(running, b);
+    acc = q_add<C>(acc, running);
   }
-  running.store(reinterpret_cast<char*>(chunkA) + (size_t)t * 128);
-  acc.store(reinterpret_cast<char*>(chunkL) + (size_t)t * 128);
+  if (valid) {
+    running.store(reinterpret_cast<char*>(chunkA) + (size_t)t * 128);
+    acc.store(reinterpret_cast<char*>(chunkL) + (size_t)t * 128);
+  }
 }
 
 // sum id s = blockIdx.y: s < nb -> sum of A_t over t with bit s set; s == nb -> sum of L_t.
@@ -436,53 +464,58 @@ template <class C>
 __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb,
                                                      void* __restrict__ bitsums) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
-  int s = blockIdx.y;
-  Xyzz<C> acc = Xyzz<C>::identity();
-  // s < nb: enumerate exactly the indices with bit s set so every lane is busy; s == nb: all of chunkL
+  const int s = blockIdx.y;
+  // s < nb: enumerate exactly the indices with bit s set so every quad is busy; s == nb: all of chunkL
   const bool plain = (s == nb);
   const uint32_t count = plain ? T : (T >> 1), lowmask = plain ? 0u : ((1u << s) - 1);
   const char* src = reinterpret_cast<const char*>(plain ? chunkL : chunkA);
+  const uint32_t quad = threadIdx.x >> 2, stride = gridDim.x * 32;
+  const uint32_t iters = (count + stride - 1) / stride;
+  QPoint<C> acc = QPoint<C>::identity();
 #pragma unroll 1
-  for (uint32_t u = blockIdx.x * 128 + threadIdx.x; u < count; u += gridDim.x * 128) {
+  for (uint32_t it = 0; it < iters; it++) {
+    uint32_t u = it * stride + blockIdx.x * 32 + quad;
     uint32_t t = plain ? u : (((u & ~lowmask) << 1) | (1u << s) | (u & lowmask));
-    Xyzz<C> p = Xyzz<C>::load(src + (size_t)t * 128);
-    xyzz_add_call<C>(acc, p);
+    QPoint<C> p = u < count ? QPoint<C>::load(src + (size_t)t * 128) : QPoint<C>::identity();
+    acc = q_add<C>(acc, p);
   }
-  block_reduce_xyzz_128<C>(acc, smem);
-  if (threadIdx.x == 0) acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * gridDim.x + blockIdx.x) * 128);
+  acc = q_block_reduce_128<C>(acc, smem);
+  if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * gridDim.x + blockIdx.x) * 128);
 }
 
 // one warp (block) per sum s: fold the G block partials, then scale by 2^(s+logK) (s < nb) -> scaled[s]
 template <class C>
 __global__ void __launch_bounds__(32) k_reduce_scale(const void* __restrict__ bitsums, int nb, int G, int logK, void* __restrict__ scaled) {
-  int s = blockIdx.x, lane = threadIdx.x;
-  Xyzz<C> acc = Xyzz<C>::identity();
+  const int s = blockIdx.x, quad = threadIdx.x >> 2;
+  QPoint<C> acc = QPoint<C>::identity();
+  const int iters = (G + 7) / 8;
 #pragma unroll 1
-  for (int g = lane; g < G; g += 32) {
-    Xyzz<C> p = Xyzz<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128);
-    xyzz_add_call<C>(acc, p);
+  for (int it = 0; it < iters; it++) {
+    int g = it * 8 + quad;
+    QPoint<C> p = g < G ? QPoint<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128) : QPoint<C>::identity();
+    acc = q_add<C>(acc, p);
   }
-  acc = warp_reduce_xyzz<C>(acc);
-  if (lane == 0) {
-    if (s < nb)
+  acc = q_warp_reduce<C>(acc);
+  const int ndbl = s < nb ? s + logK : 0;  // block-uniform
 #pragma unroll 1
-      for (int k = 0; k < s + logK; k++) xyzz_dbl_call<C>(acc);
-    acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
-  }
+  for (int k = 0; k < ndbl; k++) acc = q_dbl<C>(acc);
+  if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
 }
 
 // one warp: add the nsums (<= 32) scaled sums, convert to Jacobian
 template <class C>
 __global__ void __launch_bounds__(32) k_reduce_out(const void* __restrict__ scaled, int nsums, void* __restrict__ out_jac) {
-  int lane = threadIdx.x;
-  Xyzz<C> acc = lane < nsums ? Xyzz<C>::load(reinterpret_cast<const char*>(scaled) + (size_t)lane * 128) : Xyzz<C>::identity();
-  acc = warp_reduce_xyzz<C>(acc);
-  if (lane == 0) {
-    Fp<typename C::Fb> X, Y, Z;
-    xyzz_to_jacobian<C, MulCall>(acc, X, Y, Z);
-    char* o = reinterpret_cast<char*>(out_jac);
-    X.store(o); Y.store(o + 32); Z.store(o + 64);
+  const int quad = threadIdx.x >> 2;
+  QPoint<C> acc = QPoint<C>::identity();
+  const int iters = (nsums + 7) / 8;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    int g = it * 8 + quad;
+    QPoint<C> p = g < nsums ? QPoint<C>::load(reinterpret_cast<const char*>(scaled) + (size_t)g * 128) : QPoint<C>::identity();
+    acc = q_add<C>(acc, p);
   }
+  acc = q_warp_reduce<C>(acc);
+  q_store_jacobian<C>(acc, out_jac, threadIdx.x < 4);
 }
 
 // ---- window-table expansion (once per commitment key) ---------------------------------------
@@ -550,31 +583,29 @@ __global__ void k_point_to_affine(const void* __restrict__ pt, void* __restrict_
   a.store(out);
 }
 
-// out[t] = a[t] + r * b[t] for `count` independent pairs (one thread each); r is a Montgomery scalar.
+// out[t] = a[t] + r * b[t] for count <= 8 independent pairs, one QUAD each (one warp in total); r is a
+// Montgomery scalar shared by all pairs (RelaxedR1CSInstance::fold uses the same r for comm_W and comm_E).
 template <class C>
-__global__ void k_point_scale_add(const void* __restrict__ a, const void* __restrict__ r_mont, const void* __restrict__ b,
-                                  void* __restrict__ out, int count) {
-  using F = Fp<typename C::Fb>;
+__global__ void __launch_bounds__(32) k_point_scale_add(const void* __restrict__ a, const void* __restrict__ r_mont, const void* __restrict__ b,
+                                                        void* __restrict__ out, int count) {
   using Fs = Fp<typename C::Fs>;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+  const int t = threadIdx.x >> 2;
+  const bool valid = t < count;
   Fs r = fp_from_mont(Fs::load(r_mont));
-  const char* pb = reinterpret_cast<const char*>(b) + (size_t)t * 96;
-  const char* pa = reinterpret_cast<const char*>(a) + (size_t)t * 96;
-  Xyzz<C> base = xyzz_from_jacobian<C, MulCall>(F::load(pb), F::load(pb + 32), F::load(pb + 64));
-  Xyzz<C> acc = Xyzz<C>::identity();
+  const int tt = valid ? t : 0;
+  QPoint<C> base = q_load_jacobian<C>(reinterpret_cast<const char*>(b) + (size_t)tt * 96);
+  QPoint<C> pa = q_load_jacobian<C>(reinterpret_cast<const char*>(a) + (size_t)tt * 96);
+  QPoint<C> acc = QPoint<C>::identity();
   int top = 255;
   while (top >= 0 && !((r.v[top >> 5] >> (top & 31)) & 1)) top--;
-  for (int bit = top; bit >= 0; bit--) {
-    xyzz_dbl_call<C>(acc);
-    if ((r.v[bit >> 5] >> (bit & 31)) & 1) xyzz_add_call<C>(acc, base);
+#pragma unroll 1
+  for (int bit = top; bit >= 0; bit--) {  // r is uniform across the warp, so the branch is too
+    acc = q_dbl<C>(acc);
+    if ((r.v[bit >> 5] >> (bit & 31)) & 1) acc = q_add<C>(acc, base);
   }
-  Xyzz<C> pa_x = xyzz_from_jacobian<C, MulCall>(F::load(pa), F::load(pa + 32), F::load(pa + 64));
-  xyzz_add_call<C>(acc, pa_x);
-  F X, Y, Z;
-  xyzz_to_jacobian<C, MulCall>(acc, X, Y, Z);
-  char* o = reinterpret_cast<char*>(out) + (size_t)t * 96;
-  X.store(o); Y.store(o + 32); Z.store(o + 64);
+  acc = q_add<C>(acc, pa);
+  // each quad writes its own result (q_store_jacobian stores from lanes 0..2 of the quad)
+  q_store_jacobian<C>(acc, reinterpret_cast<char*>(out) + (size_t)tt * 96, valid);
 }
 
 // bases[i] = (k0 + i*dk) * G ; each thread walks a run of GEN_RUN consecutive multiples.
