@@ -278,6 +278,8 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
     from vimz_b200 import CommitmentEngine, CommitmentKey
     from vimz_b200 import synthetic as S
     eng = vimz_b200.Engine("pallas", device)
+    if os.environ.get("VIMZ_WINDOW_MSM"):
+        eng.set_option("msm_window", int(os.environ["VIMZ_WINDOW_MSM"]))
     n = 1 << log2n
     per = n // world
     first = rank * per
@@ -353,6 +355,14 @@ def main_gpu(args, rank, world, local_rank):
         dist = d
     peaks = load_peaks()
     steps, warmup = args.steps, max(args.warmup, 3)
+    if args.msm_only:
+        msm = [msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks) for lg in args.msm_log2]
+        if rank == 0:
+            print(json.dumps({"metric": "pallas_msm_mpts_per_sec", "msm": msm}), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # each rank folds its own transformation (different witnesses), same circuit
     prim = GpuFold("pallas", "grayscale", SEED + 100 * rank, local_rank, torch)
@@ -455,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[20])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--msm-only", action="store_true", help="skip the fold-step measurement (window sweeps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

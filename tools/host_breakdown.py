@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Wall-clock breakdown of one fold step on the host side (where does the non-kernel time go?)."""
+import os, sys, time
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from vimz_b200.field import ints_to_mont
+
+prim = bench.GpuFold("pallas", "grayscale", bench.SEED, 0, torch)
+sec = bench.GpuFold("vesta", "secondary", bench.SEED + 1, 0, torch)
+for k in range(40):
+    sec.step(k, True); prim.step(k, True)
+acc = {"begin_p": 0.0, "ro_p": 0.0, "end_p": 0.0, "begin_s": 0.0, "ro_s": 0.0, "end_s": 0.0}
+N = 50
+t_all = time.perf_counter()
+for k in range(40, 40 + N):
+    for tag, f in (("s", sec), ("p", prim)):
+        i = k % bench.NUM_WITNESSES
+        t0 = time.perf_counter()
+        cw, ct = f.acc.step_begin_dev(f.dev_W[i].data_ptr(), f.wits[i][1])
+        t1 = time.perf_counter()
+        r = ints_to_mont([bench.challenge_from(ct.tobytes(), k)], f.q)
+        t2 = time.perf_counter()
+        f.acc.step_end(r)
+        t3 = time.perf_counter()
+        acc["begin_" + tag] += t1 - t0; acc["ro_" + tag] += t2 - t1; acc["end_" + tag] += t3 - t2
+prim.eng.sync(); sec.eng.sync()
+tot = time.perf_counter() - t_all
+print({k: round(v / N * 1e6, 1) for k, v in acc.items()}, "us per step; total", round(tot / N * 1e6, 1), "us/step")

@@ -71,10 +71,9 @@ struct MsmWorkspace {
   vimz::DevBuf cursor;     // [M]   scatter cursors
   vimz::DevBuf blocksums;  // scan scratch
   vimz::DevBuf sorted;     // [E]   table index | sign<<31, grouped by bucket
-  vimz::DevBuf order;      // [M]   bucket ids, largest first
-  vimz::DevBuf cls;        // class histogram / starts / cursors + big-bucket bookkeeping
-  vimz::DevBuf biglist;    // big bucket ids, task starts
-  vimz::DevBuf partials;   // XYZZ partial sums of big-bucket tasks
+  vimz::DevBuf cls;        // control words (giant-bucket counter)
+  vimz::DevBuf biglist;    // ids of buckets cut into many segments
+  vimz::DevBuf partials;   // [2 * nthreads] XYZZ head/tail partial sums of the accumulation segments
   vimz::DevBuf buckets;    // [M] XYZZ
   vimz::DevBuf chunkA;     // [T] XYZZ chunk sums
   vimz::DevBuf chunkL;     // [T] XYZZ chunk weighted sums
@@ -84,7 +83,7 @@ struct MsmWorkspace {
   vimz::DevBuf result;     // Jacobian results (device)
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release();
-    order.release(); cls.release(); biglist.release(); partials.release(); buckets.release();
+    cls.release(); biglist.release(); partials.release(); buckets.release();
     chunkA.release(); chunkL.release(); bitsums.release(); scaled.release(); scal.release(); result.release();
   }
 };
@@ -160,8 +159,10 @@ struct vimz_shape {
   uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};  // [m+1]
   uint32_t* col[3] = {nullptr, nullptr, nullptr};     // [nnz]
   void* val[3] = {nullptr, nullptr, nullptr};         // [nnz] Montgomery scalars
-  uint32_t* long_rows = nullptr;                      // rows with > R1CS_LONG_ROW non-zeros over A+B+C
+  uint32_t* long_rows = nullptr;                      // rows with > R1CS_LONG_ROW non-zeros over A+B+C (warp each)
   size_t n_long = 0;
+  uint32_t* mid_rows = nullptr;                       // rows with R1CS_SHORT_ROW+1 .. R1CS_LONG_ROW non-zeros (8 lanes each)
+  size_t n_mid = 0;
 };
 
 struct vimz_acc {

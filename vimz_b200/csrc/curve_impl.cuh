@@ -61,16 +61,10 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   while ((1u << nb) < T) nb++;
   // second level: 32 quads per block, ~8 chunk sums per quad keeps the trees shallow without flooding the SMs
   const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 8), 1), 32);
-
-  // bucket-size classes: buckets above `cap` entries are split into block tasks
-  // A thread walks its bucket serially at ~3.5 us per insertion, the whole chip retires ~7 insertions/ns:
-  // chains longer than the throughput-bound time of the kernel (E * 4e-5 insertions) only add latency.
-  size_t lambda = E / M;
-  size_t chain = std::max<size_t>(2 * lambda + 16, (size_t)(E * 4e-5));
-  uint32_t cap = (uint32_t)std::min<size_t>(std::max<size_t>(chain, 32), MSM_MAX_CLASSES - 1);  // upper bound; device refines
-  uint32_t maxbig = (uint32_t)(E / 24 + 2);
-  size_t maxtasks = E / MSM_BIG_CHUNK + maxbig + 1;
-  const uint32_t NC = MSM_MAX_CLASSES;
+  // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
+  const uint32_t nthreads = (uint32_t)ctx->sm_count * 4 * 128;
+  const uint32_t max_giants = nthreads / COMBINE_MID + 2;
+  const uint32_t max_chunks = nthreads / GIANT_CHUNK + max_giants + 2;
 
   VIMZ_TRY(ws.counts.reserve((size_t)M * 4));
   VIMZ_TRY(ws.offsets.reserve(((size_t)M + 1) * 4));
@@ -78,10 +72,9 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   uint32_t scan_blocks = ceil_div(M, SCAN_THREADS * SCAN_ITEMS);
   VIMZ_TRY(ws.blocksums.reserve(((size_t)scan_blocks + 2) * 4));
   VIMZ_TRY(ws.sorted.reserve(E * 4));
-  VIMZ_TRY(ws.order.reserve((size_t)M * 4));
-  VIMZ_TRY(ws.cls.reserve(((size_t)3 * NC + 8) * 4));
-  VIMZ_TRY(ws.biglist.reserve(((size_t)2 * maxbig + 2) * 4));
-  VIMZ_TRY(ws.partials.reserve(maxtasks * 128));
+  VIMZ_TRY(ws.cls.reserve(64));
+  VIMZ_TRY(ws.biglist.reserve(((size_t)3 * max_giants + (size_t)2 * max_chunks + (size_t)M + 4) * 4));
+  VIMZ_TRY(ws.partials.reserve(((size_t)2 * nthreads + max_chunks) * 128));
   VIMZ_TRY(ws.buckets.reserve((size_t)M * 128));
   VIMZ_TRY(ws.chunkA.reserve((size_t)T * 128));
   VIMZ_TRY(ws.chunkL.reserve((size_t)T * 128));
@@ -93,47 +86,36 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   uint32_t* cursor = ws.cursor.as<uint32_t>();
   uint32_t* blocksums = ws.blocksums.as<uint32_t>();
   uint32_t* sorted = ws.sorted.as<uint32_t>();
-  uint32_t* order = ws.order.as<uint32_t>();
-  MsmSchedule sc;
-  sc.total = offsets + M;
-  sc.M = M;
-  sc.hist = ws.cls.as<uint32_t>();
-  sc.cstart = sc.hist + NC;
-  sc.ccursor = sc.hist + 2 * NC;
-  sc.ctrl = sc.hist + 3 * NC;
-  sc.biglist = ws.biglist.as<uint32_t>();
-  sc.taskstart = sc.biglist + maxbig;
-  sc.cap = cap;
-  sc.maxbig = maxbig;
+  MsmCombine cb;
+  cb.ctrl = ws.cls.as<uint32_t>();
+  cb.giants = ws.biglist.as<uint32_t>();
+  cb.chunk_rec = cb.giants + (size_t)3 * max_giants;
+  cb.mids = cb.chunk_rec + (size_t)2 * max_chunks;
+  cb.chunk_sums = ws.partials.as<char>() + (size_t)2 * nthreads * 128;
+  cb.max_giants = max_giants;
+  cb.max_chunks = max_chunks;
 
   VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
-  VIMZ_CUDA(cudaMemsetAsync(sc.hist, 0, ((size_t)3 * NC + 8) * 4, st));
+  VIMZ_CUDA(cudaMemsetAsync(cb.ctrl, 0, 64, st));
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
   {
-  ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
-  if (n > 0) {
-    k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
+    ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
+    if (n > 0) {
+      k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
+      VIMZ_LAUNCH_CHECK(ctx);
+    }
+    k_scan_blocksum<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums);
     VIMZ_LAUNCH_CHECK(ctx);
-  }
-  k_scan_blocksum<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_scan_top<<<1, 1024, 0, st>>>(blocksums, scan_blocks, blocksums + scan_blocks + 1);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_scan_apply<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums, offsets, cursor);
-  VIMZ_LAUNCH_CHECK(ctx);
-  if (n > 0) {
-    k_msm_scatter<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin,
-                                              (uint32_t)ck->n, (uint32_t)first, cursor, sorted);
+    k_scan_top<<<1, 1024, 0, st>>>(blocksums, scan_blocks, blocksums + scan_blocks + 1);
     VIMZ_LAUNCH_CHECK(ctx);
-  }
-  const int grid_m = (int)std::min<size_t>(ceil_div(M, 256), (size_t)ctx->sm_count * 8);
-  k_sched_hist<<<grid_m, 256, (cap + 1) * 4, st>>>(counts, M, sc);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_sched_scan<<<1, 1024, 0, st>>>(counts, sc);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_sched_scatter<<<grid_m, 256, 0, st>>>(counts, M, sc, order);
-  VIMZ_LAUNCH_CHECK(ctx);
+    k_scan_apply<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums, offsets, cursor);
+    VIMZ_LAUNCH_CHECK(ctx);
+    if (n > 0) {
+      k_msm_scatter<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin,
+                                                (uint32_t)ck->n, (uint32_t)first, cursor, sorted);
+      VIMZ_LAUNCH_CHECK(ctx);
+    }
   }
   if (ctx->prof.on) {  // total bucket insertions of this MSM = offsets[M]
     uint32_t* slot;
@@ -143,13 +125,17 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
     ctx->prof.entry_slots.push_back(slot);
   }
   {
-  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
-  k_msm_accumulate<C><<<ceil_div(M, 128), 128, 0, st>>>(order, counts, offsets, sorted, ck->table, M, sc.ctrl, ws.buckets.ptr);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_msm_accumulate_big<C><<<ctx->sm_count * 2, 128, 0, st>>>(counts, offsets, sorted, ck->table, sc, ws.partials.ptr, ws.buckets.ptr);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_msm_big_combine<C><<<64, 128, 0, st>>>(sc, ws.partials.ptr, ws.buckets.ptr);
-  VIMZ_LAUNCH_CHECK(ctx);
+    ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
+    k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, ws.buckets.ptr, ws.partials.ptr);
+    VIMZ_LAUNCH_CHECK(ctx);
+    k_msm_combine<C><<<ceil_div(M, 128), 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
+    VIMZ_LAUNCH_CHECK(ctx);
+    k_msm_combine_mid<C><<<ctx->sm_count * 4, 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
+    VIMZ_LAUNCH_CHECK(ctx);
+    k_msm_combine_big<C><<<ctx->sm_count, 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, cb);
+    VIMZ_LAUNCH_CHECK(ctx);
+    k_msm_combine_final<C><<<16, 128, 0, st>>>(cb, ws.buckets.ptr);
+    VIMZ_LAUNCH_CHECK(ctx);
   }
   ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);
   k_reduce_chunks<C><<<ceil_div((size_t)T * 4, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
@@ -214,8 +200,13 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
   k_cross_term<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(
       csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
   VIMZ_LAUNCH_CHECK(ctx);
+  if (s->n_mid) {
+    k_cross_term_group<typename C::Fs, 8><<<ceil_div(s->n_mid * 8, 128), 128, 0, ctx->stream>>>(
+        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->mid_rows, (uint32_t)s->n_mid, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
+    VIMZ_LAUNCH_CHECK(ctx);
+  }
   if (s->n_long) {
-    k_cross_term_long<typename C::Fs><<<ceil_div(s->n_long * 32, 128), 128, 0, ctx->stream>>>(
+    k_cross_term_group<typename C::Fs, 32><<<ceil_div(s->n_long * 32, 128), 128, 0, ctx->stream>>>(
         csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->long_rows, (uint32_t)s->n_long, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
     VIMZ_LAUNCH_CHECK(ctx);
   }

@@ -9,8 +9,8 @@
 //     digits then contributes d_ij * table[j][i]: every window shares ONE set of M = 2^(c-1)
 //     buckets, there is no per-window bucket reduction and no final doubling chain.
 //   * digits (k_count) -> counting sort by bucket (scan + k_scatter) -> bucket sums
-//     (k_accumulate: one thread per bucket, buckets ordered by size so a warp's lanes run the same
-//     trip count; oversized buckets are split into block tasks) -> sum_k (k+1) * B_k
+//     (k_accumulate: every thread walks an equal segment of the sorted insertions, k_combine adds the
+//     pieces of buckets cut by segment boundaries) -> sum_k (k+1) * B_k
 //     (k_reduce_chunks / k_reduce_bits / k_reduce_scale / k_reduce_out).
 //   * All arithmetic is exact; the result is the unique group element sum_i s_i * ck_i.
 #pragma once
@@ -20,8 +20,6 @@
 
 namespace vimz {
 
-constexpr int MSM_BIG_CHUNK = 256;    // entries per warp task for oversized buckets
-constexpr int MSM_MAX_CLASSES = 4096; // bucket-size classes for the size ordering
 constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
 
 // ---- signed-digit recoding -------------------------------------------------------------------
@@ -165,232 +163,122 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) offsets[n] = run;
 }
 
-// ---- bucket schedule: order buckets by size (largest first), split oversized ones ------------
-// cls layout (uint32): [0, NC) histogram, [NC, 2NC) class start, [2NC, 3NC) class cursor,
-// then ctrl: [3NC+0] nbig, [3NC+1] ntasks, [3NC+2] task counter.
-// The split threshold is decided on the device from the ACTUAL number of insertions E = offsets[M]
-// (zeros and short scalars make it much smaller than n * windows): buckets above
-// max(24, 2E/M + 8, 4e-5 E) entries are cut into warp tasks so no thread walks a long chain alone.
-struct MsmSchedule {
-  const uint32_t* total;  // &offsets[M]
-  uint32_t M;
-  uint32_t* hist;
-  uint32_t* cstart;
-  uint32_t* ccursor;
-  uint32_t* ctrl;
-  uint32_t* biglist;    // [maxbig] bucket ids
-  uint32_t* taskstart;  // [maxbig + 1]
-  uint32_t cap;         // buckets with count > cap are "big"
-  uint32_t maxbig;
+// ---- bucket accumulation: equal segments of the sorted entry list -----------------------------
+// After the counting sort the E insertions are grouped by bucket.  Thread t takes entries
+// [t*L, (t+1)*L) -- the same number for every thread, whatever the bucket sizes (uniform digits, the
+// 55k-entry 0/1 bucket of a witness vector, the short scalars of T) -- and walks them with one XYZZ
+// accumulator, flushing whenever the bucket changes:
+//   * a run that covers its bucket completely is stored straight into buckets[b];
+//   * the first / last run of a segment may be cut by the segment boundary: stored as partial 0 / 1;
+// k_msm_combine then adds the <= few partials of every cut bucket (one thread per bucket; buckets cut
+// into more than COMBINE_SPAN pieces go to k_msm_combine_big, one block of cooperating quads each).
+constexpr uint32_t SEG_MIN = 16;        // shortest segment (entries per thread)
+constexpr uint32_t COMBINE_SPAN = 4;    // a thread adds at most this many partials itself
+constexpr uint32_t COMBINE_MID = 256;   // up to this many partials: one warp (8 cooperating quads) per bucket
+constexpr uint32_t GIANT_CHUNK = 256;   // pieces of a giant bucket summed by one block (32 quads x 8)
+
+__device__ __forceinline__ uint32_t seg_len(uint32_t E, uint32_t nthreads) {
+  uint32_t L = (E + nthreads - 1) / nthreads;
+  return L < SEG_MIN ? SEG_MIN : L;
+}
+
+struct MsmCombine {
+  uint32_t* ctrl;       // [0] number of giant buckets, [1] number of giant chunks, [2] number of mid buckets
+  uint32_t* mids;       // [M] ids of buckets cut into COMBINE_SPAN+1 .. COMBINE_MID pieces
+  uint32_t* giants;     // [max_giants][3]: bucket id, first chunk, number of chunks
+  uint32_t* chunk_rec;  // [max_chunks][2]: giant index, chunk index inside the giant
+  void* chunk_sums;     // [max_chunks] XYZZ
+  uint32_t max_giants, max_chunks;
 };
 
-__device__ __forceinline__ uint32_t sched_cap(const MsmSchedule& sc) {
-  uint32_t e = *sc.total;
-  // a chain of k insertions costs ~3.5 us * k; the whole kernel needs ~e * 1.4e-4 us at full throughput,
-  // so chains up to e * 4e-5 are free, and never split below twice the mean bucket
-  uint32_t free_chain = (uint32_t)((uint64_t)e * 41u >> 20);
-  return min(sc.cap, max(max(24u, free_chain), 2u * (e / sc.M) + 8u));
-}
-
-static __global__ void k_sched_hist(const uint32_t* __restrict__ counts, uint32_t M, MsmSchedule sc) {
-  extern __shared__ uint32_t sh_hist[];  // cap + 1
-  for (uint32_t k = threadIdx.x; k <= sc.cap; k += blockDim.x) sh_hist[k] = 0;
-  __syncthreads();
-  const uint32_t cap = sched_cap(sc);
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < M; b += gridDim.x * blockDim.x) {
-    uint32_t cnt = counts[b];
-    if (cnt > cap) {
-      uint32_t e = atomicAdd(&sc.ctrl[0], 1u);
-      if (e < sc.maxbig) sc.biglist[e] = b;
-    } else {
-      atomicAdd(&sh_hist[cnt], 1u);
-    }
-  }
-  __syncthreads();
-  for (uint32_t k = threadIdx.x; k <= sc.cap; k += blockDim.x)
-    if (sh_hist[k]) atomicAdd(&sc.hist[k], sh_hist[k]);
-}
-
-// single block: class starts (descending size) and big-bucket task starts
-static __global__ void k_sched_scan(const uint32_t* __restrict__ counts, MsmSchedule sc) {
-  __shared__ uint32_t sh[1024];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  // classes in descending order: position p <-> class cap - p
-  uint32_t nc = sc.cap + 1;
-  for (uint32_t base = 0; base < nc; base += 1024) {
-    uint32_t p = base + threadIdx.x;
-    uint32_t v = p < nc ? sc.hist[sc.cap - p] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    uint32_t incl = sh[threadIdx.x];
-    if (p < nc) {
-      sc.cstart[sc.cap - p] = carry + incl - v;
-      sc.ccursor[sc.cap - p] = carry + incl - v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += incl;
-    __syncthreads();
-  }
-  // big buckets: tasks of MSM_BIG_CHUNK entries
-  uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nbig; base += 1024) {
-    uint32_t e = base + threadIdx.x;
-    uint32_t v = e < nbig ? (counts[sc.biglist[e]] + MSM_BIG_CHUNK - 1) / MSM_BIG_CHUNK : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    uint32_t incl = sh[threadIdx.x];
-    if (e < nbig) sc.taskstart[e] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    sc.taskstart[nbig] = carry;
-    sc.ctrl[1] = carry;
-  }
-}
-
-static __global__ void k_sched_scatter(const uint32_t* __restrict__ counts, uint32_t M, MsmSchedule sc, uint32_t* __restrict__ order) {
-  const uint32_t cap = sched_cap(sc);
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < M; b += gridDim.x * blockDim.x) {
-    uint32_t cnt = counts[b];
-    if (cnt <= cap) {
-      uint32_t pos = atomicAdd(&sc.ccursor[cnt], 1u);
-      order[pos] = b;
-    }
-  }
-}
-
-// ---- bucket accumulation ----------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
-                                                        const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                                                        const void* __restrict__ table, uint32_t M, const uint32_t* __restrict__ ctrl,
-                                                        void* __restrict__ buckets) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nsmall = M - min(ctrl[0], M);
-  if (j >= nsmall) return;
-  uint32_t b = order[j];
-  uint32_t cnt = counts[b];
-  const uint32_t* ent = sorted + offsets[b];
+__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
+                                                           const void* __restrict__ table, uint32_t M, uint32_t nthreads,
+                                                           void* __restrict__ buckets, void* __restrict__ partials) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nthreads) return;
+  const uint32_t E = offsets[M];
+  const uint32_t L = seg_len(E, nthreads);
+  const uint64_t beg64 = (uint64_t)t * L;
+  if (beg64 >= E) return;
+  const uint32_t beg = (uint32_t)beg64, end = min(E, beg + L);
+  // bucket of the first entry: the largest b with offsets[b] <= beg (then offsets[b+1] > beg)
+  uint32_t lo = 0, hi = M;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= beg) lo = mid; else hi = mid;
+  }
+  uint32_t b = lo, bstart = offsets[b], bend = offsets[b + 1];
+  uint32_t bnext = offsets[min(b + 2, M)];  // one boundary ahead, so a flush never waits on this load
+  uint32_t run_start = beg;
   Xyzz<C> acc = Xyzz<C>::identity();
-  if (cnt > 0) {
-    uint32_t e = ent[0];
-    Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
-    for (uint32_t k = 0; k < cnt; k++) {
-      Affine<C> cur = p;
-      bool neg = (e >> 31) != 0;
-      if (k + 1 < cnt) {  // prefetch the next base while this madd runs
-        e = ent[k + 1];
-        p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
-      }
-      xyzz_madd<C>(acc, cur, neg);
+  uint32_t e = sorted[beg];
+  Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
+  for (uint32_t k = beg; k < end; k++) {
+    if (k == bend) {  // bucket boundary: the finished run is complete unless it began at the segment start mid-bucket
+      bool complete = run_start == bstart;
+      char* dst = complete ? reinterpret_cast<char*>(buckets) + (size_t)b * 128 : reinterpret_cast<char*>(partials) + (size_t)(2 * t) * 128;
+      acc.store(dst);
+      acc = Xyzz<C>::identity();
+      run_start = k;
+      do { b++; bstart = bend; bend = bnext; bnext = offsets[min(b + 2, M)]; } while (bend == k);  // skip empty buckets
     }
+    Affine<C> cur = p;
+    bool neg = (e >> 31) != 0;
+    if (k + 1 < end) {  // prefetch the next base while this madd runs
+      e = sorted[k + 1];
+      p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
+    }
+    xyzz_madd<C>(acc, cur, neg);
   }
-  acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+  // last run: complete only if it started at its bucket's start and the segment ends exactly at the bucket end
+  bool complete = (run_start == bstart) && (end == bend);
+  char* dst = complete ? reinterpret_cast<char*>(buckets) + (size_t)b * 128
+                       : reinterpret_cast<char*>(partials) + (size_t)(2 * t + (run_start == beg ? 0 : 1)) * 128;
+  acc.store(dst);
 }
 
-// value of lane (lane + o); lanes whose partner is out of range get the identity (NOT their own value:
-// acc + acc would send them down the doubling path and the whole warp would pay for it)
-template <class C>
-__device__ __forceinline__ Xyzz<C> shfl_down_xyzz(const Xyzz<C>& acc, int o, int width = 32) {
-  Xyzz<C> other;
-  bool valid = (int)(threadIdx.x & 31) + o < width;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    other.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], o);
-    other.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], o);
-    uint32_t zz = __shfl_down_sync(0xffffffffu, acc.zz.v[k], o);
-    other.zz.v[k] = valid ? zz : 0u;
-    other.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], o);
-  }
-  return other;
+// which partial slot of segment t holds the piece of the bucket that starts at entry s
+__device__ __forceinline__ size_t seg_partial_index(uint32_t t, uint32_t t0, uint32_t s, uint32_t L) {
+  // in its first segment the bucket is the LAST run (slot 1) unless it starts exactly at the segment start
+  return (size_t)2 * t + ((t == t0 && s != t0 * L) ? 1 : 0);
 }
 
-// register-only warp tree (5 levels); result valid in lane 0
 template <class C>
-__device__ __forceinline__ Xyzz<C> warp_reduce_xyzz(Xyzz<C> acc) {
-#pragma unroll 1  // one copy of the addition: these warps run alone and are instruction-fetch bound
-  for (int o = 16; o > 0; o >>= 1) {
-    Xyzz<C> other = shfl_down_xyzz<C>(acc, o);
-    xyzz_add_call<C>(acc, other);
+__global__ void __launch_bounds__(128) k_msm_combine(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
+                                                     const void* __restrict__ partials, void* __restrict__ buckets, MsmCombine cb) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= M) return;
+  const uint32_t E = offsets[M], L = seg_len(E, nthreads);
+  const uint32_t s = offsets[b], e = offsets[b + 1];
+  char* dst = reinterpret_cast<char*>(buckets) + (size_t)b * 128;
+  if (e == s) {  // empty bucket
+    Xyzz<C>::identity().store(dst);
+    return;
   }
-  return acc;
-}
-
-// block of 128 threads: warp trees, then the 4 warp leaders are combined by warp 0; result valid in thread 0
-template <class C>
-__device__ __forceinline__ void block_reduce_xyzz_128(Xyzz<C>& acc, uint32_t* smem /* 4*32 words */) {
-  acc = warp_reduce_xyzz<C>(acc);
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) acc.store(smem + warp * 32);
-  __syncthreads();
-  if (warp == 0) {
-    acc = lane < 4 ? Xyzz<C>::load(smem + lane * 32) : Xyzz<C>::identity();
+  const uint32_t t0 = s / L, t1 = (e - 1) / L;
+  if (t0 == t1) return;  // inside one segment: stored complete by k_msm_accumulate
+  if (t1 - t0 + 1 > COMBINE_SPAN && t1 - t0 + 1 <= COMBINE_MID) {  // mid: one warp of cooperating quads (k_msm_combine_mid)
+    cb.mids[atomicAdd(&cb.ctrl[2], 1u)] = b;
+    return;
+  }
+  if (t1 - t0 + 1 > COMBINE_MID) {  // giant: hand its pieces to blocks of cooperating quads, GIANT_CHUNK pieces each
+    uint32_t nch = (t1 - t0 + 1 + GIANT_CHUNK - 1) / GIANT_CHUNK;
+    uint32_t g = atomicAdd(&cb.ctrl[0], 1u);
+    uint32_t base = atomicAdd(&cb.ctrl[1], nch);
+    if (g < cb.max_giants && base + nch <= cb.max_chunks) {
+      cb.giants[3 * g] = b; cb.giants[3 * g + 1] = base; cb.giants[3 * g + 2] = nch;
+      for (uint32_t j = 0; j < nch; j++) { cb.chunk_rec[2 * (base + j)] = g; cb.chunk_rec[2 * (base + j) + 1] = j; }
+    }
+    return;
+  }
+  Xyzz<C> acc = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t0, t0, s, L) * 128);
 #pragma unroll 1
-    for (int o = 2; o > 0; o >>= 1) {
-      Xyzz<C> other = shfl_down_xyzz<C>(acc, o, 2 * o);
-      xyzz_add_call<C>(acc, other);
-    }
+  for (uint32_t t = t0 + 1; t <= t1; t++) {
+    Xyzz<C> q = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t, t0, s, L) * 128);
+    xyzz_add_call<C>(acc, q);
   }
-  __syncthreads();
-}
-
-// persistent warps pull (big bucket, chunk) tasks of MSM_BIG_CHUNK entries; each writes one XYZZ partial
-template <class C>
-__global__ void __launch_bounds__(128) k_msm_accumulate_big(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                                            const uint32_t* __restrict__ sorted, const void* __restrict__ table,
-                                                            MsmSchedule sc, void* __restrict__ partials, void* __restrict__ buckets) {
-  uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
-  uint32_t ntasks = sc.ctrl[1];
-  uint32_t lane = threadIdx.x & 31;
-  for (;;) {
-    uint32_t task = 0;
-    if (lane == 0) task = atomicAdd(&sc.ctrl[2], 1u);
-    task = __shfl_sync(0xffffffffu, task, 0);
-    if (task >= ntasks) break;
-    // find e with taskstart[e] <= task < taskstart[e+1]
-    uint32_t lo = 0, hi = nbig;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (sc.taskstart[mid] <= task) lo = mid; else hi = mid;
-    }
-    uint32_t b = sc.biglist[lo];
-    uint32_t chunk = task - sc.taskstart[lo];
-    uint32_t cnt = counts[b];
-    uint32_t beg = chunk * MSM_BIG_CHUNK, end = min(cnt, beg + MSM_BIG_CHUNK);
-    const uint32_t* ent = sorted + offsets[b];
-    Xyzz<C> acc = Xyzz<C>::identity();
-    for (uint32_t k = beg + lane; k < end; k += 32) {
-      uint32_t e = ent[k];
-      Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
-      xyzz_madd_call<C>(acc, p, (e >> 31) != 0);
-    }
-    // 32 per-lane sums -> one point: each quad first folds its own four lanes' points, then a quad tree
-    QPoint<C> qa = QPoint<C>::identity();
-#pragma unroll 1
-    for (int j = 0; j < 4; j++) qa = q_add<C>(qa, q_from_lane<C>(acc, j));
-    qa = q_warp_reduce<C>(qa);
-    // a bucket that fits one task is finished here; otherwise k_msm_big_combine adds the partials
-    bool single = sc.taskstart[lo + 1] - sc.taskstart[lo] == 1;
-    if (lane < 4) qa.store(single ? reinterpret_cast<char*>(buckets) + (size_t)b * 128 : reinterpret_cast<char*>(partials) + (size_t)task * 128);
-  }
+  acc.store(dst);
 }
 
 // 32 quads of a 128-thread block each hold one point: warp trees, then warp 0 folds the four warp results.
@@ -409,25 +297,78 @@ __device__ __forceinline__ QPoint<C> q_block_reduce_128(QPoint<C> acc, uint32_t*
   return acc;
 }
 
-// one 128-thread block per big bucket: its task partials are summed by 32 cooperating quads
+// mid buckets: one warp each, its 8 quads stride over the pieces, then a quad tree
 template <class C>
-__global__ void __launch_bounds__(128) k_msm_big_combine(MsmSchedule sc, const void* __restrict__ partials, void* __restrict__ buckets) {
-  __shared__ __align__(16) uint32_t smem[4 * 32];
-  uint32_t nbig = min(sc.ctrl[0], sc.maxbig);
-  const uint32_t quad = threadIdx.x >> 2;
-  for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
-    uint32_t t0 = sc.taskstart[e], t1 = sc.taskstart[e + 1];
-    if (t1 - t0 <= 1) continue;  // written directly by its only task (block-uniform branch)
+__global__ void __launch_bounds__(128) k_msm_combine_mid(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
+                                                         const void* __restrict__ partials, void* __restrict__ buckets, MsmCombine cb) {
+  const uint32_t nmid = cb.ctrl[2];
+  const uint32_t E = offsets[M], L = seg_len(E, nthreads);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t quad = (threadIdx.x & 31) >> 2;
+  for (uint32_t i = warp; i < nmid; i += nwarps) {
+    const uint32_t b = cb.mids[i];
+    const uint32_t s = offsets[b], e = offsets[b + 1];
+    const uint32_t t0 = s / L, t1 = (e - 1) / L;
     QPoint<C> acc = QPoint<C>::identity();
-    uint32_t iters = (t1 - t0 + 31) / 32;
+    const uint32_t iters = (t1 - t0 + 1 + 7) / 8;
 #pragma unroll 1
-    for (uint32_t it = 0; it < iters; it++) {  // warp-uniform trip count: every lane joins the shuffles
-      uint32_t t = t0 + it * 32 + quad;
-      QPoint<C> p = t < t1 ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + (size_t)t * 128) : QPoint<C>::identity();
+    for (uint32_t it = 0; it < iters; it++) {  // warp-uniform trip count
+      uint32_t t = t0 + it * 8 + quad;
+      QPoint<C> p = t <= t1 ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t, t0, s, L) * 128)
+                            : QPoint<C>::identity();
+      acc = q_add<C>(acc, p);
+    }
+    acc = q_warp_reduce<C>(acc);
+    if ((threadIdx.x & 31) < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+  }
+}
+
+// giant buckets (cut into more than COMBINE_MID segments, e.g. the 0/1 bucket of a witness vector):
+// one 128-thread block (32 cooperating quads) per chunk of GIANT_CHUNK pieces -> chunk_sums
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_combine_big(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
+                                                         const void* __restrict__ partials, MsmCombine cb) {
+  __shared__ __align__(16) uint32_t smem[4 * 32];
+  const uint32_t nchunks = min(cb.ctrl[1], cb.max_chunks);
+  const uint32_t E = offsets[M], L = seg_len(E, nthreads);
+  const uint32_t quad = threadIdx.x >> 2;
+  for (uint32_t j = blockIdx.x; j < nchunks; j += gridDim.x) {
+    const uint32_t g = cb.chunk_rec[2 * j], idx = cb.chunk_rec[2 * j + 1];
+    const uint32_t b = cb.giants[3 * g];
+    const uint32_t s = offsets[b], e = offsets[b + 1];
+    const uint32_t t0 = s / L, t1 = (e - 1) / L;
+    const uint32_t first = t0 + idx * GIANT_CHUNK, last = min(t1, first + GIANT_CHUNK - 1);
+    QPoint<C> acc = QPoint<C>::identity();
+#pragma unroll 1
+    for (uint32_t it = 0; it < GIANT_CHUNK / 32; it++) {  // uniform trip count: every lane joins the shuffles
+      uint32_t t = first + it * 32 + quad;
+      QPoint<C> p = t <= last ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t, t0, s, L) * 128)
+                              : QPoint<C>::identity();
       acc = q_add<C>(acc, p);
     }
     acc = q_block_reduce_128<C>(acc, smem);
-    if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)sc.biglist[e] * 128);
+    if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(cb.chunk_sums) + (size_t)j * 128);
+  }
+}
+
+// one warp per giant bucket: add its chunk sums into the bucket
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_combine_final(MsmCombine cb, void* __restrict__ buckets) {
+  const uint32_t ngiant = min(cb.ctrl[0], cb.max_giants);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t quad = (threadIdx.x & 31) >> 2;
+  for (uint32_t g = warp; g < ngiant; g += nwarps) {
+    const uint32_t b = cb.giants[3 * g], base = cb.giants[3 * g + 1], nch = cb.giants[3 * g + 2];
+    QPoint<C> acc = QPoint<C>::identity();
+    const uint32_t iters = (nch + 7) / 8;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; it++) {
+      uint32_t j = it * 8 + quad;
+      QPoint<C> p = j < nch ? QPoint<C>::load(reinterpret_cast<const char*>(cb.chunk_sums) + (size_t)(base + j) * 128) : QPoint<C>::identity();
+      acc = q_add<C>(acc, p);
+    }
+    acc = q_warp_reduce<C>(acc);
+    if ((threadIdx.x & 31) < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
   }
 }
 

@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(256) k_spmv3(CsrView A, CsrView B, CsrView Cm,
   acc.store(reinterpret_cast<char*>(out) + (size_t)row * 32);
 }
 
-constexpr uint32_t R1CS_LONG_ROW = 32;  // rows with more non-zeros (A+B+C) get a whole warp
+// Row classes by non-zeros over A+B+C.  Every non-zero is a dependent chain col -> z[col] (two L2 gathers),
+// so a thread that owns a 30-term Poseidon row is latency-bound for ~60 us: give such rows several lanes.
+constexpr uint32_t R1CS_SHORT_ROW = 6;   // <= 6 : one thread   (bit / copy rows: ~3 non-zeros)
+constexpr uint32_t R1CS_LONG_ROW = 64;   // 7..64: 8 lanes ; > 64: a whole warp (240-term packing rows)
 
 // v * z with the two overwhelmingly common coefficients (1 and -1: bit / copy / C rows) short-cut
 template <class F>
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrVie
   if (row >= m) return;
   uint32_t ab = A.rowptr[row], ae = A.rowptr[row + 1], bb = B.rowptr[row], be = B.rowptr[row + 1];
   uint32_t cb = Cm.rowptr[row], ce = Cm.rowptr[row + 1];
-  if ((ae - ab) + (be - bb) + (ce - cb) > R1CS_LONG_ROW) return;  // k_cross_term_long owns this row
+  if ((ae - ab) + (be - bb) + (ce - cb) > R1CS_SHORT_ROW) return;  // k_cross_term_group owns this row
   Fp<F> a1, a2, b1, b2, c1, c2;
   row_dot2<F>(A, ab, ae, 1, n, W1, tail1, W2, tail2, a1, a2);
   row_dot2<F>(B, bb, be, 1, n, W1, tail1, W2, tail2, b1, b2);
@@ -104,9 +107,11 @@ __global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrVie
   cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1)).store(reinterpret_cast<char*>(T) + (size_t)row * 32);
 }
 
-template <class F>
-VIMZ_DI Fp<F> warp_sum_fp(Fp<F> v) {
-  for (int o = 16; o > 0; o >>= 1) {
+// sum over the GROUP lanes of a row group (GROUP = 8 or 32, groups are aligned inside the warp)
+template <class F, int GROUP>
+VIMZ_DI Fp<F> group_sum_fp(Fp<F> v) {
+#pragma unroll
+  for (int o = GROUP / 2; o > 0; o >>= 1) {
     Fp<F> other;
 #pragma unroll
     for (int k = 0; k < 8; k++) other.v[k] = __shfl_down_sync(0xffffffffu, v.v[k], o);
@@ -115,24 +120,26 @@ VIMZ_DI Fp<F> warp_sum_fp(Fp<F> v) {
   return v;
 }
 
-// One warp per long row (e.g. the 240-term Num2Bits packing rows): lanes stride the non-zeros.
-template <class F>
-__global__ void __launch_bounds__(128) k_cross_term_long(CsrView A, CsrView B, CsrView Cm, const uint32_t* __restrict__ long_rows,
-                                                         uint32_t n_long, uint32_t n,
-                                                         const void* __restrict__ W1, const void* __restrict__ tail1,
-                                                         const void* __restrict__ W2, const void* __restrict__ tail2,
-                                                         void* __restrict__ T) {
-  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n_long) return;
-  uint32_t row = long_rows[w];
+// GROUP lanes per listed row (8 for Poseidon-like rows, 32 for the 240-term Num2Bits packing rows):
+// lanes stride the non-zeros, partial dot products are folded with shuffles.
+template <class F, int GROUP>
+__global__ void __launch_bounds__(128) k_cross_term_group(CsrView A, CsrView B, CsrView Cm, const uint32_t* __restrict__ rows,
+                                                          uint32_t n_rows, uint32_t n,
+                                                          const void* __restrict__ W1, const void* __restrict__ tail1,
+                                                          const void* __restrict__ W2, const void* __restrict__ tail2,
+                                                          void* __restrict__ T) {
+  uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP, lane = threadIdx.x % GROUP;
+  bool valid = g < n_rows;  // whole groups are valid or not; invalid groups still join the shuffles
+  uint32_t row = rows[valid ? g : 0];
   Fp<F> a1, a2, b1, b2, c1, c2;
-  row_dot2<F>(A, A.rowptr[row] + lane, A.rowptr[row + 1], 32, n, W1, tail1, W2, tail2, a1, a2);
-  row_dot2<F>(B, B.rowptr[row] + lane, B.rowptr[row + 1], 32, n, W1, tail1, W2, tail2, b1, b2);
-  row_dot2<F>(Cm, Cm.rowptr[row] + lane, Cm.rowptr[row + 1], 32, n, W1, tail1, W2, tail2, c1, c2);
-  a1 = warp_sum_fp(a1); a2 = warp_sum_fp(a2);
-  b1 = warp_sum_fp(b1); b2 = warp_sum_fp(b2);
-  c1 = warp_sum_fp(c1); c2 = warp_sum_fp(c2);
-  if (lane == 0)
+  uint32_t none = 0;
+  row_dot2<F>(A, valid ? A.rowptr[row] + lane : none, valid ? A.rowptr[row + 1] : none, GROUP, n, W1, tail1, W2, tail2, a1, a2);
+  row_dot2<F>(B, valid ? B.rowptr[row] + lane : none, valid ? B.rowptr[row + 1] : none, GROUP, n, W1, tail1, W2, tail2, b1, b2);
+  row_dot2<F>(Cm, valid ? Cm.rowptr[row] + lane : none, valid ? Cm.rowptr[row + 1] : none, GROUP, n, W1, tail1, W2, tail2, c1, c2);
+  a1 = group_sum_fp<F, GROUP>(a1); a2 = group_sum_fp<F, GROUP>(a2);
+  b1 = group_sum_fp<F, GROUP>(b1); b2 = group_sum_fp<F, GROUP>(b2);
+  c1 = group_sum_fp<F, GROUP>(c1); c2 = group_sum_fp<F, GROUP>(c2);
+  if (lane == 0 && valid)
     cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1)).store(reinterpret_cast<char*>(T) + (size_t)row * 32);
 }
 
