@@ -176,3 +176,30 @@ def test_point_helpers(engines, coracle):
     exp = coracle.to_affine(c.curve_id, coracle.point_scale_add(c.curve_id, jac(A), ints_to_mont([r], c.q)[0], jac(B)))
     assert np.array_equal(eng.to_affine(got), exp)
     assert eng.to_affine_ints(eng.point_sum(np.stack([jac(A), jac(B), jac(None), jac(A)]))) == P.aff_add(c, P.aff_add(c, A, B), A)
+
+
+@pytest.mark.parametrize("window", [8, 12])
+def test_msm_skewed_buckets_all_combine_classes(window, engines, coracle):
+    """Scalar multisets built so that, with few buckets (small window) and many entries, buckets are cut into
+    a handful (thread combine), dozens (warp combine) and thousands (block-chunk combine) of segments."""
+    c = P.PALLAS
+    eng = vimz_b200.Engine("pallas", 0)
+    eng.set_option("msm_window", window)
+    n = 60000
+    bases, logs = make_bases(c, n, seed=window)
+    Bm = affine_to_mont(bases, c.p)
+    ck = CommitmentKey.from_bases(eng, Bm)
+    rng = random.Random(window)
+    G = P.generator(c)
+    for mix in ("giant+uniform", "few-values", "ones"):
+        if mix == "giant+uniform":   # 70 % ones (one giant bucket), the rest uniform
+            sc = [1 if rng.random() < 0.7 else rng.randrange(c.q) for _ in range(n)]
+        elif mix == "few-values":    # 40 distinct scalars: every touched bucket is heavy
+            pool = [rng.randrange(c.q) for _ in range(40)]
+            sc = [pool[rng.randrange(40)] for _ in range(n)]
+        else:
+            sc = [1] * n
+        got = gpu_commit_affine(eng, ck, ints_to_mont(sc, c.q))
+        assert got == P.scalar_mul(c, sum(s * k for s, k in zip(sc, logs)) % c.q, G), (window, mix)
+    ck.close()
+    eng.close()
