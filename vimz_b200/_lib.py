@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvimz_gpu.so")
+LIB_PATH = os.environ.get("VIMZ_GPU_LIB") or os.path.join(_HERE, "libvimz_gpu.so")  # override only for A/B experiments
 
 VIMZ_OK = 0
 VIMZ_ERR_CUDA = -1

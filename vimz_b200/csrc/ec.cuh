@@ -159,7 +159,7 @@ VIMZ_DI void xyzz_madd(Xyzz<C>& acc, const Affine<C>& q, bool neg) {
     if (r.is_zero()) {
       Affine<C> t;
       t.x = q.x; t.y = qy;
-      acc = xyzz_dbl_affine<C, M>(t);
+      acc = xyzz_dbl_affine<C, MulCall>(t);  // rare (q == acc): keep it out of line, out of the hot loop's I-cache footprint
     } else {
       acc = Xyzz<C>::identity();
     }
@@ -187,7 +187,7 @@ VIMZ_DI void xyzz_add(Xyzz<C>& acc, const Xyzz<C>& q) {
   F p = fp_sub(u2, u1);
   F r = fp_sub(s2, s1);
   if (p.is_zero()) {
-    if (r.is_zero()) acc = xyzz_dbl<C, M>(acc);
+    if (r.is_zero()) acc = xyzz_dbl<C, MulCall>(acc);  // rare: out of line
     else acc = Xyzz<C>::identity();
     return;
   }

@@ -173,7 +173,7 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
 // k_msm_combine then adds the <= few partials of every cut bucket (one thread per bucket; buckets cut
 // into more than COMBINE_SPAN pieces go to k_msm_combine_big, one block of cooperating quads each).
 constexpr uint32_t SEG_MIN = 16;        // shortest segment (entries per thread)
-constexpr uint32_t COMBINE_SPAN = 4;    // a thread adds at most this many partials itself
+constexpr uint32_t COMBINE_SPAN = 8;    // a thread adds at most this many partials itself
 constexpr uint32_t COMBINE_MID = 256;   // up to this many partials: one warp (8 cooperating quads) per bucket
 constexpr uint32_t GIANT_CHUNK = 256;   // pieces of a giant bucket summed by one block (32 quads x 8)
 
