@@ -65,7 +65,11 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle sampler for the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason sampler for the timed region (B200_PROFILING.md recipe).  NVML is polled
+    in-process every ~2 ms (an nvidia-smi subprocess takes longer than a short timed region); nvidia-smi is the
+    fallback when pynvml is unavailable."""
+
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
@@ -74,29 +78,56 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self._stop_evt = threading.Event()
         self.max_mhz = None
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-less single-node layout: NVML index == CUDA index here
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+            self.source = "nvidia-smi"
 
-    def run(self):
+    def _poll_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for n, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(n)
+
+    def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                if self._nv is not None:
+                    nv = self._nv
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for n, bit in self.BAD.items():
+                        if mask & bit:
+                            self.reasons.add(n)
+                    self._stop_evt.wait(0.002)
+                else:
+                    self._poll_smi()
+                    self._stop_evt.wait(0.05)
             except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+                self._stop_evt.wait(0.01)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": self.source}
 
 
 def challenge_from(comm_T_bytes: bytes, step: int) -> int:
@@ -407,8 +438,15 @@ def main_gpu(args, rank, world, local_rank):
     entries = prof["msm_entries"][1]
     imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
     achieved = imad / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
-    roofline = {"kernel": "k_msm_accumulate<Pallas> (+ big-bucket tasks)", "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
-                "unit": "TIMAD/s", "frac": (achieved / peaks["imad_tops"]) if achieved else None, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_msm_accumulate_fold_T")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_msm_accumulate<Pallas> (+ combine of cut buckets)", "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
+                "unit": "TIMAD/s", "frac": (achieved / peaks["imad_tops"]) if achieved else None, "traffic": traffic,
                 "peak_source": peaks["imad_src"],
                 "algorithmic": f"{entries} bucket insertions x {MODMUL_PER_MADD} modmul x {IMAD_PER_MODMUL} IMAD over {acc_calls} launches",
                 "share_of_step": acc_ms / ms_prof if ms_prof > 0 else None,
@@ -460,7 +498,7 @@ def main_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[20])
