@@ -232,3 +232,47 @@ def test_full_size_grayscale_step_properties(engines):
     assert eng.to_affine_ints(CommitmentEngine.commit(ck, W.W)) == eng.to_affine_ints(U.comm_W)
     assert eng.to_affine_ints(CommitmentEngine.commit(ck, W.E)) == eng.to_affine_ints(U.comm_E)
     acc.close(); shape.close(); ck.close()
+
+
+def test_fold_from_r1cs_and_wtns_files_bn254(tmp_path, engines, coracle):
+    """Real-artifact ingestion: an iden3 .r1cs + two .wtns files (circom's bn128 prime) are read,
+    uploaded and folded on the BN254 engine; result == CPU chain and the folded instance is satisfied."""
+    from vimz_b200 import circom_io as io
+    eng, c = engines["bn254"], P.BN254
+    q = c.q
+    cons = [([(2, 1)], [(2, 1)], [(3, 1)]),
+            ([(3, 1)], [(2, 1)], [(4, 1)]),
+            ([(4, 1), (2, 1), (0, 5)], [(0, 1)], [(1, 1)])]
+    rp = str(tmp_path / "cubic.r1cs")
+    io.write_r1cs(rp, q, 5, 1, 0, 1, cons)
+    m, n, nio, A, B, Cm = io.r1cs_to_shape_coo(io.load_r1cs(rp))
+    shape = R1CSShape(eng, m, n, nio, A, B, Cm)
+    bases, _ = make_bases(c, 4, seed=1)
+    Bm = affine_to_mont(bases, c.p)
+    ck = CommitmentKey.from_bases(eng, Bm)
+    acc = FoldAccumulator(shape, ck)
+    wit = []
+    for k, x in enumerate((3, 11)):
+        wp = str(tmp_path / f"w{k}.wtns")
+        io.write_wtns(wp, q, [1, x ** 3 + x + 5, x, x * x, x ** 3])
+        _, vals = io.load_wtns(wp)
+        wit.append(io.wtns_to_witness(vals, nio, q))
+    rng = random.Random(4)
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in wit]
+
+    class Sh:  # the oracle chain helper wants .num_cons/.A...
+        num_cons, num_vars, num_io = m, n, nio
+    Sh.A, Sh.B, Sh.C = A, B, Cm
+    ref = _oracle_fold_chain(coracle, c, Sh, Bm, wit, chal)
+    for (W2, X2), r in zip(wit, chal):
+        acc.step_begin(W2, X2)
+        acc.step_end(r)
+    U, W = acc.download()
+    assert np.array_equal(W.W, ref[-1]["W"]) and np.array_equal(W.E, ref[-1]["E"]) and np.array_equal(U.X, ref[-1]["X"])
+    assert eng.to_affine_ints(U.comm_E) == _affine(coracle, c, ref[-1]["cE"])
+    assert eng.to_affine_ints(U.comm_W) == _affine(coracle, c, ref[-1]["cW"])
+    Az, Bz, Cz = shape.multiply_vec(np.concatenate([W.W, U.u, U.X]))
+    a, b, cz, e = (mont_to_ints(v, q) for v in (Az, Bz, Cz, W.E))
+    u = mont_to_ints(U.u, q)[0]
+    assert all((x * y - u * w - t) % q == 0 for x, y, w, t in zip(a, b, cz, e))
+    acc.close(); shape.close(); ck.close()
