@@ -240,6 +240,8 @@ class GpuFold:
         win = os.environ.get("VIMZ_WINDOW_" + curve_name.upper())
         if win:
             self.eng.set_option("msm_window", int(win))
+        if os.environ.get("VIMZ_ACC_BLOCKS"):
+            self.eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
         sh = self.sh
         self.shape = R1CSShape(self.eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
         nck = max(sh.num_cons, sh.num_vars)

@@ -200,6 +200,31 @@ int main() {
   RUN("iadd3_x_chain", 16.0 * ITERS, (k_iadd3x<<<blocks, threads>>>(out, 3, 5, cyc)), false);
   RUN("mix_wide_plus_iadd(pairs)", 8.0 * ITERS, (k_mix<<<blocks, threads>>>(out, 3, 5, cyc)), false);
   RUN("fp_mul_pallas_base", 2.0 * MUL_ITERS, (k_fpmul<FieldPallasP><<<blocks, threads>>>(out, in, cyc)), false);
+  // occupancy sensitivity of the field multiplication: 1, 2, 4 warps per scheduler (8 above)
+  {
+    int save_blocks = blocks;
+    for (int w = 1; w <= 4; w *= 2) {
+      blocks = sms * w;  // w blocks of 128 threads per SM = w warps per SMSP
+      char name[64];
+      snprintf(name, sizeof(name), "fp_mul_pallas_%dwarp_per_smsp", w);
+      auto report2 = [&](float ms) {
+        cudaMemcpy(hcyc, cyc, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
+        double avg = 0;
+        for (int i = 0; i < blocks; i++) avg += hcyc[i];
+        avg /= blocks;
+        printf("  {\"name\": \"%s\", \"ops_per_clk_per_sm\": %.3f, \"ms\": %.3f},\n", name, 2.0 * MUL_ITERS * 128 * w / avg, ms);
+      };
+      for (int r = 0; r < 3; r++) k_fpmul<FieldPallasP><<<blocks, 128>>>(out, in, cyc);
+      cudaEventRecord(e0);
+      k_fpmul<FieldPallasP><<<blocks, 128>>>(out, in, cyc);
+      cudaEventRecord(e1);
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      report2(ms);
+    }
+    blocks = save_blocks;
+  }
   RUN("fp_mul_bn254_base", 2.0 * MUL_ITERS, (k_fpmul<FieldBnP><<<blocks, threads>>>(out, in, cyc)), true);
   printf("]}\n");
   return 0;

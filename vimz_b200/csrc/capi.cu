@@ -177,6 +177,11 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     ctx->prof.on = value != 0;
     return VIMZ_OK;
   }
+  if (strcmp(key, "msm_acc_blocks") == 0) {
+    if (value < 1 || value > 8) return set_error(VIMZ_ERR_ARG, "msm_acc_blocks must be in [1, 8]");
+    ctx->opt_acc_blocks = value;
+    return VIMZ_OK;
+  }
   if (strcmp(key, "graph") == 0) {
     ctx->opt_graph = value != 0;
     return VIMZ_OK;

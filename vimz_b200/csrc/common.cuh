@@ -112,6 +112,7 @@ struct vimz_ctx {
   int sm_count = 148;
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
+  long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points

@@ -62,7 +62,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   // second level: 32 quads per block, ~8 chunk sums per quad keeps the trees shallow without flooding the SMs
   const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 8), 1), 32);
   // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
-  const uint32_t nthreads = (uint32_t)ctx->sm_count * 4 * 128;
+  const uint32_t nthreads = (uint32_t)ctx->sm_count * (uint32_t)ctx->opt_acc_blocks * 128;
   // capacity bounds: a bucket cut into p pieces overlaps p segments and every segment boundary cuts at most one
   // bucket, so sum(pieces) <= 2 * nthreads; a giant has > COMBINE_MID pieces and ceil(p / GIANT_CHUNK) chunks
   const uint32_t max_giants = 2 * nthreads / COMBINE_MID + 2;

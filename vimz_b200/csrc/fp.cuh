@@ -254,7 +254,35 @@ VIMZ_DI void mont_row(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&a)[
   }
   uint32_t m = ev[0] * F::INV;
   constexpr bool SPARSE = (F::p(4) == 0 && F::p(5) == 0 && F::p(6) == 0);  // Pasta: p = 2^254 + t, t < 2^128
-  if (SPARSE) {
+  constexpr bool PASTA = SPARSE && F::p(0) == 1 && F::p(7) == 0x40000000u && F::INV == 0xffffffffu;
+  if (PASTA) {
+    // p = 2^254 + t with t odd < 2^128 and -p^-1 = -1 mod 2^32:  m = -acc0, m*p[0] = m just cancels limb 0
+    // (carry = acc0 != 0) and m*p[7] = m << 30 is two shifts -- only p[1], p[2], p[3] need the multiplier.
+    // (Left to ptxas, the constants 1 and 2^30 break the lo/hi pairs into half-rate IMAD.HI plus carries.)
+    m = 0u - ev[0];
+    uint32_t mlo = m << 30, mhi = m >> 2;
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, %11;\n\t"
+        "addc.u32 %7, %7, %12;"
+        : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+        : "r"(m), "r"(F::p(1)), "r"(F::p(3)), "r"(mlo), "r"(mhi));
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(od[7])
+        : "r"(m), "r"(F::p(2)));
+  } else if (SPARSE) {
     // odd lanes += m * p[1,3,-,7]; even lanes += m * p[0,2,-,-]; zero limbs only ripple the carry.
     asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
         "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"

@@ -20,6 +20,10 @@
 
 namespace vimz {
 
+#ifndef VIMZ_ACC_MUL
+#define VIMZ_ACC_MUL MulInline  // multiplication policy of the accumulation hot loop (A/B: -DVIMZ_ACC_MUL=MulCall)
+#endif
+
 constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
 
 // ---- signed-digit recoding -------------------------------------------------------------------
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint32_t* __res
       e = sorted[k + 1];
       p = Affine<C>::load_nc(reinterpret_cast<const char*>(table) + (size_t)(e & 0x7fffffffu) * 64);
     }
-    xyzz_madd<C>(acc, cur, neg);
+    xyzz_madd<C, VIMZ_ACC_MUL>(acc, cur, neg);
   }
   // last run: complete only if it started at its bucket's start and the segment ends exactly at the bucket end
   bool complete = (run_start == bstart) && (end == bend);
