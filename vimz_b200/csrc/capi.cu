@@ -301,7 +301,7 @@ int vimz_msm_async_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const voi
   CHECK_ARG(ck->ctx == ctx, "vimz_msm: commitment key belongs to another context");
   if (first + n > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_msm: vector longer than the commitment key");
   DeviceGuard g(ctx->device);
-  return curve_vtable(ctx->curve)->msm(ctx, 0, ck, first, d_scalars, n, d_out);
+  return curve_vtable(ctx->curve)->msm(ctx, 0, ck, first, d_scalars, n, d_out, false);
 }
 
 static int fetch_points(vimz_ctx* ctx, const void* d_src, void* host_dst, size_t bytes) {
@@ -502,9 +502,9 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
     VIMZ_CUDA(cudaMemcpyAsync(t1 + 32, X1, s->io * 32, cudaMemcpyHostToDevice, st));
     VIMZ_CUDA(cudaMemcpyAsync(t2 + 32, X2, s->io * 32, cudaMemcpyHostToDevice, st));
   }
-  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr));
+  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr, ck));
   if (T_out) VIMZ_CUDA(cudaMemcpyAsync(T_out, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, st));
-  VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr));
+  VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr, true));
   return fetch_points(ctx, ctx->ws.result.ptr, comm_T, 96);
 }
 
@@ -623,11 +623,11 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   // stream with its own workspace while the main stream does the cross term and commit(T).
   VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
   VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
-  VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, a->W2, s->n, fresh));
+  VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, a->W2, s->n, fresh, false));
   VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
   // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
-  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T));
-  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96));
+  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck));  // also histograms T's digits
+  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, true));
   VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   return VIMZ_OK;

@@ -16,13 +16,16 @@ struct CurveVTable {
   uint32_t scalar_one_mont[8];
   int (*precompute)(vimz_ctx*, const void* d_bases, size_t n, int c, int nwin, void* table);
   // lane 0 = context stream + main workspace, lane 1 = aux stream + second workspace (runs concurrently)
-  int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out);
+  // counted = true: the bucket histogram of the scalars is already in the lane's `counts` buffer (fused cross term)
+  int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted);
   int (*point_sum)(vimz_ctx*, const void* d_pts, size_t k, void* d_out);
   int (*point_to_affine)(vimz_ctx*, const void* d_pt, void* d_out);
   int (*point_scale_add)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count);
   int (*gen_bases)(vimz_ctx*, uint64_t k0, uint64_t dk, size_t n, void* d_out);
   int (*spmv3)(vimz_ctx*, const vimz_shape*, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz);
-  int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T);
+  // fuse_ck != nullptr: also histogram T's digits for the commit(fuse_ck, T) that follows on lane 0
+  int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
+                    const vimz_ck* fuse_ck);
   int (*axpy)(vimz_ctx*, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out);
   int (*field_op)(vimz_ctx*, int which, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 };
@@ -46,7 +49,7 @@ int impl_precompute(vimz_ctx* ctx, const void* d_bases, size_t n, int c, int nwi
 }
 
 template <class C>
-int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out) {
+int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted) {
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
   MsmWorkspace& ws = lane == 0 ? ctx->ws : ctx->ws_aux;
   const int c = ck->c, nwin = ck->nwin;
@@ -59,8 +62,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   const uint32_t T = M / K;
   int nb = 0;
   while ((1u << nb) < T) nb++;
-  // second level: 32 quads per block, ~8 chunk sums per quad keeps the trees shallow without flooding the SMs
-  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 8), 1), 32);
+  // second level: 32 quads per block, ~2 chunk sums per quad: the tree depth, not the work, sets the time
+  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 2), 1), 64);
   // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
   const uint32_t nthreads = (uint32_t)ctx->sm_count * (uint32_t)ctx->opt_acc_blocks * 128;
   // capacity bounds: a bucket cut into p pieces overlaps p segments and every segment boundary cuts at most one
@@ -97,13 +100,13 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   cb.max_giants = max_giants;
   cb.max_chunks = max_chunks;
 
-  VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
+  if (!counted) VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
   VIMZ_CUDA(cudaMemsetAsync(cb.ctrl, 0, 64, st));
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
   {
     ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
-    if (n > 0) {
+    if (n > 0 && !counted) {
       k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
       VIMZ_LAUNCH_CHECK(ctx);
     }
@@ -196,20 +199,30 @@ int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* 
   return VIMZ_OK;
 }
 template <class C>
-int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T) {
+int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
+                    const vimz_ck* fuse_ck) {
   if (s->m == 0) return VIMZ_OK;
+  DigitCount dc{nullptr, 0, 0};
+  if (fuse_ck) {  // zero lane 0's histogram, then let the cross-term kernels fill it
+    const uint32_t M = 1u << (fuse_ck->c - 1);
+    VIMZ_TRY(ctx->ws.counts.reserve((size_t)M * 4));
+    VIMZ_CUDA(cudaMemsetAsync(ctx->ws.counts.ptr, 0, (size_t)M * 4, ctx->stream));
+    dc.counts = ctx->ws.counts.as<uint32_t>();
+    dc.c = fuse_ck->c;
+    dc.nwin = fuse_ck->nwin;
+  }
   ProfScope prof(ctx, PROF_CROSS_TERM, ctx->stream);
   k_cross_term<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(
-      csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
+      csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T, dc);
   VIMZ_LAUNCH_CHECK(ctx);
   if (s->n_mid) {
     k_cross_term_group<typename C::Fs, 8><<<ceil_div(s->n_mid * 8, 128), 128, 0, ctx->stream>>>(
-        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->mid_rows, (uint32_t)s->n_mid, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
+        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->mid_rows, (uint32_t)s->n_mid, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T, dc);
     VIMZ_LAUNCH_CHECK(ctx);
   }
   if (s->n_long) {
     k_cross_term_group<typename C::Fs, 32><<<ceil_div(s->n_long * 32, 128), 128, 0, ctx->stream>>>(
-        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->long_rows, (uint32_t)s->n_long, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T);
+        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->long_rows, (uint32_t)s->n_long, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T, dc);
     VIMZ_LAUNCH_CHECK(ctx);
   }
   return VIMZ_OK;

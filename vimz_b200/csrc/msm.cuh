@@ -15,6 +15,7 @@
 //   * All arithmetic is exact; the result is the unique group element sum_i s_i * ck_i.
 #pragma once
 #include "common.cuh"
+#include "digits.cuh"
 #include "ec.cuh"
 #include "ecq.cuh"
 
@@ -26,44 +27,12 @@ namespace vimz {
 
 constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
 
-// ---- signed-digit recoding -------------------------------------------------------------------
-// raw scalar (canonical, NOT Montgomery) -> digits d_j in [-2^(c-1), 2^(c-1)], j < nwin.
-// f(j, magnitude, negative) is called for every non-zero digit.
-template <class Fn>
-__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, int nwin, Fn f) {
-  const uint32_t half = 1u << (c - 1);
-  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1);
-  uint32_t carry = 0;
-  for (int j = 0; j < nwin; j++) {
-    int pos = j * c;
-    int limb = pos >> 5, off = pos & 31;
-    uint64_t lo = 0;
-    // dynamic limb index resolved with selects (registers cannot be indexed)
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (k == limb) lo |= (uint64_t)s[k];
-      if (k == limb + 1) lo |= (uint64_t)s[k] << 32;
-    }
-    uint32_t d = (uint32_t)((lo >> off) & mask) + carry;
-    carry = 0;
-    bool neg = false;
-    if (d > half && j != nwin - 1) {
-      d = (1u << c) - d;
-      neg = true;
-      carry = 1;
-    }
-    if (d != 0) f(j, d, neg);
-  }
-}
-
 template <class C>
 __global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
                             uint32_t* __restrict__ counts) {
   using Fs = Fp<typename C::Fs>;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
-    if (fp_gt_half(s)) s = fp_neg(s);  // s*P = (q-s)*(-P): digits of the smaller magnitude
-    for_each_digit(s.v, c, nwin, [&](int, uint32_t mag, bool) { atomicAdd(&counts[mag - 1], 1u); });
+    count_scalar_digits(Fs::load_nc(scalars + 8 * (size_t)i), c, nwin, counts);
   }
 }
 
@@ -176,7 +145,7 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
 //   * the first / last run of a segment may be cut by the segment boundary: stored as partial 0 / 1;
 // k_msm_combine then adds the <= few partials of every cut bucket (one thread per bucket; buckets cut
 // into more than COMBINE_SPAN pieces go to k_msm_combine_big, one block of cooperating quads each).
-constexpr uint32_t SEG_MIN = 16;        // shortest segment (entries per thread)
+constexpr uint32_t SEG_MIN = 8;         // shortest segment (entries per thread)
 constexpr uint32_t COMBINE_SPAN = 8;    // a thread adds at most this many partials itself
 constexpr uint32_t COMBINE_MID = 256;   // up to this many partials: one warp (8 cooperating quads) per bucket
 constexpr uint32_t GIANT_CHUNK = 256;   // pieces of a giant bucket summed by one block (32 quads x 8)

@@ -9,6 +9,7 @@
 // (it is 4-22 MB and lives in the 126 MB L2), outputs are written once with 128-bit stores.
 #pragma once
 #include "common.cuh"
+#include "digits.cuh"
 #include "fp.cuh"
 
 namespace vimz {
@@ -25,6 +26,12 @@ struct CsrView {
   const uint32_t* rowptr;
   const uint32_t* col;
   const void* val;
+};
+
+// optional fusion with the MSM that follows: histogram T's bucket digits here (counts == nullptr: off)
+struct DigitCount {
+  uint32_t* counts;
+  int c, nwin;
 };
 
 // one thread per (matrix, row); blockIdx.y selects A/B/C
@@ -94,7 +101,7 @@ template <class F>
 __global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrView Cm, uint32_t m, uint32_t n,
                                                     const void* __restrict__ W1, const void* __restrict__ tail1,
                                                     const void* __restrict__ W2, const void* __restrict__ tail2,
-                                                    void* __restrict__ T) {
+                                                    void* __restrict__ T, DigitCount dc) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= m) return;
   uint32_t ab = A.rowptr[row], ae = A.rowptr[row + 1], bb = B.rowptr[row], be = B.rowptr[row + 1];
@@ -104,7 +111,9 @@ __global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrVie
   row_dot2<F>(A, ab, ae, 1, n, W1, tail1, W2, tail2, a1, a2);
   row_dot2<F>(B, bb, be, 1, n, W1, tail1, W2, tail2, b1, b2);
   row_dot2<F>(Cm, cb, ce, 1, n, W1, tail1, W2, tail2, c1, c2);
-  cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1)).store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+  Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1));
+  t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+  if (dc.counts) count_scalar_digits(t, dc.c, dc.nwin, dc.counts);
 }
 
 // sum over the GROUP lanes of a row group (GROUP = 8 or 32, groups are aligned inside the warp)
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(128) k_cross_term_group(CsrView A, CsrView B, 
                                                           uint32_t n_rows, uint32_t n,
                                                           const void* __restrict__ W1, const void* __restrict__ tail1,
                                                           const void* __restrict__ W2, const void* __restrict__ tail2,
-                                                          void* __restrict__ T) {
+                                                          void* __restrict__ T, DigitCount dc) {
   uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP, lane = threadIdx.x % GROUP;
   bool valid = g < n_rows;  // whole groups are valid or not; invalid groups still join the shuffles
   uint32_t row = rows[valid ? g : 0];
@@ -139,8 +148,11 @@ __global__ void __launch_bounds__(128) k_cross_term_group(CsrView A, CsrView B, 
   a1 = group_sum_fp<F, GROUP>(a1); a2 = group_sum_fp<F, GROUP>(a2);
   b1 = group_sum_fp<F, GROUP>(b1); b2 = group_sum_fp<F, GROUP>(b2);
   c1 = group_sum_fp<F, GROUP>(c1); c2 = group_sum_fp<F, GROUP>(c2);
-  if (lane == 0 && valid)
-    cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1)).store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+  if (lane == 0 && valid) {
+    Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1));
+    t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+    if (dc.counts) count_scalar_digits(t, dc.c, dc.nwin, dc.counts);
+  }
 }
 
 // out[i] = a[i] + r * b[i]
