@@ -313,9 +313,9 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
     eng = vimz_b200.Engine("pallas", device)
     if os.environ.get("VIMZ_WINDOW_MSM"):
         eng.set_option("msm_window", int(os.environ["VIMZ_WINDOW_MSM"]))
+    from vimz_b200.sharding import shard_range
     n = 1 << log2n
-    per = n // world
-    first = rank * per
+    first, per = shard_range(n, rank, world)   # point-range shard of this rank
     d_bases = torch.empty(per * 8, dtype=torch.int64, device=f"cuda:{device}")
     vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, K0 + first * DK, DK, per, d_bases.data_ptr()))
     ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), per)

@@ -276,3 +276,36 @@ def test_fold_from_r1cs_and_wtns_files_bn254(tmp_path, engines, coracle):
     u = mont_to_ints(U.u, q)[0]
     assert all((x * y - u * w - t) % q == 0 for x, y, w, t in zip(a, b, cz, e))
     acc.close(); shape.close(); ck.close()
+
+
+def test_is_sat_and_is_sat_relaxed(engines):
+    """RecursiveSNARK::verify's checks (R1CSShape::is_sat / is_sat_relaxed) on fresh and folded instances, and
+    their failure modes (tampered witness, error vector, commitment)."""
+    from vimz_b200 import UnSat, is_sat, is_sat_relaxed
+    eng, c = engines["vesta"], P.VESTA
+    q = c.q
+    sh, shape, ck, Bm = _setup(eng, c, 0.01, seed=77)
+    Wi, Xi = S.synthetic_witness(sh, 3)
+    W2 = R1CSWitness(ints_to_mont(Wi, q))
+    U2 = R1CSInstance(W2.commit(ck), ints_to_mont(Xi, q))
+    is_sat(shape, ck, U2, W2)                                     # a fresh satisfying instance
+    bad = R1CSWitness(W2.W.copy()); bad.W[5] = ints_to_mont([Wi[5] + 1], q)[0]
+    with pytest.raises(UnSat):
+        is_sat(shape, ck, U2, bad)
+    acc = FoldAccumulator(shape, ck)
+    rng = random.Random(6)
+    for k in range(2):
+        Wk, Xk = S.synthetic_witness(sh, 10 + k)
+        acc.step_begin(ints_to_mont(Wk, q), ints_to_mont(Xk, q))
+        acc.step_end(ints_to_mont([rng.randrange(1 << 128)], q))
+    U, W = acc.download()
+    is_sat_relaxed(shape, ck, U, W)                               # the folded accumulator verifies
+    E_bad = W.E.copy(); E_bad[0] = ints_to_mont([1], q)[0]
+    with pytest.raises(UnSat):
+        is_sat_relaxed(shape, ck, U, RelaxedR1CSWitness(W.W, E_bad))
+    U_bad = RelaxedR1CSInstance(U.comm_E, U.comm_E, U.X, U.u)     # wrong comm_W
+    with pytest.raises(UnSat):
+        is_sat_relaxed(shape, ck, U_bad, W)
+    with pytest.raises(vimz_b200.InvalidWitnessLength):
+        is_sat(shape, ck, U2, R1CSWitness(W2.W[:-1]))
+    acc.close(); shape.close(); ck.close()

@@ -17,6 +17,9 @@ from .nova import (  # noqa: F401
     RelaxedR1CSInstance,
     RelaxedR1CSWitness,
     TranscriptRO,
+    UnSat,
+    is_sat,
+    is_sat_relaxed,
 )
 
 __version__ = "0.1.0"

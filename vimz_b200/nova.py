@@ -315,6 +315,45 @@ class R1CSShape:
         return T, comm_T
 
 
+class UnSat(VimzError):
+    """nova-snark's NovaError::UnSat."""
+
+    def __init__(self, msg: str):
+        super().__init__(-100, msg)
+
+
+def _check_sat(shape: "R1CSShape", ck: CommitmentKey, W: np.ndarray, E: Optional[np.ndarray], u: np.ndarray, X: np.ndarray,
+               comm_W: np.ndarray, comm_E: Optional[np.ndarray]) -> None:
+    eng = shape.engine
+    W = as_fr(W)
+    if W.shape[0] != shape.num_vars or as_fr(X).shape[0] != shape.num_io:
+        raise InvalidWitnessLength(_lib.VIMZ_ERR_LENGTH, "is_sat: witness / instance length mismatch")
+    Az, Bz, Cz = shape.multiply_vec(np.concatenate([W, as_fr(u, 1), as_fr(X)]))
+    lhs = eng.field_op("scalar", "mul", Az, Bz)
+    rhs = eng.field_op("scalar", "mul", np.repeat(as_fr(u, 1), shape.num_cons, axis=0), Cz)
+    if E is not None:
+        rhs = eng.field_op("scalar", "add", rhs, as_fr(E, shape.num_cons))
+    if not np.array_equal(lhs, rhs):
+        raise UnSat("Az o Bz != u*Cz + E")
+    if eng.to_affine_ints(CommitmentEngine.commit(ck, W)) != eng.to_affine_ints(comm_W):
+        raise UnSat("comm_W does not open to W")
+    if E is not None and eng.to_affine_ints(CommitmentEngine.commit(ck, as_fr(E))) != eng.to_affine_ints(comm_E):
+        raise UnSat("comm_E does not open to E")
+
+
+def is_sat_relaxed(shape: "R1CSShape", ck: CommitmentKey, U: "RelaxedR1CSInstance", W: "RelaxedR1CSWitness") -> None:
+    """[EXT nova-snark] src/r1cs.rs R1CSShape::is_sat_relaxed (what RecursiveSNARK::verify runs,
+    /root/reference/vimz/src/nova_snark_backend/folding.rs:53-55): Az o Bz = u*Cz + E and both commitments open.
+    Raises UnSat; every product and both MSMs run on the GPU."""
+    _check_sat(shape, ck, W.W, W.E, U.u, U.X, U.comm_W, U.comm_E)
+
+
+def is_sat(shape: "R1CSShape", ck: CommitmentKey, U: "R1CSInstance", W: "R1CSWitness") -> None:
+    """[EXT nova-snark] src/r1cs.rs R1CSShape::is_sat: Az o Bz = Cz (u = 1) and comm_W opens."""
+    one = shape.engine.scalars([1])
+    _check_sat(shape, ck, W.W, None, one, U.X, U.comm_W, None)
+
+
 class TranscriptRO:
     """Stand-in for the random oracle of NIFS::prove.  The reference's RO is Poseidon over the base
     field ([EXT nova-snark] src/provider/poseidon.rs) and stays untouched host code (SURVEY.md row
