@@ -362,7 +362,7 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
         ms = float(t[0])
     prof = eng.profile(reset=True)
     eng.set_option("profile", 0)
-    acc_ms, acc_calls = prof["msm_accumulate"]
+    acc_ms, acc_calls = prof["msm_accumulate_kernel"]
     entries = prof["msm_entries"][1]
     res = {"log2_points": log2n, "mpts_per_s": n * iters / ms / 1e3, "ms_per_msm": ms / iters, "window_bits": ck.window_bits,
            "windows": ck.num_windows, "scalars": "uniform 255-bit", "sharding": f"point-range x{world}" if world > 1 else "none"}
@@ -428,18 +428,20 @@ def main_gpu(args, rank, world, local_rank):
     # one by one instead of replaying the captured graph, so its events can sit between kernels).
     for e in engines:
         e.set_option("profile", 1)
+        e.set_option("aux_lane", 0)   # one lane: kernel times not inflated by the concurrent commit(W2)
         e.profile(reset=True)
     ms_prof, _ = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + 2 * steps + k), steps, dist)
     prof = prim.eng.profile(reset=True)
     prof_sec = sec.eng.profile(reset=True)
     for e in engines:
         e.set_option("profile", 0)
+        e.set_option("aux_lane", 1)
 
     value = world * steps / (ms * 1e-3)
     e2e_value = world * steps / (ms_e2e * 1e-3)
 
     # roofline of the dominant kernel (primary-curve bucket accumulation)
-    acc_ms, acc_calls = prof["msm_accumulate"]
+    acc_ms, acc_calls = prof["msm_accumulate_kernel"]
     entries = prof["msm_entries"][1]
     imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
     achieved = imad / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
@@ -450,10 +452,13 @@ def main_gpu(args, rank, world, local_rank):
             traffic = json.load(open(tpath)).get("k_msm_accumulate_fold_T")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_msm_accumulate<Pallas> (+ combine of cut buckets)", "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
+    roofline = {"kernel": "k_msm_accumulate<%s>" % prim.cv.name, "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
                 "unit": "TIMAD/s", "frac": (achieved / peaks["imad_tops"]) if achieved else None, "traffic": traffic,
                 "peak_source": peaks["imad_src"],
-                "algorithmic": f"{entries} bucket insertions x {MODMUL_PER_MADD} modmul x {IMAD_PER_MODMUL} IMAD over {acc_calls} launches",
+                "algorithmic": f"{entries} bucket insertions x {MODMUL_PER_MADD} modmul x {IMAD_PER_MODMUL} IMAD over {acc_calls} launches "
+                               f"(commit(W2) and commit(T) of every step)",
+                "launch_us_avg": (acc_ms * 1e3 / acc_calls) if acc_calls else None,
+                "insertions_per_launch": (entries / acc_calls) if acc_calls else None,
                 "share_of_step": acc_ms / ms_prof if ms_prof > 0 else None,
                 "timing": "library CUDA-event pairs around the kernel over a profiled pass of the same K steps (stream launches); "
                           "`value` is timed separately with the step's launch sequence replayed as a CUDA graph",

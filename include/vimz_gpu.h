@@ -56,12 +56,12 @@ int vimz_device_count(void);
 int vimz_ctx_create(int curve_id, int device, vimz_ctx** out);
 void vimz_ctx_destroy(vimz_ctx* ctx);
 int vimz_ctx_sync(vimz_ctx* ctx);
-/* Tunables: "msm_window" (c bits, 0 = auto), "msm_acc_blocks" (accumulation blocks per SM, 1..8), "profile" (0/1), "graph" (0/1: replay a fold step's launch
+/* Tunables: "msm_window" (c bits, 0 = auto), "msm_acc_blocks" (accumulation blocks per SM, 1..8), "aux_lane" (0/1), "profile" (0/1), "graph" (0/1: replay a fold step's launch
  * sequence as a CUDA graph, default 1).  Unknown keys -> VIMZ_ERR_ARG. */
 int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value);
 /* Device-side phase timers, enabled with vimz_ctx_set_option(ctx, "profile", 1): accumulated CUDA-event
- * milliseconds and call counts for "msm_sort", "msm_accumulate", "msm_reduce", "cross_term", "axpy",
- * "spmv"; name "msm_entries" returns the number of bucket insertions in *calls.  Synchronises the stream. */
+ * milliseconds and call counts for "msm_sort", "msm_accumulate" (kernel + combine), "msm_accumulate_kernel",
+ * "msm_reduce", "cross_term", "axpy", "spmv"; name "msm_entries" returns the number of bucket insertions in *calls.  Synchronises the stream. */
 int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset);
 /* The context's CUDA stream (cudaStream_t as void*), so a caller can time on it with events. */
 void* vimz_ctx_stream(vimz_ctx* ctx);

@@ -182,6 +182,10 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     ctx->opt_acc_blocks = value;
     return VIMZ_OK;
   }
+  if (strcmp(key, "aux_lane") == 0) {
+    ctx->opt_aux_lane = value != 0;
+    return VIMZ_OK;
+  }
   if (strcmp(key, "graph") == 0) {
     ctx->opt_graph = value != 0;
     return VIMZ_OK;
@@ -189,7 +193,7 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   return set_error(VIMZ_ERR_ARG, std::string("unknown option: ") + key);
 }
 
-static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_reduce", "cross_term", "axpy", "spmv"};
+static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_reduce", "cross_term", "axpy", "spmv", "msm_accumulate_kernel"};
 
 int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset) {
   CHECK_ARG(ctx && name, "vimz_ctx_profile: null argument");
@@ -621,14 +625,19 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
   // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) -- independent of T, so it runs on the aux
   // stream with its own workspace while the main stream does the cross term and commit(T).
-  VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
-  VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
-  VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, a->W2, s->n, fresh, false));
-  VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
+  const bool two_lanes = ctx->opt_aux_lane;
+  if (two_lanes) {
+    VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
+    VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
+    VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, a->W2, s->n, fresh, false));
+    VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
+  } else {  // one lane (used by the profiled pass so kernel times are not inflated by the other lane)
+    VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->W2, s->n, fresh, false));
+  }
   // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck));  // also histograms T's digits
   VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, true));
-  VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
+  if (two_lanes) VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   return VIMZ_OK;
 }

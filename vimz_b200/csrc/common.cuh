@@ -90,7 +90,7 @@ struct MsmWorkspace {
 
 // Optional per-phase device timers (vimz_ctx_set_option("profile", 1)): event pairs are recorded on the
 // context stream around a phase and resolved when vimz_ctx_profile() is called.
-enum ProfTimer { PROF_MSM_SORT = 0, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_CROSS_TERM, PROF_AXPY, PROF_SPMV, PROF_COUNT };
+enum ProfTimer { PROF_MSM_SORT = 0, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_CROSS_TERM, PROF_AXPY, PROF_SPMV, PROF_MSM_ACC_KERNEL, PROF_COUNT };
 struct ProfSpan { cudaEvent_t a, b; int timer; };
 struct Profiler {
   bool on = false;
@@ -113,6 +113,7 @@ struct vimz_ctx {
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
+  bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points

@@ -131,7 +131,10 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   }
   {
     ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
-    k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, ws.buckets.ptr, ws.partials.ptr);
+    {
+      ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
+      k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, ws.buckets.ptr, ws.partials.ptr);
+    }
     VIMZ_LAUNCH_CHECK(ctx);
     k_msm_combine<C><<<ceil_div(M, 128), 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
     VIMZ_LAUNCH_CHECK(ctx);
