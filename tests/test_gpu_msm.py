@@ -203,3 +203,17 @@ def test_msm_skewed_buckets_all_combine_classes(window, engines, coracle):
         assert got == P.scalar_mul(c, sum(s * k for s, k in zip(sc, logs)) % c.q, G), (window, mix)
     ck.close()
     eng.close()
+
+
+def test_bn254_published_known_answers_gpu(engines):
+    """EIP-196 vectors for 2G / 3G on BN254 G1 through the GPU commit path (external pin, see tests/test_oracle.py)."""
+    from test_oracle import BN254_2G, BN254_3G
+    c = P.BN254
+    eng = engines["bn254"]
+    G = P.generator(c)
+    ck = CommitmentKey.from_bases(eng, affine_to_mont([G, G], c.p))
+    assert gpu_commit_affine(eng, ck, ints_to_mont([2, 0], c.q)) == BN254_2G
+    assert gpu_commit_affine(eng, ck, ints_to_mont([1, 1], c.q)) == BN254_2G      # P + P inside one bucket
+    assert gpu_commit_affine(eng, ck, ints_to_mont([2, 1], c.q)) == BN254_3G
+    assert gpu_commit_affine(eng, ck, ints_to_mont([c.q - 2, 0], c.q)) == P.aff_neg(c, BN254_2G)
+    ck.close()

@@ -187,3 +187,22 @@ def test_golden_fixtures(coracle):
         expect = None if v["result"] is None else (int(v["result"][0], 16), int(v["result"][1], 16))
         j = coracle.msm(c.curve_id, ints_to_mont(sc, c.q), affine_to_mont(bases, c.p), 2)
         assert mont_to_affine(coracle.to_affine(c.curve_id, j), c.p)[0] == expect
+
+
+# Published known answers for alt_bn128 / BN254 G1 (EIP-196 test vectors, also py_ecc / go-ethereum bn256 tests):
+BN254_2G = (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+            9918110051302171585080402603319702774565515993150576347155970296011118125764)
+BN254_3G = (3353031288059533942658390886683067124040920775575537747144343083137631628272,
+            19321533766552368860946552437480515441416830039777911637913418824951667761761)
+
+
+def test_bn254_published_known_answers(coracle):
+    """External pin of the group law (not derived from this repository's code): 2G and 3G on BN254 G1."""
+    c = P.BN254
+    G = P.generator(c)
+    assert P.scalar_mul(c, 2, G) == BN254_2G and P.scalar_mul(c, 3, G) == BN254_3G
+    assert P.aff_add(c, G, G) == BN254_2G and P.aff_add(c, BN254_2G, G) == BN254_3G
+    Bm = affine_to_mont([G, G], c.p)
+    for sc, exp in (([2, 0], BN254_2G), ([1, 1], BN254_2G), ([2, 1], BN254_3G)):
+        j = coracle.msm(c.curve_id, ints_to_mont(sc, c.q), Bm, 1)
+        assert mont_to_affine(coracle.to_affine(c.curve_id, j), c.p)[0] == exp

@@ -136,7 +136,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
       k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, ws.buckets.ptr, ws.partials.ptr);
     }
     VIMZ_LAUNCH_CHECK(ctx);
-    k_msm_combine<C><<<ceil_div(M, 128), 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
+    k_msm_combine<C><<<ceil_div((size_t)M * 4, 128), 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
     VIMZ_LAUNCH_CHECK(ctx);
     k_msm_combine_mid<C><<<ctx->sm_count * 4, 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
     VIMZ_LAUNCH_CHECK(ctx);

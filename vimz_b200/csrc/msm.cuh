@@ -217,41 +217,46 @@ __device__ __forceinline__ size_t seg_partial_index(uint32_t t, uint32_t t0, uin
   return (size_t)2 * t + ((t == t0 && s != t0 * L) ? 1 : 0);
 }
 
+// One QUAD per bucket (ecq.cuh): buckets cut into 2..COMBINE_SPAN pieces are summed here, serially but with the
+// 4-round cooperative addition; empty buckets get the identity; heavier buckets are listed for the next kernels.
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_combine(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
                                                      const void* __restrict__ partials, void* __restrict__ buckets, MsmCombine cb) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= M) return;
+  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool in_range = b < M;
   const uint32_t E = offsets[M], L = seg_len(E, nthreads);
-  const uint32_t s = offsets[b], e = offsets[b + 1];
-  char* dst = reinterpret_cast<char*>(buckets) + (size_t)b * 128;
-  if (e == s) {  // empty bucket
-    Xyzz<C>::identity().store(dst);
-    return;
+  const uint32_t s = in_range ? offsets[b] : 0, e = in_range ? offsets[b + 1] : 0;
+  const bool empty = in_range && e == s;
+  uint32_t t0 = 0, t1 = 0, pieces = 0;
+  if (in_range && !empty) {
+    t0 = s / L;
+    t1 = (e - 1) / L;
+    pieces = t1 - t0 + 1;  // 1: stored complete by k_msm_accumulate
   }
-  const uint32_t t0 = s / L, t1 = (e - 1) / L;
-  if (t0 == t1) return;  // inside one segment: stored complete by k_msm_accumulate
-  if (t1 - t0 + 1 > COMBINE_SPAN && t1 - t0 + 1 <= COMBINE_MID) {  // mid: one warp of cooperating quads (k_msm_combine_mid)
-    cb.mids[atomicAdd(&cb.ctrl[2], 1u)] = b;
-    return;
-  }
-  if (t1 - t0 + 1 > COMBINE_MID) {  // giant: hand its pieces to blocks of cooperating quads, GIANT_CHUNK pieces each
-    uint32_t nch = (t1 - t0 + 1 + GIANT_CHUNK - 1) / GIANT_CHUNK;
-    uint32_t g = atomicAdd(&cb.ctrl[0], 1u);
-    uint32_t base = atomicAdd(&cb.ctrl[1], nch);
-    if (g < cb.max_giants && base + nch <= cb.max_chunks) {
-      cb.giants[3 * g] = b; cb.giants[3 * g + 1] = base; cb.giants[3 * g + 2] = nch;
-      for (uint32_t j = 0; j < nch; j++) { cb.chunk_rec[2 * (base + j)] = g; cb.chunk_rec[2 * (base + j) + 1] = j; }
+  if ((threadIdx.x & 3) == 0 && pieces > COMBINE_SPAN) {  // one lane of the quad files the heavy bucket
+    if (pieces <= COMBINE_MID) {
+      cb.mids[atomicAdd(&cb.ctrl[2], 1u)] = b;
+    } else {  // giant: hand its pieces to blocks of cooperating quads, GIANT_CHUNK pieces each
+      uint32_t nch = (pieces + GIANT_CHUNK - 1) / GIANT_CHUNK;
+      uint32_t g = atomicAdd(&cb.ctrl[0], 1u);
+      uint32_t base = atomicAdd(&cb.ctrl[1], nch);
+      if (g < cb.max_giants && base + nch <= cb.max_chunks) {
+        cb.giants[3 * g] = b; cb.giants[3 * g + 1] = base; cb.giants[3 * g + 2] = nch;
+        for (uint32_t j = 0; j < nch; j++) { cb.chunk_rec[2 * (base + j)] = g; cb.chunk_rec[2 * (base + j) + 1] = j; }
+      }
     }
-    return;
   }
-  Xyzz<C> acc = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t0, t0, s, L) * 128);
+  const uint32_t mine = (pieces >= 2 && pieces <= COMBINE_SPAN) ? pieces : 0;  // pieces this quad adds itself
+  const uint32_t trips = __reduce_max_sync(0xffffffffu, mine);               // warp-uniform trip count for the shuffles
+  QPoint<C> acc = mine ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t0, t0, s, L) * 128)
+                       : QPoint<C>::identity();
 #pragma unroll 1
-  for (uint32_t t = t0 + 1; t <= t1; t++) {
-    Xyzz<C> q = Xyzz<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t, t0, s, L) * 128);
-    xyzz_add_call<C>(acc, q);
+  for (uint32_t i = 1; i < trips; i++) {
+    QPoint<C> q = i < mine ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t0 + i, t0, s, L) * 128)
+                           : QPoint<C>::identity();
+    acc = q_add<C>(acc, q);
   }
-  acc.store(dst);
+  if (empty || mine) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
 }
 
 // 32 quads of a 128-thread block each hold one point: warp trees, then warp 0 folds the four warp results.
