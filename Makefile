@@ -2,16 +2,20 @@
 # translation units in parallel.
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude
+EXTRA ?=
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude $(EXTRA)
 SRC := vimz_b200/csrc
-OBJ := build/obj
+OBJ ?= build/obj
+LIB ?= vimz_b200/libvimz_gpu.so
 CUS := capi curve_pallas curve_vesta curve_bn254 curve_grumpkin
 OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CUS)))
 HDRS := $(wildcard $(SRC)/*.cuh) include/vimz_gpu.h
 
-all: vimz_b200/libvimz_gpu.so oracle
+all: $(LIB) oracle
 
-vimz_b200/libvimz_gpu.so: $(OBJS)
+# A/B variants: make OBJ=build/v1 LIB=build/variants/x.so EXTRA="-DVIMZ_COMBINE_MID=64" build/variants/x.so
+$(LIB): $(OBJS)
+	@mkdir -p $(dir $@)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)

@@ -243,6 +243,9 @@ class GpuFold:
         win = os.environ.get("VIMZ_WINDOW_" + curve_name.upper())
         if win:
             self.eng.set_option("msm_window", int(win))
+        seg = os.environ.get("VIMZ_SEG_MIN_" + curve_name.upper())
+        if seg:
+            self.eng.set_option("msm_seg_min", int(seg))
         if os.environ.get("VIMZ_ACC_BLOCKS"):
             self.eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
         sh = self.sh

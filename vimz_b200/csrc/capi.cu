@@ -180,6 +180,13 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   if (strcmp(key, "msm_acc_blocks") == 0) {
     if (value < 1 || value > 8) return set_error(VIMZ_ERR_ARG, "msm_acc_blocks must be in [1, 8]");
     ctx->opt_acc_blocks = value;
+    alloc_epoch()++;  // captured step graphs hold the old launch geometry: rebuild them
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "msm_seg_min") == 0) {
+    if (value < 1 || value > 4096) return set_error(VIMZ_ERR_ARG, "msm_seg_min must be in [1, 4096]");
+    ctx->opt_seg_min = value;
+    alloc_epoch()++;
     return VIMZ_OK;
   }
   if (strcmp(key, "aux_lane") == 0) {
@@ -738,9 +745,7 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   VIMZ_CUDA(cudaMemcpyAsync(d_r, stage, 32, cudaMemcpyHostToDevice, st));
   VIMZ_CUDA(cudaEventRecord(a->ev_main, st));
   // ... and by value into the witness folds: W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2)
-  VIMZ_TRY(vt->axpy(ctx, a->W1, a->W2, r, s->n, a->W1));
-  VIMZ_TRY(vt->axpy(ctx, a->E1, a->T, r, s->m, a->E1));
-  VIMZ_TRY(vt->axpy(ctx, a->tail1, a->tail2, r, 1 + s->io, a->tail1));
+  VIMZ_TRY(vt->axpy3(ctx, a->W1, a->W2, s->n, a->E1, a->T, s->m, a->tail1, a->tail2, 1 + s->io, r));
   // comm_W1 += r*comm_W2 ; comm_E1 += r*comm_T : two 128-bit scalar multiplications, latency-bound,
   // so they run on the side stream and overlap the next step's MSMs.
   VIMZ_CUDA(cudaStreamWaitEvent(ctx->side, a->ev_main, 0));

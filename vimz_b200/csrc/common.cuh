@@ -113,6 +113,7 @@ struct vimz_ctx {
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
+  long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;

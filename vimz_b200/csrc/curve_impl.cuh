@@ -27,6 +27,9 @@ struct CurveVTable {
   int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
                     const vimz_ck* fuse_ck);
   int (*axpy)(vimz_ctx*, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out);
+  // three in-place folds a_k += r * b_k in one launch (witness fold W, E and the (u, X) tail)
+  int (*axpy3)(vimz_ctx*, void* a0, const void* b0, size_t n0, void* a1, const void* b1, size_t n1, void* a2, const void* b2, size_t n2,
+               const vimz_fr* r);
   int (*field_op)(vimz_ctx*, int which, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 };
 
@@ -66,6 +69,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 2), 1), 64);
   // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
   const uint32_t nthreads = (uint32_t)ctx->sm_count * (uint32_t)ctx->opt_acc_blocks * 128;
+  const uint32_t seg_min = (uint32_t)ctx->opt_seg_min;
   // capacity bounds: a bucket cut into p pieces overlaps p segments and every segment boundary cuts at most one
   // bucket, so sum(pieces) <= 2 * nthreads; a giant has > COMBINE_MID pieces and ceil(p / GIANT_CHUNK) chunks
   const uint32_t max_giants = 2 * nthreads / COMBINE_MID + 2;
@@ -77,7 +81,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   uint32_t scan_blocks = ceil_div(M, SCAN_THREADS * SCAN_ITEMS);
   VIMZ_TRY(ws.blocksums.reserve(((size_t)scan_blocks + 2) * 4));
   VIMZ_TRY(ws.sorted.reserve(E * 4));
-  VIMZ_TRY(ws.cls.reserve(64));
+  const size_t ctrl_words = CTRL_GIANT_DONE + max_giants;
+  VIMZ_TRY(ws.cls.reserve(ctrl_words * 4));
   VIMZ_TRY(ws.biglist.reserve(((size_t)3 * max_giants + (size_t)2 * max_chunks + (size_t)M + 4) * 4));
   VIMZ_TRY(ws.partials.reserve(((size_t)2 * nthreads + max_chunks) * 128));
   VIMZ_TRY(ws.buckets.reserve((size_t)M * 128));
@@ -101,7 +106,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   cb.max_chunks = max_chunks;
 
   if (!counted) VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
-  VIMZ_CUDA(cudaMemsetAsync(cb.ctrl, 0, 64, st));
+  VIMZ_CUDA(cudaMemsetAsync(cb.ctrl, 0, ctrl_words * 4, st));
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
   {
@@ -110,15 +115,20 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
       k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
       VIMZ_LAUNCH_CHECK(ctx);
     }
-    k_scan_blocksum<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums);
-    VIMZ_LAUNCH_CHECK(ctx);
-    k_scan_top<<<1, 1024, 0, st>>>(blocksums, scan_blocks, blocksums + scan_blocks + 1);
-    VIMZ_LAUNCH_CHECK(ctx);
-    k_scan_apply<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums, offsets, cursor);
-    VIMZ_LAUNCH_CHECK(ctx);
+    if (M <= SCAN1_MAX_M) {  // every fold-step MSM: one single-block launch
+      k_scan_single<<<1, SCAN1_THREADS, 0, st>>>(counts, M, offsets, cursor);
+      VIMZ_LAUNCH_CHECK(ctx);
+    } else {
+      k_scan_blocksum<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums);
+      VIMZ_LAUNCH_CHECK(ctx);
+      k_scan_top<<<1, 1024, 0, st>>>(blocksums, scan_blocks, blocksums + scan_blocks + 1);
+      VIMZ_LAUNCH_CHECK(ctx);
+      k_scan_apply<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, M, blocksums, offsets, cursor);
+      VIMZ_LAUNCH_CHECK(ctx);
+    }
     if (n > 0) {
       k_msm_scatter<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin,
-                                                (uint32_t)ck->n, (uint32_t)first, cursor, sorted);
+                                                (uint32_t)ck->n, (uint32_t)first, cursor, sorted, offsets, M, nthreads, seg_min, cb);
       VIMZ_LAUNCH_CHECK(ctx);
     }
   }
@@ -133,26 +143,20 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
     ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
     {
       ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
-      k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, ws.buckets.ptr, ws.partials.ptr);
+      k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, seg_min, ws.buckets.ptr, ws.partials.ptr);
     }
     VIMZ_LAUNCH_CHECK(ctx);
-    k_msm_combine<C><<<ceil_div((size_t)M * 4, 128), 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
-    VIMZ_LAUNCH_CHECK(ctx);
-    k_msm_combine_mid<C><<<ctx->sm_count * 4, 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, ws.buckets.ptr, cb);
-    VIMZ_LAUNCH_CHECK(ctx);
-    k_msm_combine_big<C><<<ctx->sm_count, 128, 0, st>>>(offsets, M, nthreads, ws.partials.ptr, cb);
-    VIMZ_LAUNCH_CHECK(ctx);
-    k_msm_combine_final<C><<<16, 128, 0, st>>>(cb, ws.buckets.ptr);
+    // pieces of cut buckets: giants (blocks per chunk + last-arrival fold), mids (a warp each), the rest (a quad each)
+    const uint32_t nb_big = (uint32_t)ctx->sm_count, nb_mid = (uint32_t)ctx->sm_count * 4, nb_small = ceil_div((size_t)M * 4, 128);
+    k_msm_combine_all<C><<<nb_big + nb_mid + nb_small, 128, 0, st>>>(offsets, M, nthreads, seg_min, nb_big, nb_mid, ws.partials.ptr,
+                                                                     ws.buckets.ptr, cb);
     VIMZ_LAUNCH_CHECK(ctx);
   }
   ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);
   k_reduce_chunks<C><<<ceil_div((size_t)T * 4, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-  k_reduce_bits<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, ws.bitsums.ptr);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_reduce_scale<C><<<nb + 1, 32, 0, st>>>(ws.bitsums.ptr, nb, G, logK, ws.scaled.ptr);
-  VIMZ_LAUNCH_CHECK(ctx);
-  k_reduce_out<C><<<1, 32, 0, st>>>(ws.scaled.ptr, nb + 1, d_out);
+  k_reduce_tail<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, logK, ws.bitsums.ptr, ws.scaled.ptr,
+                                                    cb.ctrl + CTRL_REDUCE, d_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -215,19 +219,14 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
     dc.nwin = fuse_ck->nwin;
   }
   ProfScope prof(ctx, PROF_CROSS_TERM, ctx->stream);
-  k_cross_term<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(
-      csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T, dc);
+  CrossArgs ca;
+  ca.A = csr_view(s, 0); ca.B = csr_view(s, 1); ca.Cm = csr_view(s, 2);
+  ca.m = (uint32_t)s->m; ca.n = (uint32_t)s->n;
+  ca.W1 = d_W1; ca.tail1 = d_tail1; ca.W2 = d_W2; ca.tail2 = d_tail2; ca.T = d_T; ca.dc = dc;
+  const uint32_t nb_long = ceil_div(s->n_long * 32, 128), nb_mid = ceil_div(s->n_mid * 8, 128), nb_short = ceil_div(s->m, 128);
+  k_cross_term<typename C::Fs><<<nb_long + nb_mid + nb_short, 128, 0, ctx->stream>>>(ca, s->long_rows, (uint32_t)s->n_long, nb_long,
+                                                                                     s->mid_rows, (uint32_t)s->n_mid, nb_mid);
   VIMZ_LAUNCH_CHECK(ctx);
-  if (s->n_mid) {
-    k_cross_term_group<typename C::Fs, 8><<<ceil_div(s->n_mid * 8, 128), 128, 0, ctx->stream>>>(
-        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->mid_rows, (uint32_t)s->n_mid, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T, dc);
-    VIMZ_LAUNCH_CHECK(ctx);
-  }
-  if (s->n_long) {
-    k_cross_term_group<typename C::Fs, 32><<<ceil_div(s->n_long * 32, 128), 128, 0, ctx->stream>>>(
-        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), s->long_rows, (uint32_t)s->n_long, (uint32_t)s->n, d_W1, d_tail1, d_W2, d_tail2, d_T, dc);
-    VIMZ_LAUNCH_CHECK(ctx);
-  }
   return VIMZ_OK;
 }
 template <class C>
@@ -238,6 +237,19 @@ int impl_axpy(vimz_ctx* ctx, const void* d_a, const void* d_b, const vimz_fr* r,
   int grid = (int)std::min<size_t>(ceil_div(len, 256), (size_t)ctx->sm_count * 16);
   ProfScope prof(ctx, PROF_AXPY, ctx->stream);
   k_axpy<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(d_a, d_b, rr, len, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_axpy3(vimz_ctx* ctx, void* a0, const void* b0, size_t n0, void* a1, const void* b1, size_t n1, void* a2, const void* b2, size_t n2,
+               const vimz_fr* r) {
+  const size_t total = n0 + n1 + n2;
+  if (total == 0) return VIMZ_OK;
+  Fp<typename C::Fs> rr;
+  memcpy(rr.v, r, 32);
+  int grid = (int)std::min<size_t>(ceil_div(total, 256), (size_t)ctx->sm_count * 16);
+  ProfScope prof(ctx, PROF_AXPY, ctx->stream);
+  k_axpy3<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(AxpySeg{a0, b0, n0}, AxpySeg{a1, b1, n1}, AxpySeg{a2, b2, n2}, rr);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -270,6 +282,7 @@ CurveVTable make_vtable(const char* name) {
   t.spmv3 = &impl_spmv3<C>;
   t.cross_term = &impl_cross_term<C>;
   t.axpy = &impl_axpy<C>;
+  t.axpy3 = &impl_axpy3<C>;
   t.field_op = &impl_field_op<C>;
   return t;
 }

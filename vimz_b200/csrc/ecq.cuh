@@ -53,6 +53,11 @@ struct QPoint {
     p.c = F::load(reinterpret_cast<const char*>(rec) + 32 * (threadIdx.x & 3));
     return p;
   }
+  VIMZ_DI static QPoint load_cg(const void* rec) {
+    QPoint p;
+    p.c = F::load_cg(reinterpret_cast<const char*>(rec) + 32 * (threadIdx.x & 3));
+    return p;
+  }
   VIMZ_DI void store(void* rec) const { c.store(reinterpret_cast<char*>(rec) + 32 * (threadIdx.x & 3)); }
   VIMZ_DI bool is_identity() const { return q_flag(c.is_zero(), 2); }  // ZZ == 0
   // the same point held by the quad `delta` quads further up the warp (garbage beyond the warp: caller masks)

@@ -75,6 +75,14 @@ struct Fp {
     r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
     return r;
   }
+  VIMZ_DI static Fp load_cg(const void* ptr) {  // through L2: data published by another block of the same launch
+    const uint4* q = reinterpret_cast<const uint4*>(ptr);
+    uint4 a = __ldcg(q), b = __ldcg(q + 1);
+    Fp r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
   VIMZ_DI void store(void* ptr) const {
     uint4* q = reinterpret_cast<uint4*>(ptr);
     q[0] = make_uint4(v[0], v[1], v[2], v[3]);

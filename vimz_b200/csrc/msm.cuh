@@ -27,6 +27,67 @@ namespace vimz {
 
 constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
 
+constexpr uint32_t SEG_MIN_DEFAULT = 8; // shortest segment (entries per thread); option "msm_seg_min"
+#ifndef VIMZ_COMBINE_SPAN
+#define VIMZ_COMBINE_SPAN 8
+#endif
+#ifndef VIMZ_COMBINE_MID
+#define VIMZ_COMBINE_MID 256
+#endif
+#ifndef VIMZ_GIANT_CHUNK
+#define VIMZ_GIANT_CHUNK 256
+#endif
+constexpr uint32_t COMBINE_SPAN = VIMZ_COMBINE_SPAN;  // a quad adds at most this many partials serially
+constexpr uint32_t COMBINE_MID = VIMZ_COMBINE_MID;    // up to this many partials: one warp (8 cooperating quads) per bucket
+constexpr uint32_t GIANT_CHUNK = VIMZ_GIANT_CHUNK;    // pieces of a giant bucket summed by one block (32 quads x GIANT_CHUNK/32)
+static_assert(GIANT_CHUNK % 32 == 0 && GIANT_CHUNK >= 32, "GIANT_CHUNK: whole rounds of the block's 32 quads");
+
+__device__ __forceinline__ uint32_t seg_len(uint32_t E, uint32_t nthreads, uint32_t seg_min) {
+  uint32_t L = (E + nthreads - 1) / nthreads;
+  return L < seg_min ? seg_min : L;
+}
+
+// Control block of one MSM (zeroed by a single memset before the launch sequence).
+constexpr uint32_t CTRL_NGIANT = 0, CTRL_NCHUNK = 1, CTRL_NMID = 2;
+constexpr uint32_t CTRL_REDUCE = 8;      // [nb + 2] arrival counters of the reduction tail (nb + 1 sums, then the final one)
+constexpr uint32_t CTRL_GIANT_DONE = 64; // [max_giants] chunks finished per giant bucket
+struct MsmCombine {
+  uint32_t* ctrl;       // see CTRL_*
+  uint32_t* mids;       // [M] ids of buckets cut into COMBINE_SPAN+1 .. COMBINE_MID pieces
+  uint32_t* giants;     // [max_giants][3]: bucket id, first chunk, number of chunks
+  uint32_t* chunk_rec;  // [max_chunks][2]: giant index, chunk index inside the giant
+  void* chunk_sums;     // [max_chunks] XYZZ
+  uint32_t max_giants, max_chunks;
+};
+
+// File bucket b = [s, e) of the sorted list by the number of segments (length L) it is cut into: 2..COMBINE_SPAN
+// pieces need no record (a quad adds them), more go to the mid list (a warp each) or the giant list (blocks of
+// GIANT_CHUNK pieces).  Depends only on the scan, so it runs BEFORE the accumulation, off its critical path.
+// Warp-collective (ballots): call with all 32 lanes; list appends are one atomic per warp.
+__device__ __forceinline__ void classify_bucket(bool valid, uint32_t b, uint32_t s, uint32_t e, uint32_t L, const MsmCombine& cb) {
+  uint32_t pieces = 0;
+  if (valid && e > s) pieces = (e - 1) / L - s / L + 1;
+  const bool mid = pieces > COMBINE_SPAN && pieces <= COMBINE_MID;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned mm = __ballot_sync(0xffffffffu, mid);
+  if (mm) {
+    const int leader = __ffs(mm) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&cb.ctrl[CTRL_NMID], (uint32_t)__popc(mm));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (mid) cb.mids[base + __popc(mm & ((1u << lane) - 1u))] = b;
+  }
+  if (pieces > COMBINE_MID) {  // giant (rare: the 0/1 bucket of a witness vector, all-equal scalars)
+    uint32_t nch = (pieces + GIANT_CHUNK - 1) / GIANT_CHUNK;
+    uint32_t g = atomicAdd(&cb.ctrl[CTRL_NGIANT], 1u);
+    uint32_t base = atomicAdd(&cb.ctrl[CTRL_NCHUNK], nch);
+    if (g < cb.max_giants && base + nch <= cb.max_chunks) {
+      cb.giants[3 * g] = b; cb.giants[3 * g + 1] = base; cb.giants[3 * g + 2] = nch;
+      for (uint32_t j = 0; j < nch; j++) { cb.chunk_rec[2 * (base + j)] = g; cb.chunk_rec[2 * (base + j) + 1] = j; }
+    }
+  }
+}
+
 template <class C>
 __global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
                             uint32_t* __restrict__ counts) {
@@ -39,8 +100,18 @@ __global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, in
 template <class C>
 __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
                               uint32_t table_stride, uint32_t first,
-                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted,
+                              const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min, MsmCombine cb) {
   using Fs = Fp<typename C::Fs>;
+  {  // bucket classification for k_msm_combine_all rides along (it only needs the finished scan): warp-collective
+    const uint32_t L = seg_len(offsets[M], nthreads, seg_min);
+    const uint32_t lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < M; base += nwarps * 32) {
+      const uint32_t b = base + lane;
+      const bool valid = b < M;
+      classify_bucket(valid, b, valid ? offsets[b] : 0u, valid ? offsets[b + 1] : 0u, L, cb);
+    }
+  }
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
     // Nova's running vectors are dominated by values of small magnitude modulo q (sums of 128-bit
@@ -145,33 +216,73 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
 //   * the first / last run of a segment may be cut by the segment boundary: stored as partial 0 / 1;
 // k_msm_combine then adds the <= few partials of every cut bucket (one thread per bucket; buckets cut
 // into more than COMBINE_SPAN pieces go to k_msm_combine_big, one block of cooperating quads each).
-constexpr uint32_t SEG_MIN = 8;         // shortest segment (entries per thread)
-constexpr uint32_t COMBINE_SPAN = 8;    // a thread adds at most this many partials itself
-constexpr uint32_t COMBINE_MID = 256;   // up to this many partials: one warp (8 cooperating quads) per bucket
-constexpr uint32_t GIANT_CHUNK = 256;   // pieces of a giant bucket summed by one block (32 quads x 8)
-
-__device__ __forceinline__ uint32_t seg_len(uint32_t E, uint32_t nthreads) {
-  uint32_t L = (E + nthreads - 1) / nthreads;
-  return L < SEG_MIN ? SEG_MIN : L;
+// Small bucket counts (M <= SCAN1_MAX_M, every fold-step MSM): ONE block scans the counts and writes the offsets and
+// the scatter cursors -- one launch instead of three on a latency-bound chain.
+constexpr uint32_t SCAN1_THREADS = 1024;
+constexpr uint32_t SCAN1_MAX_M = 32768;
+static __global__ void __launch_bounds__(SCAN1_THREADS) k_scan_single(const uint32_t* __restrict__ counts, uint32_t M,
+                                                                      uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t ipt = ((M + SCAN1_THREADS - 1) / SCAN1_THREADS + 3) & ~3u;  // consecutive counts per thread, multiple of 4
+  const uint32_t base = threadIdx.x * ipt;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t sum = 0;
+  if (base + ipt <= M) {
+    for (uint32_t k = 0; k < ipt; k += 4) {
+      uint4 v = *reinterpret_cast<const uint4*>(counts + base + k);
+      sum += v.x + v.y + v.z + v.w;
+    }
+  } else {
+    for (uint32_t k = 0; k < ipt; k++) sum += (base + k < M) ? counts[base + k] : 0u;
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if ((int)lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;  // exclusive prefix of the warp totals
+    if (lane == 31) offsets[M] = wi;
+  }
+  __syncthreads();
+  uint32_t run = warp_tot[warp] + incl - sum;  // exclusive prefix of this thread's first count
+  if (base + ipt <= M) {
+    for (uint32_t k = 0; k < ipt; k += 4) {
+      uint4 v = *reinterpret_cast<const uint4*>(counts + base + k);
+      uint4 o;
+      o.x = run; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+      run = o.w + v.w;
+      *reinterpret_cast<uint4*>(offsets + base + k) = o;
+      *reinterpret_cast<uint4*>(cursor + base + k) = o;
+    }
+  } else {
+    for (uint32_t k = 0; k < ipt; k++) {
+      if (base + k < M) {
+        offsets[base + k] = run;
+        cursor[base + k] = run;
+        run += counts[base + k];
+      }
+    }
+  }
 }
-
-struct MsmCombine {
-  uint32_t* ctrl;       // [0] number of giant buckets, [1] number of giant chunks, [2] number of mid buckets
-  uint32_t* mids;       // [M] ids of buckets cut into COMBINE_SPAN+1 .. COMBINE_MID pieces
-  uint32_t* giants;     // [max_giants][3]: bucket id, first chunk, number of chunks
-  uint32_t* chunk_rec;  // [max_chunks][2]: giant index, chunk index inside the giant
-  void* chunk_sums;     // [max_chunks] XYZZ
-  uint32_t max_giants, max_chunks;
-};
 
 template <class C>
 __global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                                                           const void* __restrict__ table, uint32_t M, uint32_t nthreads,
+                                                           const void* __restrict__ table, uint32_t M, uint32_t nthreads, uint32_t seg_min,
                                                            void* __restrict__ buckets, void* __restrict__ partials) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
   const uint32_t E = offsets[M];
-  const uint32_t L = seg_len(E, nthreads);
+  const uint32_t L = seg_len(E, nthreads, seg_min);
   const uint64_t beg64 = (uint64_t)t * L;
   if (beg64 >= E) return;
   const uint32_t beg = (uint32_t)beg64, end = min(E, beg + L);
@@ -217,48 +328,6 @@ __device__ __forceinline__ size_t seg_partial_index(uint32_t t, uint32_t t0, uin
   return (size_t)2 * t + ((t == t0 && s != t0 * L) ? 1 : 0);
 }
 
-// One QUAD per bucket (ecq.cuh): buckets cut into 2..COMBINE_SPAN pieces are summed here, serially but with the
-// 4-round cooperative addition; empty buckets get the identity; heavier buckets are listed for the next kernels.
-template <class C>
-__global__ void __launch_bounds__(128) k_msm_combine(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
-                                                     const void* __restrict__ partials, void* __restrict__ buckets, MsmCombine cb) {
-  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  const bool in_range = b < M;
-  const uint32_t E = offsets[M], L = seg_len(E, nthreads);
-  const uint32_t s = in_range ? offsets[b] : 0, e = in_range ? offsets[b + 1] : 0;
-  const bool empty = in_range && e == s;
-  uint32_t t0 = 0, t1 = 0, pieces = 0;
-  if (in_range && !empty) {
-    t0 = s / L;
-    t1 = (e - 1) / L;
-    pieces = t1 - t0 + 1;  // 1: stored complete by k_msm_accumulate
-  }
-  if ((threadIdx.x & 3) == 0 && pieces > COMBINE_SPAN) {  // one lane of the quad files the heavy bucket
-    if (pieces <= COMBINE_MID) {
-      cb.mids[atomicAdd(&cb.ctrl[2], 1u)] = b;
-    } else {  // giant: hand its pieces to blocks of cooperating quads, GIANT_CHUNK pieces each
-      uint32_t nch = (pieces + GIANT_CHUNK - 1) / GIANT_CHUNK;
-      uint32_t g = atomicAdd(&cb.ctrl[0], 1u);
-      uint32_t base = atomicAdd(&cb.ctrl[1], nch);
-      if (g < cb.max_giants && base + nch <= cb.max_chunks) {
-        cb.giants[3 * g] = b; cb.giants[3 * g + 1] = base; cb.giants[3 * g + 2] = nch;
-        for (uint32_t j = 0; j < nch; j++) { cb.chunk_rec[2 * (base + j)] = g; cb.chunk_rec[2 * (base + j) + 1] = j; }
-      }
-    }
-  }
-  const uint32_t mine = (pieces >= 2 && pieces <= COMBINE_SPAN) ? pieces : 0;  // pieces this quad adds itself
-  const uint32_t trips = __reduce_max_sync(0xffffffffu, mine);               // warp-uniform trip count for the shuffles
-  QPoint<C> acc = mine ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t0, t0, s, L) * 128)
-                       : QPoint<C>::identity();
-#pragma unroll 1
-  for (uint32_t i = 1; i < trips; i++) {
-    QPoint<C> q = i < mine ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t0 + i, t0, s, L) * 128)
-                           : QPoint<C>::identity();
-    acc = q_add<C>(acc, q);
-  }
-  if (empty || mine) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
-}
-
 // 32 quads of a 128-thread block each hold one point: warp trees, then warp 0 folds the four warp results.
 // Result valid in quad 0 of warp 0 (threads 0..3).  smem: 4 XYZZ records.
 template <class C>
@@ -275,90 +344,117 @@ __device__ __forceinline__ QPoint<C> q_block_reduce_128(QPoint<C> acc, uint32_t*
   return acc;
 }
 
-// mid buckets: one warp each, its 8 quads stride over the pieces, then a quad tree
+// All pieces of cut buckets are added in ONE launch after the accumulation; the block index selects the role
+// (longest chains first so they start first):
+//   blocks [0, nb_big)            giant buckets: a block (32 quads) per chunk of GIANT_CHUNK pieces; the block that
+//                                 finishes the last chunk of a giant also folds the chunk sums into the bucket
+//   blocks [nb_big, +nb_mid)      mid buckets: a warp each, its 8 quads stride over the pieces, then a quad tree
+//   remaining blocks              a quad per bucket: 2..COMBINE_SPAN pieces summed serially; empty buckets get the
+//                                 identity
+// The lists were filled by classify_bucket before the accumulation started.
 template <class C>
-__global__ void __launch_bounds__(128) k_msm_combine_mid(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
-                                                         const void* __restrict__ partials, void* __restrict__ buckets, MsmCombine cb) {
-  const uint32_t nmid = cb.ctrl[2];
-  const uint32_t E = offsets[M], L = seg_len(E, nthreads);
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t quad = (threadIdx.x & 31) >> 2;
-  for (uint32_t i = warp; i < nmid; i += nwarps) {
-    const uint32_t b = cb.mids[i];
-    const uint32_t s = offsets[b], e = offsets[b + 1];
-    const uint32_t t0 = s / L, t1 = (e - 1) / L;
-    QPoint<C> acc = QPoint<C>::identity();
-    const uint32_t iters = (t1 - t0 + 1 + 7) / 8;
-#pragma unroll 1
-    for (uint32_t it = 0; it < iters; it++) {  // warp-uniform trip count
-      uint32_t t = t0 + it * 8 + quad;
-      QPoint<C> p = t <= t1 ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t, t0, s, L) * 128)
-                            : QPoint<C>::identity();
-      acc = q_add<C>(acc, p);
-    }
-    acc = q_warp_reduce<C>(acc);
-    if ((threadIdx.x & 31) < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
-  }
-}
-
-// giant buckets (cut into more than COMBINE_MID segments, e.g. the 0/1 bucket of a witness vector):
-// one 128-thread block (32 cooperating quads) per chunk of GIANT_CHUNK pieces -> chunk_sums
-template <class C>
-__global__ void __launch_bounds__(128) k_msm_combine_big(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
-                                                         const void* __restrict__ partials, MsmCombine cb) {
+__global__ void __launch_bounds__(128) k_msm_combine_all(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min,
+                                                         uint32_t nb_big, uint32_t nb_mid, const void* __restrict__ partials,
+                                                         void* __restrict__ buckets, MsmCombine cb) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
-  const uint32_t nchunks = min(cb.ctrl[1], cb.max_chunks);
-  const uint32_t E = offsets[M], L = seg_len(E, nthreads);
-  const uint32_t quad = threadIdx.x >> 2;
-  for (uint32_t j = blockIdx.x; j < nchunks; j += gridDim.x) {
-    const uint32_t g = cb.chunk_rec[2 * j], idx = cb.chunk_rec[2 * j + 1];
-    const uint32_t b = cb.giants[3 * g];
-    const uint32_t s = offsets[b], e = offsets[b + 1];
-    const uint32_t t0 = s / L, t1 = (e - 1) / L;
-    const uint32_t first = t0 + idx * GIANT_CHUNK, last = min(t1, first + GIANT_CHUNK - 1);
-    QPoint<C> acc = QPoint<C>::identity();
+  __shared__ uint32_t last_flag;
+  const uint32_t E = offsets[M], L = seg_len(E, nthreads, seg_min);
+  const char* parts = reinterpret_cast<const char*>(partials);
+  if (blockIdx.x < nb_big) {
+    const uint32_t nchunks = min(cb.ctrl[CTRL_NCHUNK], cb.max_chunks);
+    const uint32_t quad = threadIdx.x >> 2;
+    for (uint32_t j = blockIdx.x; j < nchunks; j += nb_big) {
+      const uint32_t g = cb.chunk_rec[2 * j], idx = cb.chunk_rec[2 * j + 1];
+      const uint32_t b = cb.giants[3 * g], gbase = cb.giants[3 * g + 1], nch = cb.giants[3 * g + 2];
+      const uint32_t s = offsets[b], e = offsets[b + 1];
+      const uint32_t t0 = s / L, t1 = (e - 1) / L;
+      const uint32_t first = t0 + idx * GIANT_CHUNK, last = min(t1, first + GIANT_CHUNK - 1);
+      QPoint<C> acc = QPoint<C>::identity();
 #pragma unroll 1
-    for (uint32_t it = 0; it < GIANT_CHUNK / 32; it++) {  // uniform trip count: every lane joins the shuffles
-      uint32_t t = first + it * 32 + quad;
-      QPoint<C> p = t <= last ? QPoint<C>::load(reinterpret_cast<const char*>(partials) + seg_partial_index(t, t0, s, L) * 128)
-                              : QPoint<C>::identity();
-      acc = q_add<C>(acc, p);
-    }
-    acc = q_block_reduce_128<C>(acc, smem);
-    if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(cb.chunk_sums) + (size_t)j * 128);
-  }
-}
-
-// one warp per giant bucket: add its chunk sums into the bucket
-template <class C>
-__global__ void __launch_bounds__(128) k_msm_combine_final(MsmCombine cb, void* __restrict__ buckets) {
-  const uint32_t ngiant = min(cb.ctrl[0], cb.max_giants);
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t quad = (threadIdx.x & 31) >> 2;
-  for (uint32_t g = warp; g < ngiant; g += nwarps) {
-    const uint32_t b = cb.giants[3 * g], base = cb.giants[3 * g + 1], nch = cb.giants[3 * g + 2];
-    QPoint<C> acc = QPoint<C>::identity();
-    const uint32_t iters = (nch + 7) / 8;
+      for (uint32_t it = 0; it < GIANT_CHUNK / 32; it++) {  // uniform trip count: every lane joins the shuffles
+        uint32_t t = first + it * 32 + quad;
+        QPoint<C> p = t <= last ? QPoint<C>::load(parts + seg_partial_index(t, t0, s, L) * 128) : QPoint<C>::identity();
+        acc = q_add<C>(acc, p);
+      }
+      acc = q_block_reduce_128<C>(acc, smem);
+      if (threadIdx.x < 4) {
+        acc.store(reinterpret_cast<char*>(cb.chunk_sums) + (size_t)j * 128);
+        __threadfence();  // publish the chunk sum before announcing it
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) last_flag = (atomicAdd(&cb.ctrl[CTRL_GIANT_DONE + g], 1u) + 1 == nch) ? 1u : 0u;
+      __syncthreads();
+      if (last_flag && threadIdx.x < 32) {  // last chunk of giant g: one warp folds all its chunk sums (read through L2)
+        __threadfence();
+        const uint32_t q8 = threadIdx.x >> 2;
+        QPoint<C> tot = QPoint<C>::identity();
+        const uint32_t iters = (nch + 7) / 8;
 #pragma unroll 1
-    for (uint32_t it = 0; it < iters; it++) {
-      uint32_t j = it * 8 + quad;
-      QPoint<C> p = j < nch ? QPoint<C>::load(reinterpret_cast<const char*>(cb.chunk_sums) + (size_t)(base + j) * 128) : QPoint<C>::identity();
-      acc = q_add<C>(acc, p);
+        for (uint32_t it = 0; it < iters; it++) {
+          uint32_t jj = it * 8 + q8;
+          QPoint<C> p = jj < nch ? QPoint<C>::load_cg(reinterpret_cast<const char*>(cb.chunk_sums) + (size_t)(gbase + jj) * 128)
+                                 : QPoint<C>::identity();
+          tot = q_add<C>(tot, p);
+        }
+        tot = q_warp_reduce<C>(tot);
+        if (threadIdx.x < 4) tot.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+      }
+      __syncthreads();
     }
-    acc = q_warp_reduce<C>(acc);
-    if ((threadIdx.x & 31) < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+    return;
   }
+  if (blockIdx.x < nb_big + nb_mid) {
+    const uint32_t nmid = cb.ctrl[CTRL_NMID];
+    const uint32_t warp = ((blockIdx.x - nb_big) * blockDim.x + threadIdx.x) >> 5, nwarps = (nb_mid * blockDim.x) >> 5;
+    const uint32_t quad = (threadIdx.x & 31) >> 2;
+    for (uint32_t i = warp; i < nmid; i += nwarps) {
+      const uint32_t b = cb.mids[i];
+      const uint32_t s = offsets[b], e = offsets[b + 1];
+      const uint32_t t0 = s / L, t1 = (e - 1) / L;
+      QPoint<C> acc = QPoint<C>::identity();
+      const uint32_t iters = (t1 - t0 + 1 + 7) / 8;
+#pragma unroll 1
+      for (uint32_t it = 0; it < iters; it++) {  // warp-uniform trip count
+        uint32_t t = t0 + it * 8 + quad;
+        QPoint<C> p = t <= t1 ? QPoint<C>::load(parts + seg_partial_index(t, t0, s, L) * 128) : QPoint<C>::identity();
+        acc = q_add<C>(acc, p);
+      }
+      acc = q_warp_reduce<C>(acc);
+      if ((threadIdx.x & 31) < 4) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+    }
+    return;
+  }
+  const uint32_t b = ((blockIdx.x - nb_big - nb_mid) * blockDim.x + threadIdx.x) >> 2;
+  const bool in_range = b < M;
+  const uint32_t s = in_range ? offsets[b] : 0, e = in_range ? offsets[b + 1] : 0;
+  const bool empty = in_range && e == s;
+  uint32_t t0 = 0, pieces = 0;
+  if (in_range && !empty) {
+    t0 = s / L;
+    pieces = (e - 1) / L - t0 + 1;  // 1: stored complete by k_msm_accumulate
+  }
+  const uint32_t mine = (pieces >= 2 && pieces <= COMBINE_SPAN) ? pieces : 0;  // pieces this quad adds itself
+  const uint32_t trips = __reduce_max_sync(0xffffffffu, mine);               // warp-uniform trip count for the shuffles
+  QPoint<C> acc = mine ? QPoint<C>::load(parts + seg_partial_index(t0, t0, s, L) * 128) : QPoint<C>::identity();
+  QPoint<C> nxt = mine > 1 ? QPoint<C>::load(parts + seg_partial_index(t0 + 1, t0, s, L) * 128) : QPoint<C>::identity();
+#pragma unroll 1
+  for (uint32_t i = 1; i < trips; i++) {
+    QPoint<C> q = nxt;  // the next piece is fetched while this addition runs
+    nxt = i + 1 < mine ? QPoint<C>::load(parts + seg_partial_index(t0 + i + 1, t0, s, L) * 128) : QPoint<C>::identity();
+    acc = q_add<C>(acc, q);
+  }
+  if (empty || mine) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
 }
 
 // ---- bucket reduction: sum_{k=0}^{M-1} (k+1) * B_k ------------------------------------------
 // Every step below is a chain of EC additions executed by warps that run alone, so it is organised for
 // DEPTH and every addition is done by a quad of lanes (ecq.cuh):
 //   level 1 (k_reduce_chunks): quad t owns K consecutive buckets: A_t = sum B, L_t = sum (j+1) B_{tK+j}   [2K adds deep]
-//   level 2 (k_reduce_bits):   sum = S_L + K * sum_t t*A_t = S_L + sum_b 2^(b+logK) S_b with the plain sums
+//   level 2 (k_reduce_tail):   sum = S_L + K * sum_t t*A_t = S_L + sum_b 2^(b+logK) S_b with the plain sums
 //                              S_b = sum_{t: bit b set} A_t, S_L = sum L_t                                  [trees]
-//   level 3 (k_reduce_scale):  one warp per sum folds its G block partials, then applies the 2^(b+logK)
+//   level 3 (same launch):     one warp per sum folds its G block partials, then applies the 2^(b+logK)
 //                              doublings -- all sums in parallel instead of a serial Horner chain
-//   level 4 (k_reduce_out):    one warp adds the <= 32 scaled sums and writes the Jacobian result.
+//   level 4 (same launch):     one warp adds the <= 32 scaled sums and writes the Jacobian result.
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets, uint32_t T, int K,
                                                        void* __restrict__ chunkA, void* __restrict__ chunkL) {
@@ -378,12 +474,18 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
   }
 }
 
-// sum id s = blockIdx.y: s < nb -> sum of A_t over t with bit s set; s == nb -> sum of L_t.
+// Levels 2-4 in ONE launch (the chain is latency-bound, so launch boundaries are pure loss): block (g, s) sums its
+// share of sum s (s < nb: the A_t with bit s of t set; s == nb: all L_t); the block that completes sum s folds the
+// G block partials and applies the 2^(s+logK) doublings; the block that completes the last sum adds the nb+1
+// scaled sums and writes the Jacobian result.  Hand-offs: __threadfence + arrival counters (cnt[0..nb] per sum,
+// cnt[nb+1] for the final), zeroed with the MSM's control block; later stages read through L2 (ld.cg).
 template <class C>
-__global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb,
-                                                     void* __restrict__ bitsums) {
+__global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb, int logK,
+                                                     void* __restrict__ bitsums, void* __restrict__ scaled, uint32_t* __restrict__ cnt,
+                                                     void* __restrict__ out_jac) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
-  const int s = blockIdx.y;
+  __shared__ uint32_t flag;
+  const int s = blockIdx.y, G = gridDim.x;
   // s < nb: enumerate exactly the indices with bit s set so every quad is busy; s == nb: all of chunkL
   const bool plain = (s == nb);
   const uint32_t count = plain ? T : (T >> 1), lowmask = plain ? 0u : ((1u << s) - 1);
@@ -399,38 +501,45 @@ __global__ void __launch_bounds__(128) k_reduce_bits(const void* __restrict__ ch
     acc = q_add<C>(acc, p);
   }
   acc = q_block_reduce_128<C>(acc, smem);
-  if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * gridDim.x + blockIdx.x) * 128);
-}
-
-// one warp (block) per sum s: fold the G block partials, then scale by 2^(s+logK) (s < nb) -> scaled[s]
-template <class C>
-__global__ void __launch_bounds__(32) k_reduce_scale(const void* __restrict__ bitsums, int nb, int G, int logK, void* __restrict__ scaled) {
-  const int s = blockIdx.x, quad = threadIdx.x >> 2;
-  QPoint<C> acc = QPoint<C>::identity();
-  const int iters = (G + 7) / 8;
+  if (threadIdx.x < 4) {
+    acc.store(reinterpret_cast<char*>(bitsums) + ((size_t)s * G + blockIdx.x) * 128);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flag = (atomicAdd(&cnt[s], 1u) + 1 == (uint32_t)G) ? 1u : 0u;
+  __syncthreads();
+  if (!flag || threadIdx.x >= 32) return;
+  // ---- this warp completes sum s: fold the G block partials, scale by 2^(s+logK)
+  __threadfence();
+  const int q8 = threadIdx.x >> 2;
+  acc = QPoint<C>::identity();
 #pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    int g = it * 8 + quad;
-    QPoint<C> p = g < G ? QPoint<C>::load(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128) : QPoint<C>::identity();
+  for (int it = 0; it < (G + 7) / 8; it++) {
+    int g = it * 8 + q8;
+    QPoint<C> p = g < G ? QPoint<C>::load_cg(reinterpret_cast<const char*>(bitsums) + ((size_t)s * G + g) * 128) : QPoint<C>::identity();
     acc = q_add<C>(acc, p);
   }
   acc = q_warp_reduce<C>(acc);
-  const int ndbl = s < nb ? s + logK : 0;  // block-uniform
+  const int ndbl = s < nb ? s + logK : 0;  // warp-uniform
 #pragma unroll 1
   for (int k = 0; k < ndbl; k++) acc = q_dbl<C>(acc);
-  if (threadIdx.x < 4) acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
-}
-
-// one warp: add the nsums (<= 32) scaled sums, convert to Jacobian
-template <class C>
-__global__ void __launch_bounds__(32) k_reduce_out(const void* __restrict__ scaled, int nsums, void* __restrict__ out_jac) {
-  const int quad = threadIdx.x >> 2;
-  QPoint<C> acc = QPoint<C>::identity();
-  const int iters = (nsums + 7) / 8;
+  uint32_t done = 0;
+  if (threadIdx.x < 4) {
+    acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
+    __threadfence();
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) done = atomicAdd(&cnt[nb + 1], 1u) + 1;
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done != (uint32_t)(nb + 1)) return;
+  // ---- last sum finished: add the nb+1 (<= 32) scaled sums, convert to Jacobian
+  __threadfence();
+  const int nsums = nb + 1;
+  acc = QPoint<C>::identity();
 #pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    int g = it * 8 + quad;
-    QPoint<C> p = g < nsums ? QPoint<C>::load(reinterpret_cast<const char*>(scaled) + (size_t)g * 128) : QPoint<C>::identity();
+  for (int it = 0; it < (nsums + 7) / 8; it++) {
+    int g = it * 8 + q8;
+    QPoint<C> p = g < nsums ? QPoint<C>::load_cg(reinterpret_cast<const char*>(scaled) + (size_t)g * 128) : QPoint<C>::identity();
     acc = q_add<C>(acc, p);
   }
   acc = q_warp_reduce<C>(acc);

@@ -96,26 +96,6 @@ VIMZ_DI Fp<F> cross_term_row(const Fp<F>& a1, const Fp<F>& a2, const Fp<F>& b1, 
   return fp_sub(t, c1);
 }
 
-// T[i] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1   (u2 = 1; u1 = tail1[0]).  One thread per short row.
-template <class F>
-__global__ void __launch_bounds__(256) k_cross_term(CsrView A, CsrView B, CsrView Cm, uint32_t m, uint32_t n,
-                                                    const void* __restrict__ W1, const void* __restrict__ tail1,
-                                                    const void* __restrict__ W2, const void* __restrict__ tail2,
-                                                    void* __restrict__ T, DigitCount dc) {
-  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= m) return;
-  uint32_t ab = A.rowptr[row], ae = A.rowptr[row + 1], bb = B.rowptr[row], be = B.rowptr[row + 1];
-  uint32_t cb = Cm.rowptr[row], ce = Cm.rowptr[row + 1];
-  if ((ae - ab) + (be - bb) + (ce - cb) > R1CS_SHORT_ROW) return;  // k_cross_term_group owns this row
-  Fp<F> a1, a2, b1, b2, c1, c2;
-  row_dot2<F>(A, ab, ae, 1, n, W1, tail1, W2, tail2, a1, a2);
-  row_dot2<F>(B, bb, be, 1, n, W1, tail1, W2, tail2, b1, b2);
-  row_dot2<F>(Cm, cb, ce, 1, n, W1, tail1, W2, tail2, c1, c2);
-  Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1));
-  t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
-  if (dc.counts) count_scalar_digits(t, dc.c, dc.nwin, dc.counts);
-}
-
 // sum over the GROUP lanes of a row group (GROUP = 8 or 32, groups are aligned inside the warp)
 template <class F, int GROUP>
 VIMZ_DI Fp<F> group_sum_fp(Fp<F> v) {
@@ -129,29 +109,66 @@ VIMZ_DI Fp<F> group_sum_fp(Fp<F> v) {
   return v;
 }
 
-// GROUP lanes per listed row (8 for Poseidon-like rows, 32 for the 240-term Num2Bits packing rows):
-// lanes stride the non-zeros, partial dot products are folded with shuffles.
-template <class F, int GROUP>
-__global__ void __launch_bounds__(128) k_cross_term_group(CsrView A, CsrView B, CsrView Cm, const uint32_t* __restrict__ rows,
-                                                          uint32_t n_rows, uint32_t n,
-                                                          const void* __restrict__ W1, const void* __restrict__ tail1,
-                                                          const void* __restrict__ W2, const void* __restrict__ tail2,
-                                                          void* __restrict__ T, DigitCount dc) {
-  uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP, lane = threadIdx.x % GROUP;
-  bool valid = g < n_rows;  // whole groups are valid or not; invalid groups still join the shuffles
-  uint32_t row = rows[valid ? g : 0];
+struct CrossArgs {
+  CsrView A, B, Cm;
+  uint32_t m, n;
+  const void *W1, *tail1, *W2, *tail2;
+  void* T;
+  DigitCount dc;
+};
+
+// one thread per short row (<= R1CS_SHORT_ROW non-zeros over A+B+C); rows owned by the group roles are skipped
+template <class F>
+VIMZ_DI void cross_term_short(const CrossArgs& a, uint32_t row) {
+  if (row >= a.m) return;
+  uint32_t ab = a.A.rowptr[row], ae = a.A.rowptr[row + 1], bb = a.B.rowptr[row], be = a.B.rowptr[row + 1];
+  uint32_t cb = a.Cm.rowptr[row], ce = a.Cm.rowptr[row + 1];
+  if ((ae - ab) + (be - bb) + (ce - cb) > R1CS_SHORT_ROW) return;
   Fp<F> a1, a2, b1, b2, c1, c2;
-  uint32_t none = 0;
-  row_dot2<F>(A, valid ? A.rowptr[row] + lane : none, valid ? A.rowptr[row + 1] : none, GROUP, n, W1, tail1, W2, tail2, a1, a2);
-  row_dot2<F>(B, valid ? B.rowptr[row] + lane : none, valid ? B.rowptr[row + 1] : none, GROUP, n, W1, tail1, W2, tail2, b1, b2);
-  row_dot2<F>(Cm, valid ? Cm.rowptr[row] + lane : none, valid ? Cm.rowptr[row + 1] : none, GROUP, n, W1, tail1, W2, tail2, c1, c2);
+  row_dot2<F>(a.A, ab, ae, 1, a.n, a.W1, a.tail1, a.W2, a.tail2, a1, a2);
+  row_dot2<F>(a.B, bb, be, 1, a.n, a.W1, a.tail1, a.W2, a.tail2, b1, b2);
+  row_dot2<F>(a.Cm, cb, ce, 1, a.n, a.W1, a.tail1, a.W2, a.tail2, c1, c2);
+  Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1));
+  t.store(reinterpret_cast<char*>(a.T) + (size_t)row * 32);
+  if (a.dc.counts) count_scalar_digits(t, a.dc.c, a.dc.nwin, a.dc.counts);
+}
+
+// GROUP lanes per listed row (8 for Poseidon-like rows, 32 for the 240-term Num2Bits packing rows):
+// lanes stride the non-zeros, partial dot products are folded with shuffles.  g = group index (warp-collective).
+template <class F, int GROUP>
+VIMZ_DI void cross_term_grouped(const CrossArgs& a, const uint32_t* __restrict__ rows, uint32_t n_rows, uint32_t g) {
+  const uint32_t lane = threadIdx.x % GROUP;
+  const bool valid = g < n_rows;  // whole groups are valid or not; invalid groups still join the shuffles
+  const uint32_t row = rows[valid ? g : 0];
+  Fp<F> a1, a2, b1, b2, c1, c2;
+  const uint32_t none = 0;
+  row_dot2<F>(a.A, valid ? a.A.rowptr[row] + lane : none, valid ? a.A.rowptr[row + 1] : none, GROUP, a.n, a.W1, a.tail1, a.W2, a.tail2, a1, a2);
+  row_dot2<F>(a.B, valid ? a.B.rowptr[row] + lane : none, valid ? a.B.rowptr[row + 1] : none, GROUP, a.n, a.W1, a.tail1, a.W2, a.tail2, b1, b2);
+  row_dot2<F>(a.Cm, valid ? a.Cm.rowptr[row] + lane : none, valid ? a.Cm.rowptr[row + 1] : none, GROUP, a.n, a.W1, a.tail1, a.W2, a.tail2, c1, c2);
   a1 = group_sum_fp<F, GROUP>(a1); a2 = group_sum_fp<F, GROUP>(a2);
   b1 = group_sum_fp<F, GROUP>(b1); b2 = group_sum_fp<F, GROUP>(b2);
   c1 = group_sum_fp<F, GROUP>(c1); c2 = group_sum_fp<F, GROUP>(c2);
   if (lane == 0 && valid) {
-    Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1));
-    t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
-    if (dc.counts) count_scalar_digits(t, dc.c, dc.nwin, dc.counts);
+    Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1));
+    t.store(reinterpret_cast<char*>(a.T) + (size_t)row * 32);
+    if (a.dc.counts) count_scalar_digits(t, a.dc.c, a.dc.nwin, a.dc.counts);
+  }
+}
+
+// T[i] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1   (u2 = 1; u1 = tail1[0]) for ALL rows in one launch of 128-thread
+// blocks; the block index selects the row class (the classes with the longest per-row chains are scheduled first):
+//   [0, nb_long)          rows with > R1CS_LONG_ROW non-zeros: a warp each
+//   [nb_long, +nb_mid)    rows with R1CS_SHORT_ROW+1 .. R1CS_LONG_ROW non-zeros: 8 lanes each
+//   remaining blocks      every other row: a thread each
+template <class F>
+__global__ void __launch_bounds__(128) k_cross_term(CrossArgs a, const uint32_t* __restrict__ long_rows, uint32_t n_long, uint32_t nb_long,
+                                                    const uint32_t* __restrict__ mid_rows, uint32_t n_mid, uint32_t nb_mid) {
+  if (blockIdx.x < nb_long) {
+    cross_term_grouped<F, 32>(a, long_rows, n_long, (blockIdx.x * blockDim.x + threadIdx.x) / 32);
+  } else if (blockIdx.x < nb_long + nb_mid) {
+    cross_term_grouped<F, 8>(a, mid_rows, n_mid, ((blockIdx.x - nb_long) * blockDim.x + threadIdx.x) / 8);
+  } else {
+    cross_term_short<F>(a, (blockIdx.x - nb_long - nb_mid) * blockDim.x + threadIdx.x);
   }
 }
 
@@ -163,6 +180,27 @@ __global__ void __launch_bounds__(256) k_axpy(const void* __restrict__ a, const 
     Fp<F> x = Fp<F>::load(reinterpret_cast<const char*>(a) + i * 32);
     Fp<F> y = Fp<F>::load(reinterpret_cast<const char*>(b) + i * 32);
     fp_add(x, fp_mul(r, y)).store(reinterpret_cast<char*>(out) + i * 32);
+  }
+}
+
+// RelaxedR1CSWitness::fold + the scalar half of RelaxedR1CSInstance::fold in one launch:
+// W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2) -- three in-place segments sharing r.
+struct AxpySeg {
+  void* a;
+  const void* b;
+  size_t len;
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_axpy3(AxpySeg s0, AxpySeg s1, AxpySeg s2, Fp<F> r) {
+  const size_t total = s0.len + s1.len + s2.len;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const bool in0 = i < s0.len, in1 = i < s0.len + s1.len;
+    const AxpySeg& sg = in0 ? s0 : (in1 ? s1 : s2);
+    const size_t j = in0 ? i : (in1 ? i - s0.len : i - s0.len - s1.len);
+    char* pa = reinterpret_cast<char*>(sg.a) + j * 32;
+    Fp<F> x = Fp<F>::load(pa);
+    Fp<F> y = Fp<F>::load(reinterpret_cast<const char*>(sg.b) + j * 32);
+    fp_add(x, fp_mul(r, y)).store(pa);
   }
 }
 
