@@ -191,8 +191,8 @@ class CpuFold:
 CYCLES = {"pasta": ("pallas", "vesta"), "bn254": ("bn254", "grumpkin")}
 
 
-def run_cpu_steps(steps: int, warmup: int, threads: int, cycle: str = "pasta"):
-    prim = CpuFold(CYCLES[cycle][0], "grayscale", SEED, threads)
+def run_cpu_steps(steps: int, warmup: int, threads: int, cycle: str = "pasta", circuit: str = "grayscale"):
+    prim = CpuFold(CYCLES[cycle][0], circuit, SEED, threads)
     sec = CpuFold(CYCLES[cycle][1], "secondary", SEED + 1, threads)
     for k in range(warmup):
         sec.step(k); prim.step(k)
@@ -200,13 +200,23 @@ def run_cpu_steps(steps: int, warmup: int, threads: int, cycle: str = "pasta"):
     for k in range(warmup, warmup + steps):
         sec.step(k); prim.step(k)
     dt = time.perf_counter() - t0
-    return steps / dt, dt
+    return steps / dt, dt, prim.sh
 
 
-def workload_config(extra=None, cycle="pasta"):
-    cfg = {"workload": ("" if cycle == "pasta" else "[BN254/Grumpkin cycle] ") + "grayscale_step_HD fold step: primary Pallas relaxed-R1CS m=130864 n=128307 nnz=713556 (ck 2^17 points) + secondary Vesta m=n=10500; "
-                       "synthetic satisfying witnesses (86% 0/1), SHAKE-256 stand-in for the RO",
-           "curve_cycle": "/".join(CYCLES[cycle]), "l2": "no explicit flush: a step touches the 126 MB window table + 26 MB CSR + 21 MB of vectors/buckets (> 126 MB L2) and every step "
+def workload_config(sh, extra=None, cycle="pasta"):
+    """`sh` = the primary step shape actually folded (vimz_b200.synthetic.SyntheticShape)."""
+    nck = 1 << (max(sh.num_cons, sh.num_vars) - 1).bit_length()
+    prim, sec = CYCLES[cycle]
+    table_mb = nck * 64 * 17 // (1 << 20)
+    cfg = {"workload": ("" if cycle == "pasta" else "[BN254/Grumpkin cycle] ") +
+                       f"{sh.name}_step_HD fold step: primary {prim.capitalize()} relaxed-R1CS m={sh.num_cons} n={sh.num_vars} nnz={sh.nnz} "
+                       f"(ck 2^{nck.bit_length() - 1} points) + secondary {sec.capitalize()} m=n=10500; "
+                       "synthetic satisfying witnesses (86% 0/1 for the pixel circuits), SHAKE-256 stand-in for the RO",
+           "circuit": sh.name,
+           "curve_cycle": "/".join(CYCLES[cycle]),
+           "l2": f"no explicit flush: a step touches the ~{table_mb} MB window table + {sh.nnz * 36 // (1 << 20)} MB CSR + "
+                 f"{(2 * sh.num_vars + 2 * sh.num_cons) * 32 // (1 << 20)} MB of vectors "
+                 f"({'more' if table_mb + sh.nnz * 36 // (1 << 20) > 126 else 'LESS'} than the 126 MB L2) and every step "
                  "folds a different witness (32 distinct rows cycled)"}
     if extra:
         cfg.update(extra)
@@ -219,12 +229,12 @@ def main_reference(args, rank, world):
     threads = os.cpu_count() or 1
     steps = max(1, min(args.steps, 8))          # bounded sample: a CPU step is ~0.3-1 s
     warmup = max(1, min(args.warmup, 2))
-    sps, dt = run_cpu_steps(steps, warmup, threads, args.cycle)
+    sps, dt, sh = run_cpu_steps(steps, warmup, threads, args.cycle, args.circuit)
     line = {"metric": "nova_fold_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)",
             "data": "synthetic", "impl": "reference",
-            "config": workload_config(cycle=args.cycle, extra={"note": "CPU restatement of nova-snark 0.23.0 (oracle/nova_cpu.c): the Rust crate cannot be built here (no cargo/rustc)"}),
-            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": f"{steps} full grayscale_HD fold steps (primary+secondary) after {warmup} warm-up"},
+            "config": workload_config(sh, cycle=args.cycle, extra={"note": "CPU restatement of nova-snark 0.23.0 (oracle/nova_cpu.c): the Rust crate cannot be built here (no cargo/rustc)"}),
+            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": f"{steps} full {args.circuit}_HD fold steps (primary+secondary) after {warmup} warm-up"},
             "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -404,7 +414,7 @@ def main_gpu(args, rank, world, local_rank):
         return
 
     # each rank folds its own transformation (different witnesses), same circuit
-    prim = GpuFold(CYCLES[args.cycle][0], "grayscale", SEED + 100 * rank, local_rank, torch)
+    prim = GpuFold(CYCLES[args.cycle][0], args.circuit, SEED + 100 * rank, local_rank, torch)
     sec = GpuFold(CYCLES[args.cycle][1], "secondary", SEED + 100 * rank + 1, local_rank, torch)
     engines = [prim.eng, sec.eng]
 
@@ -483,16 +493,16 @@ def main_gpu(args, rank, world, local_rank):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sps, dt = run_cpu_steps(3, 1, threads, args.cycle)
+        sps, dt, _ = run_cpu_steps(3, 1, threads, args.cycle, args.circuit)
         cpu_baseline = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                        "sample": f"3 full grayscale_HD fold steps (primary+secondary) of oracle/nova_cpu.c after 1 warm-up, {dt:.1f} s"}
+                        "sample": f"3 full {args.circuit}_HD fold steps (primary+secondary) of oracle/nova_cpu.c after 1 warm-up, {dt:.1f} s"}
 
     if rank == 0:
         bad = [r for r in clocks["reasons"] if r != "sw_power_cap"]
         line = {"metric": "nova_fold_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
-                "config": workload_config(cycle=args.cycle, extra={"parallelism": f"replicas x{world} (one transformation per GPU)",
+                "config": workload_config(prim.sh, cycle=args.cycle, extra={"parallelism": f"replicas x{world} (one transformation per GPU)",
                                                                    "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows}),
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
                         "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_e2e / steps},
@@ -517,6 +527,9 @@ def main():
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[20])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--msm-only", action="store_true", help="skip the fold-step measurement (window sweeps)")
+    ap.add_argument("--circuit", default="grayscale", choices=["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash"],
+                    help="step circuit whose published size the primary shape takes (BASELINE metric: grayscale; the others are the "
+                         "remaining BASELINE configs, /root/reference/circuits/nova_snark/circuit_parameters.csv)")
     ap.add_argument("--cycle", default="pasta", choices=["pasta", "bn254"],
                     help="curve cycle: pasta = Pallas/Vesta (BASELINE metric), bn254 = BN254/Grumpkin (what the mounted vimz master instantiates)")
     args = ap.parse_args()

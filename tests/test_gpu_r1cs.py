@@ -198,19 +198,23 @@ def test_nifs_prove_host_api_matches_accumulator(engines):
     acc.close(); shape.close(); ck.close()
 
 
-def test_full_size_grayscale_step_properties(engines):
-    """BASELINE size (grayscale HD: m = 130 864, n = 128 307): two folds on the device, checked through
-    size-independent properties -- the folded instance satisfies the relaxed R1CS relation and both
-    commitments open -- since the CPU oracle is too slow to redo this inside a unit test budget."""
+@pytest.mark.parametrize("circuit", ["grayscale", "brightness", "resize", "sharpness", "hash"])
+def test_full_size_step_properties(circuit, engines):
+    """BASELINE sizes (grayscale HD: m = 130 864, n = 128 307; brightness/contrast 315 185 x 299 829; resize
+    251 968 x 244 291; sharpness 335 734 x 320 377; the running-hash step 16 672 x 16 787 --
+    /root/reference/circuits/nova_snark/circuit_parameters.csv:2-9 plus the augmented circuit): two folds on the
+    device, checked through size-independent properties -- the folded instance satisfies the relaxed R1CS
+    relation and both commitments open -- since the CPU oracle is too slow to redo this inside a unit test budget."""
     import torch
     eng, c = engines["pallas"], P.PALLAS
     q = c.q
-    sh = S.synthetic_shape(CURVES["pallas"], "grayscale")
+    sh = S.synthetic_shape(CURVES["pallas"], circuit)
     shape = R1CSShape(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
-    nck = 1 << 17
+    nck = 1 << (max(sh.num_cons, sh.num_vars) - 1).bit_length()
     d_bases = torch.empty(nck * 8, dtype=torch.int64, device="cuda")
     vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, 77, 1234577, nck, d_bases.data_ptr()))
     ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), nck)
+    del d_bases
     acc = FoldAccumulator(shape, ck)
     rng = random.Random(1)
     for k in range(2):
