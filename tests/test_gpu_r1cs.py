@@ -107,6 +107,58 @@ def test_commit_T_and_folds_vs_oracle(name, engines, coracle):
     shape.close(); ck.close()
 
 
+@pytest.mark.parametrize("name", ["pallas", "grumpkin"])
+def test_cross_term_row_classes_stream_vs_rowclass_vs_oracle(name, engines, coracle):
+    """Rows of every class of the streamed cross term -- empty, 1-3 terms, 40 terms (warp-summed in shared memory),
+    300 and 500 terms, 600 and 1100 terms (own chunk, warp over global memory), duplicates, unsorted COO -- next
+    to runs of short rows that fill chunks to the 256-row and the 1024-non-zero limit.  T must equal the oracle's
+    with the streamed kernel and with the row-class kernel (option cross_stream = 0)."""
+    eng, c = engines[name], P.CURVES[name]
+    q = c.q
+    rng = random.Random(77 + c.curve_id)
+    n, io = 900, 2
+    ncols = n + 1 + io
+    lengths = [0, 1, 2, 3, 40, 0, 300, 5, 600, 2, 1100, 33, 32, 500, 7] + [rng.choice([0, 1, 2, 3, 4, 6]) for _ in range(700)] + [12] * 90 + [64, 65, 513, 512]
+    m = len(lengths)
+    consts = [1, q - 1, 2, 5] + [rng.randrange(q) for _ in range(6)]
+
+    def matrix(scale_len):
+        rows, cols, vals = [], [], []
+        for i, L in enumerate(lengths):
+            k = L if scale_len else min(L, 2)
+            for _ in range(k):
+                rows.append(i); cols.append(rng.randrange(ncols)); vals.append(rng.choice(consts))
+        perm = list(range(len(rows)))
+        rng.shuffle(perm)
+        return (np.array([rows[j] for j in perm], np.uint32), np.array([cols[j] for j in perm], np.uint32),
+                ints_to_mont([vals[j] for j in perm], q))
+
+    A, B, Cm = matrix(True), matrix(False), matrix(False)
+    shape = R1CSShape(eng, m, n, io, A, B, Cm)
+    bases, _ = make_bases(c, max(m, n), seed=5)
+    Bm = affine_to_mont(bases, c.p)
+    ck = CommitmentKey.from_bases(eng, Bm)
+    W1 = ints_to_mont([rng.randrange(q) for _ in range(n)], q)
+    X1 = ints_to_mont([rng.randrange(q) for _ in range(io)], q)
+    u1 = ints_to_mont([rng.randrange(q)], q)
+    W2 = ints_to_mont([rng.choice([0, 1, rng.randrange(q)]) for _ in range(n)], q)
+    X2 = ints_to_mont([rng.randrange(q) for _ in range(io)], q)
+    one = ints_to_mont([1], q)
+    U1 = RelaxedR1CSInstance(np.zeros(12, np.uint64), np.zeros(12, np.uint64), X1, u1)
+    U2 = R1CSInstance(np.zeros(12, np.uint64), X2)
+    T_exp = coracle.commit_T(c.curve_id, m, n, io, A, B, Cm, W1, u1, X1, W2, X2, one, nthreads=2)
+    comm_exp = _affine(coracle, c, coracle.msm(c.curve_id, T_exp, Bm, 4))
+    try:
+        for stream in (1, 0):
+            eng.set_option("cross_stream", stream)
+            T, comm_T = shape.commit_T(ck, U1, RelaxedR1CSWitness(W1, np.zeros((m, 4), np.uint64)), U2, R1CSWitness(W2))
+            assert np.array_equal(T, T_exp), f"cross_stream={stream}"
+            assert eng.to_affine_ints(comm_T) == comm_exp
+    finally:
+        eng.set_option("cross_stream", 1)
+    shape.close(); ck.close()
+
+
 def _oracle_fold_chain(coracle, c, sh, Bm, witnesses, challenges):
     """Reference fold of a chain of fresh instances into the default relaxed instance, all on the CPU."""
     q = c.q

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 #include "curve_impl.cuh"
 
@@ -186,6 +187,11 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   if (strcmp(key, "msm_seg_min") == 0) {
     if (value < 1 || value > 4096) return set_error(VIMZ_ERR_ARG, "msm_seg_min must be in [1, 4096]");
     ctx->opt_seg_min = value;
+    alloc_epoch()++;
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "cross_stream") == 0) {
+    ctx->opt_cross_stream = value != 0;
     alloc_epoch()++;
     return VIMZ_OK;
   }
@@ -376,8 +382,30 @@ int vimz_point_scale_add(vimz_ctx* ctx, const vimz_point* a, const vimz_fr* r, c
 }
 
 // ---- R1CS shape --------------------------------------------------------------------------------------
+// Distinct coefficient values of a shape.  R1CS matrices repeat a handful of constants (1, -1, powers of two,
+// Poseidon round / MDS constants), so the streamed cross term reads a 4-byte index per non-zero instead of 32 bytes.
+struct FrHash {
+  size_t operator()(const vimz_fr& v) const { return (size_t)(v.l[0] * 0x9E3779B97F4A7C15ull ^ v.l[1] * 0xC2B2AE3D27D4EB4Full ^ v.l[2] ^ (v.l[3] << 1)); }
+};
+struct FrEq {
+  bool operator()(const vimz_fr& a, const vimz_fr& b) const { return memcmp(&a, &b, 32) == 0; }
+};
+struct ValueDict {
+  std::unordered_map<vimz_fr, uint32_t, FrHash, FrEq> index;
+  std::vector<vimz_fr> values;
+  uint32_t lookup(const vimz_fr& v) {
+    auto it = index.find(v);
+    if (it != index.end()) return it->second;
+    uint32_t id = (uint32_t)values.size();
+    values.push_back(v);
+    index.emplace(v, id);
+    return id;
+  }
+};
+
 static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row, const uint32_t* col, const vimz_fr* val, size_t nnz,
-                      uint32_t** d_rowptr, uint32_t** d_col, void** d_val, std::vector<uint32_t>& row_nnz) {
+                      uint32_t** d_rowptr, uint32_t** d_col, void** d_val, std::vector<uint32_t>& row_nnz, ValueDict& dict,
+                      uint32_t** d_vidx) {
   std::vector<uint32_t> rowptr(m + 1, 0);
   for (size_t k = 0; k < nnz; k++) {
     if (row[k] >= m || col[k] >= ncols) return set_error(VIMZ_ERR_INDEX, "vimz_shape_upload: entry out of range (InvalidIndex)");
@@ -392,6 +420,10 @@ static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row
     ccol[p] = col[k];
     cval[p] = val[k];
   }
+  std::vector<uint32_t> vidx(nnz);
+  for (size_t k = 0; k < nnz; k++) vidx[k] = dict.lookup(cval[k]);
+  VIMZ_CUDA(cudaMalloc(d_vidx, std::max<size_t>(nnz * 4, 4)));
+  VIMZ_CUDA(cudaMemcpyAsync(*d_vidx, vidx.data(), nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
   VIMZ_CUDA(cudaMalloc(d_rowptr, (m + 1) * 4));
   VIMZ_CUDA(cudaMalloc(d_col, std::max<size_t>(nnz * 4, 4)));
   VIMZ_CUDA(cudaMalloc(d_val, std::max<size_t>(nnz * 32, 32)));
@@ -410,7 +442,10 @@ void vimz_shape_destroy(vimz_shape* s) {
     if (s->rowptr[k]) cudaFree(s->rowptr[k]);
     if (s->col[k]) cudaFree(s->col[k]);
     if (s->val[k]) cudaFree(s->val[k]);
+    if (s->vidx[k]) cudaFree(s->vidx[k]);
   }
+  if (s->dict) cudaFree(s->dict);
+  if (s->chunk_start) cudaFree(s->chunk_start);
   if (s->long_rows) cudaFree(s->long_rows);
   if (s->mid_rows) cudaFree(s->mid_rows);
   delete s;
@@ -437,9 +472,25 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   const vimz_fr* vals[3] = {valA, valB, valC};
   size_t nnz[3] = {nnzA, nnzB, nnzC};
   std::vector<uint32_t> row_nnz(num_cons, 0);
+  ValueDict dict;
+  {  // fixed slots: 0 = +1, 1 = -1 (Montgomery form) -- the kernels short-cut both
+    const CurveVTable* vt = curve_vtable(ctx->curve);
+    vimz_fr one, minus_one;
+    memcpy(&one, vt->scalar_one_mont, 32);
+    unsigned __int128 borrow = 0;
+    const uint64_t* q64 = reinterpret_cast<const uint64_t*>(vt->scalar_modulus);
+    for (int i = 0; i < 4; i++) {  // q - one
+      unsigned __int128 d = (unsigned __int128)q64[i] - one.l[i] - (uint64_t)borrow;
+      minus_one.l[i] = (uint64_t)d;
+      borrow = (d >> 64) & 1;
+    }
+    dict.lookup(one);
+    dict.lookup(minus_one);
+  }
   for (int k = 0; k < 3; k++) {
     s->nnz[k] = nnz[k];
-    int rc = coo_to_csr(ctx, num_cons, ncols, rows[k], cols[k], vals[k], nnz[k], &s->rowptr[k], &s->col[k], &s->val[k], row_nnz);
+    int rc = coo_to_csr(ctx, num_cons, ncols, rows[k], cols[k], vals[k], nnz[k], &s->rowptr[k], &s->col[k], &s->val[k], row_nnz, dict,
+                        &s->vidx[k]);
     if (rc != VIMZ_OK) {
       vimz_shape_destroy(s);
       return rc;
@@ -462,6 +513,30 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
     e = cudaMalloc(&s->mid_rows, s->n_mid * 4);
     if (e == cudaSuccess) e = cudaMemcpy(s->mid_rows, mid_rows.data(), s->n_mid * 4, cudaMemcpyHostToDevice);
   }
+  // streamed cross term: consecutive rows are grouped into chunks of <= CROSS_CHUNK_NNZ non-zeros (A+B+C) and
+  // <= CROSS_CHUNK_ROWS rows; a row above CROSS_ROW_MAX non-zeros is a chunk of its own, handled by one warp
+  std::vector<uint32_t> chunk_start;
+  {
+    size_t i = 0;
+    while (i < num_cons) {
+      if (row_nnz[i] > CROSS_ROW_MAX) {
+        chunk_start.push_back((uint32_t)i | 0x80000000u);
+        i++;
+        continue;
+      }
+      chunk_start.push_back((uint32_t)i);
+      size_t acc = 0, j = i;
+      while (j < num_cons && j - i < CROSS_CHUNK_ROWS && row_nnz[j] <= CROSS_ROW_MAX && acc + row_nnz[j] <= CROSS_CHUNK_NNZ) acc += row_nnz[j++];
+      i = j;
+    }
+    s->n_chunks = chunk_start.size();
+    chunk_start.push_back((uint32_t)num_cons);
+  }
+  s->n_dict = dict.values.size();
+  if (e == cudaSuccess) e = cudaMalloc(&s->chunk_start, chunk_start.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(s->chunk_start, chunk_start.data(), chunk_start.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&s->dict, s->n_dict * 32);
+  if (e == cudaSuccess) e = cudaMemcpy(s->dict, dict.values.data(), s->n_dict * 32, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     vimz_shape_destroy(s);
     return set_error(VIMZ_ERR_CUDA, std::string("vimz_shape_upload: ") + cudaGetErrorString(e));

@@ -114,6 +114,7 @@ struct vimz_ctx {
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
+  bool opt_cross_stream = true; // cross term: chunked CSR streaming through shared memory (false: row-class kernel)
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
@@ -162,6 +163,12 @@ struct vimz_shape {
   uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};  // [m+1]
   uint32_t* col[3] = {nullptr, nullptr, nullptr};     // [nnz]
   void* val[3] = {nullptr, nullptr, nullptr};         // [nnz] Montgomery scalars
+  // streamed cross term: coefficient dictionary + per-non-zero index, rows cut into chunks of bounded non-zeros
+  uint32_t* vidx[3] = {nullptr, nullptr, nullptr};    // [nnz] index into dict (0: +1, 1: -1, no multiplication)
+  void* dict = nullptr;                               // [n_dict] distinct Montgomery coefficients of A, B, C
+  size_t n_dict = 0;
+  uint32_t* chunk_start = nullptr;                    // [n_chunks + 1] first row of every chunk; bit 31: a single long row
+  size_t n_chunks = 0;
   uint32_t* long_rows = nullptr;                      // rows with > R1CS_LONG_ROW non-zeros over A+B+C (warp each)
   size_t n_long = 0;
   uint32_t* mid_rows = nullptr;                       // rows with R1CS_SHORT_ROW+1 .. R1CS_LONG_ROW non-zeros (8 lanes each)

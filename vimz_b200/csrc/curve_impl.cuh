@@ -223,6 +223,22 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
   ca.A = csr_view(s, 0); ca.B = csr_view(s, 1); ca.Cm = csr_view(s, 2);
   ca.m = (uint32_t)s->m; ca.n = (uint32_t)s->n;
   ca.W1 = d_W1; ca.tail1 = d_tail1; ca.W2 = d_W2; ca.tail2 = d_tail2; ca.T = d_T; ca.dc = dc;
+  if (ctx->opt_cross_stream && s->n_chunks) {
+    static bool smem_set = false;  // per template instance
+    constexpr size_t SMEM = (size_t)CROSS_CHUNK_NNZ * 64;
+    if (!smem_set) {
+      VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      smem_set = true;
+    }
+    CrossStreamArgs sa;
+    sa.a = ca;
+    sa.vidx[0] = s->vidx[0]; sa.vidx[1] = s->vidx[1]; sa.vidx[2] = s->vidx[2];
+    sa.dict = s->dict;
+    sa.chunk_start = s->chunk_start;
+    k_cross_term_stream<typename C::Fs><<<(uint32_t)s->n_chunks, 256, SMEM, ctx->stream>>>(sa);
+    VIMZ_LAUNCH_CHECK(ctx);
+    return VIMZ_OK;
+  }
   const uint32_t nb_long = ceil_div(s->n_long * 32, 128), nb_mid = ceil_div(s->n_mid * 8, 128), nb_short = ceil_div(s->m, 128);
   k_cross_term<typename C::Fs><<<nb_long + nb_mid + nb_short, 128, 0, ctx->stream>>>(ca, s->long_rows, (uint32_t)s->n_long, nb_long,
                                                                                      s->mid_rows, (uint32_t)s->n_mid, nb_mid);

@@ -69,9 +69,16 @@ struct QPoint {
   }
 };
 
+// The kernels that use these operations run a few warps through long dependent chains: their time is set by
+// latency, and with every operation inlined (~15 KB of SASS per addition, 100-180 KB per kernel) the top stall was
+// instruction fetch (`no_instruction`).  q_add / q_dbl are therefore OUT OF LINE: one copy per kernel that stays
+// in the instruction caches (L0 ~6 KB, L1.5 32 KB) across the iterations of a chain.
+template <class C>
+__device__ __noinline__ QPoint<C> q_dbl(QPoint<C> p);
+
 // 2 * P   (dbl-2008-s-1, a = 0): 3 product rounds
 template <class C>
-VIMZ_DI QPoint<C> q_dbl(const QPoint<C>& p) {
+VIMZ_DI QPoint<C> q_dbl_inl(const QPoint<C>& p) {
   using F = Fp<typename C::Fb>;
   const int role = threadIdx.x & 3;
   const bool ident = p.is_identity();  // prime-order curves: no finite point with y = 0
@@ -102,9 +109,12 @@ VIMZ_DI QPoint<C> q_dbl(const QPoint<C>& p) {
   return out;
 }
 
+template <class C>
+__device__ __noinline__ QPoint<C> q_dbl(QPoint<C> p) { return q_dbl_inl<C>(p); }
+
 // P1 + P2   (add-2008-s): 4 product rounds; all exceptional cases exact
 template <class C>
-VIMZ_DI QPoint<C> q_add(const QPoint<C>& p1, const QPoint<C>& p2) {
+VIMZ_DI QPoint<C> q_add_inl(const QPoint<C>& p1, const QPoint<C>& p2) {
   using F = Fp<typename C::Fb>;
   const int role = threadIdx.x & 3;
   const bool id1 = p1.is_identity(), id2 = p2.is_identity();
@@ -146,6 +156,8 @@ VIMZ_DI QPoint<C> q_add(const QPoint<C>& p1, const QPoint<C>& p2) {
   else if (id1) out = p2;
   return out;
 }
+template <class C>
+__device__ __noinline__ QPoint<C> q_add(QPoint<C> p1, QPoint<C> p2) { return q_add_inl<C>(p1, p2); }
 
 // acc (quad) -> Jacobian {X*ZZ^4, Y*ZZZ^4, ZZ*ZZZ}; identity -> (0, R, 0).  Writes 96 bytes from the quad.
 template <class C>

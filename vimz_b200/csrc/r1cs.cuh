@@ -71,7 +71,7 @@ VIMZ_DI Fp<F> coeff_mul(const Fp<F>& v, const Fp<F>& z) {
   Fp<F> m1 = fp_neg(Fp<F>::one());
   is_m1 = (v == m1);
   if (is_m1) return fp_neg(z);
-  return fp_mul(v, z);
+  return fp_mul_noinline<F>(v, z);
 }
 
 template <class F>
@@ -91,14 +91,25 @@ VIMZ_DI void row_dot2(const CsrView& M, uint32_t beg, uint32_t end, uint32_t str
 template <class F>
 VIMZ_DI Fp<F> cross_term_row(const Fp<F>& a1, const Fp<F>& a2, const Fp<F>& b1, const Fp<F>& b2, const Fp<F>& c1, const Fp<F>& c2,
                              const Fp<F>& u1) {
-  Fp<F> t = fp_add(fp_mul(a1, b2), fp_mul(a2, b1));
-  t = fp_sub(t, fp_mul(u1, c2));
+  Fp<F> t = fp_add(fp_mul_noinline<F>(a1, b2), fp_mul_noinline<F>(a2, b1));
+  t = fp_sub(t, fp_mul_noinline<F>(u1, c2));
   return fp_sub(t, c1);
+}
+
+// T[row] = cross term of the six row products; optional digit histogram for the commit(T) that follows.
+// Out of line (with the field product): the cross-term kernels are latency-bound and were stalling on
+// instruction fetch with ~185 KB of inlined code; one shared copy keeps them inside the instruction caches.
+template <class F>
+__device__ __noinline__ void cross_term_finish(Fp<F> a1, Fp<F> a2, Fp<F> b1, Fp<F> b2, Fp<F> c1, Fp<F> c2, Fp<F> u1, void* T, uint32_t row,
+                                               DigitCount dc) {
+  Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, u1);
+  t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
+  if (dc.counts) count_scalar_digits(t, dc.c, dc.nwin, dc.counts);
 }
 
 // sum over the GROUP lanes of a row group (GROUP = 8 or 32, groups are aligned inside the warp)
 template <class F, int GROUP>
-VIMZ_DI Fp<F> group_sum_fp(Fp<F> v) {
+__device__ __noinline__ Fp<F> group_sum_fp(Fp<F> v) {
 #pragma unroll
   for (int o = GROUP / 2; o > 0; o >>= 1) {
     Fp<F> other;
@@ -128,18 +139,14 @@ VIMZ_DI void cross_term_short(const CrossArgs& a, uint32_t row) {
   row_dot2<F>(a.A, ab, ae, 1, a.n, a.W1, a.tail1, a.W2, a.tail2, a1, a2);
   row_dot2<F>(a.B, bb, be, 1, a.n, a.W1, a.tail1, a.W2, a.tail2, b1, b2);
   row_dot2<F>(a.Cm, cb, ce, 1, a.n, a.W1, a.tail1, a.W2, a.tail2, c1, c2);
-  Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1));
-  t.store(reinterpret_cast<char*>(a.T) + (size_t)row * 32);
-  if (a.dc.counts) count_scalar_digits(t, a.dc.c, a.dc.nwin, a.dc.counts);
+  cross_term_finish<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1), a.T, row, a.dc);
 }
 
-// GROUP lanes per listed row (8 for Poseidon-like rows, 32 for the 240-term Num2Bits packing rows):
-// lanes stride the non-zeros, partial dot products are folded with shuffles.  g = group index (warp-collective).
+// GROUP lanes per row (8 for Poseidon-like rows, 32 for the 240-term Num2Bits packing rows):
+// lanes stride the non-zeros, partial dot products are folded with shuffles (group-collective: invalid groups join).
 template <class F, int GROUP>
-VIMZ_DI void cross_term_grouped(const CrossArgs& a, const uint32_t* __restrict__ rows, uint32_t n_rows, uint32_t g) {
+VIMZ_DI void cross_term_grouped_row(const CrossArgs& a, uint32_t row, bool valid) {
   const uint32_t lane = threadIdx.x % GROUP;
-  const bool valid = g < n_rows;  // whole groups are valid or not; invalid groups still join the shuffles
-  const uint32_t row = rows[valid ? g : 0];
   Fp<F> a1, a2, b1, b2, c1, c2;
   const uint32_t none = 0;
   row_dot2<F>(a.A, valid ? a.A.rowptr[row] + lane : none, valid ? a.A.rowptr[row + 1] : none, GROUP, a.n, a.W1, a.tail1, a.W2, a.tail2, a1, a2);
@@ -149,10 +156,13 @@ VIMZ_DI void cross_term_grouped(const CrossArgs& a, const uint32_t* __restrict__
   b1 = group_sum_fp<F, GROUP>(b1); b2 = group_sum_fp<F, GROUP>(b2);
   c1 = group_sum_fp<F, GROUP>(c1); c2 = group_sum_fp<F, GROUP>(c2);
   if (lane == 0 && valid) {
-    Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1));
-    t.store(reinterpret_cast<char*>(a.T) + (size_t)row * 32);
-    if (a.dc.counts) count_scalar_digits(t, a.dc.c, a.dc.nwin, a.dc.counts);
+    cross_term_finish<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1), a.T, row, a.dc);
   }
+}
+template <class F, int GROUP>
+VIMZ_DI void cross_term_grouped(const CrossArgs& a, const uint32_t* __restrict__ rows, uint32_t n_rows, uint32_t g) {
+  const bool valid = g < n_rows;  // whole groups are valid or not
+  cross_term_grouped_row<F, GROUP>(a, rows[valid ? g : 0], valid);
 }
 
 // T[i] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1   (u2 = 1; u1 = tail1[0]) for ALL rows in one launch of 128-thread
@@ -169,6 +179,123 @@ __global__ void __launch_bounds__(128) k_cross_term(CrossArgs a, const uint32_t*
     cross_term_grouped<F, 8>(a, mid_rows, n_mid, ((blockIdx.x - nb_long) * blockDim.x + threadIdx.x) / 8);
   } else {
     cross_term_short<F>(a, (blockIdx.x - nb_long - nb_mid) * blockDim.x + threadIdx.x);
+  }
+}
+
+// ---- streamed cross term (default) -------------------------------------------------------------------------
+// The row-class kernel above is bound by dependent loads (rowptr -> col/val -> z) of threads that own whole rows.
+// Here a 256-thread block owns a CHUNK of consecutive rows holding <= CROSS_CHUNK_NNZ non-zeros over A+B+C:
+//   phase 1: the threads stride the chunk's non-zeros of A, then B, then C -- coalesced (col, value-index) reads,
+//            independent z1/z2 gathers (L2), products v*z1, v*z2 written to shared memory;
+//   phase 2: one thread per row sums its products out of shared memory and forms T (rows above CROSS_ROW_COOP
+//            non-zeros are summed by a warp with shuffles instead).
+// Coefficients come from the shape's value dictionary (4 B per non-zero instead of 32 B; +1 / -1 need no product).
+constexpr uint32_t CROSS_CHUNK_NNZ = 1024;  // products per chunk: 64 KB of shared memory
+constexpr uint32_t CROSS_CHUNK_ROWS = 256;  // = block size
+constexpr uint32_t CROSS_ROW_MAX = 512;     // longer rows are chunks of their own (a warp walks them in global memory)
+constexpr uint32_t CROSS_ROW_COOP = 32;     // rows above this are summed by a warp in phase 2
+
+struct CrossStreamArgs {
+  CrossArgs a;
+  const uint32_t* vidx[3];
+  const void* dict;
+  const uint32_t* chunk_start;
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
+  extern __shared__ __align__(32) unsigned char cross_smem[];
+  char* P1 = reinterpret_cast<char*>(cross_smem);
+  char* P2 = P1 + (size_t)CROSS_CHUNK_NNZ * 32;
+  __shared__ uint32_t big_rows[32];
+  __shared__ uint32_t nbig;
+  const CrossArgs& a = s.a;
+  const uint32_t cs = s.chunk_start[blockIdx.x], ce = s.chunk_start[blockIdx.x + 1];
+  const uint32_t r0 = cs & 0x7fffffffu, r1 = ce & 0x7fffffffu;
+  if (cs >> 31) {  // a single row longer than CROSS_ROW_MAX
+    if (threadIdx.x < 32) cross_term_grouped_row<F, 32>(a, r0, true);
+    return;
+  }
+  if (threadIdx.x == 0) nbig = 0;
+  const uint32_t begA = a.A.rowptr[r0], begB = a.B.rowptr[r0], begC = a.Cm.rowptr[r0];
+  const uint32_t nA = a.A.rowptr[r1] - begA, nB = a.B.rowptr[r1] - begB, nC = a.Cm.rowptr[r1] - begC;
+  const uint32_t total = nA + nB + nC;
+  // this thread's row bounds for phase 2, fetched now so their latency hides behind phase 1
+  const uint32_t row = r0 + threadIdx.x;
+  const bool have_row = row < r1;
+  uint32_t ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0, rc0 = 0, rc1 = 0;
+  if (have_row) {
+    ra0 = a.A.rowptr[row]; ra1 = a.A.rowptr[row + 1];
+    rb0 = a.B.rowptr[row]; rb1 = a.B.rowptr[row + 1];
+    rc0 = a.Cm.rowptr[row]; rc1 = a.Cm.rowptr[row + 1];
+  }
+  const Fp<F> u1 = Fp<F>::load(a.tail1);
+  auto entry = [&](uint32_t k, uint32_t& col, uint32_t& vi) {
+    if (k < nA) { col = __ldg(a.A.col + begA + k); vi = __ldg(s.vidx[0] + begA + k); }
+    else if (k < nA + nB) { col = __ldg(a.B.col + begB + (k - nA)); vi = __ldg(s.vidx[1] + begB + (k - nA)); }
+    else { col = __ldg(a.Cm.col + begC + (k - nA - nB)); vi = __ldg(s.vidx[2] + begC + (k - nA - nB)); }
+  };
+  auto product = [&](uint32_t k, uint32_t vi, Fp<F> z1, Fp<F> z2) {
+    if (vi >= 2) {
+      Fp<F> v = Fp<F>::load_nc(reinterpret_cast<const char*>(s.dict) + (size_t)vi * 32);
+      z1 = fp_mul_noinline<F>(v, z1);
+      z2 = fp_mul_noinline<F>(v, z2);
+    } else if (vi == 1) {
+      z1 = fp_neg(z1);
+      z2 = fp_neg(z2);
+    }
+    z1.store(P1 + (size_t)k * 32);
+    z2.store(P2 + (size_t)k * 32);
+  };
+  for (uint32_t k = threadIdx.x; k < total; k += 512) {  // two entries in flight per thread
+    const uint32_t k2 = k + 256;
+    const bool two = k2 < total;
+    uint32_t c0, v0, c1 = 0, v1 = 0;
+    entry(k, c0, v0);
+    if (two) entry(k2, c1, v1);
+    Fp<F> x1 = load_z<F>(a.W1, a.tail1, a.n, c0), x2 = load_z<F>(a.W2, a.tail2, a.n, c0);
+    Fp<F> y1 = Fp<F>::zero(), y2 = Fp<F>::zero();
+    if (two) { y1 = load_z<F>(a.W1, a.tail1, a.n, c1); y2 = load_z<F>(a.W2, a.tail2, a.n, c1); }
+    product(k, v0, x1, x2);
+    if (two) product(k2, v1, y1, y2);
+  }
+  __syncthreads();
+  auto sum2 = [&](uint32_t first, uint32_t count, uint32_t start, uint32_t stride, Fp<F>& d1, Fp<F>& d2) {
+    d1 = Fp<F>::zero();
+    d2 = Fp<F>::zero();
+    for (uint32_t j = start; j < count; j += stride) {
+      d1 = fp_add(d1, Fp<F>::load(P1 + (size_t)(first + j) * 32));
+      d2 = fp_add(d2, Fp<F>::load(P2 + (size_t)(first + j) * 32));
+    }
+  };
+  if (have_row) {
+    const uint32_t cnt = (ra1 - ra0) + (rb1 - rb0) + (rc1 - rc0);
+    if (cnt > CROSS_ROW_COOP) {
+      big_rows[atomicAdd(&nbig, 1u)] = threadIdx.x;  // at most CROSS_CHUNK_NNZ / (CROSS_ROW_COOP + 1) = 31 per chunk
+    } else {
+      Fp<F> a1, a2, b1, b2, c1, c2;
+      sum2(ra0 - begA, ra1 - ra0, 0, 1, a1, a2);
+      sum2(nA + (rb0 - begB), rb1 - rb0, 0, 1, b1, b2);
+      sum2(nA + nB + (rc0 - begC), rc1 - rc0, 0, 1, c1, c2);
+      cross_term_finish<F>(a1, a2, b1, b2, c1, c2, u1, a.T, row, a.dc);
+    }
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x >> 5; i < nbig; i += 8) {  // warp-uniform
+    const uint32_t br = r0 + big_rows[i];
+    const uint32_t qa0 = a.A.rowptr[br], qa1 = a.A.rowptr[br + 1], qb0 = a.B.rowptr[br], qb1 = a.B.rowptr[br + 1];
+    const uint32_t qc0 = a.Cm.rowptr[br], qc1 = a.Cm.rowptr[br + 1];
+    Fp<F> a1, a2, b1, b2, c1, c2;
+    sum2(qa0 - begA, qa1 - qa0, lane, 32, a1, a2);
+    sum2(nA + (qb0 - begB), qb1 - qb0, lane, 32, b1, b2);
+    sum2(nA + nB + (qc0 - begC), qc1 - qc0, lane, 32, c1, c2);
+    a1 = group_sum_fp<F, 32>(a1); a2 = group_sum_fp<F, 32>(a2);
+    b1 = group_sum_fp<F, 32>(b1); b2 = group_sum_fp<F, 32>(b2);
+    c1 = group_sum_fp<F, 32>(c1); c2 = group_sum_fp<F, 32>(c2);
+    if (lane == 0) {
+      cross_term_finish<F>(a1, a2, b1, b2, c1, c2, u1, a.T, br, a.dc);
+    }
   }
 }
 
