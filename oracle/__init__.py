@@ -36,6 +36,8 @@ class COracle:
         L.oracle_axpy.argtypes = [i32, sz, vp, vp, vp, vp, i32]
         L.oracle_field_op.argtypes = [i32, i32, i32, vp, vp, sz, vp]
         L.oracle_gen_bases.argtypes = [i32, vp, C.c_uint64, C.c_uint64, sz, vp]
+        L.oracle_poseidon.argtypes = [i32, i32, i32, i32, vp, vp, vp, sz]
+        self._poseidon_tables = {}
 
     @staticmethod
     def _p(a):
@@ -111,6 +113,33 @@ class COracle:
         out = np.zeros((n, 8), dtype=np.uint64)
         assert self.lib.oracle_gen_bases(curve_id, self._p(g), k0, dk, n, self._p(out)) == 0
         return out
+
+    def poseidon(self, state, curve_id=2):
+        """circomlib Poseidon permutation of one width-t state of canonical integers over the curve's scalar field
+        (default BN254 Fr); constants from oracle/poseidon.py, arithmetic in nova_cpu.c."""
+        from . import poseidon as P
+        from . import pyref
+        q = {c.curve_id: c.q for c in pyref.CURVES.values()}[curve_id]
+        t = len(state)
+        R = 1 << 256
+
+        def mont(vals):
+            out = np.zeros((len(vals), 4), dtype=np.uint64)
+            for i, v in enumerate(vals):
+                m = (v % q) * R % q
+                for k in range(4):
+                    out[i, k] = (m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+            return out
+
+        key = (curve_id, t)
+        if key not in self._poseidon_tables:
+            consts, mds = P.poseidon_params(t, q)
+            self._poseidon_tables[key] = (mont(consts), mont([x for row in mds for x in row]), pow(R, -1, q))
+        cm, mm, rinv = self._poseidon_tables[key]
+        st = mont(list(state))
+        rc = self.lib.oracle_poseidon(curve_id, t, P.N_ROUNDS_F, P.N_ROUNDS_P[t - 2], self._p(cm), self._p(mm), self._p(st), 1)
+        assert rc == 0
+        return [sum(int(st[i, k]) << (64 * k) for k in range(4)) * rinv % q for i in range(t)]
 
     def commit_T(self, curve_id, m, num_vars, num_io, A, B, Cm, W1, u1, X1, W2, X2, one_mont, nthreads=1):
         """T of R1CSShape::commit_T (the MSM is msm())."""

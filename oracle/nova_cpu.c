@@ -564,3 +564,41 @@ int oracle_gen_bases(int curve_id, const uint64_t* g_aff, uint64_t k0, uint64_t 
   free(prefix);
   return 0;
 }
+
+/* ---- circomlib Poseidon permutation over a curve's scalar field (oracle/poseidon.py is the definition-level
+ * restatement and supplies the Grain-LFSR constants; this is its fast path for the 720-row image hashes of
+ * /root/reference/marketplace/image-data/ (the .hash files).  x^5 S-box, rf full + rp partial rounds, plain form:
+ * add round constants, S-box (all cells in full rounds, cell 0 in partial rounds), multiply by the MDS matrix.
+ * consts: (rf + rp) * t, mds: t * t row-major, state: count * t in/out; all Montgomery form. */
+int oracle_poseidon(int curve_id, int t, int rf, int rp, const uint64_t* consts, const uint64_t* mds, uint64_t* state, size_t count) {
+  if (curve_id < 0 || curve_id > 3 || t < 2 || t > 17) return -2;
+  oracle_init();
+  const field_t* F = &CURVES[curve_id].fs;
+  const fe* C = (const fe*)consts;
+  const fe* M = (const fe*)mds;
+  for (size_t n = 0; n < count; n++) {
+    fe* s = (fe*)state + n * (size_t)t;
+    fe tmp[17];
+    for (int r = 0; r < rf + rp; r++) {
+      for (int i = 0; i < t; i++) f_add(F, &s[i], &s[i], &C[r * t + i]);
+      int full = (r < rf / 2) || (r >= rf / 2 + rp);
+      for (int i = 0; i < (full ? t : 1); i++) {
+        fe x2, x4;
+        f_sqr(F, &x2, &s[i]);
+        f_sqr(F, &x4, &x2);
+        f_mul(F, &s[i], &x4, &s[i]);
+      }
+      for (int i = 0; i < t; i++) {
+        fe acc = {{0, 0, 0, 0}};
+        for (int j = 0; j < t; j++) {
+          fe m;
+          f_mul(F, &m, &M[i * t + j], &s[j]);
+          f_add(F, &acc, &acc, &m);
+        }
+        tmp[i] = acc;
+      }
+      memcpy(s, tmp, (size_t)t * sizeof(fe));
+    }
+  }
+  return 0;
+}

@@ -8,22 +8,18 @@ namespace vimz {
 // ---- signed-digit recoding -------------------------------------------------------------------
 // raw scalar (canonical, NOT Montgomery) -> digits d_j in [-2^(c-1), 2^(c-1)], j < nwin.
 // f(j, magnitude, negative) is called for every non-zero digit.
+// The limbs are consumed in order through a 64-bit bit buffer, so a window costs a handful of instructions
+// (no dynamic limb indexing); the trip counts depend only on (c, nwin), i.e. they are uniform across a warp.
 template <class Fn>
 __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, int nwin, Fn f) {
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1);
+  uint64_t buf = 0;
+  int have = 0, j = 0;
   uint32_t carry = 0;
-  for (int j = 0; j < nwin; j++) {
-    int pos = j * c;
-    int limb = pos >> 5, off = pos & 31;
-    uint64_t lo = 0;
-    // dynamic limb index resolved with selects (registers cannot be indexed)
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (k == limb) lo |= (uint64_t)s[k];
-      if (k == limb + 1) lo |= (uint64_t)s[k] << 32;
-    }
-    uint32_t d = (uint32_t)((lo >> off) & mask) + carry;
+  auto emit = [&]() {
+    uint32_t d = ((uint32_t)buf & mask) + carry;
+    buf >>= c;
     carry = 0;
     bool neg = false;
     if (d > half && j != nwin - 1) {
@@ -32,16 +28,40 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, in
       carry = 1;
     }
     if (d != 0) f(j, d, neg);
+    j++;
+  };
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    buf |= (uint64_t)s[k] << have;  // have < c <= 32 here, so the 32 new bits fit
+    have += 32;
+    while (have >= c && j < nwin) {
+      emit();
+      have -= c;
+    }
   }
+  while (j < nwin) emit();  // windows reaching past bit 255: the missing bits are zero
 }
 
 
+// Warp-aggregated bucket counters.  A witness vector is ~90 % 0/1, so most lanes of a warp hit the SAME bucket
+// (digit 1 of window 0) and T's top window lands in a few dozen buckets: same-address atomics serialise in L2 and
+// made k_msm_count atomics-bound (the scatter, whose atomics return values, did not gain and keeps plain atomics).  The lanes that are converged here and target the same counter
+// are matched (MATCH.ANY); one of them adds the group's size.
+__device__ __forceinline__ void warp_count_add(uint32_t* counter) {
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(counter, (uint32_t)__popc(peers));
+}
 // histogram the bucket digits of one Montgomery-form scalar (the counting half of the counting sort)
-template <class F>
+// AGG: warp-aggregate the counter updates (pays for witness vectors; costs ~20 % on uniform digits)
+template <class F, bool AGG = false>
 __device__ __forceinline__ void count_scalar_digits(const Fp<F>& mont, int c, int nwin, uint32_t* __restrict__ counts) {
   Fp<F> s = fp_from_mont(mont);
   if (fp_gt_half(s)) s = fp_neg(s);  // s*P = (q-s)*(-P): digits of the smaller magnitude
-  for_each_digit(s.v, c, nwin, [&](int, uint32_t mag, bool) { atomicAdd(&counts[mag - 1], 1u); });
+  for_each_digit(s.v, c, nwin, [&](int, uint32_t mag, bool) {
+    if (AGG) warp_count_add(&counts[mag - 1]);
+    else atomicAdd(&counts[mag - 1], 1u);
+  });
 }
 
 }  // namespace vimz

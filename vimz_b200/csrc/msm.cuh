@@ -93,7 +93,7 @@ __global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, in
                             uint32_t* __restrict__ counts) {
   using Fs = Fp<typename C::Fs>;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    count_scalar_digits(Fs::load_nc(scalars + 8 * (size_t)i), c, nwin, counts);
+    count_scalar_digits<typename C::Fs, true>(Fs::load_nc(scalars + 8 * (size_t)i), c, nwin, counts);
   }
 }
 
@@ -119,10 +119,17 @@ __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t n, 
     // costs as few bucket insertions as a positive one instead of all windows.
     bool flip = fp_gt_half(s);
     if (flip) s = fp_neg(s);
+    // the store of one digit is issued after the NEXT digit's cursor atomic, so two atomic round trips overlap
+    uint32_t pend_pos = 0, pend_val = 0;
+    bool pend = false;
     for_each_digit(s.v, c, nwin, [&](int j, uint32_t mag, bool neg) {
       uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
-      sorted[pos] = ((uint32_t)j * table_stride + first + i) | ((neg != flip) ? 0x80000000u : 0u);
+      if (pend) sorted[pend_pos] = pend_val;
+      pend_pos = pos;
+      pend_val = ((uint32_t)j * table_stride + first + i) | ((neg != flip) ? 0x80000000u : 0u);
+      pend = true;
     });
+    if (pend) sorted[pend_pos] = pend_val;
   }
 }
 
