@@ -74,3 +74,28 @@ def test_reference_hash_fixture_reproduced(name):
     rows = [[int(h, 16) for h in r] for r in compress_by_rows(np.array(Image.open(os.path.join(REF_DATA, name + ".png"))))]
     assert len(rows) == 720 and len(rows[0]) == 128
     assert str(P.image_running_hash(rows)) == expected
+
+
+REF_PROOFS = "/root/reference/marketplace/proofs"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PROOFS), reason="reference fixtures not mounted (GPU box)")
+@pytest.mark.parametrize("name, z_len, extra", [("img1-grayscale", 2, []), ("img1-sharpness-grayscale", 2, []), ("img1-blur", 4, None),
+                                                ("img1-sharpness", 4, None), ("img2-contrast", 3, [14]), ("img2-contrast-sharpness", 4, None)])
+def test_marketplace_proof_public_io_matches_running_hashes(name, z_len, extra):
+    """The reference's marketplace proofs (calldata: selector, step count i, z_0, z_i, ...) carry the IVC public IO
+    of a 720-step HD run: z_0 = zeros (plus the transformation factor), z_i = (running hash of the source image,
+    running hash of the transformed image, ...).  Both hashes must be the values oracle/poseidon.py computes from the
+    PNGs -- i.e. the state any backend folding these step circuits must end on."""
+    fix = json.load(open(os.path.join(GOLDEN, "running_hash.json")))["final_hashes"]
+    data = open(os.path.join(REF_PROOFS, name + ".proof"), "rb").read()
+    words = [int.from_bytes(data[4 + k:4 + k + 32], "big") for k in range(0, len(data) - 4, 32)]
+    assert words[0] == 720                                   # HD: one step per image row
+    z0, zi = words[1:1 + z_len], words[1 + z_len:1 + 2 * z_len]
+    base, last = name.split("-")[0], name
+    source = "-".join(name.split("-")[:-1])                  # the image the last transformation was applied to
+    assert zi[0] == int(fix[source]) and zi[1] == int(fix[last])
+    assert z0[0] == 0 and z0[1] == 0
+    if extra is not None:
+        assert z0[2:] == extra and zi[2:] == extra           # the factor is carried unchanged
+    assert base in fix

@@ -70,6 +70,7 @@ struct MsmWorkspace {
   vimz::DevBuf offsets;    // [M+1] exclusive prefix of counts
   vimz::DevBuf cursor;     // [M]   scatter cursors
   vimz::DevBuf blocksums;  // scan scratch
+  vimz::DevBuf digits;     // [nwin][n] recoded digits (magnitude | sign<<31, 0 = none), written once per MSM
   vimz::DevBuf sorted;     // [E]   table index | sign<<31, grouped by bucket
   vimz::DevBuf cls;        // control words (giant-bucket counter)
   vimz::DevBuf biglist;    // ids of buckets cut into many segments
@@ -82,7 +83,7 @@ struct MsmWorkspace {
   vimz::DevBuf scal;       // staged scalars (host-pointer entry points)
   vimz::DevBuf result;     // Jacobian results (device)
   void release() {
-    counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release();
+    counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release(); digits.release();
     cls.release(); biglist.release(); partials.release(); buckets.release();
     chunkA.release(); chunkL.release(); bitsums.release(); scaled.release(); scal.release(); result.release();
   }

@@ -81,6 +81,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   uint32_t scan_blocks = ceil_div(M, SCAN_THREADS * SCAN_ITEMS);
   VIMZ_TRY(ws.blocksums.reserve(((size_t)scan_blocks + 2) * 4));
   VIMZ_TRY(ws.sorted.reserve(E * 4));
+  VIMZ_TRY(ws.digits.reserve(E * 4));
   const size_t ctrl_words = CTRL_GIANT_DONE + max_giants;
   VIMZ_TRY(ws.cls.reserve(ctrl_words * 4));
   VIMZ_TRY(ws.biglist.reserve(((size_t)3 * max_giants + (size_t)2 * max_chunks + (size_t)M + 4) * 4));
@@ -112,7 +113,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   {
     ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
     if (n > 0 && !counted) {
-      k_msm_count<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts);
+      k_msm_digits<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts,
+                                              ws.digits.as<uint32_t>());
       VIMZ_LAUNCH_CHECK(ctx);
     }
     if (M <= SCAN1_MAX_M) {  // every fold-step MSM: one single-block launch
@@ -127,8 +129,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
       VIMZ_LAUNCH_CHECK(ctx);
     }
     if (n > 0) {
-      k_msm_scatter<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin,
-                                                (uint32_t)ck->n, (uint32_t)first, cursor, sorted, offsets, M, nthreads, seg_min, cb);
+      k_msm_scatter<<<dim3(grid_n, nwin), 256, 0, st>>>(ws.digits.as<uint32_t>(), (uint32_t)n, nwin, (uint32_t)ck->n, (uint32_t)first, cursor, sorted,
+                                            offsets, M, nthreads, seg_min, cb);
       VIMZ_LAUNCH_CHECK(ctx);
     }
   }
@@ -209,10 +211,13 @@ template <class C>
 int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
                     const vimz_ck* fuse_ck) {
   if (s->m == 0) return VIMZ_OK;
-  DigitCount dc{nullptr, 0, 0};
-  if (fuse_ck) {  // zero lane 0's histogram, then let the cross-term kernels fill it
+  DigitCount dc{nullptr, 0, 0, nullptr, 0};
+  if (fuse_ck) {  // zero lane 0's histogram, then let the cross-term kernels fill it and the digit array
     const uint32_t M = 1u << (fuse_ck->c - 1);
     VIMZ_TRY(ctx->ws.counts.reserve((size_t)M * 4));
+    VIMZ_TRY(ctx->ws.digits.reserve(std::max<size_t>(s->m * (size_t)fuse_ck->nwin, 1) * 4));
+    dc.digits = ctx->ws.digits.as<uint32_t>();
+    dc.stride = s->m;
     VIMZ_CUDA(cudaMemsetAsync(ctx->ws.counts.ptr, 0, (size_t)M * 4, ctx->stream));
     dc.counts = ctx->ws.counts.as<uint32_t>();
     dc.c = fuse_ck->c;

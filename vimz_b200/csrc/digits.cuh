@@ -45,7 +45,7 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, in
 
 // Warp-aggregated bucket counters.  A witness vector is ~90 % 0/1, so most lanes of a warp hit the SAME bucket
 // (digit 1 of window 0) and T's top window lands in a few dozen buckets: same-address atomics serialise in L2 and
-// made k_msm_count atomics-bound (the scatter, whose atomics return values, did not gain and keeps plain atomics).  The lanes that are converged here and target the same counter
+// made the histogram atomics-bound (the scatter, whose atomics return values, did not gain and keeps plain atomics).  The lanes that are converged here and target the same counter
 // are matched (MATCH.ANY); one of them adds the group's size.
 __device__ __forceinline__ void warp_count_add(uint32_t* counter) {
   const unsigned active = __activemask();
@@ -53,15 +53,26 @@ __device__ __forceinline__ void warp_count_add(uint32_t* counter) {
   if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(counter, (uint32_t)__popc(peers));
 }
 // histogram the bucket digits of one Montgomery-form scalar (the counting half of the counting sort)
-// AGG: warp-aggregate the counter updates (pays for witness vectors; costs ~20 % on uniform digits)
+// The recoded digits of scalar i, written ONCE: digits[j * stride + i] = magnitude | sign << 31 (0 = no insertion),
+// and histogrammed into counts[magnitude - 1].  The counting sort then runs one thread per (scalar, window) entry
+// (k_msm_scatter) instead of one thread per scalar walking its windows behind a chain of atomic round trips.
+// s*P = (q-s)*(-P): scalars above (q-1)/2 are recoded by their (smaller) negative, with the point's sign flipped.
+// AGG: warp-aggregate the counter updates (pays for witness vectors; costs ~20 % on uniform digits).
 template <class F, bool AGG = false>
-__device__ __forceinline__ void count_scalar_digits(const Fp<F>& mont, int c, int nwin, uint32_t* __restrict__ counts) {
+__device__ __forceinline__ void recode_scalar(const Fp<F>& mont, int c, int nwin, uint32_t* __restrict__ counts,
+                                              uint32_t* __restrict__ digits, size_t stride, size_t i) {
   Fp<F> s = fp_from_mont(mont);
-  if (fp_gt_half(s)) s = fp_neg(s);  // s*P = (q-s)*(-P): digits of the smaller magnitude
-  for_each_digit(s.v, c, nwin, [&](int, uint32_t mag, bool) {
+  const bool flip = fp_gt_half(s);
+  if (flip) s = fp_neg(s);
+  int next = 0;  // windows below `next` are written
+  for_each_digit(s.v, c, nwin, [&](int j, uint32_t mag, bool neg) {
+    for (; next < j; next++) digits[(size_t)next * stride + i] = 0;
+    digits[(size_t)j * stride + i] = mag | ((neg != flip) ? 0x80000000u : 0u);
+    next = j + 1;
     if (AGG) warp_count_add(&counts[mag - 1]);
     else atomicAdd(&counts[mag - 1], 1u);
   });
+  for (; next < nwin; next++) digits[(size_t)next * stride + i] = 0;
 }
 
 }  // namespace vimz

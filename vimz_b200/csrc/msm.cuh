@@ -89,47 +89,38 @@ __device__ __forceinline__ void classify_bucket(bool valid, uint32_t b, uint32_t
 }
 
 template <class C>
-__global__ void k_msm_count(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
-                            uint32_t* __restrict__ counts) {
+__global__ void k_msm_digits(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
+                             uint32_t* __restrict__ counts, uint32_t* __restrict__ digits) {
   using Fs = Fp<typename C::Fs>;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    count_scalar_digits<typename C::Fs, true>(Fs::load_nc(scalars + 8 * (size_t)i), c, nwin, counts);
+    recode_scalar<typename C::Fs, true>(Fs::load_nc(scalars + 8 * (size_t)i), c, nwin, counts, digits, n, i);
   }
 }
 
-template <class C>
-__global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t n, int c, int nwin,
-                              uint32_t table_stride, uint32_t first,
-                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted,
-                              const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min, MsmCombine cb) {
-  using Fs = Fp<typename C::Fs>;
+// One thread per (window, scalar) entry of the digit array: a non-zero digit takes the next slot of its bucket.
+// sorted[] holds table indices (window row * table_stride + point) with the sign in bit 31.
+static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ digits, uint32_t n, int nwin,
+                                                            uint32_t table_stride, uint32_t first,
+                                                            uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted,
+                                                            const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads,
+                                                            uint32_t seg_min, MsmCombine cb) {
   {  // bucket classification for k_msm_combine_all rides along (it only needs the finished scan): warp-collective
     const uint32_t L = seg_len(offsets[M], nthreads, seg_min);
-    const uint32_t lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < M; base += nwarps * 32) {
+    const uint32_t lane = threadIdx.x & 31, nwarps = (gridDim.x * gridDim.y * blockDim.x) >> 5;
+    const uint32_t block = blockIdx.y * gridDim.x + blockIdx.x;
+    for (uint32_t base = ((block * blockDim.x + threadIdx.x) >> 5) * 32; base < M; base += nwarps * 32) {
       const uint32_t b = base + lane;
       const bool valid = b < M;
       classify_bucket(valid, b, valid ? offsets[b] : 0u, valid ? offsets[b + 1] : 0u, L, cb);
     }
   }
+  const uint32_t j = blockIdx.y;  // window
+  const uint32_t* row = digits + (size_t)j * n;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    Fs s = fp_from_mont(Fs::load_nc(scalars + 8 * (size_t)i));
-    // Nova's running vectors are dominated by values of small magnitude modulo q (sums of 128-bit
-    // challenges and their negatives): recode q - s with the point negated, so a "negative small" scalar
-    // costs as few bucket insertions as a positive one instead of all windows.
-    bool flip = fp_gt_half(s);
-    if (flip) s = fp_neg(s);
-    // the store of one digit is issued after the NEXT digit's cursor atomic, so two atomic round trips overlap
-    uint32_t pend_pos = 0, pend_val = 0;
-    bool pend = false;
-    for_each_digit(s.v, c, nwin, [&](int j, uint32_t mag, bool neg) {
-      uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
-      if (pend) sorted[pend_pos] = pend_val;
-      pend_pos = pos;
-      pend_val = ((uint32_t)j * table_stride + first + i) | ((neg != flip) ? 0x80000000u : 0u);
-      pend = true;
-    });
-    if (pend) sorted[pend_pos] = pend_val;
+    const uint32_t d = __ldg(row + i);
+    if (d == 0) continue;
+    const uint32_t pos = atomicAdd(&cursor[(d & 0x7fffffffu) - 1], 1u);
+    sorted[pos] = (j * table_stride + first + i) | (d & 0x80000000u);
   }
 }
 
