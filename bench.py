@@ -290,8 +290,11 @@ class GpuFold:
         return (self.sh.num_vars + self.sh.num_io + 1 + 1) * 32
 
     def cross_term_bytes(self):
+        """Algorithmic HBM bytes of one k_cross_term_stream launch: (col, value-index) per non-zero, T written, three row
+        pointer arrays, one pass over z1 and z2, and the recoded digit array of T written for the MSM that follows."""
         sh = self.sh
-        return sh.nnz * 36 + sh.num_cons * 32 + 3 * (sh.num_cons + 1) * 4 + 2 * (sh.num_vars + 1 + sh.num_io) * 32
+        return (sh.nnz * 8 + sh.num_cons * 32 + 3 * (sh.num_cons + 1) * 4 + 2 * (sh.num_vars + 1 + sh.num_io) * 32
+                + sh.num_cons * self.ck.num_windows * 4)
 
 
 def timed_region(torch, engines, fn, steps, dist):
@@ -479,9 +482,9 @@ def main_gpu(args, rank, world, local_rank):
     ct_ms, ct_calls = prof["cross_term"]
     ct_bytes = prim.cross_term_bytes()
     ct_gbs = ct_bytes * ct_calls / (ct_ms * 1e-3) / 1e9 if ct_ms > 0 else None
-    roofline_hbm = {"kernel": "k_cross_term<VestaP> (6 mat-vecs + T fused)", "bound": "hbm", "achieved": ct_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roofline_hbm = {"kernel": "k_cross_term_stream (6 mat-vecs + T + digit recoding of T fused; scalar field of %s)" % prim.cv.name, "bound": "hbm", "achieved": ct_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": (ct_gbs / peaks["hbm_gbs"]) if ct_gbs else None, "traffic": None, "peak_source": peaks["hbm_src"],
-                    "algorithmic": f"{ct_bytes} B per launch = nnz*36 + m*32 + 3(m+1)*4 + 2(n+3)*32"}
+                    "algorithmic": f"{ct_bytes} B per launch = nnz*8 (col + coefficient index) + m*32 + 3(m+1)*4 + 2(n+3)*32 + m*W*4 (digits of T)"}
     phases = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof.items() if k != "msm_entries"}
     phases_sec = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof_sec.items() if k != "msm_entries"}
 

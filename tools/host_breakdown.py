@@ -28,3 +28,5 @@ for k in range(40, 40 + N):
 prim.eng.sync(); sec.eng.sync()
 tot = time.perf_counter() - t_all
 print({k: round(v / N * 1e6, 1) for k, v in acc.items()}, "us per step; total", round(tot / N * 1e6, 1), "us/step")
+print("primary lanes (0 = commit(T), 1 = commit(W2)):", prim.eng.lane_stats(), "window", prim.ck.window_bits)
+print("secondary lanes:", sec.eng.lane_stats(), "window", sec.ck.window_bits)

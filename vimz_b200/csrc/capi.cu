@@ -235,6 +235,26 @@ int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* call
     if (calls) *calls = p.msm_entries;
     rc = VIMZ_OK;
   }
+  // statistics of the last MSM of a lane: "lane0_entries" (bucket insertions), "lane0_nmid" / "lane0_ngiant" /
+  // "lane0_nchunk" (buckets / chunks handled by the warp and block roles of k_msm_combine_all); same for lane1
+  if (strncmp(name, "lane", 4) == 0 && (name[4] == '0' || name[4] == '1') && name[5] == '_') {
+    MsmWorkspace& ws = name[4] == '0' ? ctx->ws : ctx->ws_aux;
+    const char* what = name + 6;
+    uint32_t v = 0;
+    const uint32_t* src = nullptr;
+    if (ws.last_M && ws.cls.ptr && ws.offsets.ptr) {
+      if (strcmp(what, "entries") == 0) src = ws.offsets.as<uint32_t>() + ws.last_M;
+      else if (strcmp(what, "nmid") == 0) src = ws.cls.as<uint32_t>() + CTRL_NMID;
+      else if (strcmp(what, "ngiant") == 0) src = ws.cls.as<uint32_t>() + CTRL_NGIANT;
+      else if (strcmp(what, "nchunk") == 0) src = ws.cls.as<uint32_t>() + CTRL_NCHUNK;
+    }
+    if (src) {
+      VIMZ_CUDA(cudaMemcpy(&v, src, 4, cudaMemcpyDeviceToHost));
+      if (ms) *ms = 0;
+      if (calls) *calls = v;
+      rc = VIMZ_OK;
+    }
+  }
   for (int k = 0; k < PROF_COUNT && rc != VIMZ_OK; k++)
     if (strcmp(name, PROF_NAMES[k]) == 0) {
       if (ms) *ms = p.ms[k];

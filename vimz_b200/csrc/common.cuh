@@ -82,6 +82,7 @@ struct MsmWorkspace {
   vimz::DevBuf scaled;     // [nb+1] XYZZ
   vimz::DevBuf scal;       // staged scalars (host-pointer entry points)
   vimz::DevBuf result;     // Jacobian results (device)
+  uint32_t last_M = 0;     // buckets of the last MSM run on this workspace (statistics: vimz_ctx_profile "laneK_*")
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release(); digits.release();
     cls.release(); biglist.release(); partials.release(); buckets.release();

@@ -7,6 +7,10 @@
 #include "msm.cuh"
 #include "r1cs.cuh"
 
+#ifndef VIMZ_BIG_BLOCKS_PER_SM
+#define VIMZ_BIG_BLOCKS_PER_SM 1  // blocks of the giant-bucket role of k_msm_combine_all per SM
+#endif
+
 namespace vimz {
 
 struct CurveVTable {
@@ -106,6 +110,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   cb.max_giants = max_giants;
   cb.max_chunks = max_chunks;
 
+  ws.last_M = M;
   if (!counted) VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
   VIMZ_CUDA(cudaMemsetAsync(cb.ctrl, 0, ctrl_words * 4, st));
 
@@ -149,7 +154,8 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
     }
     VIMZ_LAUNCH_CHECK(ctx);
     // pieces of cut buckets: giants (blocks per chunk + last-arrival fold), mids (a warp each), the rest (a quad each)
-    const uint32_t nb_big = (uint32_t)ctx->sm_count, nb_mid = (uint32_t)ctx->sm_count * 4, nb_small = ceil_div((size_t)M * 4, 128);
+    const uint32_t nb_big = (uint32_t)ctx->sm_count * VIMZ_BIG_BLOCKS_PER_SM, nb_mid = (uint32_t)ctx->sm_count * 4,
+                   nb_small = ceil_div((size_t)M * 4, 128);
     k_msm_combine_all<C><<<nb_big + nb_mid + nb_small, 128, 0, st>>>(offsets, M, nthreads, seg_min, nb_big, nb_mid, ws.partials.ptr,
                                                                      ws.buckets.ptr, cb);
     VIMZ_LAUNCH_CHECK(ctx);

@@ -68,6 +68,17 @@ class Engine:
             out[name] = (ms.value, calls.value)
         return out
 
+    def lane_stats(self) -> dict:
+        """Statistics of the last MSM run on each lane: bucket insertions and how many cut buckets went to the warp
+        (mid) and block (giant, in chunks) roles of the combine kernel."""
+        out = {}
+        for lane in (0, 1):
+            for what in ("entries", "nmid", "ngiant", "nchunk"):
+                calls = C.c_uint64(0)
+                rc = lib.vimz_ctx_profile(self._h, f"lane{lane}_{what}".encode(), None, C.byref(calls), 0)
+                out[f"lane{lane}_{what}"] = int(calls.value) if rc == 0 else None
+        return out
+
     @property
     def stream(self) -> int:
         return int(lib.vimz_ctx_stream(self._h) or 0)
