@@ -297,6 +297,85 @@ class GpuFold:
                 + sh.num_cons * self.ck.num_windows * 4)
 
 
+class GpuFoldSharded:
+    """ONE transformation folded by all ranks together (strong scaling): the primary curve's
+    constraint rows, E / T and both commitment-key ranges are split across the ranks (vimz_b200.sharding.FoldShard);
+    the step's only collective is the NCCL all-gather of the two partial commitments.  Every rank builds the same
+    problem (same seed) and keeps W replicated."""
+
+    def __init__(self, curve_name, circuit, seed, device, torch, dist, rank, world):
+        import vimz_b200
+        from vimz_b200 import CommitmentKey
+        from vimz_b200.sharding import FoldShard, ShardedFoldAccumulator
+        self.torch, self.dist, self.rank = torch, dist, rank
+        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.eng = eng = vimz_b200.Engine(curve_name, device)
+        self.dev = f"cuda:{device}"
+        sh = self.sh
+
+        def make_ck(first, count):
+            d = torch.empty(max(count, 1) * 8, dtype=torch.int64, device=self.dev)
+            vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, K0 + first * DK, DK, count, d.data_ptr()))
+            return CommitmentKey.from_device(eng, d.data_ptr(), count)
+
+        self.shard = FoldShard(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, make_ck, rank, world)
+        self.acc = ShardedFoldAccumulator(dist, self.shard, eng.point_sum, device=self.dev)
+        self.dev_W = [torch.from_numpy(w.view(np.int64)).to(self.dev) for w, _ in self.wits]
+        self.pin_W = [torch.from_numpy(w.view(np.int64).copy()).pin_memory() for w, _ in self.wits] if rank == 0 else None
+        self.stage = torch.empty_like(self.dev_W[0])
+        self.q = self.cv.scalar_modulus
+
+    def step(self, k: int, resident: bool):
+        from vimz_b200.field import ints_to_mont
+        i = k % NUM_WITNESSES
+        X2 = self.wits[i][1]
+        if resident:
+            cw, ct = self.acc.step_begin_dev(self.dev_W[i].data_ptr(), X2)
+        else:  # the fresh witness exists on rank 0's host only: H2D there, NCCL broadcast to the other ranks
+            if self.rank == 0:
+                self.stage.copy_(self.pin_W[i], non_blocking=True)
+            self.dist.broadcast(self.stage, src=0)
+            self.torch.cuda.current_stream().synchronize()
+            cw, ct = self.acc.step_begin_dev(self.stage.data_ptr(), X2)
+        r = ints_to_mont([challenge_from(ct.tobytes(), k)], self.q)
+        self.acc.step_end(r)
+        return ct
+
+
+def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup):
+    """Strong-scaling leg of an N > 1 run: the same grayscale (or --circuit) proof folded by all ranks together."""
+    prim = GpuFoldSharded(CYCLES[args.cycle][0], args.circuit, SEED, local_rank, torch, dist, rank, world)
+    sec = GpuFold(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch)   # 10.5k rows: replicated, not sharded
+    engines = [prim.eng, sec.eng]
+    last = {}
+
+    def step_resident(k):
+        sec.step(k, True); last["ct"] = prim.step(k, True)
+
+    def step_e2e(k):
+        sec.step(k, False); last["ct"] = prim.step(k, False)
+
+    for k in range(PREFOLD + warmup):
+        step_resident(k)
+    for k in range(2):
+        step_e2e(k)
+    ms, _ = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + k), steps, dist)
+    ms_e2e, _ = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
+    # every rank must have derived the same transcript: compare the last comm_T across ranks
+    t = torch.from_numpy(last["ct"].view(np.int64).copy()).to(f"cuda:{local_rank}")
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    same = all(bool((p == parts[0]).all()) for p in parts)
+    res = {"steps_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_steps_per_s": steps / (ms_e2e * 1e-3),
+           "e2e_ms_per_step": ms_e2e / steps, "scaling": "strong", "ranks_agree_on_comm_T": same,
+           "rows_per_rank": prim.shard.m_local, "vars_per_rank": prim.shard.var_count,
+           "exchange": "NCCL all-gather of 2 partial commitments (192 B per rank) per step; e2e adds the NCCL broadcast of W2 "
+                       f"({prim.sh.num_vars * 32} B) from rank 0",
+           "parallelism": f"primary rows / E / T / ck sharded x{world} by constraint-row range, W replicated; secondary replicated"}
+    prim.shard.close()
+    return res
+
+
 def timed_region(torch, engines, fn, steps, dist):
     """barrier + sync; CUDA events on the primary context's stream around `steps` calls of fn; max over ranks."""
     stream = torch.cuda.ExternalStream(engines[0].stream)
@@ -493,6 +572,10 @@ def main_gpu(args, rank, world, local_rank):
     for lg in args.msm_log2:
         msm.append(msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks))
 
+    sharded = None
+    if world > 1 and not args.no_sharded_step:
+        sharded = sharded_step_bench(args, torch, dist, rank, world, local_rank, min(steps, 100), warmup)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -514,7 +597,7 @@ def main_gpu(args, rank, world, local_rank):
                 "clocks": clocks, "clock_verdict": "rejected: " + ",".join(bad) if bad else "ok",
                 "phases_primary": phases, "phases_secondary": phases_sec,
                 "wall_ms_per_step": wall * 1e3 / steps, "profiled_pass_ms_per_step": ms_prof / steps,
-                "msm": msm, "published_reference": "README-derived >= 2.99 steps/s end-to-end on a Ryzen 9 (BASELINE.md section 1), other hardware"}
+                "msm": msm, "sharded_step": sharded, "published_reference": "README-derived >= 2.99 steps/s end-to-end on a Ryzen 9 (BASELINE.md section 1), other hardware"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -529,6 +612,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[20])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-step", action="store_true", help="N > 1: skip the strong-scaling leg (one proof folded by all ranks)")
     ap.add_argument("--msm-only", action="store_true", help="skip the fold-step measurement (window sweeps)")
     ap.add_argument("--circuit", default="grayscale", choices=["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash"],
                     help="step circuit whose published size the primary shape takes (BASELINE metric: grayscale; the others are the "

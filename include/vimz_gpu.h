@@ -139,6 +139,15 @@ int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r,
  * vimz_acc_init starts from the default (all-zero, u = 0) relaxed instance like
  * RelaxedR1CSWitness::default / RelaxedR1CSInstance::default; vimz_acc_load starts from given values. */
 int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_acc** out);
+/* Row-range shard of one fold across GPUs: this rank's accumulator holds the constraint
+ * rows [row_first, row_first + m_local) of A, B, C (`s_rows`: num_cons = m_local, same column space), the matching
+ * slice of E / T, and commits with two resident key shards: ck_rows = ck[row_first ..) for T / E and
+ * ck_vars = ck[var_first .. var_first + var_count) for its share of commit(W2).  W stays replicated (every rank
+ * needs the whole z).  step_begin returns this rank's PARTIAL (comm_W2, comm_T); the caller all-gathers and adds
+ * them (vimz_point_sum) before the RO; the running commitments kept here are partial sums as well (the fold
+ * comm + r*comm' is linear), so vimz_acc_download returns shard values to be added across ranks. */
+int vimz_acc_init_sharded(vimz_ctx* ctx, const vimz_shape* s_rows, const vimz_ck* ck_rows, const vimz_ck* ck_vars,
+                          size_t var_first, size_t var_count, vimz_acc** out);
 int vimz_acc_load(vimz_acc* acc, const vimz_fr* W, const vimz_fr* E, const vimz_fr* u, const vimz_fr* X,
                   const vimz_point* comm_W, const vimz_point* comm_E);
 int vimz_acc_step_begin(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);

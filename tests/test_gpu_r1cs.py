@@ -365,3 +365,58 @@ def test_is_sat_and_is_sat_relaxed(engines):
     with pytest.raises(vimz_b200.InvalidWitnessLength):
         is_sat(shape, ck, U2, R1CSWitness(W2.W[:-1]))
     acc.close(); shape.close(); ck.close()
+
+
+@pytest.mark.parametrize("name,world", [("pallas", 3), ("bn254", 2)])
+def test_row_sharded_fold_matches_unsharded_chain(name, world, engines, coracle):
+    """the fold sharded by constraint-row range.  `world` FoldShards (here all on cuda:0, one per would-be
+    rank) step through the same chain; the sums of their partial commitments, the concatenation of their E / T rows
+    and the replicated W equal the CPU chain bit for bit at every step."""
+    from vimz_b200.sharding import FoldShard
+    eng, c = engines[name], P.CURVES[name]
+    q = c.q
+    sh = S.synthetic_shape(CURVES[c.name], "grayscale", seed=44, scale=0.012)
+    nck = max(sh.num_cons, sh.num_vars)
+    bases, _ = make_bases(c, nck, seed=44)
+    Bm = affine_to_mont(bases, c.p)
+    rng = random.Random(8)
+    wit = []
+    for k in range(3):
+        Wi, Xi = S.synthetic_witness(sh, 300 + k)
+        wit.append((ints_to_mont(Wi, q), ints_to_mont(Xi, q)))
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(3)]
+    ref = _oracle_fold_chain(coracle, c, sh, Bm, wit, chal)
+
+    def make_ck(first, count):
+        return CommitmentKey.from_bases(eng, Bm[first:first + count])
+
+    shards = [FoldShard(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, make_ck, r, world) for r in range(world)]
+    assert sum(s.m_local for s in shards) == sh.num_cons and sum(s.var_count for s in shards) == sh.num_vars
+    for k in range(3):
+        parts = [s.step_begin(*wit[k]) for s in shards]
+        comm_W2 = eng.point_sum(np.stack([p[0] for p in parts]))
+        comm_T = eng.point_sum(np.stack([p[1] for p in parts]))
+        assert eng.to_affine_ints(comm_W2) == _affine(coracle, c, ref[k]["comm_W2"])
+        assert eng.to_affine_ints(comm_T) == _affine(coracle, c, ref[k]["comm_T"])
+        assert np.array_equal(np.concatenate([s.last_T() for s in shards]), ref[k]["T"])
+        for s in shards:
+            s.step_end(chal[k])
+    outs = [s.download() for s in shards]
+    last = ref[-1]
+    for U, W in outs:
+        assert np.array_equal(W.W, last["W"]) and np.array_equal(U.u, last["u"]) and np.array_equal(U.X, last["X"])
+    assert np.array_equal(np.concatenate([W.E for _, W in outs]), last["E"])
+    assert eng.to_affine_ints(eng.point_sum(np.stack([U.comm_W for U, _ in outs]))) == _affine(coracle, c, last["cW"])
+    assert eng.to_affine_ints(eng.point_sum(np.stack([U.comm_E for U, _ in outs]))) == _affine(coracle, c, last["cE"])
+    for s in shards:
+        s.close()
+    # range errors of vimz_acc_init_sharded
+    import ctypes as C
+    shape = R1CSShape(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
+    small = CommitmentKey.from_bases(eng, Bm[:10])
+    h = C.c_void_p()
+    rc = vimz_b200.lib.vimz_acc_init_sharded(eng._h, shape._h, small._h, small._h, 0, 10, C.byref(h))
+    assert rc == vimz_b200._lib.VIMZ_ERR_LENGTH          # ck_rows shorter than the rows
+    rc = vimz_b200.lib.vimz_acc_init_sharded(eng._h, shape._h, small._h, small._h, sh.num_vars - 5, 10, C.byref(h))
+    assert rc == vimz_b200._lib.VIMZ_ERR_LENGTH          # variable range leaves the witness
+    shape.close(); small.close()

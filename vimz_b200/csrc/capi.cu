@@ -656,15 +656,16 @@ void vimz_acc_destroy(vimz_acc* a) {
   delete a;
 }
 
-int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_acc** out) {
-  CHECK_ARG(ctx && s && ck && out, "vimz_acc_init: null argument");
-  CHECK_ARG(s->ctx == ctx && ck->ctx == ctx, "vimz_acc_init: shape / key belong to another context");
-  if (ck->n < s->m || ck->n < s->n) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_init: commitment key shorter than the shape");
+static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, const vimz_ck* ck_w, size_t w_first, size_t w_count,
+                      vimz_acc** out) {
   DeviceGuard g(ctx->device);
   vimz_acc* a = new vimz_acc();
   a->ctx = ctx;
   a->shape = s;
   a->ck = ck;
+  a->ck_w = ck_w;
+  a->w_first = w_first;
+  a->w_count = w_count;
   size_t nb = std::max<size_t>(s->n * 32, 32), mb = std::max<size_t>(s->m * 32, 32), tb = (1 + s->io) * 32;
   cudaError_t e = cudaSuccess;
   auto alloc0 = [&](void** p, size_t bytes) {
@@ -686,6 +687,24 @@ int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_ac
   }
   *out = a;
   return VIMZ_OK;
+}
+
+int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_acc** out) {
+  CHECK_ARG(ctx && s && ck && out, "vimz_acc_init: null argument");
+  CHECK_ARG(s->ctx == ctx && ck->ctx == ctx, "vimz_acc_init: shape / key belong to another context");
+  if (ck->n < s->m || ck->n < s->n) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_init: commitment key shorter than the shape");
+  return acc_create(ctx, s, ck, ck, 0, s->n, out);
+}
+
+int vimz_acc_init_sharded(vimz_ctx* ctx, const vimz_shape* s_rows, const vimz_ck* ck_rows, const vimz_ck* ck_vars,
+                          size_t var_first, size_t var_count, vimz_acc** out) {
+  CHECK_ARG(ctx && s_rows && ck_rows && ck_vars && out, "vimz_acc_init_sharded: null argument");
+  CHECK_ARG(s_rows->ctx == ctx && ck_rows->ctx == ctx && ck_vars->ctx == ctx, "vimz_acc_init_sharded: shape / key belong to another context");
+  if (var_first > s_rows->n || var_count > s_rows->n - var_first)
+    return set_error(VIMZ_ERR_LENGTH, "vimz_acc_init_sharded: variable range outside the witness");
+  if (ck_rows->n < s_rows->m || ck_vars->n < var_count)
+    return set_error(VIMZ_ERR_LENGTH, "vimz_acc_init_sharded: commitment key shard shorter than its range");
+  return acc_create(ctx, s_rows, ck_rows, ck_vars, var_first, var_count, out);
 }
 
 // main stream waits for the commitment folds still running on the side stream
@@ -731,10 +750,10 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   if (two_lanes) {
     VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
     VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
-    VIMZ_TRY(vt->msm(ctx, 1, a->ck, 0, a->W2, s->n, fresh, false));
+    VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
     VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
   } else {  // one lane (used by the profiled pass so kernel times are not inflated by the other lane)
-    VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->W2, s->n, fresh, false));
+    VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
   }
   // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck));  // also histograms T's digits

@@ -180,7 +180,11 @@ struct vimz_shape {
 struct vimz_acc {
   vimz_ctx* ctx = nullptr;
   const vimz_shape* shape = nullptr;
-  const vimz_ck* ck = nullptr;
+  const vimz_ck* ck = nullptr;    // table over the rows of this accumulator's shape (commit(T), commit(E))
+  // commit(W2) = msm(ck_w, W2[w_first .. w_first + w_count)).  Unsharded: ck_w = ck, the whole witness.  Row-range
+  // shard (vimz_acc_init_sharded): ck_w covers ck[w_first ..), W stays replicated, E / T hold only the local rows.
+  const vimz_ck* ck_w = nullptr;
+  size_t w_first = 0, w_count = 0;
   void *W1 = nullptr, *E1 = nullptr, *W2 = nullptr, *T = nullptr;
   void *tail1 = nullptr, *tail2 = nullptr;  // [1+io]: (u, X)
   // Jacobian points comm_W1, comm_E1, then two alternating (comm_W2, comm_T) pairs, then two r slots

@@ -42,3 +42,108 @@ def sharded_commit(dist, n: int, local_commit: Callable[[int, int], np.ndarray],
     first, count = shard_range(n, dist.get_rank(), dist.get_world_size())
     local = local_commit(first, count)
     return point_sum(gather_partial_points(dist, local, device))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# One fold step sharded by constraint-row range ("SpMV / cross-term / E-fold")
+# ------------------------------------------------------------------------------------------------------------
+def shard_matrix(M, first: int, count: int):
+    """Rows [first, first+count) of a COO matrix (rows, cols, vals), re-based to row 0; entry order preserved."""
+    rows, cols, vals = M
+    rows = np.asarray(rows, dtype=np.uint32)
+    keep = (rows >= first) & (rows < first + count)
+    return (rows[keep] - np.uint32(first)).astype(np.uint32), np.asarray(cols, dtype=np.uint32)[keep], np.asarray(vals)[keep]
+
+
+class FoldShard:
+    """One rank's part of a fold sharded across GPUs (`vimz_acc_init_sharded`): constraint rows
+    [row_first, row_first + m_local) of A, B, C with the matching slices of E, T and of the commitment key,
+    plus the variable range [var_first, var_first + var_count) of commit(W2).  W stays replicated: every rank
+    needs the whole z = (W, u, X) for its rows, and folding W redundantly (n x 96 B of axpy) is cheaper than a
+    collective.  step_begin returns PARTIAL commitments."""
+
+    def __init__(self, engine, num_cons: int, num_vars: int, num_io: int, A, B, C_, make_ck: Callable, rank: int, world: int):
+        import ctypes as C
+        from ._lib import check, lib
+        from .nova import FoldAccumulator, R1CSShape
+        self.engine = engine
+        self.rank, self.world = rank, world
+        self.num_cons, self.num_vars, self.num_io = int(num_cons), int(num_vars), int(num_io)
+        self.row_first, self.m_local = shard_range(self.num_cons, rank, world)
+        self.var_first, self.var_count = shard_range(self.num_vars, rank, world)
+        loc = [shard_matrix(M, self.row_first, self.m_local) for M in (A, B, C_)]
+        self.shape = R1CSShape(engine, self.m_local, self.num_vars, self.num_io, *loc)
+        # make_ck(first, count) -> CommitmentKey over ck[first .. first+count), resident on this rank's GPU
+        self.ck_rows = make_ck(self.row_first, self.m_local)
+        self.ck_vars = make_ck(self.var_first, self.var_count)
+        h = C.c_void_p()
+        check(lib.vimz_acc_init_sharded(engine._h, self.shape._h, self.ck_rows._h, self.ck_vars._h, self.var_first, self.var_count,
+                                        C.byref(h)))
+        self.acc = FoldAccumulator.__new__(FoldAccumulator)
+        self.acc.shape, self.acc.ck, self.acc.engine, self.acc._h = self.shape, self.ck_rows, engine, h
+
+    def step_begin(self, W2: np.ndarray, X2: np.ndarray):
+        return self.acc.step_begin(W2, X2)
+
+    def step_begin_dev(self, d_W2: int, X2: np.ndarray):
+        return self.acc.step_begin_dev(d_W2, X2)
+
+    def step_end(self, r: np.ndarray):
+        self.acc.step_end(r)
+
+    def download(self):
+        """(U, W) of this shard: W.W is the whole (replicated) witness, W.E the local rows, U.comm_* partial sums."""
+        return self.acc.download()
+
+    def last_T(self) -> np.ndarray:
+        return self.acc.last_T()
+
+    def close(self):
+        self.acc.close()
+        self.shape.close()
+        self.ck_rows.close()
+        self.ck_vars.close()
+
+
+class ShardedFoldAccumulator:
+    """`FoldAccumulator` interface over one FoldShard per rank.  The only exchange of a step is the all-gather of
+    the two partial commitments (2 x 96 B per rank) followed by point additions on every rank's GPU, so every
+    rank derives the same challenge r from the same (comm_W2, comm_T).  `shard` may be any object with FoldShard's
+    step/download methods and `point_sum` any callable adding (k, 12) Jacobian points (tests/test_dist.py drives
+    this logic over gloo with CPU stand-ins)."""
+
+    def __init__(self, dist, shard, point_sum: Callable[[np.ndarray], np.ndarray], device=None):
+        self.dist, self.shard, self.point_sum, self.device = dist, shard, point_sum, device
+
+    def _combine(self, cw: np.ndarray, ct: np.ndarray):
+        both = np.concatenate([np.asarray(cw, np.uint64).reshape(12), np.asarray(ct, np.uint64).reshape(12)])
+        import torch
+        world = self.dist.get_world_size()
+        t = torch.from_numpy(both.view(np.int64).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        self.dist.all_gather(parts, t)
+        g = torch.stack(parts).cpu().numpy().view(np.uint64).reshape(world, 2, 12)
+        return self.point_sum(np.ascontiguousarray(g[:, 0])), self.point_sum(np.ascontiguousarray(g[:, 1]))
+
+    def step_begin(self, W2: np.ndarray, X2: np.ndarray):
+        return self._combine(*self.shard.step_begin(W2, X2))
+
+    def step_begin_dev(self, d_W2: int, X2: np.ndarray):
+        return self._combine(*self.shard.step_begin_dev(d_W2, X2))
+
+    def step_end(self, r: np.ndarray):
+        self.shard.step_end(r)
+
+    def download(self):
+        """Whole relaxed instance / witness on every rank: E rows concatenated in rank order, commitments summed."""
+        from .nova import RelaxedR1CSInstance, RelaxedR1CSWitness
+        U, W = self.shard.download()
+        world = self.dist.get_world_size()
+        objs = [None] * world
+        self.dist.all_gather_object(objs, (np.asarray(W.E), np.asarray(U.comm_W), np.asarray(U.comm_E)))
+        E = np.concatenate([o[0].reshape(-1, 4) for o in objs])
+        comm_W = self.point_sum(np.stack([o[1].reshape(12) for o in objs]))
+        comm_E = self.point_sum(np.stack([o[2].reshape(12) for o in objs]))
+        return RelaxedR1CSInstance(comm_W, comm_E, U.X, U.u), RelaxedR1CSWitness(W.W, E)
