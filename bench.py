@@ -256,6 +256,10 @@ class GpuFold:
         seg = os.environ.get("VIMZ_SEG_MIN_" + curve_name.upper())
         if seg:
             self.eng.set_option("msm_seg_min", int(seg))
+        if os.environ.get("VIMZ_DIRECT_BPS"):
+            self.eng.set_option("msm_direct_bps", int(os.environ["VIMZ_DIRECT_BPS"]))
+        if os.environ.get("VIMZ_DIRECT_MAX"):
+            self.eng.set_option("msm_direct_max", int(os.environ["VIMZ_DIRECT_MAX"]))
         if os.environ.get("VIMZ_ACC_BLOCKS"):
             self.eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
         sh = self.sh
@@ -402,7 +406,7 @@ def timed_region(torch, engines, fn, steps, dist):
     return ms, wall
 
 
-def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
+def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist="uniform"):
     """Pallas MSM over 2^log2n resident points, uniform full-width scalars resident in HBM.  world > 1: point-range
     shards, per-rank partial sums all-gathered over NCCL and added on the GPU."""
     import vimz_b200
@@ -418,8 +422,18 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
     vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, K0 + first * DK, DK, per, d_bases.data_ptr()))
     ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), per)
     del d_bases
-    sc = [torch.from_numpy(S.uniform_scalars_mont(per, eng.curve.scalar_modulus, SEED + 7 * rank + j).view(np.int64)).to(f"cuda:{device}")
-          for j in range(2)]
+    q = eng.curve.scalar_modulus
+
+    def gen(j):  # SURVEY.md section 8d distributions: U uniform (T / E-like), B witness-like (93 % 0/1), Z edge sets
+        if scalar_dist == "witness":
+            return S.witness_like_scalars_mont(per, q, SEED + 7 * rank + j)
+        if scalar_dist == "edge":  # thirds of zero / one / q - 1: every scalar lands in bucket 1 or nowhere (giant-bucket path)
+            from vimz_b200.field import ints_to_mont
+            pat = ints_to_mont([0, 1, q - 1], q)
+            return np.ascontiguousarray(pat[(np.arange(per) + j) % 3])
+        return S.uniform_scalars_mont(per, q, SEED + 7 * rank + j)
+
+    sc = [torch.from_numpy(gen(j).view(np.int64)).to(f"cuda:{device}") for j in range(2)]
     d_out = torch.zeros(12, dtype=torch.int64, device=f"cuda:{device}")
     stream = torch.cuda.ExternalStream(eng.stream)
 
@@ -460,7 +474,8 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks):
     acc_ms, acc_calls = prof["msm_accumulate_kernel"]
     entries = prof["msm_entries"][1]
     res = {"log2_points": log2n, "mpts_per_s": n * iters / ms / 1e3, "ms_per_msm": ms / iters, "window_bits": ck.window_bits,
-           "windows": ck.num_windows, "scalars": "uniform 255-bit", "sharding": f"point-range x{world}" if world > 1 else "none"}
+           "windows": ck.num_windows,
+           "scalars": {"uniform": "uniform 255-bit", "witness": "witness-like: 93% 0/1, 2% bytes, 5% uniform", "edge": "edge: 0 / 1 / q-1 in thirds"}[scalar_dist], "sharding": f"point-range x{world}" if world > 1 else "none"}
     if acc_ms > 0:
         imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
         res["accumulate_ms"] = acc_ms / max(acc_calls, 1)
@@ -487,7 +502,7 @@ def main_gpu(args, rank, world, local_rank):
     peaks = load_peaks()
     steps, warmup = args.steps, max(args.warmup, 3)
     if args.msm_only:
-        msm = [msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks) for lg in args.msm_log2]
+        msm = [msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks, args.msm_dist) for lg in args.msm_log2]
         if rank == 0:
             print(json.dumps({"metric": "pallas_msm_mpts_per_sec", "msm": msm}), flush=True)
         if dist is not None:
@@ -534,6 +549,19 @@ def main_gpu(args, rank, world, local_rank):
 
     value = world * steps / (ms * 1e-3)
     e2e_value = world * steps / (ms_e2e * 1e-3)
+    # what the e2e path pays for: the pinned-host -> HBM copy of one fresh primary witness, timed alone
+    probe_dst = torch.empty_like(prim.dev_W[0])
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe_dst.copy_(prim.pin_W[0], non_blocking=True)
+    torch.cuda.synchronize()
+    pe0.record()
+    for j in range(10):
+        probe_dst.copy_(prim.pin_W[j % NUM_WITNESSES], non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_us = pe0.elapsed_time(pe1) * 1e3 / 10
+    h2d_gbs = prim.pin_W[0].numel() * 8 / (h2d_us * 1e-6) / 1e9
+    del probe_dst
 
     # roofline of the dominant kernel (primary-curve bucket accumulation)
     acc_ms, acc_calls = prof["msm_accumulate_kernel"]
@@ -570,7 +598,7 @@ def main_gpu(args, rank, world, local_rank):
     # Pallas MSM throughput (second half of the metric)
     msm = []
     for lg in args.msm_log2:
-        msm.append(msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks))
+        msm.append(msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks, args.msm_dist))
 
     sharded = None
     if world > 1 and not args.no_sharded_step:
@@ -591,7 +619,8 @@ def main_gpu(args, rank, world, local_rank):
                 "config": workload_config(prim.sh, cycle=args.cycle, extra={"parallelism": f"replicas x{world} (one transformation per GPU)",
                                                                    "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows}),
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
-                        "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_e2e / steps},
+                        "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_e2e / steps,
+                        "h2d_primary_witness_us": h2d_us, "h2d_gbs": h2d_gbs},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
                 "clocks": clocks, "clock_verdict": "rejected: " + ",".join(bad) if bad else "ok",
@@ -612,6 +641,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[20])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--msm-dist", default="uniform", choices=["uniform", "witness", "edge"],
+                    help="scalar distribution of the MSM sweep (SURVEY.md section 8d: U / B / Z)")
     ap.add_argument("--no-sharded-step", action="store_true", help="N > 1: skip the strong-scaling leg (one proof folded by all ranks)")
     ap.add_argument("--msm-only", action="store_true", help="skip the fold-step measurement (window sweeps)")
     ap.add_argument("--circuit", default="grayscale", choices=["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash"],

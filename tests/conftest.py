@@ -23,14 +23,18 @@ def coracle():
 _engines = {}
 
 
-@pytest.fixture(scope="session")
-def engines():
-    """curve name -> vimz_b200.Engine on cuda:0 (created lazily, shared by the session)."""
+@pytest.fixture(scope="session", params=["direct", "buckets"])
+def engines(request):
+    """curve name -> vimz_b200.Engine on cuda:0 (created lazily, shared by the session).  Every GPU test runs twice:
+    with short commitment keys on the direct multiples table (the default, option msm_direct_max = 32768) and with the
+    bucket pipeline forced for every key (msm_direct_max = 0), so both MSM paths see all the small-size cases."""
     import vimz_b200
 
     class Lazy(dict):
         def __missing__(self, name):
             e = vimz_b200.Engine(name, 0)
+            if request.param == "buckets":
+                e.set_option("msm_direct_max", 0)
             self[name] = e
             return e
 

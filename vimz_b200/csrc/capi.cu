@@ -195,6 +195,17 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     alloc_epoch()++;
     return VIMZ_OK;
   }
+  if (strcmp(key, "msm_direct_max") == 0) {  // applies to keys uploaded afterwards
+    if (value < 0 || value > (1 << 20)) return set_error(VIMZ_ERR_ARG, "msm_direct_max must be in [0, 2^20]");
+    ctx->opt_direct_max = value;
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "msm_direct_bps") == 0) {
+    if (value < 1 || value > 4) return set_error(VIMZ_ERR_ARG, "msm_direct_bps must be in [1, 4]");
+    ctx->opt_direct_bps = value;
+    alloc_epoch()++;
+    return VIMZ_OK;
+  }
   if (strcmp(key, "aux_lane") == 0) {
     ctx->opt_aux_lane = value != 0;
     return VIMZ_OK;
@@ -274,8 +285,23 @@ uint64_t vimz_ctx_launch_count(vimz_ctx* ctx) { return ctx ? ctx->launches : 0; 
 // ---- commitment key --------------------------------------------------------------------------------
 static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out) {
   const CurveVTable* vt = curve_vtable(ctx->curve);
-  int c = ctx->opt_window ? (int)ctx->opt_window : msm_pick_window(vt->scalar_modulus, n);
+  // short keys (the secondary curve of the fold, the hash / redact circuits) take the direct multiples table unless a
+  // window size was forced; if its allocation fails the key falls back to the bucket pipeline
+  bool direct = !ctx->opt_window && n > 0 && (long)n <= ctx->opt_direct_max;
+  int c = ctx->opt_window ? (int)ctx->opt_window : (direct ? DIRECT_C : msm_pick_window(vt->scalar_modulus, n));
   int nwin = msm_num_windows(vt->scalar_modulus, c);
+  if (direct && nwin > MSM_MAX_WINDOWS) {
+    direct = false;
+    c = msm_pick_window(vt->scalar_modulus, n);
+    nwin = msm_num_windows(vt->scalar_modulus, c);
+  }
+  void* dtable = nullptr;
+  if (direct && cudaMalloc(&dtable, (n * (size_t)nwin * 64) << (DIRECT_C - 1)) != cudaSuccess) {
+    cudaGetLastError();
+    dtable = nullptr;
+    c = msm_pick_window(vt->scalar_modulus, n);
+    nwin = msm_num_windows(vt->scalar_modulus, c);
+  }
   if (nwin > MSM_MAX_WINDOWS) return set_error(VIMZ_ERR_ARG, "msm_window too small: more than 32 windows");
   if ((double)n * nwin >= 2147483648.0) return set_error(VIMZ_ERR_ARG, "commitment key too long for this window size");
   vimz_ck* ck = new vimz_ck();
@@ -286,16 +312,20 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
   size_t bytes = std::max<size_t>(n * (size_t)nwin * 64, 64);
   cudaError_t e = cudaMalloc(&ck->table, bytes);
   if (e != cudaSuccess) {
+    if (dtable) cudaFree(dtable);
     delete ck;
     return set_error(VIMZ_ERR_CUDA, std::string("cudaMalloc(window table) failed: ") + cudaGetErrorString(e));
   }
+  ck->dtable = dtable;
   int rc = vt->precompute(ctx, d_bases, n, c, nwin, ck->table);
+  if (rc == VIMZ_OK && dtable) rc = vt->precompute_direct(ctx, ck->table, n, c, nwin, dtable);
   if (rc == VIMZ_OK) {
     cudaError_t s = cudaStreamSynchronize(ctx->stream);
     if (s != cudaSuccess) rc = set_error(VIMZ_ERR_CUDA, std::string("window-table expansion failed: ") + cudaGetErrorString(s));
   }
   if (rc != VIMZ_OK) {
     cudaFree(ck->table);
+    if (ck->dtable) cudaFree(ck->dtable);
     delete ck;
     return rc;
   }
@@ -326,6 +356,7 @@ void vimz_ck_destroy(vimz_ck* ck) {
   cudaSetDevice(ck->ctx->device);
   cudaStreamSynchronize(ck->ctx->stream);
   if (ck->table) cudaFree(ck->table);
+  if (ck->dtable) cudaFree(ck->dtable);
   delete ck;
 }
 size_t vimz_ck_len(const vimz_ck* ck) { return ck ? ck->n : 0; }

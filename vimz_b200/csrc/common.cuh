@@ -118,6 +118,8 @@ struct vimz_ctx {
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
   bool opt_cross_stream = true; // cross term: chunked CSR streaming through shared memory (false: row-class kernel)
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
+  long opt_direct_bps = 4;     // k_msm_direct blocks per SM (1..4)
+  long opt_direct_max = 32768; // keys up to this many points get the direct multiples table (256 KB per point); 0 = never
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points
@@ -156,6 +158,9 @@ struct vimz_ck {
   int c = 0;          // window bits
   int nwin = 0;       // windows
   void* table = nullptr;  // [nwin][n] affine points, row j = 2^(c*j) * base
+  // short keys (n <= option "msm_direct_max"): every digit multiple k * table[j][i], k = 1 .. 2^(c-1), so the MSM is a
+  // plain sum with no buckets (msm.cuh, k_msm_direct); nullptr = bucket pipeline
+  void* dtable = nullptr;
 };
 
 struct vimz_shape {

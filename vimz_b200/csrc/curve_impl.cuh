@@ -19,6 +19,8 @@ struct CurveVTable {
   uint32_t scalar_modulus[8];
   uint32_t scalar_one_mont[8];
   int (*precompute)(vimz_ctx*, const void* d_bases, size_t n, int c, int nwin, void* table);
+  // dtable[((j*n + i) << (c-1)) + k-1] = k * table[j][i]  (direct-table keys)
+  int (*precompute_direct)(vimz_ctx*, const void* table, size_t n, int c, int nwin, void* dtable);
   // lane 0 = context stream + main workspace, lane 1 = aux stream + second workspace (runs concurrently)
   // counted = true: the bucket histogram of the scalars is already in the lane's `counts` buffer (fused cross term)
   int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted);
@@ -56,9 +58,48 @@ int impl_precompute(vimz_ctx* ctx, const void* d_bases, size_t n, int c, int nwi
 }
 
 template <class C>
+int impl_precompute_direct(vimz_ctx* ctx, const void* table, size_t n, int c, int nwin, void* dtable) {
+  if (n == 0) return VIMZ_OK;
+  const size_t entries = n * (size_t)nwin;
+  k_precompute_direct<C><<<ceil_div(entries, 128), 128, 0, ctx->stream>>>(table, (uint32_t)entries, c - 1, dtable);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+
+// MSM over a direct-table key: digits (unless the cross term already wrote them) + one launch.
+template <class C>
+int impl_msm_direct(vimz_ctx* ctx, cudaStream_t st, MsmWorkspace& ws, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n,
+                    void* d_out, bool digits_ready) {
+  const int c = ck->c, nwin = ck->nwin;
+  const size_t E = std::max<size_t>(n * (size_t)nwin, 1);
+  const uint32_t max_blocks = std::min<uint32_t>((uint32_t)ctx->sm_count * (uint32_t)ctx->opt_direct_bps, DIRECT_MAX_BLOCKS);
+  const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(ceil_div(E, 128 * 2), max_blocks));
+  const uint32_t ngroups = ceil_div(blocks, DIRECT_GROUP);
+  VIMZ_TRY(ws.digits.reserve(E * 4));
+  VIMZ_TRY(ws.cls.reserve(64 * 4));
+  VIMZ_TRY(ws.partials.reserve(((size_t)blocks + ngroups) * 128));
+  ws.last_M = 0;
+  VIMZ_CUDA(cudaMemsetAsync(ws.cls.ptr, 0, 64 * 4, st));
+  if (n > 0 && !digits_ready) {
+    ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
+    const int grid_n = (int)std::min<size_t>(ceil_div(n, 256), (size_t)ctx->sm_count * 8);
+    k_msm_digits<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, nullptr,
+                                            ws.digits.as<uint32_t>());
+    VIMZ_LAUNCH_CHECK(ctx);
+  }
+  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
+  ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
+  k_msm_direct<C><<<blocks, 128, 0, st>>>(ws.digits.as<uint32_t>(), (uint32_t)n, nwin, (uint32_t)ck->n, (uint32_t)first, c - 1, ck->dtable,
+                                          ws.partials.ptr, ws.cls.as<uint32_t>(), d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+
+template <class C>
 int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted) {
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
   MsmWorkspace& ws = lane == 0 ? ctx->ws : ctx->ws_aux;
+  if (ck->dtable) return impl_msm_direct<C>(ctx, st, ws, ck, first, d_scalars, n, d_out, counted);
   const int c = ck->c, nwin = ck->nwin;
   const uint32_t M = 1u << (c - 1);
   const size_t E = std::max<size_t>(n * (size_t)nwin, 1);
@@ -220,12 +261,14 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
   DigitCount dc{nullptr, 0, 0, nullptr, 0};
   if (fuse_ck) {  // zero lane 0's histogram, then let the cross-term kernels fill it and the digit array
     const uint32_t M = 1u << (fuse_ck->c - 1);
-    VIMZ_TRY(ctx->ws.counts.reserve((size_t)M * 4));
     VIMZ_TRY(ctx->ws.digits.reserve(std::max<size_t>(s->m * (size_t)fuse_ck->nwin, 1) * 4));
     dc.digits = ctx->ws.digits.as<uint32_t>();
     dc.stride = s->m;
-    VIMZ_CUDA(cudaMemsetAsync(ctx->ws.counts.ptr, 0, (size_t)M * 4, ctx->stream));
-    dc.counts = ctx->ws.counts.as<uint32_t>();
+    if (!fuse_ck->dtable) {  // a direct-table key has no buckets: digits only
+      VIMZ_TRY(ctx->ws.counts.reserve((size_t)M * 4));
+      VIMZ_CUDA(cudaMemsetAsync(ctx->ws.counts.ptr, 0, (size_t)M * 4, ctx->stream));
+      dc.counts = ctx->ws.counts.as<uint32_t>();
+    }
     dc.c = fuse_ck->c;
     dc.nwin = fuse_ck->nwin;
   }
@@ -301,6 +344,7 @@ CurveVTable make_vtable(const char* name) {
     t.scalar_one_mont[i] = C::Fs::one(i);
   }
   t.precompute = &impl_precompute<C>;
+  t.precompute_direct = &impl_precompute_direct<C>;
   t.msm = &impl_msm<C>;
   t.point_sum = &impl_point_sum<C>;
   t.point_to_affine = &impl_point_to_affine<C>;

@@ -69,8 +69,10 @@ __device__ __forceinline__ void recode_scalar(const Fp<F>& mont, int c, int nwin
     for (; next < j; next++) digits[(size_t)next * stride + i] = 0;
     digits[(size_t)j * stride + i] = mag | ((neg != flip) ? 0x80000000u : 0u);
     next = j + 1;
-    if (AGG) warp_count_add(&counts[mag - 1]);
-    else atomicAdd(&counts[mag - 1], 1u);
+    if (counts) {  // nullptr: digits only (direct-table keys have no buckets to size)
+      if (AGG) warp_count_add(&counts[mag - 1]);
+      else atomicAdd(&counts[mag - 1], 1u);
+    }
   });
   for (; next < nwin; next++) digits[(size_t)next * stride + i] = 0;
 }

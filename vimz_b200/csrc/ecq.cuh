@@ -191,11 +191,12 @@ VIMZ_DI QPoint<C> q_load_jacobian(const void* in) {
 }
 
 // Tree-sum of the eight points held by the eight quads of a warp; result valid in quad 0 (lanes 0..3).
+// first_delta = 2: only quads 0..3 hold points (two levels instead of three).
 template <class C>
-VIMZ_DI QPoint<C> q_warp_reduce(QPoint<C> acc) {
+VIMZ_DI QPoint<C> q_warp_reduce(QPoint<C> acc, int first_delta = 4) {
   using F = Fp<typename C::Fb>;
 #pragma unroll 1
-  for (int delta = 4; delta > 0; delta >>= 1) {
+  for (int delta = first_delta; delta > 0; delta >>= 1) {
     QPoint<C> other = acc.from_quad_above(delta);
     if ((int)(threadIdx.x & 31) + 4 * delta >= 32) other.c = F::zero();  // no partner: add the identity
     acc = q_add<C>(acc, other);

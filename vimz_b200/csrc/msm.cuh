@@ -336,7 +336,7 @@ __device__ __forceinline__ QPoint<C> q_block_reduce_128(QPoint<C> acc, uint32_t*
   __syncthreads();
   if (warp == 0) {  // warp-uniform: all 32 lanes run the cooperative tree; quads >= 4 contribute the identity
     acc = lane < 16 ? QPoint<C>::load(smem + (lane >> 2) * 32) : QPoint<C>::identity();
-    acc = q_warp_reduce<C>(acc);
+    acc = q_warp_reduce<C>(acc, 2);  // four points: two levels
   }
   __syncthreads();
   return acc;
@@ -580,6 +580,130 @@ __global__ void __launch_bounds__(128) k_precompute(const void* __restrict__ bas
     a.y = fp_mul(pts[j].y, zi);
     a.store(reinterpret_cast<char*>(table) + ((size_t)j * n + i) * 64);
   }
+}
+
+// ---- direct-table MSM for short commitment keys ------------------------------------------------------------
+// The fold step's secondary curve (and the hash / redact step circuits) commit ~10^4-point vectors: there the
+// bucket pipeline is pure latency -- sort, accumulate, combine and a ~40-addition-deep bucket reduction for a few
+// hundred thousand insertions.  With 180 GB of HBM the key can instead hold EVERY digit multiple:
+//   dtable[((j * n + i) << (c-1)) + (k-1)] = k * 2^(c*j) * ck_i,   k = 1 .. 2^(c-1)   (c = 8: 256 KB per point)
+// so a signed digit is one gather + one mixed addition into a per-thread accumulator and the MSM is a plain sum:
+// no buckets, no sort, no bucket reduction -- digits kernel + ONE launch (thread sums -> quad sums -> block sum ->
+// last-arriving block of each group of DIRECT_GROUP blocks -> last-arriving group writes the Jacobian result).
+#ifndef VIMZ_DIRECT_MUL
+#define VIMZ_DIRECT_MUL MulCall  // few additions per thread: a small kernel that stays in the instruction caches
+#endif
+constexpr int DIRECT_C = 8;
+constexpr uint32_t DIRECT_GROUP = 32;
+constexpr uint32_t DIRECT_CTRL_FINAL = 32;  // ctrl[0..31]: per-group arrival counters, ctrl[32]: groups finished
+constexpr uint32_t DIRECT_MAX_BLOCKS = DIRECT_GROUP * 32;
+constexpr int DIRECT_BATCH = 4;             // multiples normalised per inversion in k_precompute_direct
+
+// one thread per (window j, point i): the 2^(c-1) multiples of table[j][i], affine, DIRECT_BATCH per inversion
+template <class C>
+__global__ void __launch_bounds__(128) k_precompute_direct(const void* __restrict__ table, uint32_t entries, int cshift,
+                                                           void* __restrict__ dtable) {
+  using F = Fp<typename C::Fb>;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  const Affine<C> base = Affine<C>::load(reinterpret_cast<const char*>(table) + (size_t)e * 64);
+  char* dst = reinterpret_cast<char*>(dtable) + (((size_t)e) << cshift) * 64;
+  const uint32_t K = 1u << cshift;
+  if (base.is_identity()) {
+    Affine<C> zero;
+    zero.x = F::zero(); zero.y = F::zero();
+    for (uint32_t k = 0; k < K; k++) zero.store(dst + (size_t)k * 64);
+    return;
+  }
+  base.store(dst);
+  Xyzz<C> cur = Xyzz<C>::from_affine(base);
+  for (uint32_t k0 = 1; k0 < K; k0 += DIRECT_BATCH) {  // multiples k0+1 .. k0+DIRECT_BATCH
+    Xyzz<C> pts[DIRECT_BATCH];
+    F prefix[DIRECT_BATCH];
+    F run = F::one();
+    const int cnt = (int)min((uint32_t)DIRECT_BATCH, K - k0);
+    for (int b = 0; b < cnt; b++) {
+      xyzz_madd_call<C>(cur, base, false);  // prime-order group: k * P is never the identity for k <= 2^(c-1)
+      pts[b] = cur;
+      prefix[b] = run;
+      run = fp_mul_noinline<typename C::Fb>(run, cur.zzz);
+    }
+    F inv = fp_inv(run);
+    for (int b = cnt - 1; b >= 0; b--) {
+      F zi = fp_mul_noinline<typename C::Fb>(inv, prefix[b]);       // 1 / zzz_b
+      inv = fp_mul_noinline<typename C::Fb>(inv, pts[b].zzz);
+      F t = fp_mul_noinline<typename C::Fb>(pts[b].zz, zi);
+      F zzi = fp_mul_noinline<typename C::Fb>(t, t);                // 1 / zz_b
+      Affine<C> a;
+      a.x = fp_mul_noinline<typename C::Fb>(pts[b].x, zzi);
+      a.y = fp_mul_noinline<typename C::Fb>(pts[b].y, zi);
+      a.store(dst + (size_t)(k0 + b) * 64);
+    }
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restrict__ digits, uint32_t n, int nwin, uint32_t ck_n, uint32_t first,
+                                                       int cshift, const void* __restrict__ dtable, void* __restrict__ partials,
+                                                       uint32_t* __restrict__ ctrl, void* __restrict__ out_jac) {
+  __shared__ __align__(16) uint32_t smem[4 * 32];
+  __shared__ uint32_t flag;
+  const uint32_t nthreads = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = n * (uint32_t)nwin;
+  const char* tab = reinterpret_cast<const char*>(dtable);
+  auto address = [&](uint32_t e, uint32_t d) {
+    const uint32_t j = e / n, i = e - j * n;
+    return tab + ((((size_t)j * ck_n + first + i) << cshift) + ((d & 0x7fffffffu) - 1)) * 64;
+  };
+  // entry e = j * n + i of the recoded digit array; thread t takes e = t, t + nthreads, ... (coalesced digit reads)
+  Xyzz<C> acc = Xyzz<C>::identity();
+  uint32_t e = t;
+  uint32_t d = e < total ? __ldg(digits + e) : 0u;
+  while (e < total) {
+    const uint32_t en = e + nthreads;
+    const uint32_t dn = en < total ? __ldg(digits + en) : 0u;  // next digit in flight during this addition
+    if (d != 0) {
+      Affine<C> p = Affine<C>::load_nc(address(e, d));
+      xyzz_madd<C, VIMZ_DIRECT_MUL>(acc, p, (d >> 31) != 0);
+    }
+    e = en;
+    d = dn;
+  }
+  // thread sums -> one point per quad -> block sum
+  QPoint<C> q = q_from_lane<C>(acc, 0);
+#pragma unroll 1
+  for (int j = 1; j < 4; j++) q = q_add<C>(q, q_from_lane<C>(acc, j));
+  q = q_block_reduce_128<C>(q, smem);
+  char* parts = reinterpret_cast<char*>(partials);
+  const uint32_t nblocks = gridDim.x, ngroups = (nblocks + DIRECT_GROUP - 1) / DIRECT_GROUP;
+  const uint32_t g = blockIdx.x / DIRECT_GROUP;
+  const uint32_t gsize = min(DIRECT_GROUP, nblocks - g * DIRECT_GROUP);
+  if (threadIdx.x < 4) {
+    q.store(parts + (size_t)blockIdx.x * 128);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flag = (atomicAdd(&ctrl[g], 1u) + 1 == gsize) ? 1u : 0u;
+  __syncthreads();
+  if (!flag) return;
+  // last block of group g: its 32 quads fetch the group's block sums (through L2) and add them
+  __threadfence();
+  const uint32_t quad = threadIdx.x >> 2;
+  q = quad < gsize ? QPoint<C>::load_cg(parts + (size_t)(g * DIRECT_GROUP + quad) * 128) : QPoint<C>::identity();
+  q = q_block_reduce_128<C>(q, smem);
+  if (threadIdx.x < 4) {
+    q.store(parts + (size_t)(nblocks + g) * 128);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flag = (atomicAdd(&ctrl[DIRECT_CTRL_FINAL], 1u) + 1 == ngroups) ? 1u : 0u;
+  __syncthreads();
+  if (!flag) return;
+  // last group: add the <= 32 group sums, write the Jacobian result
+  __threadfence();
+  q = quad < ngroups ? QPoint<C>::load_cg(parts + (size_t)(nblocks + quad) * 128) : QPoint<C>::identity();
+  q = q_block_reduce_128<C>(q, smem);
+  if (threadIdx.x < 32) q_store_jacobian<C>(q, out_jac, threadIdx.x < 4);
 }
 
 // ---- small single-thread group kernels ---------------------------------------------------------

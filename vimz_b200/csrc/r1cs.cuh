@@ -28,7 +28,8 @@ struct CsrView {
   const void* val;
 };
 
-// optional fusion with the MSM that follows: recode and histogram T's bucket digits here (counts == nullptr: off)
+// optional fusion with the MSM that follows: recode (digits != nullptr) and histogram (counts != nullptr: bucket path;
+// a direct-table key needs no histogram) T's digits here
 struct DigitCount {
   uint32_t* counts;
   int c, nwin;
@@ -106,7 +107,7 @@ __device__ __noinline__ void cross_term_finish(Fp<F> a1, Fp<F> a2, Fp<F> b1, Fp<
                                                DigitCount dc) {
   Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, u1);
   t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
-  if (dc.counts) recode_scalar<F, false>(t, dc.c, dc.nwin, dc.counts, dc.digits, dc.stride, row);
+  if (dc.digits) recode_scalar<F, false>(t, dc.c, dc.nwin, dc.counts, dc.digits, dc.stride, row);
 }
 
 // sum over the GROUP lanes of a row group (GROUP = 8 or 32, groups are aligned inside the warp)
