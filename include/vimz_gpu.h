@@ -150,6 +150,12 @@ int vimz_acc_init(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, vimz_ac
  * comm + r*comm' is linear), so vimz_acc_download returns shard values to be added across ranks. */
 int vimz_acc_init_sharded(vimz_ctx* ctx, const vimz_shape* s_rows, const vimz_ck* ck_rows, const vimz_ck* ck_vars,
                           size_t var_first, size_t var_count, vimz_acc** out);
+/* Sharded step without host round trips: step_begin_dev_async only ENQUEUES the step on the context stream and returns
+ * the device address of this rank's partial (comm_W2, comm_T) pair (2 x 96 bytes, valid until the next step_begin); the
+ * caller all-gathers those 192 bytes over NCCL on the same stream (vimz_ctx_stream) into d_gathered[world][2] and
+ * step_combine_dev adds them on the GPU, copies the two full commitments back and synchronises once. */
+int vimz_acc_step_begin_dev_async(vimz_acc* acc, const void* d_W2, const vimz_fr* X2, void** d_partials);
+int vimz_acc_step_combine_dev(vimz_acc* acc, const void* d_gathered, size_t world, vimz_point* comm_W2, vimz_point* comm_T);
 int vimz_acc_load(vimz_acc* acc, const vimz_fr* W, const vimz_fr* E, const vimz_fr* u, const vimz_fr* X,
                   const vimz_point* comm_W, const vimz_point* comm_E);
 int vimz_acc_step_begin(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);

@@ -381,10 +381,10 @@ def test_row_sharded_fold_matches_unsharded_chain(name, world, engines, coracle)
     Bm = affine_to_mont(bases, c.p)
     rng = random.Random(8)
     wit = []
-    for k in range(3):
+    for k in range(4):
         Wi, Xi = S.synthetic_witness(sh, 300 + k)
         wit.append((ints_to_mont(Wi, q), ints_to_mont(Xi, q)))
-    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(3)]
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(4)]
     ref = _oracle_fold_chain(coracle, c, sh, Bm, wit, chal)
 
     def make_ck(first, count):
@@ -401,6 +401,22 @@ def test_row_sharded_fold_matches_unsharded_chain(name, world, engines, coracle)
         assert np.array_equal(np.concatenate([s.last_T() for s in shards]), ref[k]["T"])
         for s in shards:
             s.step_end(chal[k])
+    # fourth step through the no-host-round-trip entry points: enqueue on every shard, gather the partial pairs on the
+    # device (what the NCCL all-gather does across ranks), add them with vimz_acc_step_combine_dev
+    import torch
+    from vimz_b200.sharding import _DevWords
+    d_W2 = torch.from_numpy(wit[3][0].view(np.int64)).cuda()
+    gathered = torch.empty(world * 24, dtype=torch.int64, device="cuda")
+    st = torch.cuda.ExternalStream(eng.stream)
+    for r, s in enumerate(shards):
+        part = torch.as_tensor(_DevWords(s.step_begin_dev_async(d_W2.data_ptr(), wit[3][1]), 24), device="cuda")
+        with torch.cuda.stream(st):
+            gathered[24 * r:24 * (r + 1)].copy_(part, non_blocking=True)
+    comm_W2, comm_T = shards[0].step_combine_dev(gathered.data_ptr(), world)
+    assert eng.to_affine_ints(comm_W2) == _affine(coracle, c, ref[3]["comm_W2"])
+    assert eng.to_affine_ints(comm_T) == _affine(coracle, c, ref[3]["comm_T"])
+    for s in shards:
+        s.step_end(chal[3])
     outs = [s.download() for s in shards]
     last = ref[-1]
     for U, W in outs:

@@ -77,6 +77,8 @@ def _load() -> C.CDLL:
         "vimz_fold_witness": (i32, [vp, vp, vp, vp, sz, vp, vp, sz, vp, vp]),
         "vimz_acc_init": (i32, [vp, vp, vp, pp]),
         "vimz_acc_init_sharded": (i32, [vp, vp, vp, vp, sz, sz, pp]),
+        "vimz_acc_step_begin_dev_async": (i32, [vp, vp, vp, pp]),
+        "vimz_acc_step_combine_dev": (i32, [vp, vp, sz, vp, vp]),
         "vimz_acc_load": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "vimz_acc_step_begin": (i32, [vp, vp, vp, vp, vp]),
         "vimz_acc_step_begin_dev": (i32, [vp, vp, vp, vp, vp]),

@@ -794,7 +794,8 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   return VIMZ_OK;
 }
 
-static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
+// sync = false: enqueue only (sharded fold: the partial commitments stay on the device for the all-gather)
+static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T, bool sync = true) {
   vimz_ctx* ctx = a->ctx;
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
@@ -849,9 +850,35 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
     VIMZ_TRY(enqueue_step_begin(a, fresh));
     a->warm[p] = true;
   }
+  if (!sync) return VIMZ_OK;
   VIMZ_CUDA(cudaStreamSynchronize(st));
   memcpy(comm_W2, ctx->pinned, 96);
   memcpy(comm_T, (char*)ctx->pinned + 96, 96);
+  return VIMZ_OK;
+}
+
+int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* X2, void** d_partials) {
+  CHECK_ARG(a && d_partials && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev_async: null argument");
+  DeviceGuard g(a->ctx->device);
+  size_t io = a->shape->io;
+  if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
+  VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
+  VIMZ_TRY(acc_step_begin_common(a, X2, nullptr, nullptr, false));
+  *d_partials = (char*)a->comms + (2 + 2 * a->parity) * 96;
+  return VIMZ_OK;
+}
+
+int vimz_acc_step_combine_dev(vimz_acc* a, const void* d_gathered, size_t world, vimz_point* comm_W2, vimz_point* comm_T) {
+  CHECK_ARG(a && d_gathered && world >= 1 && comm_W2 && comm_T, "vimz_acc_step_combine_dev: null argument");
+  vimz_ctx* ctx = a->ctx;
+  DeviceGuard g(ctx->device);
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  VIMZ_TRY(ctx->ws.result.reserve(2 * 96));
+  VIMZ_TRY(vt->point_sum_batch(ctx, d_gathered, world, 2, ctx->ws.result.ptr));
+  VIMZ_CUDA(cudaMemcpyAsync((char*)ctx->pinned + 3072, ctx->ws.result.ptr, 2 * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(comm_W2, (char*)ctx->pinned + 3072, 96);
+  memcpy(comm_T, (char*)ctx->pinned + 3072 + 96, 96);
   return VIMZ_OK;
 }
 
@@ -859,7 +886,7 @@ int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_
   CHECK_ARG(a && comm_W2 && comm_T && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin: null argument");
   DeviceGuard g(a->ctx->device);
   size_t io = a->shape->io;
-  if (1024 + (1 + io) * 32 > 4096) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
+  if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
@@ -868,7 +895,7 @@ int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vi
   CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
   DeviceGuard g(a->ctx->device);
   size_t io = a->shape->io;
-  if (1024 + (1 + io) * 32 > 4096) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
+  if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   // keep W2 resident for step_end
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);

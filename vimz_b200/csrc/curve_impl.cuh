@@ -25,6 +25,7 @@ struct CurveVTable {
   // counted = true: the bucket histogram of the scalars is already in the lane's `counts` buffer (fused cross term)
   int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted);
   int (*point_sum)(vimz_ctx*, const void* d_pts, size_t k, void* d_out);
+  int (*point_sum_batch)(vimz_ctx*, const void* d_pts, size_t k, size_t sets, void* d_out);
   int (*point_to_affine)(vimz_ctx*, const void* d_pt, void* d_out);
   int (*point_scale_add)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count);
   int (*gen_bases)(vimz_ctx*, uint64_t k0, uint64_t dk, size_t n, void* d_out);
@@ -217,6 +218,13 @@ int impl_point_sum(vimz_ctx* ctx, const void* d_pts, size_t k, void* d_out) {
   return VIMZ_OK;
 }
 template <class C>
+int impl_point_sum_batch(vimz_ctx* ctx, const void* d_pts, size_t k, size_t sets, void* d_out) {
+  if (sets == 0) return VIMZ_OK;
+  k_point_sum_batch<C><<<(uint32_t)sets, 32, 0, ctx->stream>>>(d_pts, (uint32_t)k, (uint32_t)sets, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
 int impl_point_to_affine(vimz_ctx* ctx, const void* d_pt, void* d_out) {
   k_point_to_affine<C><<<1, 32, 0, ctx->stream>>>(d_pt, d_out);
   VIMZ_LAUNCH_CHECK(ctx);
@@ -347,6 +355,7 @@ CurveVTable make_vtable(const char* name) {
   t.precompute_direct = &impl_precompute_direct<C>;
   t.msm = &impl_msm<C>;
   t.point_sum = &impl_point_sum<C>;
+  t.point_sum_batch = &impl_point_sum_batch<C>;
   t.point_to_affine = &impl_point_to_affine<C>;
   t.point_scale_add = &impl_point_scale_add<C>;
   t.gen_bases = &impl_gen_bases<C>;

@@ -733,6 +733,23 @@ __global__ void k_point_to_affine(const void* __restrict__ pt, void* __restrict_
   a.store(out);
 }
 
+// out[s] = sum_r pts[r * sets + s] for `sets` independent sums of k Jacobian points each (combining the per-rank
+// partial commitments of a sharded fold step): block s, one warp, its 8 quads stride over the k points.
+template <class C>
+__global__ void __launch_bounds__(32) k_point_sum_batch(const void* __restrict__ pts, uint32_t k, uint32_t sets, void* __restrict__ out) {
+  const uint32_t s = blockIdx.x, quad = threadIdx.x >> 2;
+  QPoint<C> acc = QPoint<C>::identity();
+#pragma unroll 1
+  for (uint32_t it = 0; it < (k + 7) / 8; it++) {  // warp-uniform trip count
+    const uint32_t r = it * 8 + quad;
+    QPoint<C> p = q_load_jacobian<C>(reinterpret_cast<const char*>(pts) + ((size_t)(r < k ? r : 0) * sets + s) * 96);
+    if (r >= k) p = QPoint<C>::identity();
+    acc = q_add<C>(acc, p);
+  }
+  acc = q_warp_reduce<C>(acc);
+  q_store_jacobian<C>(acc, reinterpret_cast<char*>(out) + (size_t)s * 96, threadIdx.x < 4);
+}
+
 // out[t] = a[t] + r * b[t] for count <= 8 independent pairs, one QUAD each (one warp in total); r is a
 // Montgomery scalar shared by all pairs (RelaxedR1CSInstance::fold uses the same r for comm_W and comm_E).
 template <class C>

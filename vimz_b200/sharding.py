@@ -55,6 +55,13 @@ def shard_matrix(M, first: int, count: int):
     return (rows[keep] - np.uint32(first)).astype(np.uint32), np.asarray(cols, dtype=np.uint32)[keep], np.asarray(vals)[keep]
 
 
+class _DevWords:
+    """`n` int64 words of device memory at `ptr`, exposed through __cuda_array_interface__ so torch can view them."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2, "strides": None}
+
+
 class FoldShard:
     """One rank's part of a fold sharded across GPUs (`vimz_acc_init_sharded`): constraint rows
     [row_first, row_first + m_local) of A, B, C with the matching slices of E, T and of the commitment key,
@@ -87,6 +94,24 @@ class FoldShard:
 
     def step_begin_dev(self, d_W2: int, X2: np.ndarray):
         return self.acc.step_begin_dev(d_W2, X2)
+
+    def step_begin_dev_async(self, d_W2: int, X2: np.ndarray) -> int:
+        """Enqueue the step; -> device address of this rank's partial (comm_W2, comm_T) pair (24 x u64)."""
+        import ctypes as C
+        from ._lib import check, lib
+        from .field import as_fr
+        X2 = as_fr(X2, self.num_io)
+        p = C.c_void_p()
+        check(lib.vimz_acc_step_begin_dev_async(self.acc._h, C.c_void_p(d_W2), X2.ctypes.data_as(C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def step_combine_dev(self, d_gathered: int, world: int):
+        import ctypes as C
+        from ._lib import check, lib
+        cw, ct = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
+        check(lib.vimz_acc_step_combine_dev(self.acc._h, C.c_void_p(d_gathered), world, cw.ctypes.data_as(C.c_void_p),
+                                            ct.ctypes.data_as(C.c_void_p)))
+        return cw, ct
 
     def step_end(self, r: np.ndarray):
         self.acc.step_end(r)
@@ -131,7 +156,24 @@ class ShardedFoldAccumulator:
         return self._combine(*self.shard.step_begin(W2, X2))
 
     def step_begin_dev(self, d_W2: int, X2: np.ndarray):
+        if self.device is not None and hasattr(self.shard, "step_begin_dev_async"):
+            return self._step_begin_on_stream(d_W2, X2)
         return self._combine(*self.shard.step_begin_dev(d_W2, X2))
+
+    def _step_begin_on_stream(self, d_W2: int, X2: np.ndarray):
+        """GPU path: the step is enqueued on the context stream, its 192-byte partial pair is all-gathered by NCCL in
+        stream order on that same stream (no host copy of the partials), the shards are added on the GPU, and the host
+        waits once for the two full commitments."""
+        import torch
+        world = self.dist.get_world_size()
+        if getattr(self, "_recv", None) is None:
+            self._recv = torch.empty(world * 24, dtype=torch.int64, device=self.device)
+            self._stream = torch.cuda.ExternalStream(self.shard.engine.stream, device=self.device)
+        d_part = self.shard.step_begin_dev_async(d_W2, X2)
+        send = torch.as_tensor(_DevWords(d_part, 24), device=self.device)   # zero-copy view of the accumulator's slot pair
+        with torch.cuda.stream(self._stream):
+            self.dist.all_gather_into_tensor(self._recv, send)
+        return self.shard.step_combine_dev(self._recv.data_ptr(), world)
 
     def step_end(self, r: np.ndarray):
         self.shard.step_end(r)
