@@ -260,6 +260,8 @@ class GpuFold:
         seg = os.environ.get("VIMZ_SEG_MIN_" + curve_name.upper())
         if seg:
             self.eng.set_option("msm_seg_min", int(seg))
+        if os.environ.get("VIMZ_DIRECT_C"):
+            self.eng.set_option("msm_direct_c", int(os.environ["VIMZ_DIRECT_C"]))
         if os.environ.get("VIMZ_DIRECT_BPS"):
             self.eng.set_option("msm_direct_bps", int(os.environ["VIMZ_DIRECT_BPS"]))
         if os.environ.get("VIMZ_DIRECT_MAX"):
@@ -353,7 +355,10 @@ class GpuFoldSharded:
 def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup):
     """Strong-scaling leg of an N > 1 run: the same grayscale (or --circuit) proof folded by all ranks together."""
     prim = GpuFoldSharded(CYCLES[args.cycle][0], args.circuit, SEED, local_rank, torch, dist, rank, world)
-    sec = GpuFold(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch)   # 10.5k rows: replicated, not sharded
+    if os.environ.get("VIMZ_SHARD_SECONDARY", "1") == "1":   # the secondary curve's 10.5k rows are sharded the same way
+        sec = GpuFoldSharded(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch, dist, rank, world)
+    else:
+        sec = GpuFold(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch)
     engines = [prim.eng, sec.eng]
     last = {}
 
@@ -379,7 +384,8 @@ def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup
            "rows_per_rank": prim.shard.m_local, "vars_per_rank": prim.shard.var_count,
            "exchange": "NCCL all-gather of 2 partial commitments (192 B per rank) per step; e2e adds the NCCL broadcast of W2 "
                        f"({prim.sh.num_vars * 32} B) from rank 0",
-           "parallelism": f"primary rows / E / T / ck sharded x{world} by constraint-row range, W replicated; secondary replicated"}
+           "parallelism": f"rows / E / T / ck of {'both curves' if isinstance(sec, GpuFoldSharded) else 'the primary curve (secondary replicated)'} "
+                          f"sharded x{world} by constraint-row range, W replicated"}
     prim.shard.close()
     return res
 

@@ -200,6 +200,11 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     ctx->opt_direct_max = value;
     return VIMZ_OK;
   }
+  if (strcmp(key, "msm_direct_c") == 0) {  // applies to keys uploaded afterwards; 0 = by key length
+    if (value != 0 && (value < 4 || value > 12)) return set_error(VIMZ_ERR_ARG, "msm_direct_c must be 0 or in [4, 12]");
+    ctx->opt_direct_c = value;
+    return VIMZ_OK;
+  }
   if (strcmp(key, "msm_direct_bps") == 0) {
     if (value < 1 || value > 4) return set_error(VIMZ_ERR_ARG, "msm_direct_bps must be in [1, 4]");
     ctx->opt_direct_bps = value;
@@ -288,7 +293,9 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
   // short keys (the secondary curve of the fold, the hash / redact circuits) take the direct multiples table unless a
   // window size was forced; if its allocation fails the key falls back to the bucket pipeline
   bool direct = !ctx->opt_window && n > 0 && (long)n <= ctx->opt_direct_max;
-  int c = ctx->opt_window ? (int)ctx->opt_window : (direct ? DIRECT_C : msm_pick_window(vt->scalar_modulus, n));
+  // 2^(c-1) multiples per (window, point): c = 10 (26 windows, 832 KB per point) up to 16 384 points, c = 8 (32 windows, 256 KB) above
+  const int direct_c = ctx->opt_direct_c ? (int)ctx->opt_direct_c : (n <= 16384 ? DIRECT_C_SHORT : DIRECT_C);
+  int c = ctx->opt_window ? (int)ctx->opt_window : (direct ? direct_c : msm_pick_window(vt->scalar_modulus, n));
   int nwin = msm_num_windows(vt->scalar_modulus, c);
   if (direct && nwin > MSM_MAX_WINDOWS) {
     direct = false;
@@ -296,7 +303,7 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
     nwin = msm_num_windows(vt->scalar_modulus, c);
   }
   void* dtable = nullptr;
-  if (direct && cudaMalloc(&dtable, (n * (size_t)nwin * 64) << (DIRECT_C - 1)) != cudaSuccess) {
+  if (direct && cudaMalloc(&dtable, (n * (size_t)nwin * 64) << (c - 1)) != cudaSuccess) {
     cudaGetLastError();
     dtable = nullptr;
     c = msm_pick_window(vt->scalar_modulus, n);

@@ -118,6 +118,7 @@ struct vimz_ctx {
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
   bool opt_cross_stream = true; // cross term: chunked CSR streaming through shared memory (false: row-class kernel)
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
+  long opt_direct_c = 0;       // digit width of the direct table (0 = chosen by key length)
   long opt_direct_bps = 4;     // k_msm_direct blocks per SM (1..4)
   long opt_direct_max = 32768; // keys up to this many points get the direct multiples table (256 KB per point); 0 = never
   uint64_t launches = 0;

@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(128) k_precompute(const void* __restrict__ bas
 // The fold step's secondary curve (and the hash / redact step circuits) commit ~10^4-point vectors: there the
 // bucket pipeline is pure latency -- sort, accumulate, combine and a ~40-addition-deep bucket reduction for a few
 // hundred thousand insertions.  With 180 GB of HBM the key can instead hold EVERY digit multiple:
-//   dtable[((j * n + i) << (c-1)) + (k-1)] = k * 2^(c*j) * ck_i,   k = 1 .. 2^(c-1)   (c = 8: 256 KB per point)
+//   dtable[((j * n + i) << (c-1)) + (k-1)] = k * 2^(c*j) * ck_i,   k = 1 .. 2^(c-1)   (c = 8: 256 KB per point, c = 10: 832 KB)
 // so a signed digit is one gather + one mixed addition into a per-thread accumulator and the MSM is a plain sum:
 // no buckets, no sort, no bucket reduction -- digits kernel + ONE launch (thread sums -> quad sums -> block sum ->
 // last-arriving block of each group of DIRECT_GROUP blocks -> last-arriving group writes the Jacobian result).
@@ -594,6 +594,7 @@ __global__ void __launch_bounds__(128) k_precompute(const void* __restrict__ bas
 #define VIMZ_DIRECT_MUL MulCall  // few additions per thread: a small kernel that stays in the instruction caches
 #endif
 constexpr int DIRECT_C = 8;
+constexpr int DIRECT_C_SHORT = 10;  // keys of <= 16 384 points: 26 windows instead of 32 (832 KB per point)
 constexpr uint32_t DIRECT_GROUP = 32;
 constexpr uint32_t DIRECT_CTRL_FINAL = 32;  // ctrl[0..31]: per-group arrival counters, ctrl[32]: groups finished
 constexpr uint32_t DIRECT_MAX_BLOCKS = DIRECT_GROUP * 32;
