@@ -58,6 +58,14 @@ extern "C" {
     pub fn vimz_fold_witness(ctx: *mut vimz_ctx, r: *const Scalar, w1: *const Scalar, w2: *const Scalar, n: usize,
         e1: *const Scalar, t: *const Scalar, m: usize, w_out: *mut Scalar, e_out: *mut Scalar) -> c_int;
     pub fn vimz_acc_init(ctx: *mut vimz_ctx, s: *const vimz_shape, ck: *const vimz_ck, out: *mut *mut vimz_acc) -> c_int;
+    /// Row-range shard of one fold across GPUs (include/vimz_gpu.h): partial commitments per rank.
+    pub fn vimz_acc_init_sharded(ctx: *mut vimz_ctx, s_rows: *const vimz_shape, ck_rows: *const vimz_ck, ck_vars: *const vimz_ck,
+        var_first: usize, var_count: usize, out: *mut *mut vimz_acc) -> c_int;
+    pub fn vimz_acc_step_begin_dev_async(acc: *mut vimz_acc, d_w2: *const core::ffi::c_void, x2: *const Scalar,
+        d_partials: *mut *mut core::ffi::c_void) -> c_int;
+    pub fn vimz_acc_step_combine_dev(acc: *mut vimz_acc, d_gathered: *const core::ffi::c_void, world: usize,
+        comm_w2: *mut Point, comm_t: *mut Point) -> c_int;
+    pub fn vimz_point_sum(ctx: *mut vimz_ctx, pts: *const Point, k: usize, out: *mut Point) -> c_int;
     pub fn vimz_acc_load(acc: *mut vimz_acc, w: *const Scalar, e: *const Scalar, u: *const Scalar, x: *const Scalar,
         comm_w: *const Point, comm_e: *const Point) -> c_int;
     pub fn vimz_acc_step_begin(acc: *mut vimz_acc, w2: *const Scalar, x2: *const Scalar, comm_w2: *mut Point, comm_t: *mut Point) -> c_int;

@@ -217,3 +217,41 @@ def test_bn254_published_known_answers_gpu(engines):
     assert gpu_commit_affine(eng, ck, ints_to_mont([2, 1], c.q)) == BN254_3G
     assert gpu_commit_affine(eng, ck, ints_to_mont([c.q - 2, 0], c.q)) == P.aff_neg(c, BN254_2G)
     ck.close()
+
+
+@pytest.mark.parametrize("direct_c", [0, 6, 8])
+def test_msm_direct_table_ranges_and_digit_widths(direct_c, coracle):
+    """Short keys commit from the direct multiples table (k_msm_direct): every digit width gives the oracle's group
+    element, prefixes and point-range shards (`first` > 0) index the table correctly, and the key reports its geometry."""
+    import torch
+    c = P.VESTA
+    eng = vimz_b200.Engine("vesta", 0)
+    if direct_c:
+        eng.set_option("msm_direct_c", direct_c)
+    n = 3001
+    rng = random.Random(direct_c)
+    bases, logs = make_bases(c, n, seed=70 + direct_c)
+    Bm = affine_to_mont(bases, c.p)
+    ck = CommitmentKey.from_bases(eng, Bm)
+    assert ck.window_bits == (direct_c or 10)           # a direct key: fixed digit width, not the cost-model window
+    G = P.generator(c)
+    for dist in ("uniform", "bits", "edge"):
+        if dist == "uniform":
+            sc = [rng.randrange(c.q) for _ in range(n)]
+        elif dist == "bits":
+            sc = [rng.randrange(2) if rng.random() < 0.93 else rng.randrange(c.q) for _ in range(n)]
+        else:
+            pool = [0, 1, c.q - 1, (c.q - 1) // 2, (c.q + 1) // 2, 1 << 254, (1 << 254) - 1, 127, 128, 129, 511, 512, 513]
+            sc = [pool[i % len(pool)] % c.q for i in range(n)]
+        Sm = ints_to_mont(sc, c.q)
+        whole = gpu_commit_affine(eng, ck, Sm)
+        assert whole == P.scalar_mul(c, sum(s * k for s, k in zip(sc, logs)) % c.q, G), (direct_c, dist)
+        assert gpu_commit_affine(eng, ck, Sm[:777]) == oracle_commit_affine(coracle, c, Sm[:777], Bm[:777])   # prefix
+        d_S = torch.from_numpy(Sm.view(np.int64)).cuda()
+        parts, first = [], 0
+        for cnt in (1000, 1, 0, 2000):                   # ragged point-range shards, one of them empty
+            parts.append(CommitmentEngine.commit_dev(ck, d_S.data_ptr() + first * 32, cnt, first=first))
+            first += cnt
+        assert first == n and eng.to_affine_ints(eng.point_sum(np.stack(parts))) == whole
+    ck.close()
+    eng.close()

@@ -193,9 +193,12 @@ __global__ void __launch_bounds__(128) k_cross_term(CrossArgs a, const uint32_t*
 //   phase 2: one thread per row sums its products out of shared memory and forms T (rows above CROSS_ROW_COOP
 //            non-zeros are summed by a warp with shuffles instead).
 // Coefficients come from the shape's value dictionary (4 B per non-zero instead of 32 B; +1 / -1 need no product).
-constexpr uint32_t CROSS_CHUNK_NNZ = 1024;  // products per chunk: 64 KB of shared memory
+#ifndef VIMZ_CROSS_CHUNK_NNZ
+#define VIMZ_CROSS_CHUNK_NNZ 1024
+#endif
+constexpr uint32_t CROSS_CHUNK_NNZ = VIMZ_CROSS_CHUNK_NNZ;  // products per chunk: 64 B of shared memory each
 constexpr uint32_t CROSS_CHUNK_ROWS = 256;  // = block size
-constexpr uint32_t CROSS_ROW_MAX = 512;     // longer rows are chunks of their own (a warp walks them in global memory)
+constexpr uint32_t CROSS_ROW_MAX = CROSS_CHUNK_NNZ < 512 ? CROSS_CHUNK_NNZ : 512;     // longer rows are chunks of their own (a warp walks them in global memory)
 constexpr uint32_t CROSS_ROW_COOP = 32;     // rows above this are summed by a warp in phase 2
 
 struct CrossStreamArgs {
