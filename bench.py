@@ -284,16 +284,20 @@ class GpuFold:
             t = torch.from_numpy(w.view(np.int64).copy()).pin_memory()
             self.pin_W.append(t)
         self.q = self.cv.scalar_modulus
+        # host-side constants of the loop, prepared once: device addresses, host views of the pinned witnesses, X2 as raw bytes
+        self.dev_ptr = [t.data_ptr() for t in self.dev_W]
+        self.pin_np = [t.numpy().view(np.uint64).reshape(-1, 4) for t in self.pin_W]
+        self.X2_bytes = [np.ascontiguousarray(x, dtype=np.uint64).tobytes() for _, x in self.wits]
 
     def step(self, k: int, resident: bool):
-        from vimz_b200.field import ints_to_mont
         i = k % NUM_WITNESSES
-        X2 = self.wits[i][1]
+        X2 = self.X2_bytes[i]
         if resident:
-            cw, ct = self.acc.step_begin_dev(self.dev_W[i].data_ptr(), X2)
+            cw, ct = self.acc.step_begin_dev(self.dev_ptr[i], X2)
         else:
-            cw, ct = self.acc.step_begin(self.pin_W[i].numpy().view(np.uint64), X2)
-        r = ints_to_mont([challenge_from(ct.tobytes(), k)], self.q)
+            cw, ct = self.acc.step_begin(self.pin_np[i], X2)
+        # r = RO(comm_T) as a Montgomery-form scalar, 32 little-endian bytes (what the Rust side hands over)
+        r = ((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little")
         self.acc.step_end(r)
 
     def h2d_bytes(self):

@@ -857,8 +857,10 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
     VIMZ_TRY(enqueue_step_begin(a, fresh));
     a->warm[p] = true;
   }
+  a->fresh_complete = false;
   if (!sync) return VIMZ_OK;
   VIMZ_CUDA(cudaStreamSynchronize(st));
+  a->fresh_complete = true;
   memcpy(comm_W2, ctx->pinned, 96);
   memcpy(comm_T, (char*)ctx->pinned + 96, 96);
   return VIMZ_OK;
@@ -884,6 +886,7 @@ int vimz_acc_step_combine_dev(vimz_acc* a, const void* d_gathered, size_t world,
   VIMZ_TRY(vt->point_sum_batch(ctx, d_gathered, world, 2, ctx->ws.result.ptr));
   VIMZ_CUDA(cudaMemcpyAsync((char*)ctx->pinned + 3072, ctx->ws.result.ptr, 2 * 96, cudaMemcpyDeviceToHost, ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  a->fresh_complete = true;
   memcpy(comm_W2, (char*)ctx->pinned + 3072, 96);
   memcpy(comm_T, (char*)ctx->pinned + 3072 + 96, 96);
   return VIMZ_OK;
@@ -917,18 +920,17 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   cudaStream_t st = ctx->stream;
   char* comms = (char*)a->comms;
   char* fresh = comms + (2 + 2 * a->parity) * 96;
-  char* d_r = comms + 6 * 96 + 32 * a->parity;
-  // r goes to the device once for the commitment folds (side stream) ...
-  uint8_t* stage = (uint8_t*)ctx->pinned + 2048 + 32 * a->parity;
-  memcpy(stage, r, 32);
-  VIMZ_CUDA(cudaMemcpyAsync(d_r, stage, 32, cudaMemcpyHostToDevice, st));
-  VIMZ_CUDA(cudaEventRecord(a->ev_main, st));
-  // ... and by value into the witness folds: W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2)
+  // r travels by value in both launches: W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2) on the main stream ...
   VIMZ_TRY(vt->axpy3(ctx, a->W1, a->W2, s->n, a->E1, a->T, s->m, a->tail1, a->tail2, 1 + s->io, r));
-  // comm_W1 += r*comm_W2 ; comm_E1 += r*comm_T : two 128-bit scalar multiplications, latency-bound,
-  // so they run on the side stream and overlap the next step's MSMs.
-  VIMZ_CUDA(cudaStreamWaitEvent(ctx->side, a->ev_main, 0));
-  VIMZ_TRY(vt->point_scale_add(ctx, ctx->side, comms, d_r, fresh, comms, 2));
+  // ... and comm_W1 += r*comm_W2 ; comm_E1 += r*comm_T on the side stream: two 128-bit scalar multiplications,
+  // latency-bound, overlapping the next step's MSMs.  Their inputs (the step's fresh pair) were complete when
+  // step_begin returned, and the running pair is only touched on the side stream, so no cross-stream wait is needed
+  // (unless the step was only enqueued and never waited for: then the side stream waits for the main stream).
+  if (!a->fresh_complete) {
+    VIMZ_CUDA(cudaEventRecord(a->ev_main, st));
+    VIMZ_CUDA(cudaStreamWaitEvent(ctx->side, a->ev_main, 0));
+  }
+  VIMZ_TRY(vt->point_scale_add_val(ctx, ctx->side, comms, r, fresh, comms, 2));
   VIMZ_CUDA(cudaEventRecord(a->ev_side[a->parity], ctx->side));
   a->side_pending[a->parity] = true;
   return VIMZ_OK;

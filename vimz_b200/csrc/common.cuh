@@ -197,6 +197,7 @@ struct vimz_acc {
   void* comms = nullptr;
   cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr}, ev_w2 = nullptr, ev_aux = nullptr;
   bool side_pending[2] = {false, false};
+  bool fresh_complete = false;  // the host has waited for the last step_begin (sync entry points, step_combine_dev)
   int parity = 0;
   // step_begin's launch sequence (cross term + both MSMs, ~35 kernels on two streams) captured once per
   // parity slot and replayed: the step is latency-bound and stream launches cost more than the small kernels

@@ -28,6 +28,7 @@ struct CurveVTable {
   int (*point_sum_batch)(vimz_ctx*, const void* d_pts, size_t k, size_t sets, void* d_out);
   int (*point_to_affine)(vimz_ctx*, const void* d_pt, void* d_out);
   int (*point_scale_add)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count);
+  int (*point_scale_add_val)(vimz_ctx*, cudaStream_t, const void* d_a, const vimz_fr* r, const void* d_b, void* d_out, int count);
   int (*gen_bases)(vimz_ctx*, uint64_t k0, uint64_t dk, size_t n, void* d_out);
   int (*spmv3)(vimz_ctx*, const vimz_shape*, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz);
   // fuse_ck != nullptr: also histogram T's digits for the commit(fuse_ck, T) that follows on lane 0
@@ -238,6 +239,15 @@ int impl_point_scale_add(vimz_ctx* ctx, cudaStream_t st, const void* d_a, const 
   return VIMZ_OK;
 }
 template <class C>
+int impl_point_scale_add_val(vimz_ctx* ctx, cudaStream_t st, const void* d_a, const vimz_fr* r, const void* d_b, void* d_out, int count) {
+  if (count > 8) return set_error(VIMZ_ERR_ARG, "point_scale_add: at most 8 pairs per call");
+  Fp<typename C::Fs> rr;
+  memcpy(rr.v, r, 32);
+  k_point_scale_add_val<C><<<1, 32, 0, st>>>(d_a, rr, d_b, d_out, count);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
 int impl_gen_bases(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* d_out) {
   if (n == 0) return VIMZ_OK;
   k_gen_bases<C><<<ceil_div(ceil_div(n, GEN_RUN), 128), 128, 0, ctx->stream>>>(k0, dk, (uint32_t)n, d_out);
@@ -358,6 +368,7 @@ CurveVTable make_vtable(const char* name) {
   t.point_sum_batch = &impl_point_sum_batch<C>;
   t.point_to_affine = &impl_point_to_affine<C>;
   t.point_scale_add = &impl_point_scale_add<C>;
+  t.point_scale_add_val = &impl_point_scale_add_val<C>;
   t.gen_bases = &impl_gen_bases<C>;
   t.spmv3 = &impl_spmv3<C>;
   t.cross_term = &impl_cross_term<C>;

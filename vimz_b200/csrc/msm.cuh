@@ -754,12 +754,12 @@ __global__ void __launch_bounds__(32) k_point_sum_batch(const void* __restrict__
 // out[t] = a[t] + r * b[t] for count <= 8 independent pairs, one QUAD each (one warp in total); r is a
 // Montgomery scalar shared by all pairs (RelaxedR1CSInstance::fold uses the same r for comm_W and comm_E).
 template <class C>
-__global__ void __launch_bounds__(32) k_point_scale_add(const void* __restrict__ a, const void* __restrict__ r_mont, const void* __restrict__ b,
-                                                        void* __restrict__ out, int count) {
+__device__ __forceinline__ void point_scale_add_body(const void* __restrict__ a, Fp<typename C::Fs> r_mont, const void* __restrict__ b,
+                                                     void* __restrict__ out, int count) {
   using Fs = Fp<typename C::Fs>;
   const int t = threadIdx.x >> 2;
   const bool valid = t < count;
-  Fs r = fp_from_mont(Fs::load(r_mont));
+  Fs r = fp_from_mont(r_mont);
   const int tt = valid ? t : 0;
   QPoint<C> base = q_load_jacobian<C>(reinterpret_cast<const char*>(b) + (size_t)tt * 96);
   QPoint<C> pa = q_load_jacobian<C>(reinterpret_cast<const char*>(a) + (size_t)tt * 96);
@@ -774,6 +774,17 @@ __global__ void __launch_bounds__(32) k_point_scale_add(const void* __restrict__
   acc = q_add<C>(acc, pa);
   // each quad writes its own result (q_store_jacobian stores from lanes 0..2 of the quad)
   q_store_jacobian<C>(acc, reinterpret_cast<char*>(out) + (size_t)tt * 96, valid);
+}
+template <class C>
+__global__ void __launch_bounds__(32) k_point_scale_add(const void* __restrict__ a, const void* __restrict__ r_mont, const void* __restrict__ b,
+                                                        void* __restrict__ out, int count) {
+  point_scale_add_body<C>(a, Fp<typename C::Fs>::load(r_mont), b, out, count);
+}
+// r by value (the fold step: no staging copy, no cross-stream event for the challenge)
+template <class C>
+__global__ void __launch_bounds__(32) k_point_scale_add_val(const void* __restrict__ a, Fp<typename C::Fs> r_mont, const void* __restrict__ b,
+                                                            void* __restrict__ out, int count) {
+  point_scale_add_body<C>(a, r_mont, b, out, count);
 }
 
 // bases[i] = (k0 + i*dk) * G ; each thread walks a run of GEN_RUN consecutive multiples.

@@ -437,26 +437,46 @@ class FoldAccumulator:
         ce = np.ascontiguousarray(U.comm_E, dtype=np.uint64).reshape(12)
         check(lib.vimz_acc_load(self._h, _ptr(Wv), _ptr(E), _ptr(u), _ptr(X), _ptr(cw), _ptr(ce)))
 
+    # The three per-step calls are the host side of a ~1 ms loop: output buffers and their ctypes pointers are made once
+    # (numpy's .ctypes accessor costs microseconds per use), inputs that already are (n, 4) uint64 arrays skip the checks.
+    def _io(self):
+        io = getattr(self, "_io_cache", None)
+        if io is None:
+            out = np.zeros(24, dtype=np.uint64)
+            base = out.ctypes.data
+            io = self._io_cache = (out, C.c_void_p(base), C.c_void_p(base + 96))
+        return io
+
+    @staticmethod
+    def _fr_ptr(a, n):
+        if type(a) is bytes:  # 32*n raw bytes (little-endian Montgomery limbs): ctypes passes the buffer as is
+            if len(a) != 32 * n:
+                raise ValueError(f"expected {n} field elements ({32 * n} bytes), got {len(a)} bytes")
+            return a, a
+        if not (type(a) is np.ndarray and a.dtype == np.uint64 and a.ndim == 2 and a.shape == (n, 4) and a.flags.c_contiguous):
+            a = as_fr(a, n)
+        return a, C.c_void_p(a.__array_interface__["data"][0])
+
     def step_begin(self, W2: np.ndarray, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """-> (comm_W2, comm_T).  W2 is a host array (copied H2D inside the call)."""
         s = self.shape
-        W2 = as_fr(W2)
-        if W2.shape[0] != s.num_vars:
+        W2 = as_fr(W2) if not (type(W2) is np.ndarray and W2.dtype == np.uint64 and W2.ndim == 2 and W2.flags.c_contiguous) else W2
+        if W2.shape[0] != s.num_vars or W2.shape[1] != 4:
             raise InvalidWitnessLength(_lib.VIMZ_ERR_LENGTH, "step_begin: witness length != num_vars")
-        X2 = as_fr(X2, s.num_io)
-        cw, ct = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
-        check(lib.vimz_acc_step_begin(self._h, _ptr(W2), _ptr(X2), _ptr(cw), _ptr(ct)))
-        return cw, ct
+        X2, px = self._fr_ptr(X2, s.num_io)
+        out, pw, pt = self._io()
+        check(lib.vimz_acc_step_begin(self._h, C.c_void_p(W2.__array_interface__["data"][0]), px, pw, pt))
+        return out[:12].copy(), out[12:].copy()
 
     def step_begin_dev(self, d_W2: int, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        X2 = as_fr(X2, self.shape.num_io)
-        cw, ct = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
-        check(lib.vimz_acc_step_begin_dev(self._h, C.c_void_p(d_W2), _ptr(X2), _ptr(cw), _ptr(ct)))
-        return cw, ct
+        X2, px = self._fr_ptr(X2, self.shape.num_io)
+        out, pw, pt = self._io()
+        check(lib.vimz_acc_step_begin_dev(self._h, C.c_void_p(d_W2), px, pw, pt))
+        return out[:12].copy(), out[12:].copy()
 
     def step_end(self, r: np.ndarray):
-        r = as_fr(r, 1)
-        check(lib.vimz_acc_step_end(self._h, _ptr(r)))
+        r, pr = self._fr_ptr(r, 1)
+        check(lib.vimz_acc_step_end(self._h, pr))
 
     def last_T(self) -> np.ndarray:
         T = fr_array(self.shape.num_cons)
