@@ -436,3 +436,42 @@ def test_row_sharded_fold_matches_unsharded_chain(name, world, engines, coracle)
     rc = vimz_b200.lib.vimz_acc_init_sharded(eng._h, shape._h, small._h, small._h, sh.num_vars - 5, 10, C.byref(h))
     assert rc == vimz_b200._lib.VIMZ_ERR_LENGTH          # variable range leaves the witness
     shape.close(); small.close()
+
+
+def test_row_sharded_fold_with_empty_shards(engines, coracle):
+    """More ranks than constraint rows / variables: shards with zero rows, zero variables or both still step, and the
+    sums over all shards equal the CPU fold."""
+    from vimz_b200.sharding import FoldShard
+    eng, c = engines["pallas"], P.PALLAS
+    q = c.q
+    m, n, io, world = 5, 3, 2, 7
+    rng = random.Random(77)
+    A, B, Cm = (rand_coo(rng, m, n + 1 + io, k, q) for k in (9, 7, 4))
+    bases, _ = make_bases(c, max(m, n), seed=5)
+    Bm = affine_to_mont(bases, c.p)
+
+    class Sh:  # what _oracle_fold_chain reads
+        num_cons, num_vars, num_io = m, n, io
+    Sh.A, Sh.B, Sh.C = A, B, Cm
+    wit = [(ints_to_mont([rng.randrange(q) for _ in range(n)], q), ints_to_mont([rng.randrange(q) for _ in range(io)], q)) for _ in range(2)]
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(2)]
+    ref = _oracle_fold_chain(coracle, c, Sh, Bm, wit, chal)
+
+    def make_ck(first, count):
+        return CommitmentKey.from_bases(eng, Bm[first:first + count])
+
+    shards = [FoldShard(eng, m, n, io, A, B, Cm, make_ck, r, world) for r in range(world)]
+    assert sum(1 for s in shards if s.m_local == 0) >= 2 and sum(1 for s in shards if s.var_count == 0) >= 4
+    for k in range(2):
+        parts = [s.step_begin(*wit[k]) for s in shards]
+        assert eng.to_affine_ints(eng.point_sum(np.stack([p[0] for p in parts]))) == _affine(coracle, c, ref[k]["comm_W2"])
+        assert eng.to_affine_ints(eng.point_sum(np.stack([p[1] for p in parts]))) == _affine(coracle, c, ref[k]["comm_T"])
+        for s in shards:
+            s.step_end(chal[k])
+    outs = [s.download() for s in shards]
+    assert np.array_equal(np.concatenate([W.E for _, W in outs]), ref[-1]["E"])
+    assert all(np.array_equal(W.W, ref[-1]["W"]) for _, W in outs)
+    assert eng.to_affine_ints(eng.point_sum(np.stack([U.comm_E for U, _ in outs]))) == _affine(coracle, c, ref[-1]["cE"])
+    assert eng.to_affine_ints(eng.point_sum(np.stack([U.comm_W for U, _ in outs]))) == _affine(coracle, c, ref[-1]["cW"])
+    for s in shards:
+        s.close()
