@@ -438,6 +438,27 @@ def test_row_sharded_fold_matches_unsharded_chain(name, world, engines, coracle)
     shape.close(); small.close()
 
 
+def test_commit_T_on_shape_without_rows(engines):
+    """num_cons = 0 (what a row shard beyond the last constraint looks like): T is empty and comm_T the identity, whatever
+    an earlier commit left in the workspace."""
+    eng, c = engines["pallas"], P.PALLAS
+    q = c.q
+    bases, _ = make_bases(c, 40, seed=9)
+    ck = CommitmentKey.from_bases(eng, affine_to_mont(bases, c.p))
+    CommitmentEngine.commit(ck, ints_to_mont(list(range(1, 41)), q))           # leaves a histogram / digit array behind
+    e = (np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros((0, 4), np.uint64))
+    shape = R1CSShape(eng, 0, 3, 1, e, e, e)
+    W = RelaxedR1CSWitness(ints_to_mont([5, 6, 7], q), fr_zero(0))
+    U = RelaxedR1CSInstance(np.zeros(12, np.uint64), np.zeros(12, np.uint64), ints_to_mont([3], q), ints_to_mont([2], q))
+    T, comm_T = shape.commit_T(ck, U, W, R1CSInstance(np.zeros(12, np.uint64), ints_to_mont([4], q)), R1CSWitness(ints_to_mont([1, 0, 1], q)))
+    assert T.shape == (0, 4) and eng.to_affine_ints(comm_T) is None
+    shape.close(); ck.close()
+
+
+def fr_zero(n):
+    return np.zeros((n, 4), np.uint64)
+
+
 def test_row_sharded_fold_with_empty_shards(engines, coracle):
     """More ranks than constraint rows / variables: shards with zero rows, zero variables or both still step, and the
     sums over all shards equal the CPU fold."""

@@ -648,7 +648,7 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
   }
   VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr, ck));
   if (T_out) VIMZ_CUDA(cudaMemcpyAsync(T_out, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, st));
-  VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr, true));
+  VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr, s->m > 0));  // no rows: no cross term ran, nothing was recoded
   return fetch_points(ctx, ctx->ws.result.ptr, comm_T, 96);
 }
 
@@ -795,7 +795,9 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   }
   // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck));  // also histograms T's digits
-  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, true));
+  // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
+  // so nothing recoded T: the commit then does its own, empty, digit pass)
+  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
   if (two_lanes) VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   return VIMZ_OK;
