@@ -258,3 +258,39 @@ def test_msm_direct_table_ranges_and_digit_widths(direct_c, coracle):
         assert first == n and eng.to_affine_ints(eng.point_sum(np.stack(parts))) == whole
     ck.close()
     eng.close()
+
+
+def test_concurrent_commits_on_one_context(engines, coracle):
+    """CompressedSNARK::prove / RecursiveSNARK::verify commit from several rayon workers at once (SURVEY 8b).  Calls from
+    different threads on ONE context are serialised inside the library (ctypes releases the GIL, so they really overlap):
+    every thread must get exactly the commitment a sequential call gives."""
+    import threading
+    c = P.PALLAS
+    eng = engines["pallas"]
+    n = 3000
+    bases, _ = make_bases(c, n, seed=123)
+    Bm = affine_to_mont(bases, c.p)
+    ck = CommitmentKey.from_bases(eng, Bm)
+    rng = random.Random(9)
+    vecs = [ints_to_mont([rng.randrange(c.q) for _ in range(n - 17 * t)], c.q) for t in range(6)]
+    expect = [gpu_commit_affine(eng, ck, v) for v in vecs]
+    assert expect[0] == oracle_commit_affine(coracle, c, vecs[0], Bm)
+    got = [[None] * 4 for _ in vecs]
+    errs = []
+
+    def worker(t):
+        try:
+            for rep in range(4):
+                got[t][rep] = gpu_commit_affine(eng, ck, vecs[t])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(len(vecs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    for t in range(len(vecs)):
+        assert got[t] == [expect[t]] * 4
+    ck.close()

@@ -103,6 +103,12 @@ struct DeviceGuard {
     if (prev != dev) cudaSetDevice(dev);
   }
 };
+// context lock (see vimz_ctx::mu) + current device, for the duration of an entry point
+struct CtxGuard {
+  std::unique_lock<std::recursive_mutex> lock;
+  DeviceGuard dev;
+  explicit CtxGuard(vimz_ctx* ctx) : lock(ctx->mu), dev(ctx->device) {}
+};
 
 extern "C" {
 
@@ -161,6 +167,7 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
 
 int vimz_ctx_sync(vimz_ctx* ctx) {
   CHECK_ARG(ctx, "vimz_ctx_sync: null ctx");
+  CtxGuard g(ctx);
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
@@ -169,6 +176,7 @@ int vimz_ctx_sync(vimz_ctx* ctx) {
 
 int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   CHECK_ARG(ctx && key, "vimz_ctx_set_option: null argument");
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (strcmp(key, "msm_window") == 0) {
     if (value != 0 && (value < 2 || value > 24)) return set_error(VIMZ_ERR_ARG, "msm_window must be 0 (auto) or in [2, 24]");
     ctx->opt_window = value;
@@ -226,7 +234,7 @@ static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_
 
 int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset) {
   CHECK_ARG(ctx && name, "vimz_ctx_profile: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
   Profiler& p = ctx->prof;
@@ -342,13 +350,13 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
 
 int vimz_ck_upload_dev(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out) {
   CHECK_ARG(ctx && out && (d_bases || n == 0), "vimz_ck_upload_dev: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   return ck_build(ctx, d_bases, n, out);
 }
 
 int vimz_ck_upload(vimz_ctx* ctx, const vimz_affine* bases, size_t n, vimz_ck** out) {
   CHECK_ARG(ctx && out && (bases || n == 0), "vimz_ck_upload: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   void* d = nullptr;
   VIMZ_CUDA(cudaMalloc(&d, std::max<size_t>(n * 64, 64)));
   cudaError_t e = cudaMemcpyAsync(d, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream);
@@ -360,8 +368,9 @@ int vimz_ck_upload(vimz_ctx* ctx, const vimz_affine* bases, size_t n, vimz_ck** 
 
 void vimz_ck_destroy(vimz_ck* ck) {
   if (!ck) return;
-  cudaSetDevice(ck->ctx->device);
+  CtxGuard g(ck->ctx);
   cudaStreamSynchronize(ck->ctx->stream);
+  cudaStreamSynchronize(ck->ctx->aux);
   if (ck->table) cudaFree(ck->table);
   if (ck->dtable) cudaFree(ck->dtable);
   delete ck;
@@ -375,7 +384,7 @@ int vimz_msm_async_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const voi
   CHECK_ARG(ctx && ck && d_out && (d_scalars || n == 0), "vimz_msm: null argument");
   CHECK_ARG(ck->ctx == ctx, "vimz_msm: commitment key belongs to another context");
   if (first + n > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_msm: vector longer than the commitment key");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   return curve_vtable(ctx->curve)->msm(ctx, 0, ck, first, d_scalars, n, d_out, false);
 }
 
@@ -389,7 +398,7 @@ static int fetch_points(vimz_ctx* ctx, const void* d_src, void* host_dst, size_t
 int vimz_msm_range_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, vimz_point* out) {
   CHECK_ARG(out, "vimz_msm: out is null");
   VIMZ_TRY(vimz_msm_async_dev(ctx, ck, first, d_scalars, n, ctx ? ctx->ws.result.ptr : nullptr));
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   return fetch_points(ctx, ctx->ws.result.ptr, out, 96);
 }
 
@@ -400,7 +409,7 @@ int vimz_msm_dev(vimz_ctx* ctx, const vimz_ck* ck, const void* d_scalars, size_t
 int vimz_msm(vimz_ctx* ctx, const vimz_ck* ck, const vimz_fr* scalars, size_t n, vimz_point* out) {
   CHECK_ARG(ctx && ck && out && (scalars || n == 0), "vimz_msm: null argument");
   if (n > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_msm: vector longer than the commitment key");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(ctx->ws.scal.reserve(std::max<size_t>(n * 32, 32)));
   VIMZ_CUDA(cudaMemcpyAsync(ctx->ws.scal.ptr, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   return vimz_msm_range_dev(ctx, ck, 0, ctx->ws.scal.ptr, n, out);
@@ -409,7 +418,7 @@ int vimz_msm(vimz_ctx* ctx, const vimz_ck* ck, const vimz_fr* scalars, size_t n,
 // ---- group helpers ---------------------------------------------------------------------------------
 int vimz_point_sum(vimz_ctx* ctx, const vimz_point* pts, size_t k, vimz_point* out) {
   CHECK_ARG(ctx && out && (pts || k == 0), "vimz_point_sum: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(ctx->tmp0.reserve(std::max<size_t>(k * 96, 96) + 96));
   char* d = ctx->tmp0.as<char>();
   VIMZ_CUDA(cudaMemcpyAsync(d + 96, pts, k * 96, cudaMemcpyHostToDevice, ctx->stream));
@@ -419,7 +428,7 @@ int vimz_point_sum(vimz_ctx* ctx, const vimz_point* pts, size_t k, vimz_point* o
 
 int vimz_point_to_affine(vimz_ctx* ctx, const vimz_point* p, vimz_affine* out) {
   CHECK_ARG(ctx && p && out, "vimz_point_to_affine: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(ctx->tmp0.reserve(256));
   char* d = ctx->tmp0.as<char>();
   VIMZ_CUDA(cudaMemcpyAsync(d, p, 96, cudaMemcpyHostToDevice, ctx->stream));
@@ -429,7 +438,7 @@ int vimz_point_to_affine(vimz_ctx* ctx, const vimz_point* p, vimz_affine* out) {
 
 int vimz_point_scale_add(vimz_ctx* ctx, const vimz_point* a, const vimz_fr* r, const vimz_point* b, vimz_point* out) {
   CHECK_ARG(ctx && a && r && b && out, "vimz_point_scale_add: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(ctx->tmp0.reserve(512));
   char* d = ctx->tmp0.as<char>();
   VIMZ_CUDA(cudaMemcpyAsync(d, a, 96, cudaMemcpyHostToDevice, ctx->stream));
@@ -494,7 +503,7 @@ static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row
 
 void vimz_shape_destroy(vimz_shape* s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
+  CtxGuard g(s->ctx);
   cudaStreamSynchronize(s->ctx->stream);
   for (int k = 0; k < 3; k++) {
     if (s->rowptr[k]) cudaFree(s->rowptr[k]);
@@ -518,7 +527,7 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   CHECK_ARG((nnzA == 0 || (rowA && colA && valA)) && (nnzB == 0 || (rowB && colB && valB)) && (nnzC == 0 || (rowC && colC && valC)),
             "vimz_shape_upload: null matrix arrays");
   CHECK_ARG(num_cons < (1ull << 31) && num_vars + num_io + 1 < (1ull << 31), "vimz_shape_upload: shape too large");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   vimz_shape* s = new vimz_shape();
   s->ctx = ctx;
   s->m = num_cons;
@@ -606,7 +615,7 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
 int vimz_multiply_vec(vimz_ctx* ctx, const vimz_shape* s, const vimz_fr* z, size_t z_len, vimz_fr* Az, vimz_fr* Bz, vimz_fr* Cz) {
   CHECK_ARG(ctx && s && z && Az && Bz && Cz, "vimz_multiply_vec: null argument");
   if (z_len != s->n + 1 + s->io) return set_error(VIMZ_ERR_LENGTH, "vimz_multiply_vec: z.len() != num_io + num_vars + 1 (InvalidWitnessLength)");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   size_t mb = std::max<size_t>(s->m * 32, 32);
   VIMZ_TRY(ctx->tmp0.reserve(z_len * 32));
   VIMZ_TRY(ctx->tmp1.reserve(mb));
@@ -628,7 +637,7 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
   CHECK_ARG(ctx && s && ck && u1 && comm_T && (W1 || s->n == 0) && (W2 || s->n == 0) && ((X1 && X2) || s->io == 0),
             "vimz_commit_T: null argument");
   if (s->m > ck->n) return set_error(VIMZ_ERR_LENGTH, "vimz_commit_T: commitment key shorter than num_cons");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   const CurveVTable* vt = curve_vtable(ctx->curve);
   size_t nb = std::max<size_t>(s->n * 32, 32), tb = (1 + s->io) * 32;
   VIMZ_TRY(ctx->tmp0.reserve(nb));
@@ -655,7 +664,7 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
 int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r, const vimz_fr* W1, const vimz_fr* W2, size_t n,
                       const vimz_fr* E1, const vimz_fr* T, size_t m, vimz_fr* W_out, vimz_fr* E_out) {
   CHECK_ARG(ctx && r && (n == 0 || (W1 && W2 && W_out)) && (m == 0 || (E1 && T && E_out)), "vimz_fold_witness: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
   VIMZ_TRY(ctx->tmp0.reserve(std::max<size_t>(n * 32, 32)));
@@ -677,7 +686,7 @@ int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r, const vimz_fr* W1, const 
 // ---- device-resident running instance --------------------------------------------------------------
 void vimz_acc_destroy(vimz_acc* a) {
   if (!a) return;
-  cudaSetDevice(a->ctx->device);
+  CtxGuard g(a->ctx);
   cudaStreamSynchronize(a->ctx->stream);
   cudaStreamSynchronize(a->ctx->side);
   cudaStreamSynchronize(a->ctx->aux);
@@ -696,7 +705,7 @@ void vimz_acc_destroy(vimz_acc* a) {
 
 static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, const vimz_ck* ck_w, size_t w_first, size_t w_count,
                       vimz_acc** out) {
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   vimz_acc* a = new vimz_acc();
   a->ctx = ctx;
   a->shape = s;
@@ -760,7 +769,7 @@ int vimz_acc_load(vimz_acc* a, const vimz_fr* W, const vimz_fr* E, const vimz_fr
   CHECK_ARG(a && u && comm_W && comm_E && (W || a->shape->n == 0) && (E || a->shape->m == 0) && (X || a->shape->io == 0),
             "vimz_acc_load: null argument");
   vimz_ctx* ctx = a->ctx;
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(acc_wait_side(a));
   cudaStream_t st = ctx->stream;
   const vimz_shape* s = a->shape;
@@ -870,7 +879,7 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
 
 int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* X2, void** d_partials) {
   CHECK_ARG(a && d_partials && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev_async: null argument");
-  DeviceGuard g(a->ctx->device);
+  CtxGuard g(a->ctx);
   size_t io = a->shape->io;
   if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
@@ -882,7 +891,7 @@ int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* 
 int vimz_acc_step_combine_dev(vimz_acc* a, const void* d_gathered, size_t world, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && d_gathered && world >= 1 && comm_W2 && comm_T, "vimz_acc_step_combine_dev: null argument");
   vimz_ctx* ctx = a->ctx;
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   const CurveVTable* vt = curve_vtable(ctx->curve);
   VIMZ_TRY(ctx->ws.result.reserve(2 * 96));
   VIMZ_TRY(vt->point_sum_batch(ctx, d_gathered, world, 2, ctx->ws.result.ptr));
@@ -896,7 +905,7 @@ int vimz_acc_step_combine_dev(vimz_acc* a, const void* d_gathered, size_t world,
 
 int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin: null argument");
-  DeviceGuard g(a->ctx->device);
+  CtxGuard g(a->ctx);
   size_t io = a->shape->io;
   if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
@@ -905,7 +914,7 @@ int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_
 
 int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
-  DeviceGuard g(a->ctx->device);
+  CtxGuard g(a->ctx);
   size_t io = a->shape->io;
   if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   // keep W2 resident for step_end
@@ -916,7 +925,7 @@ int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vi
 int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   CHECK_ARG(a && r, "vimz_acc_step_end: null argument");
   vimz_ctx* ctx = a->ctx;
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
@@ -941,7 +950,7 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
 int vimz_acc_download(vimz_acc* a, vimz_fr* W, vimz_fr* E, vimz_fr* u, vimz_fr* X, vimz_point* comm_W, vimz_point* comm_E) {
   CHECK_ARG(a, "vimz_acc_download: null argument");
   vimz_ctx* ctx = a->ctx;
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(acc_wait_side(a));
   cudaStream_t st = ctx->stream;
   const vimz_shape* s = a->shape;
@@ -957,7 +966,7 @@ int vimz_acc_download(vimz_acc* a, vimz_fr* W, vimz_fr* E, vimz_fr* u, vimz_fr* 
 
 int vimz_acc_last_T(vimz_acc* a, vimz_fr* T) {
   CHECK_ARG(a && (T || a->shape->m == 0), "vimz_acc_last_T: null argument");
-  DeviceGuard g(a->ctx->device);
+  CtxGuard g(a->ctx);
   VIMZ_CUDA(cudaMemcpyAsync(T, a->T, a->shape->m * 32, cudaMemcpyDeviceToHost, a->ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(a->ctx->stream));
   return VIMZ_OK;
@@ -966,7 +975,7 @@ int vimz_acc_last_T(vimz_acc* a, vimz_fr* T) {
 // ---- test / bench utilities --------------------------------------------------------------------------
 int vimz_gen_bases_dev(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* d_out) {
   CHECK_ARG(ctx && (d_out || n == 0), "vimz_gen_bases_dev: null argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   VIMZ_TRY(curve_vtable(ctx->curve)->gen_bases(ctx, k0, dk, n, d_out));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return VIMZ_OK;
@@ -974,7 +983,7 @@ int vimz_gen_bases_dev(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* 
 
 int vimz_field_op(vimz_ctx* ctx, int which, int op, const vimz_fr* a, const vimz_fr* b, size_t n, vimz_fr* out) {
   CHECK_ARG(ctx && (n == 0 || (a && b && out)) && which >= 0 && which <= 1 && op >= 0 && op <= 2, "vimz_field_op: bad argument");
-  DeviceGuard g(ctx->device);
+  CtxGuard g(ctx);
   size_t bytes = std::max<size_t>(n * 32, 32);
   VIMZ_TRY(ctx->tmp0.reserve(bytes));
   VIMZ_TRY(ctx->tmp1.reserve(bytes));

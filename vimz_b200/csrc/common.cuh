@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/vimz_gpu.h"
@@ -33,8 +35,8 @@ inline int set_error(int code, const std::string& msg) {
   } while (0)
 
 // Bumped whenever a DevBuf is (re)allocated: captured CUDA graphs hold raw pointers and are rebuilt when it moves.
-inline uint64_t& alloc_epoch() {
-  static uint64_t e = 0;
+inline std::atomic<uint64_t>& alloc_epoch() {
+  static std::atomic<uint64_t> e{0};
   return e;
 }
 
@@ -106,6 +108,10 @@ struct Profiler {
 };
 
 struct vimz_ctx {
+  // Every entry point that touches the context's streams or workspaces holds this lock for the call: nova-snark's
+  // prove_step is sequential, but CompressedSNARK::prove / RecursiveSNARK::verify commit from several rayon workers at
+  // once, and those calls must not interleave on one workspace.  Recursive: entry points nest.
+  std::recursive_mutex mu;
   int curve = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
