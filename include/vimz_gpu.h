@@ -14,8 +14,10 @@
  *     available from vimz_last_error() (thread-local).  No entry point has a CPU fallback.
  *   - "host" pointers are borrowed for the duration of the call; "_dev" variants take device
  *     pointers (e.g. torch tensor .data_ptr()) that live on the context's device.
- *   - one context = one curve on one GPU with its own stream; calls on a context are serialised
- *     by the caller (nova-snark's prove_step is sequential; use one context per rayon worker).
+ *   - one context = one curve on one GPU with its own streams and workspaces.  Entry points may be called from
+ *     any host thread: calls on the SAME context are serialised inside the library (a per-context lock held for
+ *     the call -- CompressedSNARK::prove and RecursiveSNARK::verify commit from several rayon workers at once);
+ *     use one context per curve, or one per worker if the commits should overlap on the GPU.
  */
 #ifndef VIMZ_GPU_H
 #define VIMZ_GPU_H
