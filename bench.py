@@ -260,6 +260,8 @@ class GpuFold:
         seg = os.environ.get("VIMZ_SEG_MIN_" + curve_name.upper())
         if seg:
             self.eng.set_option("msm_seg_min", int(seg))
+        if os.environ.get("VIMZ_CROSS_CACHE"):
+            self.eng.set_option("cross_cache", int(os.environ["VIMZ_CROSS_CACHE"]))
         if os.environ.get("VIMZ_DIRECT_C"):
             self.eng.set_option("msm_direct_c", int(os.environ["VIMZ_DIRECT_C"]))
         if os.environ.get("VIMZ_DIRECT_BPS"):

@@ -61,7 +61,9 @@ int vimz_ctx_sync(vimz_ctx* ctx);
 /* Tunables: "msm_window" (c bits, 0 = auto), "msm_acc_blocks" (accumulation blocks per SM, 1..8), "msm_seg_min" (shortest accumulation segment, 1..4096),
  * "msm_direct_c" (digit width of that table, 0 = by key length: 10 up to 16 384 points, else 8),
  * "msm_direct_max" (keys uploaded afterwards with at most this many points keep ALL digit multiples resident -- 256 KB per point at c = 8 --
- * and commit without buckets; default 32768, 0 = always the bucket pipeline; a forced msm_window also selects buckets), "aux_lane" (0/1), "profile" (0/1), "graph" (0/1: replay a fold step's launch
+ * and commit without buckets; default 32768, 0 = always the bucket pipeline; a forced msm_window also selects buckets), "cross_cache" (0/1, default 1:
+ * accumulators created afterwards keep (Az1, Bz1, Cz1) of the running instance resident and fold them in step_end instead of
+ * recomputing them in every step_begin), "aux_lane" (0/1), "profile" (0/1), "graph" (0/1: replay a fold step's launch
  * sequence as a CUDA graph, default 1).  Unknown keys -> VIMZ_ERR_ARG. */
 int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value);
 /* Device-side phase timers, enabled with vimz_ctx_set_option(ctx, "profile", 1): accumulated CUDA-event

@@ -496,3 +496,40 @@ def test_row_sharded_fold_with_empty_shards(engines, coracle):
     assert eng.to_affine_ints(eng.point_sum(np.stack([U.comm_W for U, _ in outs]))) == _affine(coracle, c, ref[-1]["cW"])
     for s in shards:
         s.close()
+
+
+@pytest.mark.parametrize("cache", [0, 1])
+def test_accumulator_cached_products_vs_recomputed(cache, coracle):
+    """The resident accumulator keeps (Az1, Bz1, Cz1) and folds them (A(z1 + r z2) = Az1 + r Az2) instead of recomputing
+    them every step (option cross_cache, default on).  Both variants, started from a LOADED mid-proof instance (whose
+    products are computed once by multiply_vec), must reproduce the CPU chain bit for bit; so must the row-class kernel
+    (cross_stream = 0), which fills the cache with an explicit mat-vec."""
+    c = P.PALLAS
+    q = c.q
+    eng = vimz_b200.Engine("pallas", 0)
+    eng.set_option("cross_cache", cache)
+    sh, shape, ck, Bm = _setup(eng, c, 0.012, seed=71)
+    rng = random.Random(3)
+    wit = []
+    for k in range(5):
+        Wi, Xi = S.synthetic_witness(sh, 500 + k)
+        wit.append((ints_to_mont(Wi, q), ints_to_mont(Xi, q)))
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(5)]
+    ref = _oracle_fold_chain(coracle, c, sh, Bm, wit, chal)
+    # start from the CPU's state after two folds
+    acc = FoldAccumulator(shape, ck)
+    st = ref[1]
+    acc.load(RelaxedR1CSInstance(st["cW"], st["cE"], st["X"], st["u"]), RelaxedR1CSWitness(st["W"], st["E"]))
+    for k in range(2, 5):
+        if k == 4:
+            eng.set_option("cross_stream", 0)      # row-class kernel for the last step
+        comm_W2, comm_T = acc.step_begin(*wit[k])
+        assert eng.to_affine_ints(comm_T) == _affine(coracle, c, ref[k]["comm_T"]), (cache, k)
+        assert eng.to_affine_ints(comm_W2) == _affine(coracle, c, ref[k]["comm_W2"])
+        assert np.array_equal(acc.last_T(), ref[k]["T"])
+        acc.step_end(chal[k])
+    U, W = acc.download()
+    assert np.array_equal(W.W, ref[4]["W"]) and np.array_equal(W.E, ref[4]["E"]) and np.array_equal(U.u, ref[4]["u"])
+    assert eng.to_affine_ints(U.comm_E) == _affine(coracle, c, ref[4]["cE"])
+    vimz_b200.is_sat_relaxed(shape, ck, U, W)
+    acc.close(); shape.close(); ck.close(); eng.close()

@@ -219,6 +219,10 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     alloc_epoch()++;
     return VIMZ_OK;
   }
+  if (strcmp(key, "cross_cache") == 0) {  // applies to accumulators created afterwards
+    ctx->opt_cross_cache = value != 0;
+    return VIMZ_OK;
+  }
   if (strcmp(key, "aux_lane") == 0) {
     ctx->opt_aux_lane = value != 0;
     return VIMZ_OK;
@@ -655,7 +659,7 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
     VIMZ_CUDA(cudaMemcpyAsync(t1 + 32, X1, s->io * 32, cudaMemcpyHostToDevice, st));
     VIMZ_CUDA(cudaMemcpyAsync(t2 + 32, X2, s->io * 32, cudaMemcpyHostToDevice, st));
   }
-  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr, ck));
+  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr, ck, nullptr, nullptr));
   if (T_out) VIMZ_CUDA(cudaMemcpyAsync(T_out, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, st));
   VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr, s->m > 0));  // no rows: no cross term ran, nothing was recoded
   return fetch_points(ctx, ctx->ws.result.ptr, comm_T, 96);
@@ -690,7 +694,7 @@ void vimz_acc_destroy(vimz_acc* a) {
   cudaStreamSynchronize(a->ctx->stream);
   cudaStreamSynchronize(a->ctx->side);
   cudaStreamSynchronize(a->ctx->aux);
-  void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms};
+  void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int k = 0; k < 2; k++)
@@ -722,6 +726,10 @@ static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, con
   };
   alloc0(&a->W1, nb); alloc0(&a->W2, nb); alloc0(&a->E1, mb); alloc0(&a->T, mb);
   alloc0(&a->tail1, tb); alloc0(&a->tail2, tb); alloc0(&a->comms, 6 * 96 + 2 * 32);
+  if (ctx->opt_cross_cache) {  // the default instance is all zero, and so are its products
+    alloc0(&a->cache1, 3 * mb);
+    alloc0(&a->cache2, 3 * mb);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_w2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_aux, cudaEventDisableTiming);
@@ -779,6 +787,10 @@ int vimz_acc_load(vimz_acc* a, const vimz_fr* W, const vimz_fr* E, const vimz_fr
   if (s->io) VIMZ_CUDA(cudaMemcpyAsync((char*)a->tail1 + 32, X, s->io * 32, cudaMemcpyHostToDevice, st));
   VIMZ_CUDA(cudaMemcpyAsync(a->comms, comm_W, 96, cudaMemcpyHostToDevice, st));
   VIMZ_CUDA(cudaMemcpyAsync((char*)a->comms + 96, comm_E, 96, cudaMemcpyHostToDevice, st));
+  if (a->cache1 && s->m) {  // (Az1, Bz1, Cz1) of the loaded instance, once
+    char* c1 = (char*)a->cache1;
+    VIMZ_TRY(curve_vtable(ctx->curve)->spmv3(ctx, s, a->W1, a->tail1, c1, c1 + s->m * 32, c1 + 2 * s->m * 32));
+  }
   VIMZ_CUDA(cudaStreamSynchronize(st));
   return VIMZ_OK;
 }
@@ -803,7 +815,7 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
     VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
   }
   // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
-  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck));  // also histograms T's digits
+  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2));  // also histograms T's digits
   // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
   // so nothing recoded T: the commit then does its own, empty, digit pass)
   VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
@@ -932,7 +944,8 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   char* comms = (char*)a->comms;
   char* fresh = comms + (2 + 2 * a->parity) * 96;
   // r travels by value in both launches: W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2) on the main stream ...
-  VIMZ_TRY(vt->axpy3(ctx, a->W1, a->W2, s->n, a->E1, a->T, s->m, a->tail1, a->tail2, 1 + s->io, r));
+  AxpySeg segs[4] = {{a->W1, a->W2, s->n}, {a->E1, a->T, s->m}, {a->tail1, a->tail2, 1 + s->io}, {a->cache1, a->cache2, a->cache1 ? 3 * s->m : 0}};
+  VIMZ_TRY(vt->axpyn(ctx, segs, 4, r));
   // ... and comm_W1 += r*comm_W2 ; comm_E1 += r*comm_T on the side stream: two 128-bit scalar multiplications,
   // latency-bound, overlapping the next step's MSMs.  Their inputs (the step's fresh pair) were complete when
   // step_begin returned, and the running pair is only touched on the side stream, so no cross-stream wait is needed

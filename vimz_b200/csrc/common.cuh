@@ -123,6 +123,7 @@ struct vimz_ctx {
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
   bool opt_cross_stream = true; // cross term: chunked CSR streaming through shared memory (false: row-class kernel)
+  bool opt_cross_cache = true;  // accumulators created from now on keep (Az1, Bz1, Cz1) resident instead of recomputing them
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
   long opt_direct_c = 0;       // digit width of the direct table (0 = chosen by key length)
   long opt_direct_bps = 4;     // k_msm_direct blocks per SM (1..4)
@@ -199,6 +200,9 @@ struct vimz_acc {
   size_t w_first = 0, w_count = 0;
   void *W1 = nullptr, *E1 = nullptr, *W2 = nullptr, *T = nullptr;
   void *tail1 = nullptr, *tail2 = nullptr;  // [1+io]: (u, X)
+  // cached products (option "cross_cache", fixed when the accumulator is created): cache1 = (Az1, Bz1, Cz1)[3][m] of the
+  // running instance, folded in step_end with cache2 = (Az2, Bz2, Cz2)[3][m] of the fresh one -- linear, so exact
+  void *cache1 = nullptr, *cache2 = nullptr;
   // Jacobian points comm_W1, comm_E1, then two alternating (comm_W2, comm_T) pairs, then two r slots
   void* comms = nullptr;
   cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr}, ev_w2 = nullptr, ev_aux = nullptr;

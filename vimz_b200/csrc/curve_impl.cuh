@@ -32,12 +32,13 @@ struct CurveVTable {
   int (*gen_bases)(vimz_ctx*, uint64_t k0, uint64_t dk, size_t n, void* d_out);
   int (*spmv3)(vimz_ctx*, const vimz_shape*, const void* d_W, const void* d_tail, void* d_Az, void* d_Bz, void* d_Cz);
   // fuse_ck != nullptr: also histogram T's digits for the commit(fuse_ck, T) that follows on lane 0
+  // cache1 / cache2 != nullptr (resident accumulator): (Az1, Bz1, Cz1) are READ from cache1[3][m] instead of being
+  // recomputed and (Az2, Bz2, Cz2) are written to cache2[3][m] for the fold in step_end
   int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
-                    const vimz_ck* fuse_ck);
+                    const vimz_ck* fuse_ck, const void* cache1, void* cache2);
   int (*axpy)(vimz_ctx*, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out);
-  // three in-place folds a_k += r * b_k in one launch (witness fold W, E and the (u, X) tail)
-  int (*axpy3)(vimz_ctx*, void* a0, const void* b0, size_t n0, void* a1, const void* b1, size_t n1, void* a2, const void* b2, size_t n2,
-               const vimz_fr* r);
+  // up to AXPY_MAX_SEGS in-place folds a_k += r * b_k in one launch (witness fold W, E, the (u, X) tail, cached products)
+  int (*axpyn)(vimz_ctx*, const vimz::AxpySeg* segs, int count, const vimz_fr* r);
   int (*field_op)(vimz_ctx*, int which, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 };
 
@@ -274,7 +275,7 @@ int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* 
 }
 template <class C>
 int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
-                    const vimz_ck* fuse_ck) {
+                    const vimz_ck* fuse_ck, const void* cache1, void* cache2) {
   if (s->m == 0) return VIMZ_OK;
   DigitCount dc{nullptr, 0, 0, nullptr, 0};
   if (fuse_ck) {  // zero lane 0's histogram, then let the cross-term kernels fill it and the digit array
@@ -296,18 +297,30 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
   ca.m = (uint32_t)s->m; ca.n = (uint32_t)s->n;
   ca.W1 = d_W1; ca.tail1 = d_tail1; ca.W2 = d_W2; ca.tail2 = d_tail2; ca.T = d_T; ca.dc = dc;
   if (ctx->opt_cross_stream && s->n_chunks) {
-    static bool smem_set = false;  // per template instance
-    constexpr size_t SMEM = (size_t)CROSS_CHUNK_NNZ * 64;
-    if (!smem_set) {
-      VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-      smem_set = true;
-    }
     CrossStreamArgs sa;
     sa.a = ca;
     sa.vidx[0] = s->vidx[0]; sa.vidx[1] = s->vidx[1]; sa.vidx[2] = s->vidx[2];
     sa.dict = s->dict;
     sa.chunk_start = s->chunk_start;
-    k_cross_term_stream<typename C::Fs><<<(uint32_t)s->n_chunks, 256, SMEM, ctx->stream>>>(sa);
+    sa.cache1 = cache1;
+    sa.cache2 = cache2;
+    if (cache1 && cache2) {
+      static bool smem_set_c = false;  // per template instance
+      constexpr size_t SMEM_C = (size_t)CROSS_CHUNK_NNZ * 32;
+      if (!smem_set_c) {
+        VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
+        smem_set_c = true;
+      }
+      k_cross_term_stream<typename C::Fs, true><<<(uint32_t)s->n_chunks, 256, SMEM_C, ctx->stream>>>(sa);
+    } else {
+      static bool smem_set = false;  // per template instance
+      constexpr size_t SMEM = (size_t)CROSS_CHUNK_NNZ * 64;
+      if (!smem_set) {
+        VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        smem_set = true;
+      }
+      k_cross_term_stream<typename C::Fs, false><<<(uint32_t)s->n_chunks, 256, SMEM, ctx->stream>>>(sa);
+    }
     VIMZ_LAUNCH_CHECK(ctx);
     return VIMZ_OK;
   }
@@ -315,6 +328,12 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
   k_cross_term<typename C::Fs><<<nb_long + nb_mid + nb_short, 128, 0, ctx->stream>>>(ca, s->long_rows, (uint32_t)s->n_long, nb_long,
                                                                                      s->mid_rows, (uint32_t)s->n_mid, nb_mid);
   VIMZ_LAUNCH_CHECK(ctx);
+  if (cache2) {  // the row-class kernel recomputes the z1 products itself; the accumulator still needs (Az2, Bz2, Cz2) for its fold
+    char* c2 = reinterpret_cast<char*>(cache2);
+    k_spmv3<typename C::Fs><<<dim3(ceil_div(s->m, 256), 3), 256, 0, ctx->stream>>>(
+        csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W2, d_tail2, c2, c2 + s->m * 32, c2 + 2 * s->m * 32);
+    VIMZ_LAUNCH_CHECK(ctx);
+  }
   return VIMZ_OK;
 }
 template <class C>
@@ -329,15 +348,22 @@ int impl_axpy(vimz_ctx* ctx, const void* d_a, const void* d_b, const vimz_fr* r,
   return VIMZ_OK;
 }
 template <class C>
-int impl_axpy3(vimz_ctx* ctx, void* a0, const void* b0, size_t n0, void* a1, const void* b1, size_t n1, void* a2, const void* b2, size_t n2,
-               const vimz_fr* r) {
-  const size_t total = n0 + n1 + n2;
+int impl_axpyn(vimz_ctx* ctx, const AxpySeg* segs, int count, const vimz_fr* r) {
+  if (count < 1 || count > AXPY_MAX_SEGS) return set_error(VIMZ_ERR_ARG, "axpyn: 1..6 segments");
+  AxpySegs sg;
+  size_t total = 0;
+  for (int k = 0; k < AXPY_MAX_SEGS; k++) {
+    sg.s[k] = k < count ? segs[k] : AxpySeg{nullptr, nullptr, 0};
+    total += sg.s[k].len;
+    sg.end[k] = total;
+  }
+  sg.count = count;
   if (total == 0) return VIMZ_OK;
   Fp<typename C::Fs> rr;
   memcpy(rr.v, r, 32);
   int grid = (int)std::min<size_t>(ceil_div(total, 256), (size_t)ctx->sm_count * 16);
   ProfScope prof(ctx, PROF_AXPY, ctx->stream);
-  k_axpy3<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(AxpySeg{a0, b0, n0}, AxpySeg{a1, b1, n1}, AxpySeg{a2, b2, n2}, rr);
+  k_axpy3<typename C::Fs><<<grid, 256, 0, ctx->stream>>>(sg, rr);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -373,7 +399,7 @@ CurveVTable make_vtable(const char* name) {
   t.spmv3 = &impl_spmv3<C>;
   t.cross_term = &impl_cross_term<C>;
   t.axpy = &impl_axpy<C>;
-  t.axpy3 = &impl_axpy3<C>;
+  t.axpyn = &impl_axpyn<C>;
   t.field_op = &impl_field_op<C>;
   return t;
 }

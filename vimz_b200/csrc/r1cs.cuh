@@ -102,12 +102,15 @@ VIMZ_DI Fp<F> cross_term_row(const Fp<F>& a1, const Fp<F>& a2, const Fp<F>& b1, 
 // T[row] = cross term of the six row products; optional digit histogram for the commit(T) that follows.
 // Out of line (with the field product): the cross-term kernels are latency-bound and were stalling on
 // instruction fetch with ~185 KB of inlined code; one shared copy keeps them inside the instruction caches.
+#ifndef VIMZ_CROSS_AGG
+#define VIMZ_CROSS_AGG false
+#endif
 template <class F>
 __device__ __noinline__ void cross_term_finish(Fp<F> a1, Fp<F> a2, Fp<F> b1, Fp<F> b2, Fp<F> c1, Fp<F> c2, Fp<F> u1, void* T, uint32_t row,
                                                DigitCount dc) {
   Fp<F> t = cross_term_row<F>(a1, a2, b1, b2, c1, c2, u1);
   t.store(reinterpret_cast<char*>(T) + (size_t)row * 32);
-  if (dc.digits) recode_scalar<F, false>(t, dc.c, dc.nwin, dc.counts, dc.digits, dc.stride, row);
+  if (dc.digits) recode_scalar<F, VIMZ_CROSS_AGG>(t, dc.c, dc.nwin, dc.counts, dc.digits, dc.stride, row);
 }
 
 // sum over the GROUP lanes of a row group (GROUP = 8 or 32, groups are aligned inside the warp)
@@ -206,20 +209,51 @@ struct CrossStreamArgs {
   const uint32_t* vidx[3];
   const void* dict;
   const uint32_t* chunk_start;
+  // CACHED variant (the resident accumulator): the products with the running z1 are linear in the fold,
+  //   A (z1 + r z2) = A z1 + r A z2,
+  // so the accumulator keeps (Az1, Bz1, Cz1) = cache1[3][m] resident and folds them in step_end with the
+  // (Az2, Bz2, Cz2) = cache2[3][m] written here: no z1 gather, no z1 product, half the shared memory.
+  const void* cache1;
+  void* cache2;
 };
 
-template <class F>
-__global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
+#ifndef VIMZ_CROSS_MINB
+#define VIMZ_CROSS_MINB 2
+#endif
+template <class F, bool CACHED>
+__global__ void __launch_bounds__(256, CACHED ? VIMZ_CROSS_MINB : 2) k_cross_term_stream(CrossStreamArgs s) {
   extern __shared__ __align__(32) unsigned char cross_smem[];
   char* P1 = reinterpret_cast<char*>(cross_smem);
-  char* P2 = P1 + (size_t)CROSS_CHUNK_NNZ * 32;
+  char* P2 = CACHED ? P1 : P1 + (size_t)CROSS_CHUNK_NNZ * 32;  // CACHED: only the z2 products are staged
   __shared__ uint32_t big_rows[32];
   __shared__ uint32_t nbig;
   const CrossArgs& a = s.a;
   const uint32_t cs = s.chunk_start[blockIdx.x], ce = s.chunk_start[blockIdx.x + 1];
   const uint32_t r0 = cs & 0x7fffffffu, r1 = ce & 0x7fffffffu;
-  if (cs >> 31) {  // a single row longer than CROSS_ROW_MAX
-    if (threadIdx.x < 32) cross_term_grouped_row<F, 32>(a, r0, true);
+  const size_t m32 = (size_t)a.m * 32;
+  auto keep2 = [&](uint32_t row_, const Fp<F>& a2_, const Fp<F>& b2_, const Fp<F>& c2_) {  // (Az2, Bz2, Cz2)[row] for step_end
+    char* c2p = reinterpret_cast<char*>(s.cache2) + (size_t)row_ * 32;
+    a2_.store(c2p); b2_.store(c2p + m32); c2_.store(c2p + 2 * m32);
+  };
+  if (cs >> 31) {  // a single row longer than CROSS_ROW_MAX: a warp walks it in global memory (both z: rare)
+    if (threadIdx.x < 32) {
+      if (!CACHED) {
+        cross_term_grouped_row<F, 32>(a, r0, true);
+      } else {
+        const uint32_t lane = threadIdx.x;
+        Fp<F> a1, a2, b1, b2, c1, c2;
+        row_dot2<F>(a.A, a.A.rowptr[r0] + lane, a.A.rowptr[r0 + 1], 32, a.n, a.W1, a.tail1, a.W2, a.tail2, a1, a2);
+        row_dot2<F>(a.B, a.B.rowptr[r0] + lane, a.B.rowptr[r0 + 1], 32, a.n, a.W1, a.tail1, a.W2, a.tail2, b1, b2);
+        row_dot2<F>(a.Cm, a.Cm.rowptr[r0] + lane, a.Cm.rowptr[r0 + 1], 32, a.n, a.W1, a.tail1, a.W2, a.tail2, c1, c2);
+        a1 = group_sum_fp<F, 32>(a1); a2 = group_sum_fp<F, 32>(a2);
+        b1 = group_sum_fp<F, 32>(b1); b2 = group_sum_fp<F, 32>(b2);
+        c1 = group_sum_fp<F, 32>(c1); c2 = group_sum_fp<F, 32>(c2);
+        if (lane == 0) {
+          cross_term_finish<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1), a.T, r0, a.dc);
+          keep2(r0, a2, b2, c2);
+        }
+      }
+    }
     return;
   }
   if (threadIdx.x == 0) nbig = 0;
@@ -244,13 +278,13 @@ __global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
   auto product = [&](uint32_t k, uint32_t vi, Fp<F> z1, Fp<F> z2) {
     if (vi >= 2) {
       Fp<F> v = Fp<F>::load_nc(reinterpret_cast<const char*>(s.dict) + (size_t)vi * 32);
-      z1 = fp_mul_noinline<F>(v, z1);
+      if (!CACHED) z1 = fp_mul_noinline<F>(v, z1);
       z2 = fp_mul_noinline<F>(v, z2);
     } else if (vi == 1) {
-      z1 = fp_neg(z1);
+      if (!CACHED) z1 = fp_neg(z1);
       z2 = fp_neg(z2);
     }
-    z1.store(P1 + (size_t)k * 32);
+    if (!CACHED) z1.store(P1 + (size_t)k * 32);
     z2.store(P2 + (size_t)k * 32);
   };
   for (uint32_t k = threadIdx.x; k < total; k += 512) {  // two entries in flight per thread
@@ -259,9 +293,13 @@ __global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
     uint32_t c0, v0, c1 = 0, v1 = 0;
     entry(k, c0, v0);
     if (two) entry(k2, c1, v1);
-    Fp<F> x1 = load_z<F>(a.W1, a.tail1, a.n, c0), x2 = load_z<F>(a.W2, a.tail2, a.n, c0);
-    Fp<F> y1 = Fp<F>::zero(), y2 = Fp<F>::zero();
-    if (two) { y1 = load_z<F>(a.W1, a.tail1, a.n, c1); y2 = load_z<F>(a.W2, a.tail2, a.n, c1); }
+    Fp<F> x1 = Fp<F>::zero(), y1 = Fp<F>::zero(), y2 = Fp<F>::zero();
+    if (!CACHED) x1 = load_z<F>(a.W1, a.tail1, a.n, c0);
+    Fp<F> x2 = load_z<F>(a.W2, a.tail2, a.n, c0);
+    if (two) {
+      if (!CACHED) y1 = load_z<F>(a.W1, a.tail1, a.n, c1);
+      y2 = load_z<F>(a.W2, a.tail2, a.n, c1);
+    }
     product(k, v0, x1, x2);
     if (two) product(k2, v1, y1, y2);
   }
@@ -270,9 +308,13 @@ __global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
     d1 = Fp<F>::zero();
     d2 = Fp<F>::zero();
     for (uint32_t j = start; j < count; j += stride) {
-      d1 = fp_add(d1, Fp<F>::load(P1 + (size_t)(first + j) * 32));
+      if (!CACHED) d1 = fp_add(d1, Fp<F>::load(P1 + (size_t)(first + j) * 32));
       d2 = fp_add(d2, Fp<F>::load(P2 + (size_t)(first + j) * 32));
     }
+  };
+  auto cached1 = [&](uint32_t row_, Fp<F>& a1_, Fp<F>& b1_, Fp<F>& c1_) {  // (Az1, Bz1, Cz1)[row] kept by the accumulator
+    const char* c1p = reinterpret_cast<const char*>(s.cache1) + (size_t)row_ * 32;
+    a1_ = Fp<F>::load(c1p); b1_ = Fp<F>::load(c1p + m32); c1_ = Fp<F>::load(c1p + 2 * m32);
   };
   if (have_row) {
     const uint32_t cnt = (ra1 - ra0) + (rb1 - rb0) + (rc1 - rc0);
@@ -283,7 +325,9 @@ __global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
       sum2(ra0 - begA, ra1 - ra0, 0, 1, a1, a2);
       sum2(nA + (rb0 - begB), rb1 - rb0, 0, 1, b1, b2);
       sum2(nA + nB + (rc0 - begC), rc1 - rc0, 0, 1, c1, c2);
+      if (CACHED) cached1(row, a1, b1, c1);
       cross_term_finish<F>(a1, a2, b1, b2, c1, c2, u1, a.T, row, a.dc);
+      if (CACHED) keep2(row, a2, b2, c2);
     }
   }
   __syncthreads();
@@ -296,11 +340,14 @@ __global__ void __launch_bounds__(256) k_cross_term_stream(CrossStreamArgs s) {
     sum2(qa0 - begA, qa1 - qa0, lane, 32, a1, a2);
     sum2(nA + (qb0 - begB), qb1 - qb0, lane, 32, b1, b2);
     sum2(nA + nB + (qc0 - begC), qc1 - qc0, lane, 32, c1, c2);
-    a1 = group_sum_fp<F, 32>(a1); a2 = group_sum_fp<F, 32>(a2);
-    b1 = group_sum_fp<F, 32>(b1); b2 = group_sum_fp<F, 32>(b2);
-    c1 = group_sum_fp<F, 32>(c1); c2 = group_sum_fp<F, 32>(c2);
+    if (!CACHED) { a1 = group_sum_fp<F, 32>(a1); b1 = group_sum_fp<F, 32>(b1); c1 = group_sum_fp<F, 32>(c1); }
+    a2 = group_sum_fp<F, 32>(a2);
+    b2 = group_sum_fp<F, 32>(b2);
+    c2 = group_sum_fp<F, 32>(c2);
     if (lane == 0) {
+      if (CACHED) cached1(br, a1, b1, c1);
       cross_term_finish<F>(a1, a2, b1, b2, c1, c2, u1, a.T, br, a.dc);
+      if (CACHED) keep2(br, a2, b2, c2);
     }
   }
 }
@@ -323,16 +370,24 @@ struct AxpySeg {
   const void* b;
   size_t len;
 };
+constexpr int AXPY_MAX_SEGS = 6;
+struct AxpySegs {
+  AxpySeg s[AXPY_MAX_SEGS];
+  size_t end[AXPY_MAX_SEGS];  // running end offsets
+  int count;
+};
 template <class F>
-__global__ void __launch_bounds__(256) k_axpy3(AxpySeg s0, AxpySeg s1, AxpySeg s2, Fp<F> r) {
-  const size_t total = s0.len + s1.len + s2.len;
+__global__ void __launch_bounds__(256) k_axpy3(AxpySegs segs, Fp<F> r) {
+  const size_t total = segs.end[segs.count - 1];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const bool in0 = i < s0.len, in1 = i < s0.len + s1.len;
-    const AxpySeg& sg = in0 ? s0 : (in1 ? s1 : s2);
-    const size_t j = in0 ? i : (in1 ? i - s0.len : i - s0.len - s1.len);
-    char* pa = reinterpret_cast<char*>(sg.a) + j * 32;
+    int k = 0;
+#pragma unroll
+    for (int q = 0; q < AXPY_MAX_SEGS - 1; q++)
+      if (q < segs.count - 1 && i >= segs.end[q]) k = q + 1;
+    const size_t j = i - (k ? segs.end[k - 1] : 0);
+    char* pa = reinterpret_cast<char*>(segs.s[k].a) + j * 32;
     Fp<F> x = Fp<F>::load(pa);
-    Fp<F> y = Fp<F>::load(reinterpret_cast<const char*>(sg.b) + j * 32);
+    Fp<F> y = Fp<F>::load(reinterpret_cast<const char*>(segs.s[k].b) + j * 32);
     fp_add(x, fp_mul(r, y)).store(pa);
   }
 }
