@@ -314,6 +314,89 @@ class GpuFold:
                 + sh.num_cons * self.ck.num_windows * 4)
 
 
+class GpuFoldSharded:
+    """ONE transformation folded by all ranks together (strong scaling): the primary curve's
+    constraint rows, E / T and both commitment-key ranges are split across the ranks (vimz_b200.sharding.FoldShard);
+    the step's only collective is the NCCL all-gather of the two partial commitments.  Every rank builds the same
+    problem (same seed) and keeps W replicated."""
+
+    def __init__(self, curve_name, circuit, seed, device, torch, dist, rank, world):
+        import vimz_b200
+        from vimz_b200 import CommitmentKey
+        from vimz_b200.sharding import FoldShard, ShardedFoldAccumulator
+        self.torch, self.dist, self.rank = torch, dist, rank
+        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.eng = eng = vimz_b200.Engine(curve_name, device)
+        self.dev = f"cuda:{device}"
+        sh = self.sh
+
+        def make_ck(first, count):
+            d = torch.empty(max(count, 1) * 8, dtype=torch.int64, device=self.dev)
+            vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, K0 + first * DK, DK, count, d.data_ptr()))
+            return CommitmentKey.from_device(eng, d.data_ptr(), count)
+
+        self.shard = FoldShard(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, make_ck, rank, world)
+        self.acc = ShardedFoldAccumulator(dist, self.shard, eng.point_sum, device=self.dev)
+        self.dev_W = [torch.from_numpy(w.view(np.int64)).to(self.dev) for w, _ in self.wits]
+        self.pin_W = [torch.from_numpy(w.view(np.int64).copy()).pin_memory() for w, _ in self.wits] if rank == 0 else None
+        self.stage = torch.empty_like(self.dev_W[0])
+        self.q = self.cv.scalar_modulus
+
+    def step(self, k: int, resident: bool):
+        from vimz_b200.field import ints_to_mont
+        i = k % NUM_WITNESSES
+        X2 = self.wits[i][1]
+        if resident:
+            cw, ct = self.acc.step_begin_dev(self.dev_W[i].data_ptr(), X2)
+        else:  # the fresh witness exists on rank 0's host only: H2D there, NCCL broadcast to the other ranks
+            if self.rank == 0:
+                self.stage.copy_(self.pin_W[i], non_blocking=True)
+            self.dist.broadcast(self.stage, src=0)
+            self.torch.cuda.current_stream().synchronize()
+            cw, ct = self.acc.step_begin_dev(self.stage.data_ptr(), X2)
+        r = ints_to_mont([challenge_from(ct.tobytes(), k)], self.q)
+        self.acc.step_end(r)
+        return ct
+
+
+def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup):
+    """Strong-scaling leg of an N > 1 run: the same grayscale (or --circuit) proof folded by all ranks together."""
+    prim = GpuFoldSharded(CYCLES[args.cycle][0], args.circuit, SEED, local_rank, torch, dist, rank, world)
+    if os.environ.get("VIMZ_SHARD_SECONDARY", "1") == "1":   # the secondary curve's 10.5k rows are sharded the same way
+        sec = GpuFoldSharded(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch, dist, rank, world)
+    else:
+        sec = GpuFold(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch)
+    engines = [prim.eng, sec.eng]
+    last = {}
+
+    def step_resident(k):
+        sec.step(k, True); last["ct"] = prim.step(k, True)
+
+    def step_e2e(k):
+        sec.step(k, False); last["ct"] = prim.step(k, False)
+
+    for k in range(PREFOLD + warmup):
+        step_resident(k)
+    for k in range(2):
+        step_e2e(k)
+    ms, _ = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + k), steps, dist)
+    ms_e2e, _ = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
+    # every rank must have derived the same transcript: compare the last comm_T across ranks
+    t = torch.from_numpy(last["ct"].view(np.int64).copy()).to(f"cuda:{local_rank}")
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    same = all(bool((p == parts[0]).all()) for p in parts)
+    res = {"steps_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_steps_per_s": steps / (ms_e2e * 1e-3),
+           "e2e_ms_per_step": ms_e2e / steps, "scaling": "strong", "ranks_agree_on_comm_T": same,
+           "rows_per_rank": prim.shard.m_local, "vars_per_rank": prim.shard.var_count,
+           "exchange": "NCCL all-gather of 2 partial commitments (192 B per rank) per step; e2e adds the NCCL broadcast of W2 "
+                       f"({prim.sh.num_vars * 32} B) from rank 0",
+           "parallelism": f"rows / E / T / ck of {'both curves' if isinstance(sec, GpuFoldSharded) else 'the primary curve (secondary replicated)'} "
+                          f"sharded x{world} by constraint-row range, W replicated"}
+    prim.shard.close()
+    return res
+
+
 def timed_region(torch, engines, fn, steps, dist):
     """barrier + sync; CUDA events on the primary context's stream around `steps` calls of fn; max over ranks."""
     stream = torch.cuda.ExternalStream(engines[0].stream)

@@ -31,3 +31,26 @@ def test_gpu_arm_refuses_without_device():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
     assert p.stdout.strip() == ""
+
+
+def test_bench_module_has_no_undefined_globals():
+    """Every global name bench.py's functions load is defined in the module or is a builtin (a deleted helper would
+    otherwise only surface on the multi-GPU leg, which runs nowhere but on the GPU box)."""
+    import builtins
+    import importlib.util
+    import symtable
+    path = os.path.join(ROOT, "bench.py")
+    spec = importlib.util.spec_from_file_location("bench_under_test", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    missing = set()
+
+    def walk(tab):
+        for sym in tab.get_symbols():
+            if sym.is_global() and sym.is_referenced() and not hasattr(mod, sym.get_name()) and not hasattr(builtins, sym.get_name()):
+                missing.add((tab.get_name(), sym.get_name()))
+        for child in tab.get_children():
+            walk(child)
+
+    walk(symtable.symtable(open(path).read(), path, "exec"))
+    assert not missing, missing
