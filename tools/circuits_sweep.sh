@@ -1,5 +1,5 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/s3_pytest2.log 2>&1; tail -3 gpurun_out/s3_pytest2.log
-for c in brightness contrast resize crop blur sharpness hash; do
+
+for c in grayscale brightness contrast resize crop blur sharpness hash; do
   python bench.py --circuit $c --steps 100 --no-cpu-baseline --msm-log2 > gpurun_out/s3_circuit_$c.json 2>> gpurun_out/s3_circuits.err
   python - <<PY
 import json
