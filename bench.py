@@ -37,7 +37,12 @@ sys.path.insert(0, ROOT)
 SEED = 0xB200
 K0, DK = 77, 1234577           # bases (K0 + i*DK) * G
 NUM_WITNESSES = 32             # distinct fresh witnesses (one image row each) cycled through the steps
-PREFOLD = 32                   # untimed folds before measuring, so W1/E1 are full-width and well mixed like mid-proof
+# Untimed folds before measuring.  The step cost depends (mildly) on how far the proof is: the cross-term scalars T are
+# ~(128 + log2(folds))-bit values, and once they pass 135 bits (fold ~130) they spill into one more 15-bit window -- +10 %
+# bucket insertions and a few giant buckets: 0.89 ms/step before, 0.95 ms/step after (measured).  An HD
+# proof is 720 steps, so the timed window is placed around its median step (folds 263..463 with the default --steps 200),
+# not in the cheaper first 130 folds.
+PREFOLD = int(os.environ.get("VIMZ_BENCH_PREFOLD", "260"))   # the ncu scripts under tools/ use 32 to keep their captures short
 IMAD_PER_MODMUL = 272          # 8-limb CIOS: 2*8^2 + 8 products x 2 IMAD
 MODMUL_PER_MADD = 10           # XYZZ mixed add 8M + 2S
 

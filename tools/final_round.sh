@@ -1,14 +1,17 @@
 #!/bin/bash
 # Round-end evidence on the final build: launch list of the default command, then the two bench arms.
 TAG=${1:-r1s3}
+# ncu replays every kernel: keep the pre-folds short (the captures below then sit at folds 38..41 of the run, where T still
+# fits nine 15-bit windows; bench.py itself measures around fold 360, see PREFOLD there)
+export VIMZ_BENCH_PREFOLD=32
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --msm-log2 20 > gpurun_out/${TAG}_launches_bench.log 2>&1
 W=$(python tools/step_window.py gpurun_out/${TAG}_launches.csv 38 41)
 echo "window $W"
 python tools/launch_table.py gpurun_out/${TAG}_launches.csv $W > gpurun_out/${TAG}_launches_fold_step.txt
 cat gpurun_out/${TAG}_launches_fold_step.txt
-python bench.py > gpurun_out/${TAG}_bench_final.json 2> gpurun_out/${TAG}_bench_final.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref_final.json 2>> gpurun_out/${TAG}_bench_final.err
+env -u VIMZ_BENCH_PREFOLD python bench.py > gpurun_out/${TAG}_bench_final.json 2> gpurun_out/${TAG}_bench_final.err
+env -u VIMZ_BENCH_PREFOLD python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref_final.json 2>> gpurun_out/${TAG}_bench_final.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/${TAG}_bench_final.json").read().strip().splitlines()[-1])

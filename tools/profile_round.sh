@@ -2,6 +2,9 @@
 # Round evidence: launch list of the default bench command (per-kernel device times, cold-cache & serialised under ncu:
 # compare SHARES), then ncu --set full of the accumulation kernel inside a fold step, of a 2^20 MSM, and of the direct kernel.
 TAG=${1:-r1s3}
+# ncu replays every kernel: keep the pre-folds short (the captures below then sit at folds 38..41 of the run, where T still
+# fits nine 15-bit windows; bench.py itself measures around fold 360, see PREFOLD there)
+export VIMZ_BENCH_PREFOLD=32
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --msm-log2 20 > gpurun_out/${TAG}_launches_bench.log 2>&1
 W=$(python tools/step_window.py gpurun_out/${TAG}_launches.csv 38 41)
