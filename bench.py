@@ -545,8 +545,21 @@ def main_gpu(args, rank, world, local_rank):
     def step_e2e(k):
         sec.step(k, False); prim.step(k, False)
 
-    for k in range(PREFOLD):          # untimed: mix the running instance
-        step_resident(k)
+    if os.environ.get("VIMZ_BENCH_TRACE"):   # per-50-fold wall time of the pre-folds (how the step cost moves along a proof)
+        t_blk = time.perf_counter()
+        for k in range(PREFOLD):
+            step_resident(k)
+            if (k + 1) % 50 == 0:
+                for e in engines:
+                    e.sync()
+                now = time.perf_counter()
+                st = prim.eng.lane_stats()
+                print(f"[trace] folds {k - 48:4d}..{k + 1:4d}: {(now - t_blk) * 1e3 / 50:.4f} ms/step  lane0 entries {st.get('lane0_entries')} "
+                      f"giants {st.get('lane0_ngiant')} chunks {st.get('lane0_nchunk')} mids {st.get('lane0_nmid')}", file=sys.stderr, flush=True)
+                t_blk = now
+    else:
+        for k in range(PREFOLD):          # untimed: mix the running instance
+            step_resident(k)
     for k in range(warmup):
         step_resident(PREFOLD + k)
     for k in range(2):

@@ -28,6 +28,9 @@ namespace vimz {
 constexpr int MSM_MAX_WINDOWS = 32;  // c >= 8 for 255-bit scalars
 
 constexpr uint32_t SEG_MIN_DEFAULT = 8; // shortest segment (entries per thread); option "msm_seg_min"
+#ifndef VIMZ_SCATTER_AGG
+#define VIMZ_SCATTER_AGG 1
+#endif
 #ifndef VIMZ_COMBINE_SPAN
 #define VIMZ_COMBINE_SPAN 8
 #endif
@@ -116,12 +119,35 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __re
   }
   const uint32_t j = blockIdx.y;  // window
   const uint32_t* row = digits + (size_t)j * n;
+#if VIMZ_SCATTER_AGG
+  // Warp-aggregated cursors.  Late in a proof the top window of T holds one or two bits, so ~10^5 entries of that window
+  // carry the SAME digit (and a witness vector puts half its scalars into bucket 1): one returning atomic per entry on a
+  // single address serialises in L2 (+0.15 ms per step, measured).  The lanes of a warp that target the same bucket are
+  // matched, one of them claims the whole run, the others take consecutive slots.  Every warp runs the same number of
+  // iterations, so the collectives see converged lanes.
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + lane;
+    const uint32_t d = i < n ? __ldg(row + i) : 0u;
+    const unsigned active = __ballot_sync(0xffffffffu, d != 0);
+    if (d != 0) {
+      const uint32_t b = (d & 0x7fffffffu) - 1;
+      const unsigned peers = __match_any_sync(active, b);
+      const int leader = __ffs(peers) - 1;
+      uint32_t slot = 0;
+      if ((int)lane == leader) slot = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+      slot = __shfl_sync(peers, slot, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      sorted[slot] = (j * table_stride + first + i) | (d & 0x80000000u);
+    }
+  }
+#else
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t d = __ldg(row + i);
     if (d == 0) continue;
     const uint32_t pos = atomicAdd(&cursor[(d & 0x7fffffffu) - 1], 1u);
     sorted[pos] = (j * table_stride + first + i) | (d & 0x80000000u);
   }
+#endif
 }
 
 // ---- exclusive scan over the bucket counts (3 small kernels) --------------------------------

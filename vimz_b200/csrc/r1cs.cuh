@@ -103,7 +103,7 @@ VIMZ_DI Fp<F> cross_term_row(const Fp<F>& a1, const Fp<F>& a2, const Fp<F>& b1, 
 // Out of line (with the field product): the cross-term kernels are latency-bound and were stalling on
 // instruction fetch with ~185 KB of inlined code; one shared copy keeps them inside the instruction caches.
 #ifndef VIMZ_CROSS_AGG
-#define VIMZ_CROSS_AGG false
+#define VIMZ_CROSS_AGG true  // warp-aggregated histogram of T's digits: late in a proof ~10^5 rows share the top window's digit
 #endif
 template <class F>
 __device__ __noinline__ void cross_term_finish(Fp<F> a1, Fp<F> a2, Fp<F> b1, Fp<F> b2, Fp<F> c1, Fp<F> c2, Fp<F> u1, void* T, uint32_t row,
