@@ -45,7 +45,7 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, in
 
 // Warp-aggregated bucket counters.  A witness vector is ~90 % 0/1, so most lanes of a warp hit the SAME bucket
 // (digit 1 of window 0) and T's top window lands in a few dozen buckets: same-address atomics serialise in L2 and
-// made the histogram atomics-bound (the scatter, whose atomics return values, did not gain and keeps plain atomics).  The lanes that are converged here and target the same counter
+// made the histogram atomics-bound (k_msm_scatter aggregates its returning atomics the same way).  The lanes that are converged here and target the same counter
 // are matched (MATCH.ANY); one of them adds the group's size.
 __device__ __forceinline__ void warp_count_add(uint32_t* counter) {
   const unsigned active = __activemask();
