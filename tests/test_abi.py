@@ -50,3 +50,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_accumulator_input_fast_paths():
+    """Host side of the step loop (no GPU needed): small inputs may be raw little-endian bytes or (n, 4) uint64 arrays;
+    anything else goes through the checked conversion, and wrong lengths are refused before the library is called."""
+    import numpy as np
+    from vimz_b200.nova import FoldAccumulator
+    a = np.arange(8, dtype=np.uint64).reshape(2, 4)
+    arr, ptr = FoldAccumulator._fr_ptr(a, 2)
+    assert arr is a and ptr.value == a.ctypes.data                      # already in layout: no copy
+    raw = a.tobytes()
+    b, pb = FoldAccumulator._fr_ptr(raw, 2)
+    assert b is raw and pb is raw                                       # bytes are handed to ctypes as they are
+    with pytest.raises(ValueError):
+        FoldAccumulator._fr_ptr(raw, 3)
+    flat, pf = FoldAccumulator._fr_ptr(a.reshape(-1), 2)               # 1-D input is reshaped by the checked path
+    assert flat.shape == (2, 4) and np.array_equal(flat, a)
+    with pytest.raises(ValueError):
+        FoldAccumulator._fr_ptr(np.zeros((3, 4), np.uint64), 2)
+
+
+def test_dev_words_exposes_cuda_array_interface():
+    from vimz_b200.sharding import _DevWords
+    w = _DevWords(0x7F0000001000, 24)
+    cai = w.__cuda_array_interface__
+    assert cai["shape"] == (24,) and cai["typestr"] == "<i8" and cai["data"] == (0x7F0000001000, False)
