@@ -533,3 +533,29 @@ def test_accumulator_cached_products_vs_recomputed(cache, coracle):
     assert eng.to_affine_ints(U.comm_E) == _affine(coracle, c, ref[4]["cE"])
     vimz_b200.is_sat_relaxed(shape, ck, U, W)
     acc.close(); shape.close(); ck.close(); eng.close()
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+def test_fold_chain_golden_fixture(name, engines):
+    """The committed fold-chain vectors (tests/golden/fold_chain.json, python big-int model): the resident accumulator
+    reproduces T, both fresh commitments and the folded instance / witness of every step, on all four curves."""
+    from test_oracle import golden_coo, golden_pt, load_fold_golden
+    g = load_fold_golden()[name]
+    eng, c = engines[name], P.CURVES[name]
+    q = c.q
+    m, n, io = g["num_cons"], g["num_vars"], g["num_io"]
+    A, B, Cm = (golden_coo(g[k], q) for k in "ABC")
+    ck = CommitmentKey.from_bases(eng, affine_to_mont([golden_pt(b) for b in g["ck"]], c.p))
+    shape = R1CSShape(eng, m, n, io, A, B, Cm)
+    acc = FoldAccumulator(shape, ck)
+    ints = lambda hs: [int(h, 16) for h in hs]
+    for st in g["steps"]:
+        comm_W2, comm_T = acc.step_begin(ints_to_mont(ints(st["W2"]), q), ints_to_mont(ints(st["X2"]), q))
+        assert eng.to_affine_ints(comm_W2) == golden_pt(st["comm_W2"]) and eng.to_affine_ints(comm_T) == golden_pt(st["comm_T"])
+        assert mont_to_ints(acc.last_T(), q) == ints(st["T"])
+        acc.step_end(ints_to_mont([int(st["r"], 16)], q))
+        U, W = acc.download()
+        assert mont_to_ints(W.W, q) == ints(st["W"]) and mont_to_ints(W.E, q) == ints(st["E"])
+        assert mont_to_ints(U.u, q) == [int(st["u"], 16)] and mont_to_ints(U.X, q) == ints(st["X"])
+        assert eng.to_affine_ints(U.comm_W) == golden_pt(st["comm_W"]) and eng.to_affine_ints(U.comm_E) == golden_pt(st["comm_E"])
+    acc.close(); shape.close(); ck.close()

@@ -206,3 +206,51 @@ def test_bn254_published_known_answers(coracle):
     for sc, exp in (([2, 0], BN254_2G), ([1, 1], BN254_2G), ([2, 1], BN254_3G)):
         j = coracle.msm(c.curve_id, ints_to_mont(sc, c.q), Bm, 1)
         assert mont_to_affine(coracle.to_affine(c.curve_id, j), c.p)[0] == exp
+
+
+def load_fold_golden():
+    with open(os.path.join(GOLDEN, "fold_chain.json")) as f:
+        return json.load(f)["curves"]
+
+
+def golden_coo(entries, q):
+    rows = np.array([e[0] for e in entries], np.uint32)
+    cols = np.array([e[1] for e in entries], np.uint32)
+    vals = ints_to_mont([int(e[2], 16) for e in entries], q) if entries else np.zeros((0, 4), np.uint64)
+    return rows, cols, vals
+
+
+def golden_pt(p):
+    return None if p is None else (int(p[0], 16), int(p[1], 16))
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+def test_fold_chain_golden_c_oracle(name, coracle):
+    """tests/golden/fold_chain.json (python big-int model, tests/golden/make_fold_golden.py): the C restatement reproduces
+    every intermediate of three consecutive NIFS folds -- T, both fresh commitments, the folded witness and instance."""
+    g = load_fold_golden()[name]
+    c = P.CURVES[name]
+    q, cid = c.q, c.curve_id
+    m, n, io = g["num_cons"], g["num_vars"], g["num_io"]
+    A, B, Cm = (golden_coo(g[k], q) for k in "ABC")
+    Bm = affine_to_mont([golden_pt(b) for b in g["ck"]], c.p)
+    one = ints_to_mont([1], q)
+    aff = lambda j: mont_to_affine(coracle.to_affine(cid, j), c.p)[0]
+    ints = lambda hs: [int(h, 16) for h in hs]
+    W1 = np.zeros((n, 4), np.uint64); E1 = np.zeros((m, 4), np.uint64)
+    u1 = np.zeros((1, 4), np.uint64); X1 = np.zeros((io, 4), np.uint64)
+    cW = np.zeros(12, np.uint64); cE = np.zeros(12, np.uint64)
+    for st in g["steps"]:
+        W2, X2, r = ints_to_mont(ints(st["W2"]), q), ints_to_mont(ints(st["X2"]), q), ints_to_mont([int(st["r"], 16)], q)
+        comm_W2 = coracle.msm(cid, W2, Bm[:n], 1)
+        T = coracle.commit_T(cid, m, n, io, A, B, Cm, W1, u1, X1, W2, X2, one)
+        comm_T = coracle.msm(cid, T, Bm[:m], 1)
+        assert mont_to_ints(T, q) == ints(st["T"])
+        assert aff(comm_W2) == golden_pt(st["comm_W2"]) and aff(comm_T) == golden_pt(st["comm_T"])
+        W1 = coracle.axpy(cid, W1, W2, r); E1 = coracle.axpy(cid, E1, T, r)
+        tail = coracle.axpy(cid, np.concatenate([u1, X1]), np.concatenate([one, X2]), r)
+        u1, X1 = tail[:1], tail[1:]
+        cW = coracle.point_scale_add(cid, cW, r, comm_W2); cE = coracle.point_scale_add(cid, cE, r, comm_T)
+        assert mont_to_ints(W1, q) == ints(st["W"]) and mont_to_ints(E1, q) == ints(st["E"])
+        assert mont_to_ints(u1, q) == [int(st["u"], 16)] and mont_to_ints(X1, q) == ints(st["X"])
+        assert aff(cW) == golden_pt(st["comm_W"]) and aff(cE) == golden_pt(st["comm_E"])
