@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The shared library is a build artefact (git-ignored): a fresh checkout has none.  Build it before collection
+    (the test modules import vimz_b200, which refuses to load without it) -- the same `make` target __graft_entry__.build() uses."""
+    lib = os.path.join(ROOT, "vimz_b200", "libvimz_gpu.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-j8", "vimz_b200/libvimz_gpu.so"], cwd=ROOT, stdout=subprocess.DEVNULL)
+
+
 @pytest.fixture(scope="session")
 def coracle():
     from oracle import c
