@@ -184,7 +184,7 @@ class CpuFold:
     def step(self, k: int):
         from vimz_b200.field import ints_to_mont
         o, cid, sh, t = self.o, self.cid, self.sh, self.threads
-        W2, X2 = self.wits[k % NUM_WITNESSES]
+        W2, X2 = self.wits[k % len(self.wits)]
         comm_W2 = o.msm(cid, W2, self.bases, t)
         T = o.commit_T(cid, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, self.W1, self.u1, self.X1, W2, X2, self.one, nthreads=t)
         comm_T = o.msm(cid, T, self.bases, t)
@@ -297,7 +297,7 @@ class GpuFold:
         self.X2_bytes = [np.ascontiguousarray(x, dtype=np.uint64).tobytes() for _, x in self.wits]
 
     def step(self, k: int, resident: bool):
-        i = k % NUM_WITNESSES
+        i = k % len(self.wits)
         X2 = self.X2_bytes[i]
         if resident:
             cw, ct = self.acc.step_begin_dev(self.dev_ptr[i], X2)
@@ -349,7 +349,7 @@ class GpuFoldSharded:
 
     def step(self, k: int, resident: bool):
         from vimz_b200.field import ints_to_mont
-        i = k % NUM_WITNESSES
+        i = k % len(self.wits)
         X2 = self.wits[i][1]
         if resident:
             cw, ct = self.acc.step_begin_dev(self.dev_W[i].data_ptr(), X2)
@@ -593,7 +593,7 @@ def main_gpu(args, rank, world, local_rank):
     torch.cuda.synchronize()
     pe0.record()
     for j in range(10):
-        probe_dst.copy_(prim.pin_W[j % NUM_WITNESSES], non_blocking=True)
+        probe_dst.copy_(prim.pin_W[j % len(prim.pin_W)], non_blocking=True)
     pe1.record()
     torch.cuda.synchronize()
     h2d_us = pe0.elapsed_time(pe1) * 1e3 / 10
@@ -698,7 +698,7 @@ def main():
                     help="scalar distribution of the MSM sweep (SURVEY.md section 8d: U / B / Z)")
     ap.add_argument("--no-sharded-step", action="store_true", help="N > 1: skip the strong-scaling leg (one proof folded by all ranks)")
     ap.add_argument("--msm-only", action="store_true", help="skip the fold-step measurement (window sweeps)")
-    ap.add_argument("--circuit", default="grayscale", choices=["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash"],
+    ap.add_argument("--circuit", default="grayscale", choices=["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash", "blur4k", "sharpness4k"],
                     help="step circuit whose published size the primary shape takes (BASELINE metric: grayscale; the others are the "
                          "remaining BASELINE configs, /root/reference/circuits/nova_snark/circuit_parameters.csv)")
     ap.add_argument("--cycle", default="pasta", choices=["pasta", "bn254"],

@@ -254,3 +254,24 @@ def test_fold_chain_golden_c_oracle(name, coracle):
         assert mont_to_ints(W1, q) == ints(st["W"]) and mont_to_ints(E1, q) == ints(st["E"])
         assert mont_to_ints(u1, q) == [int(st["u"], 16)] and mont_to_ints(X1, q) == ints(st["X"])
         assert aff(cW) == golden_pt(st["comm_W"]) and aff(cE) == golden_pt(st["comm_E"])
+
+
+@pytest.mark.parametrize("circuit", ["grayscale", "blur4k", "sharpness4k", "hash"])
+def test_synthetic_step_shapes_are_satisfied(circuit, coracle):
+    """The synthetic step circuits bench.py folds (published sizes; the 4K ones are the x3-width estimates): a scaled-down
+    instance of each is satisfied by its generated witness (A z o B z = C z with u = 1), mostly 0/1 for the pixel circuits."""
+    from vimz_b200 import synthetic as S
+    from vimz_b200.field import CURVES
+    cv = CURVES["pallas"]
+    q = cv.scalar_modulus
+    sh = S.synthetic_shape(cv, circuit, seed=5, scale=0.01 if circuit != "hash" else 0.2)
+    Wi, Xi = S.synthetic_witness(sh, 9)
+    assert len(Wi) == sh.num_vars and len(Xi) == sh.num_io
+    z = ints_to_mont(list(Wi) + [1] + list(Xi), q)
+    Az, Bz, Cz = coracle.multiply_vec(cv.curve_id, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, z)
+    a, b, c_ = (mont_to_ints(v, q) for v in (Az, Bz, Cz))
+    assert all((x * y - w) % q == 0 for x, y, w in zip(a, b, c_))
+    if circuit != "hash":
+        assert sum(1 for w in Wi if w < 2) / len(Wi) > 0.6
+    full = S.STEP_CIRCUITS[circuit]
+    assert sh.num_cons == int((full[0] + S.NOVA_AUGMENTED) * (0.01 if circuit != "hash" else 0.2))

@@ -36,6 +36,11 @@ STEP_CIRCUITS: Dict[str, Tuple[int, int, int, int, int, int]] = {
     "blur": (248_934, 241_257, 512, 7_680, 12, 720),
     "sharpness": (325_734, 310_377, 512, 15_360, 12, 720),
     "hash": (6_672, 6_787, 0, 0, 0, 720),
+    # 4K variants (BASELINE config "blur/sharpness convolution steps on 4K.png"): no such circuit exists in the reference (the
+    # row width is hard-wired to 128 words, circuits/src/blur_step.circom:17), so these are the x3-width ESTIMATES of
+    # three times the HD constraints / wires / packed words / comparators, 2160 rows per image
+    "blur4k": (746_802, 723_771, 1_536, 23_040, 12, 2_160),
+    "sharpness4k": (977_202, 931_131, 1_536, 46_080, 12, 2_160),
     # the secondary-curve shape: TrivialTestCircuit inside the augmented circuit, ~10.5k rows
     "secondary": (500, 500, 0, 0, 0, 0),
 }
