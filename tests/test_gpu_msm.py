@@ -68,9 +68,11 @@ def test_msm_vs_oracle_small(name, n, engines, coracle):
     ck.close()
 
 
-@pytest.mark.parametrize("window", [8, 11, 16])
+@pytest.mark.parametrize("window", [8, 11, 16, 17, 20, 22])
 def test_msm_windows_agree(window, engines, coracle):
-    """Every window size must give the same group element (prefix commit too)."""
+    """Every window size must give the same group element (prefix commit too).  Windows above 16 bits have more than
+    32 768 buckets: the multi-block scan (k_scan_blocksum / top / apply) and the deeper reduction geometry that the
+    2^20 .. 2^24-point MSMs of bench.py run."""
     c = P.PALLAS
     eng = vimz_b200.Engine("pallas", 0)
     eng.set_option("msm_window", window)
@@ -157,6 +159,45 @@ def test_msm_large_closed_form_and_linearity(name, engines):
         parts.append(CommitmentEngine.commit_dev(ck, Sm.data_ptr() + first * 32, cnt, first=first))
     assert eng.to_affine_ints(eng.point_sum(np.stack(parts))) == eng.to_affine_ints(ca)
     ck.close()
+
+
+@pytest.mark.parametrize("log2n,dist", [(20, "uniform"), (20, "witness"), (20, "edge"), (22, "uniform"), (22, "witness")])
+def test_msm_bench_sizes_closed_form(log2n, dist):
+    """The MSM half of the metric at the sizes bench.py times: Pallas, 2^20 points (window c = 17) and 2^22 (c = 20),
+    device-generated bases (k0 + i*dk)*G, the three scalar distributions of SURVEY 8d.  The commitment must equal
+    (sum s_i k_i)*G -- one big-integer scalar multiplication by the python oracle, independent of any MSM code."""
+    import torch
+    from vimz_host import synthetic as S
+    c = P.PALLAS
+    eng = vimz_b200.Engine("pallas", 0)
+    n = 1 << log2n
+    k0, dk = 77, 1234577
+    d_bases = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, k0, dk, n, d_bases.data_ptr()))
+    ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), n)
+    G = P.generator(c)
+    host = d_bases[-8:].cpu().numpy().view(np.uint64).reshape(-1, 8)            # the LAST base against the oracle
+    assert mont_to_affine(host, c.p)[0] == P.scalar_mul(c, k0 + (n - 1) * dk, G)
+    del d_bases
+    assert ck.window_bits == {20: 17, 22: 20}[log2n], "bench.py's MSM numbers are quoted on these windows"
+    if dist == "uniform":
+        Sm = S.uniform_scalars_mont(n, c.q, 11 + log2n)
+    elif dist == "witness":
+        Sm = S.witness_like_scalars_mont(n, c.q, 12 + log2n)
+    else:
+        pat = ints_to_mont([0, 1, c.q - 1], c.q)
+        Sm = np.ascontiguousarray(pat[np.arange(n) % 3])
+    d_S = torch.from_numpy(Sm.view(np.int64)).cuda()
+    got = eng.to_affine_ints(CommitmentEngine.commit_dev(ck, d_S.data_ptr(), n))
+    assert got == P.scalar_mul(c, S.closed_form_log(Sm, k0, dk, c.q), G), (log2n, dist)
+    # a ragged prefix and a point-range shard pair through the same table
+    n1 = n // 3 + 5
+    a = CommitmentEngine.commit_dev(ck, d_S.data_ptr(), n1)
+    b = CommitmentEngine.commit_dev(ck, d_S.data_ptr() + n1 * 32, n - n1, first=n1)
+    assert eng.to_affine_ints(a) == P.scalar_mul(c, S.closed_form_log(Sm[:n1], k0, dk, c.q), G)
+    assert eng.to_affine_ints(eng.point_sum(np.stack([a, b]))) == got
+    ck.close()
+    eng.close()
 
 
 def test_point_helpers(engines, coracle):

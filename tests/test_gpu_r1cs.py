@@ -290,6 +290,88 @@ def test_full_size_step_properties(circuit, engines):
     acc.close(); shape.close(); ck.close()
 
 
+def _mid_proof_instance(coracle, c, sh, Bm, seeds=(900, 901), rs=(130, 131)):
+    """A relaxed instance with the magnitudes of the MIDDLE of an HD proof, built on the CPU without folding hundreds
+    of steps: z1 = R*z_a + S*z_b for two satisfying fresh instances and R, S = sums of ~130 128-bit challenges
+    (~135-bit numbers).  Folding is linear, so this is exactly what ~260 folds of those two rows give:
+    u1 = R + S, X1 = R*X_a + S*X_b, E1 = R*S*T_ab with T_ab the cross term of a and b.  The instance satisfies the
+    relaxed relation, W1's entries are ~136-bit values (the 0/1 wires) and E1 is full-width -- the regime bench.py times."""
+    q, cid = c.q, c.curve_id
+    rng = random.Random(5150)
+    R = sum(rng.randrange(1 << 128) for _ in range(rs[0]))
+    Sv = sum(rng.randrange(1 << 128) for _ in range(rs[1]))
+    one = ints_to_mont([1], q)
+    m, n, io = sh.num_cons, sh.num_vars, sh.num_io
+    (Wa, Xa), (Wb, Xb) = [tuple(ints_to_mont(v, q) for v in S.synthetic_witness(sh, sd)) for sd in seeds]
+    Rm, Sm, RSm = ints_to_mont([R], q), ints_to_mont([Sv], q), ints_to_mont([R * Sv % q], q)
+    zero_n, zero_m = np.zeros((n, 4), np.uint64), np.zeros((m, 4), np.uint64)
+    W1 = coracle.axpy(cid, coracle.axpy(cid, zero_n, Wa, Rm, 4), Wb, Sm, 4)
+    X1 = coracle.axpy(cid, coracle.axpy(cid, np.zeros((io, 4), np.uint64), Xa, Rm), Xb, Sm)
+    u1 = ints_to_mont([(R + Sv) % q], q)
+    T_ab = coracle.commit_T(cid, m, n, io, sh.A, sh.B, sh.C, Wa, one, Xa, Wb, Xb, one, nthreads=4)
+    E1 = coracle.axpy(cid, zero_m, T_ab, RSm, 4)
+    cW = coracle.msm(cid, W1, Bm, 8)
+    cE = coracle.msm(cid, E1, Bm, 8)
+    return dict(W=W1, E=E1, u=u1, X=X1, cW=cW, cE=cE)
+
+
+def test_full_size_grayscale_fold_bit_exact_vs_c_oracle(coracle):
+    """THE configuration bench.py times, checked against the CPU restatement limb for limb: grayscale_step_HD
+    (m = 130 864, n = 128 307, commitment key 2^17 points, window c = 15), starting from a loaded mid-proof relaxed
+    instance (~136-bit running scalars, full-width E), two consecutive folds.  T then spills into the tenth 15-bit window
+    and its top-digit entries form a giant bucket (asserted through the lane statistics), the second step uses the
+    FOLDED cached products.  Compared with oracle/nova_cpu.c: T, comm_T, comm_W2 of both steps and the folded
+    W / E / u / X / comm_W / comm_E -- the reference's own acceptance test is RecursiveSNARK::verify on these values
+    (/root/reference/vimz/src/nova_snark_backend/folding.rs:46-56)."""
+    import torch
+    c = P.PALLAS
+    q, cid = c.q, c.curve_id
+    eng = vimz_b200.Engine("pallas", 0)
+    sh = S.synthetic_shape(CURVES["pallas"], "grayscale")
+    assert (sh.num_cons, sh.num_vars) == (130_864, 128_307)
+    shape = R1CSShape(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
+    nck = 1 << 17
+    k0, dk = 77, 1234577
+    g = affine_to_mont([P.generator(c)], c.p)[0]
+    Bm = coracle.gen_bases(cid, g, k0, dk, nck)                               # CPU copy of the key ...
+    d_bases = torch.empty(nck * 8, dtype=torch.int64, device="cuda")
+    vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, k0, dk, nck, d_bases.data_ptr()))
+    assert np.array_equal(d_bases.cpu().numpy().view(np.uint64).reshape(-1, 8), Bm)   # ... identical to the GPU's
+    ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), nck)
+    del d_bases
+    assert ck.window_bits == 15 and ck.num_windows == 17
+    st = _mid_proof_instance(coracle, c, sh, Bm)
+    acc = FoldAccumulator(shape, ck)
+    acc.load(RelaxedR1CSInstance(st["cW"], st["cE"], st["X"], st["u"]), RelaxedR1CSWitness(st["W"], st["E"]))
+    one = ints_to_mont([1], q)
+    rng = random.Random(77)
+    W1, E1, u1, X1, cW, cE = st["W"], st["E"], st["u"], st["X"], st["cW"], st["cE"]
+    for k in range(2):
+        Wi, Xi = S.synthetic_witness(sh, 910 + k)
+        W2, X2 = ints_to_mont(Wi, q), ints_to_mont(Xi, q)
+        comm_W2, comm_T = acc.step_begin(W2, X2)
+        T = coracle.commit_T(cid, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, W1, u1, X1, W2, X2, one, nthreads=4)
+        spill = sum(1 for t in mont_to_ints(T, q) if 135 <= min(t, q - t).bit_length() <= 150)
+        assert spill > 10_000, "T must reach into the tenth 15-bit window like the mid-proof steps bench.py times"
+        stats = eng.lane_stats()
+        assert stats["lane0_entries"] > 9 * sh.num_cons and stats["lane0_ngiant"] >= 1, stats
+        assert np.array_equal(acc.last_T(), T), f"T differs at step {k}"
+        exp_T, exp_W2 = coracle.msm(cid, T, Bm, 8), coracle.msm(cid, W2, Bm, 8)
+        assert eng.to_affine_ints(comm_T) == _affine(coracle, c, exp_T), f"comm_T differs at step {k}"
+        assert eng.to_affine_ints(comm_W2) == _affine(coracle, c, exp_W2), f"comm_W2 differs at step {k}"
+        r = ints_to_mont([rng.randrange(1 << 128)], q)
+        acc.step_end(r)
+        W1 = coracle.axpy(cid, W1, W2, r, 4); E1 = coracle.axpy(cid, E1, T, r, 4)
+        tail = coracle.axpy(cid, np.concatenate([u1, X1]), np.concatenate([one, X2]), r)
+        u1, X1 = tail[:1], tail[1:]
+        cW = coracle.point_scale_add(cid, cW, r, exp_W2); cE = coracle.point_scale_add(cid, cE, r, exp_T)
+    U, W = acc.download()
+    assert np.array_equal(W.W, W1) and np.array_equal(W.E, E1) and np.array_equal(U.u, u1) and np.array_equal(U.X, X1)
+    assert eng.to_affine_ints(U.comm_W) == _affine(coracle, c, cW) and eng.to_affine_ints(U.comm_E) == _affine(coracle, c, cE)
+    vimz_b200.is_sat_relaxed(shape, ck, U, W)       # and the folded instance verifies (folding.rs:53-55)
+    acc.close(); shape.close(); ck.close(); eng.close()
+
+
 def test_fold_from_r1cs_and_wtns_files_bn254(tmp_path, engines, coracle):
     """Real-artifact ingestion: an iden3 .r1cs + two .wtns files (circom's bn128 prime) are read,
     uploaded and folded on the BN254 engine; result == CPU chain and the folded instance is satisfied."""

@@ -96,12 +96,19 @@ using namespace vimz;
     if (!(cond)) return set_error(VIMZ_ERR_ARG, msg); \
   } while (0)
 
+// Makes the context's device current for the duration of an entry point and restores the caller's device afterwards
+// (a single-process multi-GPU host -- torch, a Rust prover with its own CUDA code -- must not find its current device changed).
 struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     if (prev != dev) cudaSetDevice(dev);
   }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 // context lock (see vimz_ctx::mu) + current device, for the duration of an entry point
 struct CtxGuard {
@@ -109,6 +116,66 @@ struct CtxGuard {
   DeviceGuard dev;
   explicit CtxGuard(vimz_ctx* ctx) : lock(ctx->mu), dev(ctx->device) {}
 };
+
+// ---- handle lifetimes ----------------------------------------------------------------------------------
+// Children (keys, shapes, accumulators) hold a reference on their context, accumulators also on their shape and keys.
+// A *_destroy call on a parent that still has children only drops the owner's reference: the object is freed when the
+// last child goes, so destruction order on the host side (Drop order in Rust, garbage collection in Python) is free.
+static void ctx_free(vimz_ctx* ctx) {
+  DeviceGuard dg(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->side);
+  cudaStreamSynchronize(ctx->aux);
+  ctx->ws.release();
+  ctx->ws_aux.release();
+  ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
+  ctx->tmp3.release(); ctx->tmp4.release(); ctx->tmp5.release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (ProfSpan& sp : ctx->prof.open) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
+  for (uint32_t* slot : ctx->prof.entry_slots) cudaFreeHost(slot);
+  for (uint32_t* slot : ctx->prof.entry_pool) cudaFreeHost(slot);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->side);
+  cudaStreamDestroy(ctx->aux);
+  delete ctx;
+}
+static void ctx_release(vimz_ctx* ctx) {
+  if (ctx->refs.fetch_sub(1) == 1) ctx_free(ctx);
+}
+static void ck_release(vimz_ck* ck) {
+  if (ck->refs.fetch_sub(1) != 1) return;
+  vimz_ctx* ctx = ck->ctx;
+  {
+    CtxGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux);
+    if (ck->table) cudaFree(ck->table);
+    if (ck->dtable) cudaFree(ck->dtable);
+    delete ck;
+  }
+  ctx_release(ctx);
+}
+static void shape_release(vimz_shape* s) {
+  if (s->refs.fetch_sub(1) != 1) return;
+  vimz_ctx* ctx = s->ctx;
+  {
+    CtxGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 3; k++) {
+      if (s->rowptr[k]) cudaFree(s->rowptr[k]);
+      if (s->col[k]) cudaFree(s->col[k]);
+      if (s->val[k]) cudaFree(s->val[k]);
+      if (s->vidx[k]) cudaFree(s->vidx[k]);
+    }
+    if (s->dict) cudaFree(s->dict);
+    if (s->chunk_start) cudaFree(s->chunk_start);
+    if (s->long_rows) cudaFree(s->long_rows);
+    if (s->mid_rows) cudaFree(s->mid_rows);
+    delete s;
+  }
+  ctx_release(ctx);
+}
 
 extern "C" {
 
@@ -130,39 +197,44 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
   int ndev = vimz_device_count();
   if (ndev <= 0) return set_error(VIMZ_ERR_NO_DEVICE, "vimz_ctx_create: no CUDA device visible (this library has no CPU path)");
   if (device < 0 || device >= ndev) return set_error(VIMZ_ERR_ARG, "vimz_ctx_create: device index out of range");
-  VIMZ_CUDA(cudaSetDevice(device));
+  DeviceGuard dg(device);
   vimz_ctx* ctx = new vimz_ctx();
   ctx->curve = curve_id;
   ctx->device = device;
-  VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
-  VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
-  VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
-  VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
-  VIMZ_TRY(ctx->ws.result.reserve(4096));
+  auto init = [&]() -> int {
+    VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
+    VIMZ_TRY(ctx->ws.result.reserve(4096));
+    return curve_vtable(curve_id)->init_device(ctx);
+  };
+  int rc = init();
+  if (rc != VIMZ_OK) {
+    std::string msg = g_last_error;
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->ws.release();
+    delete ctx;
+    cudaGetLastError();
+    return set_error(rc, msg);
+  }
   *out = ctx;
   return VIMZ_OK;
 }
 
 void vimz_ctx_destroy(vimz_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->side);
-  cudaStreamSynchronize(ctx->aux);
-  ctx->ws.release();
-  ctx->ws_aux.release();
-  ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
-  ctx->tmp3.release(); ctx->tmp4.release(); ctx->tmp5.release();
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  for (ProfSpan& sp : ctx->prof.open) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
-  for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
-  for (uint32_t* slot : ctx->prof.entry_slots) cudaFreeHost(slot);
-  for (uint32_t* slot : ctx->prof.entry_pool) cudaFreeHost(slot);
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->side);
-  cudaStreamDestroy(ctx->aux);
-  delete ctx;
+  {  // wait for a call still running on another thread, then for the streams
+    CtxGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side);
+    cudaStreamSynchronize(ctx->aux);
+  }
+  ctx_release(ctx);  // freed now, or when the last key / shape / accumulator created on it is destroyed
 }
 
 int vimz_ctx_sync(vimz_ctx* ctx) {
@@ -225,6 +297,7 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   }
   if (strcmp(key, "aux_lane") == 0) {
     ctx->opt_aux_lane = value != 0;
+    alloc_epoch()++;  // changes the captured launch sequence
     return VIMZ_OK;
   }
   if (strcmp(key, "graph") == 0) {
@@ -325,6 +398,7 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
   if ((double)n * nwin >= 2147483648.0) return set_error(VIMZ_ERR_ARG, "commitment key too long for this window size");
   vimz_ck* ck = new vimz_ck();
   ck->ctx = ctx;
+  ctx->refs++;
   ck->n = n;
   ck->c = c;
   ck->nwin = nwin;
@@ -333,6 +407,7 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
   if (e != cudaSuccess) {
     if (dtable) cudaFree(dtable);
     delete ck;
+    ctx->refs--;
     return set_error(VIMZ_ERR_CUDA, std::string("cudaMalloc(window table) failed: ") + cudaGetErrorString(e));
   }
   ck->dtable = dtable;
@@ -346,6 +421,7 @@ static int ck_build(vimz_ctx* ctx, const void* d_bases, size_t n, vimz_ck** out)
     cudaFree(ck->table);
     if (ck->dtable) cudaFree(ck->dtable);
     delete ck;
+    ctx->refs--;
     return rc;
   }
   *out = ck;
@@ -371,13 +447,7 @@ int vimz_ck_upload(vimz_ctx* ctx, const vimz_affine* bases, size_t n, vimz_ck** 
 }
 
 void vimz_ck_destroy(vimz_ck* ck) {
-  if (!ck) return;
-  CtxGuard g(ck->ctx);
-  cudaStreamSynchronize(ck->ctx->stream);
-  cudaStreamSynchronize(ck->ctx->aux);
-  if (ck->table) cudaFree(ck->table);
-  if (ck->dtable) cudaFree(ck->dtable);
-  delete ck;
+  if (ck) ck_release(ck);  // freed when no accumulator uses it any more
 }
 size_t vimz_ck_len(const vimz_ck* ck) { return ck ? ck->n : 0; }
 int vimz_ck_window_bits(const vimz_ck* ck) { return ck ? ck->c : 0; }
@@ -400,9 +470,11 @@ static int fetch_points(vimz_ctx* ctx, const void* d_src, void* host_dst, size_t
 }
 
 int vimz_msm_range_dev(vimz_ctx* ctx, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, vimz_point* out) {
-  CHECK_ARG(out, "vimz_msm: out is null");
-  VIMZ_TRY(vimz_msm_async_dev(ctx, ck, first, d_scalars, n, ctx ? ctx->ws.result.ptr : nullptr));
+  CHECK_ARG(ctx && out, "vimz_msm: null argument");
+  // one lock around enqueue AND fetch: two host threads committing on the same context share ws.result, and with the
+  // lock dropped in between, thread A could read thread B's commitment (the mutex is recursive, the nested call is fine)
   CtxGuard g(ctx);
+  VIMZ_TRY(vimz_msm_async_dev(ctx, ck, first, d_scalars, n, ctx->ws.result.ptr));
   return fetch_points(ctx, ctx->ws.result.ptr, out, 96);
 }
 
@@ -506,20 +578,7 @@ static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row
 }
 
 void vimz_shape_destroy(vimz_shape* s) {
-  if (!s) return;
-  CtxGuard g(s->ctx);
-  cudaStreamSynchronize(s->ctx->stream);
-  for (int k = 0; k < 3; k++) {
-    if (s->rowptr[k]) cudaFree(s->rowptr[k]);
-    if (s->col[k]) cudaFree(s->col[k]);
-    if (s->val[k]) cudaFree(s->val[k]);
-    if (s->vidx[k]) cudaFree(s->vidx[k]);
-  }
-  if (s->dict) cudaFree(s->dict);
-  if (s->chunk_start) cudaFree(s->chunk_start);
-  if (s->long_rows) cudaFree(s->long_rows);
-  if (s->mid_rows) cudaFree(s->mid_rows);
-  delete s;
+  if (s) shape_release(s);  // freed when no accumulator uses it any more
 }
 
 int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_io,
@@ -534,6 +593,7 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   CtxGuard g(ctx);
   vimz_shape* s = new vimz_shape();
   s->ctx = ctx;
+  ctx->refs++;
   s->m = num_cons;
   s->n = num_vars;
   s->io = num_io;
@@ -688,23 +748,33 @@ int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r, const vimz_fr* W1, const 
 }
 
 // ---- device-resident running instance --------------------------------------------------------------
+constexpr size_t ACC_PIN_FRESH = 0, ACC_PIN_COMBINED = 256, ACC_PIN_STAGE = 512;  // layout of vimz_acc::pinned
 void vimz_acc_destroy(vimz_acc* a) {
   if (!a) return;
-  CtxGuard g(a->ctx);
-  cudaStreamSynchronize(a->ctx->stream);
-  cudaStreamSynchronize(a->ctx->side);
-  cudaStreamSynchronize(a->ctx->aux);
-  void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2};
-  for (void* b : bufs)
-    if (b) cudaFree(b);
-  for (int k = 0; k < 2; k++)
-    if (a->graph[k]) cudaGraphExecDestroy(a->graph[k]);
-  if (a->ev_main) cudaEventDestroy(a->ev_main);
-  if (a->ev_w2) cudaEventDestroy(a->ev_w2);
-  if (a->ev_aux) cudaEventDestroy(a->ev_aux);
-  for (int k = 0; k < 2; k++)
-    if (a->ev_side[k]) cudaEventDestroy(a->ev_side[k]);
+  vimz_ctx* ctx = a->ctx;
+  {
+    CtxGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side);
+    cudaStreamSynchronize(ctx->aux);
+    void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2};
+    for (void* b : bufs)
+      if (b) cudaFree(b);
+    if (a->pinned) cudaFreeHost(a->pinned);
+    for (int k = 0; k < 2; k++)
+      if (a->graph[k]) cudaGraphExecDestroy(a->graph[k]);
+    if (a->ev_main) cudaEventDestroy(a->ev_main);
+    if (a->ev_w2) cudaEventDestroy(a->ev_w2);
+    if (a->ev_aux) cudaEventDestroy(a->ev_aux);
+    for (int k = 0; k < 2; k++)
+      if (a->ev_side[k]) cudaEventDestroy(a->ev_side[k]);
+  }
+  // the references taken in acc_create: a key / shape / context destroyed earlier by its owner is freed here
+  if (a->ck_w) ck_release(const_cast<vimz_ck*>(a->ck_w));
+  if (a->ck) ck_release(const_cast<vimz_ck*>(a->ck));
+  if (a->shape) shape_release(const_cast<vimz_shape*>(a->shape));
   delete a;
+  ctx_release(ctx);
 }
 
 static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, const vimz_ck* ck_w, size_t w_first, size_t w_count,
@@ -715,6 +785,10 @@ static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, con
   a->shape = s;
   a->ck = ck;
   a->ck_w = ck_w;
+  ctx->refs++;
+  const_cast<vimz_shape*>(s)->refs++;
+  const_cast<vimz_ck*>(ck)->refs++;
+  const_cast<vimz_ck*>(ck_w)->refs++;
   a->w_first = w_first;
   a->w_count = w_count;
   size_t nb = std::max<size_t>(s->n * 32, 32), mb = std::max<size_t>(s->m * 32, 32), tb = (1 + s->io) * 32;
@@ -726,6 +800,7 @@ static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, con
   };
   alloc0(&a->W1, nb); alloc0(&a->W2, nb); alloc0(&a->E1, mb); alloc0(&a->T, mb);
   alloc0(&a->tail1, tb); alloc0(&a->tail2, tb); alloc0(&a->comms, 6 * 96 + 2 * 32);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&a->pinned), ACC_PIN_STAGE + tb);
   if (ctx->opt_cross_cache) {  // the default instance is all zero, and so are its products
     alloc0(&a->cache1, 3 * mb);
     alloc0(&a->cache2, 3 * mb);
@@ -801,8 +876,7 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
-  uint8_t* stage = (uint8_t*)ctx->pinned + 1024;
-  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, a->pinned + ACC_PIN_STAGE, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
   // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) -- independent of T, so it runs on the aux
   // stream with its own workspace while the main stream does the cross term and commit(T).
   const bool two_lanes = ctx->opt_aux_lane;
@@ -820,7 +894,7 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   // so nothing recoded T: the commit then does its own, empty, digit pass)
   VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
   if (two_lanes) VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
-  VIMZ_CUDA(cudaMemcpyAsync(ctx->pinned, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   return VIMZ_OK;
 }
 
@@ -839,8 +913,10 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
     a->side_pending[p] = false;
   }
   char* fresh = (char*)a->comms + (2 + 2 * p) * 96;
-  // tail2 = (1, X2) staged in pinned memory (read by the copy when it executes)
-  uint8_t* stage = (uint8_t*)ctx->pinned + 1024;
+  // tail2 = (1, X2) staged in this accumulator's pinned block (read by the copy when the stream reaches it).  A step that
+  // was only enqueued (sharded fold) may still have that copy pending: wait for it before overwriting the block.
+  if (a->step_enqueued && !a->fresh_complete) VIMZ_CUDA(cudaStreamSynchronize(st));
+  uint8_t* stage = a->pinned + ACC_PIN_STAGE;
   memcpy(stage, vt->scalar_one_mont, 32);
   if (s->io) memcpy(stage + 32, X2, s->io * 32);
 
@@ -881,19 +957,18 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
     a->warm[p] = true;
   }
   a->fresh_complete = false;
+  a->step_enqueued = true;
   if (!sync) return VIMZ_OK;
   VIMZ_CUDA(cudaStreamSynchronize(st));
   a->fresh_complete = true;
-  memcpy(comm_W2, ctx->pinned, 96);
-  memcpy(comm_T, (char*)ctx->pinned + 96, 96);
+  memcpy(comm_W2, a->pinned + ACC_PIN_FRESH, 96);
+  memcpy(comm_T, a->pinned + ACC_PIN_FRESH + 96, 96);
   return VIMZ_OK;
 }
 
 int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* X2, void** d_partials) {
   CHECK_ARG(a && d_partials && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev_async: null argument");
   CtxGuard g(a->ctx);
-  size_t io = a->shape->io;
-  if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
   VIMZ_TRY(acc_step_begin_common(a, X2, nullptr, nullptr, false));
   *d_partials = (char*)a->comms + (2 + 2 * a->parity) * 96;
@@ -907,19 +982,17 @@ int vimz_acc_step_combine_dev(vimz_acc* a, const void* d_gathered, size_t world,
   const CurveVTable* vt = curve_vtable(ctx->curve);
   VIMZ_TRY(ctx->ws.result.reserve(2 * 96));
   VIMZ_TRY(vt->point_sum_batch(ctx, d_gathered, world, 2, ctx->ws.result.ptr));
-  VIMZ_CUDA(cudaMemcpyAsync((char*)ctx->pinned + 3072, ctx->ws.result.ptr, 2 * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_COMBINED, ctx->ws.result.ptr, 2 * 96, cudaMemcpyDeviceToHost, ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   a->fresh_complete = true;
-  memcpy(comm_W2, (char*)ctx->pinned + 3072, 96);
-  memcpy(comm_T, (char*)ctx->pinned + 3072 + 96, 96);
+  memcpy(comm_W2, a->pinned + ACC_PIN_COMBINED, 96);
+  memcpy(comm_T, a->pinned + ACC_PIN_COMBINED + 96, 96);
   return VIMZ_OK;
 }
 
 int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin: null argument");
   CtxGuard g(a->ctx);
-  size_t io = a->shape->io;
-  if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
@@ -927,8 +1000,6 @@ int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_
 int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
   CtxGuard g(a->ctx);
-  size_t io = a->shape->io;
-  if (1024 + (1 + io) * 32 > 2048) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_begin: num_io too large for the staging block");
   // keep W2 resident for step_end
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);

@@ -112,6 +112,9 @@ struct vimz_ctx {
   // prove_step is sequential, but CompressedSNARK::prove / RecursiveSNARK::verify commit from several rayon workers at
   // once, and those calls must not interleave on one workspace.  Recursive: entry points nest.
   std::recursive_mutex mu;
+  // 1 for the handle returned by vimz_ctx_create + 1 per live key / shape / accumulator: vimz_ctx_destroy only drops
+  // the owner's reference, the context is freed when the last child is destroyed (see capi.cu "handle lifetimes")
+  std::atomic<int> refs{1};
   int curve = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -162,6 +165,7 @@ struct ProfScope {
 
 struct vimz_ck {
   vimz_ctx* ctx = nullptr;
+  std::atomic<int> refs{1};  // owner handle + accumulators committing with this key
   size_t n = 0;
   int c = 0;          // window bits
   int nwin = 0;       // windows
@@ -173,6 +177,7 @@ struct vimz_ck {
 
 struct vimz_shape {
   vimz_ctx* ctx = nullptr;
+  std::atomic<int> refs{1};  // owner handle + accumulators folding over this shape
   size_t m = 0, n = 0, io = 0;
   size_t nnz[3] = {0, 0, 0};
   uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};  // [m+1]
@@ -205,9 +210,14 @@ struct vimz_acc {
   void *cache1 = nullptr, *cache2 = nullptr;
   // Jacobian points comm_W1, comm_E1, then two alternating (comm_W2, comm_T) pairs, then two r slots
   void* comms = nullptr;
+  // pinned host block of THIS accumulator (several accumulators may share a context and have steps in flight at once):
+  // [0, 192) the step's (comm_W2, comm_T) as copied back by the stream, [256, 448) the combined pair of a sharded step,
+  // [512, ..) the staged (1, X2) tail that the step's H2D copy reads when the stream reaches it
+  uint8_t* pinned = nullptr;
   cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr}, ev_w2 = nullptr, ev_aux = nullptr;
   bool side_pending[2] = {false, false};
   bool fresh_complete = false;  // the host has waited for the last step_begin (sync entry points, step_combine_dev)
+  bool step_enqueued = false;   // a step_begin has been issued on this accumulator
   int parity = 0;
   // step_begin's launch sequence (cross term + both MSMs, ~35 kernels on two streams) captured once per
   // parity slot and replayed: the step is latency-bound and stream launches cost more than the small kernels

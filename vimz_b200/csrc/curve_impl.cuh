@@ -18,6 +18,7 @@ struct CurveVTable {
   const char* name;
   uint32_t scalar_modulus[8];
   uint32_t scalar_one_mont[8];
+  int (*init_device)(vimz_ctx*);  // per-device kernel attributes, once per context
   int (*precompute)(vimz_ctx*, const void* d_bases, size_t n, int c, int nwin, void* table);
   // dtable[((j*n + i) << (c-1)) + k-1] = k * table[j][i]  (direct-table keys)
   int (*precompute_direct)(vimz_ctx*, const void* table, size_t n, int c, int nwin, void* dtable);
@@ -51,6 +52,17 @@ const CurveVTable* curve_vtable(int curve_id);
   } while (0)
 
 inline uint32_t ceil_div(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+constexpr size_t CROSS_SMEM_CACHED = (size_t)CROSS_CHUNK_NNZ * 32, CROSS_SMEM_UNCACHED = (size_t)CROSS_CHUNK_NNZ * 64;
+
+// Per-DEVICE kernel attributes (cudaFuncSetAttribute applies to the current device only): called by vimz_ctx_create
+// for every context, so a process driving several GPUs gets the > 48 KB shared-memory opt-in on each of them.
+template <class C>
+int impl_init_device(vimz_ctx*) {
+  VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CROSS_SMEM_CACHED));
+  VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CROSS_SMEM_UNCACHED));
+  return VIMZ_OK;
+}
 
 template <class C>
 int impl_precompute(vimz_ctx* ctx, const void* d_bases, size_t n, int c, int nwin, void* table) {
@@ -304,22 +316,11 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
     sa.chunk_start = s->chunk_start;
     sa.cache1 = cache1;
     sa.cache2 = cache2;
+    // (the dynamic shared memory opt-in of both variants is made per device in impl_init_device)
     if (cache1 && cache2) {
-      static bool smem_set_c = false;  // per template instance
-      constexpr size_t SMEM_C = (size_t)CROSS_CHUNK_NNZ * 32;
-      if (!smem_set_c) {
-        VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
-        smem_set_c = true;
-      }
-      k_cross_term_stream<typename C::Fs, true><<<(uint32_t)s->n_chunks, 256, SMEM_C, ctx->stream>>>(sa);
+      k_cross_term_stream<typename C::Fs, true><<<(uint32_t)s->n_chunks, 256, CROSS_SMEM_CACHED, ctx->stream>>>(sa);
     } else {
-      static bool smem_set = false;  // per template instance
-      constexpr size_t SMEM = (size_t)CROSS_CHUNK_NNZ * 64;
-      if (!smem_set) {
-        VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        smem_set = true;
-      }
-      k_cross_term_stream<typename C::Fs, false><<<(uint32_t)s->n_chunks, 256, SMEM, ctx->stream>>>(sa);
+      k_cross_term_stream<typename C::Fs, false><<<(uint32_t)s->n_chunks, 256, CROSS_SMEM_UNCACHED, ctx->stream>>>(sa);
     }
     VIMZ_LAUNCH_CHECK(ctx);
     return VIMZ_OK;
@@ -387,6 +388,7 @@ CurveVTable make_vtable(const char* name) {
     t.scalar_modulus[i] = C::Fs::p(i);
     t.scalar_one_mont[i] = C::Fs::one(i);
   }
+  t.init_device = &impl_init_device<C>;
   t.precompute = &impl_precompute<C>;
   t.precompute_direct = &impl_precompute_direct<C>;
   t.msm = &impl_msm<C>;
