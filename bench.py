@@ -48,8 +48,11 @@ MODMUL_PER_MADD = 10           # XYZZ mixed add 8M + 2S
 
 
 def load_peaks():
+    """Roofline denominators: HBM copy bandwidth from MEASURED_PEAKS.json (driver-written), integer multiply from
+    profiles/int_peak.json (tools/int_peak.cu: register-only IMAD loop with the NVML clock / power / event reasons it ran
+    under recorded per test); nominal fallbacks when a file is missing."""
     peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "imad_tops": 148 * 64 * 1.965e9 / 1e12,
-             "imad_src": "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (SURVEY.md section 8d)"}
+             "imad_src": "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (SURVEY.md section 8d)", "modmul_peak": None}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
@@ -60,14 +63,16 @@ def load_peaks():
     p = os.path.join(ROOT, "profiles", "int_peak.json")
     if os.path.exists(p):
         try:
-            tests = {t["name"]: t for t in json.load(open(p))["tests"]}
             pk = json.load(open(p))
-            peaks["imad_tops"] = float(tests["imad32"]["Gops_per_s"]) / 1e3
-            # the same issue rate at the part's maximum SM clock: the sustained figure above is power-limited (a kernel that
-            # keeps the multiplier pipe 100 % busy pulls the clock down to ~1.2 GHz; the MSM kernels run at ~1.95 GHz)
-            peaks["imad_nominal_tops"] = float(tests["imad32"]["ops_per_clk_per_sm"]) * pk["sms"] * pk["max_clock_mhz"] * 1e6 / 1e12
-            peaks["imad_src"] = ("measured 32-bit IMAD rate of tools/int_peak.cu (profiles/int_peak.json: %.0f IMAD/clk/SM at %.0f MHz)"
-                                 % (tests["imad32"]["ops_per_clk_per_sm"], tests["imad32"]["eff_clock_mhz"]))
+            tests = {t["name"]: t for t in pk["tests"]}
+            t = tests["imad32"]
+            peaks["imad_tops"] = float(t["Gops_per_s"]) / 1e3
+            peaks["imad_src"] = ("measured 32-bit IMAD rate of tools/int_peak.cu (profiles/int_peak.json: %.0f IMAD/clk/SM at %.0f MHz%s)"
+                                 % (t["ops_per_clk_per_sm"], t["eff_clock_mhz"],
+                                    (", NVML %s MHz / %s W / reasons %s" % (t.get("nvml_sm_mhz"), t.get("nvml_power_w"), t.get("nvml_reasons")))
+                                    if "nvml_sm_mhz" in t else ""))
+            if "fp_mul_pallas_base" in tests:
+                peaks["modmul_peak"] = float(tests["fp_mul_pallas_base"]["Gops_per_s"]) * 1e9
         except Exception:
             pass
     return peaks
@@ -144,14 +149,14 @@ def challenge_from(comm_T_bytes: bytes, step: int) -> int:
     return int.from_bytes(hashlib.shake_256(comm_T_bytes + step.to_bytes(4, "little")).digest(16), "little")
 
 
-def build_problem(curve_name: str, circuit: str, seed: int):
+def build_problem(curve_name: str, circuit: str, seed: int, num_witnesses: int = 0):
     """Host-side synthetic shape + NUM_WITNESSES satisfying witnesses (Montgomery arrays)."""
-    from vimz_b200 import synthetic as S
-    from vimz_b200.field import CURVES, ints_to_mont
+    from vimz_host import synthetic as S       # neutral host package: does not load libvimz_gpu.so
+    from vimz_host.field import CURVES, ints_to_mont
     cv = CURVES[curve_name]
     sh = S.synthetic_shape(cv, circuit, seed=seed)
     wits = []
-    for k in range(NUM_WITNESSES):
+    for k in range(num_witnesses or NUM_WITNESSES):
         Wi, Xi = S.synthetic_witness(sh, seed + 1000 + k)
         wits.append((ints_to_mont(Wi, cv.scalar_modulus), ints_to_mont(Xi, cv.scalar_modulus)))
     return cv, sh, wits
@@ -161,11 +166,11 @@ def build_problem(curve_name: str, circuit: str, seed: int):
 # reference arm: CPU restatement of nova-snark's path (oracle/), all host cores
 # ------------------------------------------------------------------------------------------------
 class CpuFold:
-    def __init__(self, curve_name, circuit, seed, threads):
+    def __init__(self, curve_name, circuit, seed, threads, num_witnesses=0, problem=None):
         from oracle import c as oracle_c
-        from vimz_b200.field import affine_to_mont, ints_to_mont
+        from vimz_host.field import affine_to_mont, ints_to_mont
         self.o = oracle_c()
-        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.cv, self.sh, self.wits = problem or build_problem(curve_name, circuit, seed, num_witnesses)
         self.cid = self.cv.curve_id
         self.threads = threads
         gens = {"pallas": (self.cv.base_modulus - 1, 2), "vesta": (self.cv.base_modulus - 1, 2), "bn254": (1, 2),
@@ -182,34 +187,58 @@ class CpuFold:
         self.q = q
 
     def step(self, k: int):
-        from vimz_b200.field import ints_to_mont
+        from vimz_host.field import ints_to_mont
         o, cid, sh, t = self.o, self.cid, self.sh, self.threads
         W2, X2 = self.wits[k % len(self.wits)]
         comm_W2 = o.msm(cid, W2, self.bases, t)
         T = o.commit_T(cid, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, self.W1, self.u1, self.X1, W2, X2, self.one, nthreads=t)
         comm_T = o.msm(cid, T, self.bases, t)
-        r = ints_to_mont([challenge_from(comm_T.tobytes(), k)], self.q)
+        # r from the CANONICAL (affine) bytes of comm_T, as the reference's RO absorbs coordinates: both arms of the
+        # parity replay then derive the same challenge whatever Jacobian representative their MSM returned
+        r = ints_to_mont([challenge_from(self.affine(comm_T), k)], self.q)
         self.W1 = o.axpy(cid, self.W1, W2, r, t)
         self.E1 = o.axpy(cid, self.E1, T, r, t)
         tail = o.axpy(cid, np.concatenate([self.u1, self.X1]), np.concatenate([self.one, X2]), r, 1)
         self.u1, self.X1 = tail[:1], tail[1:]
         self.cW = o.point_scale_add(cid, self.cW, r, comm_W2)
         self.cE = o.point_scale_add(cid, self.cE, r, comm_T)
+        self.last = (comm_W2, comm_T)
+
+    def affine(self, jac):
+        return self.o.to_affine(self.cid, jac).tobytes()
 
 
 CYCLES = {"pasta": ("pallas", "vesta"), "bn254": ("bn254", "grumpkin")}
 
 
-def run_cpu_steps(steps: int, warmup: int, threads: int, cycle: str = "pasta", circuit: str = "grayscale"):
-    prim = CpuFold(CYCLES[cycle][0], circuit, SEED, threads)
-    sec = CpuFold(CYCLES[cycle][1], "secondary", SEED + 1, threads)
+def run_cpu_steps(steps: int, warmup: int, threads: int, cycle: str = "pasta", circuit: str = "grayscale", problems=None,
+                  budget_s: float = 150.0, record: bool = False):
+    """`warmup` + `steps` fold steps of the CPU restatement (oracle/nova_cpu.c) from the default relaxed instance.  The
+    timed steps are cut short if they would exceed `budget_s` (returned as the number actually run).  record = True also
+    returns what the parity replay compares: per step the canonical bytes of (comm_W2, comm_T) of both curves, and the
+    final folded pairs."""
+    prim = CpuFold(CYCLES[cycle][0], circuit, SEED, threads, problem=problems[0] if problems else None)
+    sec = CpuFold(CYCLES[cycle][1], "secondary", SEED + 1, threads, problem=problems[1] if problems else None)
+    recs = []
+
+    def one(k):
+        sec.step(k); prim.step(k)
+        if record:
+            recs.append(tuple(f.affine(pt) for f in (sec, prim) for pt in f.last))
+
+    t_w = time.perf_counter()
     for k in range(warmup):
-        sec.step(k); prim.step(k)
+        one(k)
+    per = (time.perf_counter() - t_w) / max(warmup, 1)
+    run = steps if per <= 0 else max(1, min(steps, int(budget_s / per)))
     t0 = time.perf_counter()
-    for k in range(warmup, warmup + steps):
-        sec.step(k); prim.step(k)
+    for k in range(warmup, warmup + run):
+        one(k)
     dt = time.perf_counter() - t0
-    return steps / dt, dt, prim.sh
+    final = None
+    if record:
+        final = [(f.W1, f.E1, f.u1, f.X1, f.affine(f.cW), f.affine(f.cE)) for f in (sec, prim)]
+    return run / dt, dt, prim.sh, run, recs, final
 
 
 def workload_config(sh, extra=None, cycle="pasta"):
@@ -233,19 +262,24 @@ def workload_config(sh, extra=None, cycle="pasta"):
 
 
 def main_reference(args, rank, world):
+    """--impl reference: the CPU restatement of nova-snark's path on all host cores, same workload / metric / unit.  Imports
+    only oracle/ and vimz_host/ (the product library is never loaded by this arm).  Rank 0 alone runs under torchrun."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 8))          # bounded sample: a CPU step is ~0.3-1 s
-    warmup = max(1, min(args.warmup, 2))
-    sps, dt, sh = run_cpu_steps(steps, warmup, threads, args.cycle, args.circuit)
-    line = {"metric": "nova_fold_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+    warmup = max(1, args.warmup)
+    sps, dt, sh, run, _, _ = run_cpu_steps(args.steps, warmup, threads, args.cycle, args.circuit)
+    sample = f"{run} full {args.circuit}_HD fold steps (primary+secondary) after {warmup} warm-up, {dt:.1f} s"
+    if run != args.steps:
+        sample += f" (cut from the requested {args.steps}: the CPU arm is bounded to ~150 s of timed work)"
+    line = {"metric": "nova_fold_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": run, "warmup": warmup,
             "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)",
             "data": "synthetic", "impl": "reference",
             "config": workload_config(sh, cycle=args.cycle, extra={"note": "CPU restatement of nova-snark 0.23.0 (oracle/nova_cpu.c): the Rust crate cannot be built here (no cargo/rustc)"}),
-            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": f"{steps} full {args.circuit}_HD fold steps (primary+secondary) after {warmup} warm-up"},
+            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "loaded_native": sorted({os.path.basename(l.split()[-1]) for l in open("/proc/self/maps") if "/libvimz_gpu" in l or "/liboracle" in l})}
     emit(line)
 
 
@@ -253,11 +287,11 @@ def main_reference(args, rank, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class GpuFold:
-    def __init__(self, curve_name, circuit, seed, device, torch):
+    def __init__(self, curve_name, circuit, seed, device, torch, num_witnesses=0):
         import vimz_b200
         from vimz_b200 import CommitmentKey, FoldAccumulator, R1CSShape
         self.torch = torch
-        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed, num_witnesses)
         self.eng = vimz_b200.Engine(curve_name, device)
         win = os.environ.get("VIMZ_WINDOW_" + curve_name.upper())
         if win:
@@ -296,16 +330,39 @@ class GpuFold:
         self.pin_np = [t.numpy().view(np.uint64).reshape(-1, 4) for t in self.pin_W]
         self.X2_bytes = [np.ascontiguousarray(x, dtype=np.uint64).tobytes() for _, x in self.wits]
 
-    def step(self, k: int, resident: bool):
+    def step(self, k: int, resident, acc=None):
+        """resident: True = W2 already in HBM (`value`); False = pinned host buffer (`e2e`); "pageable" = plain numpy memory,
+        what a Rust Vec<Scalar> is (`e2e.pageable_value`)."""
         i = k % len(self.wits)
         X2 = self.X2_bytes[i]
-        if resident:
-            cw, ct = self.acc.step_begin_dev(self.dev_ptr[i], X2)
+        acc = acc or self.acc
+        if resident is True:
+            cw, ct = acc.step_begin_dev(self.dev_ptr[i], X2)
+        elif resident == "pageable":
+            cw, ct = acc.step_begin(self.wits[i][0], X2)
         else:
-            cw, ct = self.acc.step_begin(self.pin_np[i], X2)
+            cw, ct = acc.step_begin(self.pin_np[i], X2)
         # r = RO(comm_T) as a Montgomery-form scalar, 32 little-endian bytes (what the Rust side hands over)
         r = ((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little")
-        self.acc.step_end(r)
+        acc.step_end(r)
+
+    def replay_from_zero(self, nsteps: int):
+        """Parity replay: `nsteps` folds from the default relaxed instance on a FRESH accumulator over the same shape / key,
+        host witnesses through the C ABI, challenge from the canonical bytes of comm_T (as CpuFold does).  Returns the per-step
+        canonical (comm_W2, comm_T) bytes and the final folded pair."""
+        from vimz_b200 import FoldAccumulator
+        acc = FoldAccumulator(self.shape, self.ck)
+        recs = []
+        for k in range(nsteps):
+            i = k % len(self.wits)
+            cw, ct = acc.step_begin(self.wits[i][0], self.X2_bytes[i])
+            aw, at = self.eng.to_affine(cw).tobytes(), self.eng.to_affine(ct).tobytes()
+            acc.step_end(((challenge_from(at, k) << 256) % self.q).to_bytes(32, "little"))
+            recs.append((aw, at))
+        U, W = acc.download()
+        final = (W.W, W.E, U.u, U.X, self.eng.to_affine(U.comm_W).tobytes(), self.eng.to_affine(U.comm_E).tobytes())
+        acc.close()
+        return recs, final
 
     def h2d_bytes(self):
         return (self.sh.num_vars + self.sh.num_io + 1 + 1) * 32
@@ -348,7 +405,7 @@ class GpuFoldSharded:
         self.q = self.cv.scalar_modulus
 
     def step(self, k: int, resident: bool):
-        from vimz_b200.field import ints_to_mont
+        from vimz_host.field import ints_to_mont
         i = k % len(self.wits)
         X2 = self.wits[i][1]
         if resident:
@@ -428,12 +485,12 @@ def timed_region(torch, engines, fn, steps, dist):
     return ms, wall
 
 
-def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist="uniform"):
+def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist="uniform", check=True):
     """Pallas MSM over 2^log2n resident points, uniform full-width scalars resident in HBM.  world > 1: point-range
     shards, per-rank partial sums all-gathered over NCCL and added on the GPU."""
     import vimz_b200
     from vimz_b200 import CommitmentEngine, CommitmentKey
-    from vimz_b200 import synthetic as S
+    from vimz_host import synthetic as S
     eng = vimz_b200.Engine("pallas", device)
     if os.environ.get("VIMZ_WINDOW_MSM"):
         eng.set_option("msm_window", int(os.environ["VIMZ_WINDOW_MSM"]))
@@ -450,7 +507,7 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
         if scalar_dist == "witness":
             return S.witness_like_scalars_mont(per, q, SEED + 7 * rank + j)
         if scalar_dist == "edge":  # thirds of zero / one / q - 1: every scalar lands in bucket 1 or nowhere (giant-bucket path)
-            from vimz_b200.field import ints_to_mont
+            from vimz_host.field import ints_to_mont
             pat = ints_to_mont([0, 1, q - 1], q)
             return np.ascontiguousarray(pat[(np.arange(per) + j) % 3])
         return S.uniform_scalars_mont(per, q, SEED + 7 * rank + j)
@@ -493,9 +550,24 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
         ms = float(t[0])
     prof = eng.profile(reset=True)
     eng.set_option("profile", 0)
+    # parity of what was just timed: the commitment must be (sum_i s_i k_i) * G for the bases k_i * G -- one scalar
+    # multiplication by the python big-integer oracle (the checker, not the thing measured), independent of any MSM code
+    verified = None
+    if check:
+        from oracle import pyref as P
+        from vimz_host.synthetic import closed_form_log
+        c = P.CURVES["pallas"]
+        local = CommitmentEngine.commit_dev(ck, sc[0].data_ptr(), per)
+        exp = P.scalar_mul(c, closed_form_log(sc[0].cpu().numpy().view(np.uint64).reshape(-1, 4), K0, DK, q, first), P.generator(c))
+        verified = bool(eng.to_affine_ints(local) == exp)
+        if world > 1:   # every rank's shard must check out
+            t = torch.tensor([1 if verified else 0], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            verified = bool(int(t[0]))
     acc_ms, acc_calls = prof["msm_accumulate_kernel"]
     entries = prof["msm_entries"][1]
     res = {"log2_points": log2n, "mpts_per_s": n * iters / ms / 1e3, "ms_per_msm": ms / iters, "window_bits": ck.window_bits,
+           "result_equals_closed_form": verified,
            "windows": ck.num_windows,
            "scalars": {"uniform": "uniform 255-bit", "witness": "witness-like: 93% 0/1, 2% bytes, 5% uniform", "edge": "edge: 0 / 1 / q-1 in thirds"}[scalar_dist], "sharding": f"point-range x{world}" if world > 1 else "none"}
     if acc_ms > 0:
@@ -505,8 +577,6 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
         res["reduce_ms"] = prof["msm_reduce"][0] / max(prof["msm_reduce"][1], 1)
         res["accumulate_timad_per_s"] = imad / (acc_ms * 1e-3) / 1e12
         res["accumulate_frac_of_imad_peak"] = res["accumulate_timad_per_s"] / peaks["imad_tops"]
-        if peaks.get("imad_nominal_tops"):
-            res["accumulate_frac_of_peak_at_max_clock"] = res["accumulate_timad_per_s"] / peaks["imad_nominal_tops"]
         res["whole_msm_timad_per_s"] = (n * iters * ck.num_windows * MODMUL_PER_MADD * IMAD_PER_MODMUL) / (ms * 1e-3) / 1e12 / world * world
     ck.close()
     eng.close()
@@ -571,6 +641,13 @@ def main_gpu(args, rank, world, local_rank):
     clocks = sampler.stop()
     launches = sum(e.launch_count for e in engines) - launches0
     ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
+
+    def step_pageable(k):   # W2 in plain (pageable) host memory, as a Rust Vec<Scalar> would be
+        sec.step(k, "pageable"); prim.step(k, "pageable")
+
+    for k in range(2):
+        step_pageable(k)
+    ms_page, _ = timed_region(torch, engines, lambda k: step_pageable(PREFOLD + warmup + 3 * steps + k), steps, dist)
     # Same K steps once more with the library's per-phase CUDA-event timers on (this pass launches the kernels
     # one by one instead of replaying the captured graph, so its events can sit between kernels).
     for e in engines:
@@ -605,18 +682,23 @@ def main_gpu(args, rank, world, local_rank):
     entries = prof["msm_entries"][1]
     imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
     achieved = imad / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1s3_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("k_msm_accumulate_fold_T")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = None, None
+    for tname in ("r2_traffic.json", "r1s3_traffic.json"):   # dram__bytes of one ncu --set full capture of this kernel, per launch
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_msm_accumulate_fold_T")
+                traffic_src = f"profiles/{tname} (ncu --set full capture of commit(T)'s launch; not measured by this run)"
+                break
+            except Exception:
+                traffic = None
+    modmul_per_s = entries * MODMUL_PER_MADD / (acc_ms * 1e-3) if acc_ms > 0 else None
     roofline = {"kernel": "k_msm_accumulate<%s>" % prim.cv.name, "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
                 "unit": "TIMAD/s", "frac": (achieved / peaks["imad_tops"]) if achieved else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peaks["imad_src"],
-                "peak_at_max_clock": peaks.get("imad_nominal_tops"),
-                "frac_of_peak_at_max_clock": (achieved / peaks["imad_nominal_tops"]) if achieved and peaks.get("imad_nominal_tops") else None,
+                "modmul_per_s": modmul_per_s, "modmul_peak_per_s": peaks.get("modmul_peak"),
+                "modmul_frac": (modmul_per_s / peaks["modmul_peak"]) if modmul_per_s and peaks.get("modmul_peak") else None,
                 "algorithmic": f"{entries} bucket insertions x {MODMUL_PER_MADD} modmul x {IMAD_PER_MODMUL} IMAD over {acc_calls} launches "
                                f"(commit(W2) and commit(T) of every step)",
                 "launch_us_avg": (acc_ms * 1e3 / acc_calls) if acc_calls else None,
@@ -624,7 +706,10 @@ def main_gpu(args, rank, world, local_rank):
                 "share_of_step": acc_ms / ms_prof if ms_prof > 0 else None,
                 "timing": "library CUDA-event pairs around the kernel over a profiled pass of the same K steps (stream launches); "
                           "`value` is timed separately with the step's launch sequence replayed as a CUDA graph",
-                "note": "integer-multiply bound, not hbm/tensor: nothing on this path is a dense contraction (BASELINE.json north_star)"}
+                "note": "integer-multiply bound, not hbm/tensor: nothing on this path is a dense contraction (BASELINE.json north_star). "
+                        "ONE denominator: the 32-bit IMAD rate measured by tools/int_peak.cu on this pool's B200 with its clock / power / "
+                        "event reasons recorded beside it; modmul_frac is the same kernel against the measured field-multiplication peak "
+                        "(a Pasta product executes fewer than the algorithmic 272 IMAD)"}
     ct_ms, ct_calls = prof["cross_term"]
     ct_bytes = prim.cross_term_bytes()
     ct_gbs = ct_bytes * ct_calls / (ct_ms * 1e-3) / 1e9 if ct_ms > 0 else None
@@ -643,12 +728,25 @@ def main_gpu(args, rank, world, local_rank):
     if world > 1 and not args.no_sharded_step:
         sharded = sharded_step_bench(args, torch, dist, rank, world, local_rank, min(steps, 100), warmup)
 
-    cpu_baseline = None
+    # CPU restatement on the host cores: the reported baseline AND the checker of the parity replay -- the same K = 3 (+1
+    # warm-up) steps from the default relaxed instance are folded by both arms on the same witnesses and compared value by value
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sps, dt, _ = run_cpu_steps(3, 1, threads, args.cycle, args.circuit)
+        K = 3
+        sps, dt, _, run, cpu_recs, cpu_final = run_cpu_steps(K, 1, threads, args.cycle, args.circuit, record=True,
+                                                             problems=((prim.cv, prim.sh, prim.wits), (sec.cv, sec.sh, sec.wits)))
         cpu_baseline = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                        "sample": f"3 full {args.circuit}_HD fold steps (primary+secondary) of oracle/nova_cpu.c after 1 warm-up, {dt:.1f} s"}
+                        "sample": f"{run} full {args.circuit}_HD fold steps (primary+secondary) of oracle/nova_cpu.c after 1 warm-up, {dt:.1f} s"}
+        g_sec, f_sec = sec.replay_from_zero(1 + run)
+        g_prim, f_prim = prim.replay_from_zero(1 + run)
+        commit_eq = all(c[0] == gs[0] and c[1] == gs[1] and c[2] == gp[0] and c[3] == gp[1] for c, gs, gp in zip(cpu_recs, g_sec, g_prim))
+        final_eq = all(all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b for a, b in zip(cf, gf))
+                       for cf, gf in zip(cpu_final, (f_sec, f_prim)))
+        parity = {"steps": run, "warmup_steps_also_compared": 1, "equal": bool(commit_eq and final_eq and len(cpu_recs) == 1 + run),
+                  "compared": "canonical affine (comm_W2, comm_T) of every step on both curves; final W, E, u, X limb for limb and affine "
+                              "comm_W, comm_E on both curves; GPU through the host-pointer C ABI vs oracle/nova_cpu.c",
+                  "commitments_equal": bool(commit_eq), "folded_instances_equal": bool(final_eq)}
 
     if rank == 0:
         bad = [r for r in clocks["reasons"] if r != "sw_power_cap"]
@@ -659,9 +757,12 @@ def main_gpu(args, rank, world, local_rank):
                                                                    "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows}),
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
                         "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_e2e / steps,
+                        "host_buffers": "pinned (cudaHostAlloc)", "pageable_value": world * steps / (ms_page * 1e-3),
+                        "pageable_ms_per_step": ms_page / steps,
+                        "pageable_note": "same call with W2 in ordinary pageable memory (what a Rust Vec<Scalar> is): the driver stages the copy",
                         "h2d_primary_witness_us": h2d_us, "h2d_gbs": h2d_gbs},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "parity_check": parity,
                 "clocks": clocks, "clock_verdict": "rejected: " + ",".join(bad) if bad else "ok",
                 "phases_primary": phases, "phases_secondary": phases_sec,
                 "wall_ms_per_step": wall * 1e3 / steps, "profiled_pass_ms_per_step": ms_prof / steps,

@@ -165,6 +165,14 @@ int vimz_acc_load(vimz_acc* acc, const vimz_fr* W, const vimz_fr* E, const vimz_
                   const vimz_point* comm_W, const vimz_point* comm_E);
 int vimz_acc_step_begin(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);
 int vimz_acc_step_begin_dev(vimz_acc* acc, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);
+/* The two halves of step_begin as separate calls, for the SECONDARY curve of RecursiveSNARK::prove_step ([EXT nova-snark]
+ * src/lib.rs): its fresh witness is committed at the end of step i (r1cs_instance_and_witness -> commit_fresh, which also
+ * stages W2 / X2 in the accumulator) and folded at the start of step i+1 (NIFS::prove -> cross_begin: T and comm_T);
+ * vimz_acc_step_end follows as usual.  vimz_acc_fresh_witness reads the staged (W2, X2) back (l_w_secondary, checked by
+ * RecursiveSNARK::verify with is_sat before it is ever folded). */
+int vimz_acc_commit_fresh(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2);
+int vimz_acc_cross_begin(vimz_acc* acc, vimz_point* comm_T);
+int vimz_acc_fresh_witness(vimz_acc* acc, vimz_fr* W2, vimz_fr* X2);
 int vimz_acc_step_end(vimz_acc* acc, const vimz_fr* r);
 int vimz_acc_download(vimz_acc* acc, vimz_fr* W, vimz_fr* E, vimz_fr* u, vimz_fr* X, vimz_point* comm_W, vimz_point* comm_E);
 /* T of the last step_begin (m elements), for callers that keep nova-snark's (T, comm_T) pair. */

@@ -354,7 +354,8 @@ def test_full_size_grayscale_fold_bit_exact_vs_c_oracle(coracle):
         spill = sum(1 for t in mont_to_ints(T, q) if 135 <= min(t, q - t).bit_length() <= 150)
         assert spill > 10_000, "T must reach into the tenth 15-bit window like the mid-proof steps bench.py times"
         stats = eng.lane_stats()
-        assert stats["lane0_entries"] > 9 * sh.num_cons and stats["lane0_ngiant"] >= 1, stats
+        # (copy rows have T = 0 and insert nothing; the others carry ten or more digits)
+        assert stats["lane0_entries"] > 7 * sh.num_cons and stats["lane0_ngiant"] >= 1, stats
         assert np.array_equal(acc.last_T(), T), f"T differs at step {k}"
         exp_T, exp_W2 = coracle.msm(cid, T, Bm, 8), coracle.msm(cid, W2, Bm, 8)
         assert eng.to_affine_ints(comm_T) == _affine(coracle, c, exp_T), f"comm_T differs at step {k}"

@@ -22,4 +22,6 @@ from .nova import (  # noqa: F401
     is_sat_relaxed,
 )
 
-__version__ = "0.1.0"
+from .recursive import PublicParams, RecursiveSNARK, fold_input, verify_folded_proof  # noqa: F401
+
+__version__ = "0.2.0"

@@ -82,6 +82,9 @@ def _load() -> C.CDLL:
         "vimz_acc_load": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "vimz_acc_step_begin": (i32, [vp, vp, vp, vp, vp]),
         "vimz_acc_step_begin_dev": (i32, [vp, vp, vp, vp, vp]),
+        "vimz_acc_commit_fresh": (i32, [vp, vp, vp, vp]),
+        "vimz_acc_cross_begin": (i32, [vp, vp]),
+        "vimz_acc_fresh_witness": (i32, [vp, vp, vp]),
         "vimz_acc_step_end": (i32, [vp, vp]),
         "vimz_acc_download": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "vimz_acc_last_T": (i32, [vp, vp]),

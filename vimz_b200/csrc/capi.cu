@@ -1005,10 +1005,79 @@ int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vi
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
+// ---- the two halves of step_begin as separate calls (strict prove_step order on the secondary curve) --------------
+// RecursiveSNARK::prove_step commits the fresh secondary witness at the END of step i (r1cs_instance_and_witness, (6) in
+// SURVEY.md section 3.2) and folds it at the START of step i+1 (NIFS::prove, (1)); with host code in between the two
+// halves cannot share one call.  commit_fresh opens a step (stages W2 / X2 in the accumulator, returns comm_W2),
+// cross_begin finishes what step_begin would have done (T, comm_T); step_end follows as usual.
+int vimz_acc_commit_fresh(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2) {
+  CHECK_ARG(a && comm_W2 && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_commit_fresh: null argument");
+  vimz_ctx* ctx = a->ctx;
+  CtxGuard g(ctx);
+  const vimz_shape* s = a->shape;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  cudaStream_t st = ctx->stream;
+  if (a->step_enqueued && !a->fresh_complete) VIMZ_CUDA(cudaStreamSynchronize(st));
+  a->parity ^= 1;
+  const int p = a->parity;
+  if (a->side_pending[p]) {
+    VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_side[p], 0));
+    a->side_pending[p] = false;
+  }
+  char* fresh = (char*)a->comms + (2 + 2 * p) * 96;
+  uint8_t* stage = a->pinned + ACC_PIN_STAGE;
+  memcpy(stage, vt->scalar_one_mont, 32);
+  if (s->io) memcpy(stage + 32, X2, s->io * 32);
+  VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, s->n * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, stage, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
+  VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH, fresh, 96, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  a->step_enqueued = true;
+  a->fresh_complete = false;
+  a->half_open = true;
+  memcpy(comm_W2, a->pinned + ACC_PIN_FRESH, 96);
+  return VIMZ_OK;
+}
+
+int vimz_acc_cross_begin(vimz_acc* a, vimz_point* comm_T) {
+  CHECK_ARG(a && comm_T, "vimz_acc_cross_begin: null argument");
+  vimz_ctx* ctx = a->ctx;
+  CtxGuard g(ctx);
+  if (!a->half_open) return set_error(VIMZ_ERR_ARG, "vimz_acc_cross_begin: no vimz_acc_commit_fresh before it");
+  const vimz_shape* s = a->shape;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  cudaStream_t st = ctx->stream;
+  char* fresh = (char*)a->comms + (2 + 2 * a->parity) * 96;
+  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2));
+  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
+  VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH + 96, fresh + 96, 96, cudaMemcpyDeviceToHost, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  a->half_open = false;
+  a->fresh_complete = true;
+  memcpy(comm_T, a->pinned + ACC_PIN_FRESH + 96, 96);
+  return VIMZ_OK;
+}
+
+// The fresh witness staged by the last step_begin / commit_fresh (what nova-snark keeps as l_w_secondary): RecursiveSNARK::verify
+// checks it with is_sat before it has been folded.
+int vimz_acc_fresh_witness(vimz_acc* a, vimz_fr* W2, vimz_fr* X2) {
+  CHECK_ARG(a, "vimz_acc_fresh_witness: null argument");
+  vimz_ctx* ctx = a->ctx;
+  CtxGuard g(ctx);
+  const vimz_shape* s = a->shape;
+  if (W2 && s->n) VIMZ_CUDA(cudaMemcpyAsync(W2, a->W2, s->n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (X2 && s->io) VIMZ_CUDA(cudaMemcpyAsync(X2, (char*)a->tail2 + 32, s->io * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIMZ_OK;
+}
+
 int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   CHECK_ARG(a && r, "vimz_acc_step_end: null argument");
   vimz_ctx* ctx = a->ctx;
   CtxGuard g(ctx);
+  if (a->half_open) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_end: vimz_acc_commit_fresh without vimz_acc_cross_begin");
+  if (!a->step_enqueued) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_end: no step_begin before it");
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;

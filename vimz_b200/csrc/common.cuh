@@ -218,6 +218,7 @@ struct vimz_acc {
   bool side_pending[2] = {false, false};
   bool fresh_complete = false;  // the host has waited for the last step_begin (sync entry points, step_combine_dev)
   bool step_enqueued = false;   // a step_begin has been issued on this accumulator
+  bool half_open = false;       // vimz_acc_commit_fresh done, vimz_acc_cross_begin still to come
   int parity = 0;
   // step_begin's launch sequence (cross term + both MSMs, ~35 kernels on two streams) captured once per
   // parity slot and replayed: the step is latency-bound and stream launches cost more than the small kernels

@@ -474,6 +474,29 @@ class FoldAccumulator:
         check(lib.vimz_acc_step_begin_dev(self._h, C.c_void_p(d_W2), px, pw, pt))
         return out[:12].copy(), out[12:].copy()
 
+    def commit_fresh(self, W2: np.ndarray, X2: np.ndarray) -> np.ndarray:
+        """First half of step_begin: stage (W2, X2) in the accumulator, -> comm_W2 (r1cs_instance_and_witness)."""
+        s = self.shape
+        W2 = as_fr(W2)
+        if W2.shape[0] != s.num_vars:
+            raise InvalidWitnessLength(_lib.VIMZ_ERR_LENGTH, "commit_fresh: witness length != num_vars")
+        X2, px = self._fr_ptr(X2, s.num_io)
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib.vimz_acc_commit_fresh(self._h, _ptr(W2), px, _ptr(out)))
+        return out
+
+    def cross_begin(self) -> np.ndarray:
+        """Second half of step_begin on the staged witness: -> comm_T (R1CSShape::commit_T inside NIFS::prove)."""
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib.vimz_acc_cross_begin(self._h, _ptr(out)))
+        return out
+
+    def fresh_witness(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(W2, X2) staged by the last step_begin / commit_fresh (nova-snark's l_w_secondary / l_u_secondary.X)."""
+        W2, X2 = fr_array(self.shape.num_vars), fr_array(self.shape.num_io)
+        check(lib.vimz_acc_fresh_witness(self._h, _ptr(W2), _ptr(X2)))
+        return W2, X2
+
     def step_end(self, r: np.ndarray):
         r, pr = self._fr_ptr(r, 1)
         check(lib.vimz_acc_step_end(self._h, pr))
@@ -482,6 +505,14 @@ class FoldAccumulator:
         T = fr_array(self.shape.num_cons)
         check(lib.vimz_acc_last_T(self._h, _ptr(T)))
         return T
+
+    def instance(self) -> RelaxedR1CSInstance:
+        """The running RelaxedR1CSInstance only (comm_W, comm_E, X, u -- 256 bytes): what the RO absorbs as U1."""
+        s = self.shape
+        u, X = fr_array(1), fr_array(s.num_io)
+        cw, ce = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
+        check(lib.vimz_acc_download(self._h, None, None, _ptr(u), _ptr(X), _ptr(cw), _ptr(ce)))
+        return RelaxedR1CSInstance(cw, ce, X, u)
 
     def download(self) -> Tuple[RelaxedR1CSInstance, RelaxedR1CSWitness]:
         s = self.shape
