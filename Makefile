@@ -7,7 +7,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-cons
 SRC := vimz_b200/csrc
 OBJ ?= build/obj
 LIB ?= vimz_b200/libvimz_gpu.so
-CUS := capi curve_pallas curve_vesta curve_bn254 curve_grumpkin
+CUS := capi comm curve_pallas curve_vesta curve_bn254 curve_grumpkin
 OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CUS)))
 HDRS := $(wildcard $(SRC)/*.cuh) include/vimz_gpu.h
 
@@ -16,7 +16,7 @@ all: $(LIB) oracle
 # A/B variants: make OBJ=build/v1 LIB=build/variants/x.so EXTRA="-DVIMZ_COMBINE_MID=64" build/variants/x.so
 $(LIB): $(OBJS)
 	@mkdir -p $(dir $@)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -26,7 +26,7 @@ oracle:
 	$(MAKE) -C oracle
 
 tools/int_peak: tools/int_peak.cu $(SRC)/fp.cuh
-	$(NVCC) $(ARCH) -O3 -I$(SRC) -o $@ $<
+	$(NVCC) $(ARCH) -O3 -I$(SRC) -o $@ $< -ldl
 
 clean:
 	rm -rf build vimz_b200/libvimz_gpu.so tools/int_peak

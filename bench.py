@@ -307,6 +307,8 @@ class GpuFold:
             self.eng.set_option("msm_direct_bps", int(os.environ["VIMZ_DIRECT_BPS"]))
         if os.environ.get("VIMZ_DIRECT_MAX"):
             self.eng.set_option("msm_direct_max", int(os.environ["VIMZ_DIRECT_MAX"]))
+        if os.environ.get("VIMZ_SPIN_WAIT"):
+            self.eng.set_option("spin_wait", int(os.environ["VIMZ_SPIN_WAIT"]))
         if os.environ.get("VIMZ_ACC_BLOCKS"):
             self.eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
         sh = self.sh
@@ -346,6 +348,25 @@ class GpuFold:
         r = ((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little")
         acc.step_end(r)
 
+    # -- pipelined end-to-end path: the fold-independent part of the witness is handed over early -------------------------------
+    def staged_split(self):
+        """Rows [0, n_early) of W2 are the Circom step circuit's variables: they depend on the image row and the running hash only,
+        not on the previous fold, so the host can produce and upload them ahead; the last NOVA_AUGMENTED (~10 k) variables are those of
+        Nova's augmented circuit (hashes of the folded instances) and exist only once the previous step has finished."""
+        from vimz_host.synthetic import NOVA_AUGMENTED
+        n = self.sh.num_vars
+        return max(0, n - NOVA_AUGMENTED) if n > 2 * NOVA_AUGMENTED else 0
+
+    def stage(self, k: int):
+        i = k % len(self.wits)
+        self.acc.stage_fresh(self.pin_np[i], 0, self.staged_split())
+
+    def step_staged(self, k: int):
+        i = k % len(self.wits)
+        e = self.staged_split()
+        cw, ct = self.acc.step_begin_staged(self.pin_np[i], e, self.sh.num_vars - e, self.X2_bytes[i])
+        self.acc.step_end(((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little"))
+
     def replay_from_zero(self, nsteps: int):
         """Parity replay: `nsteps` folds from the default relaxed instance on a FRESH accumulator over the same shape / key,
         host witnesses through the C ABI, challenge from the canonical bytes of comm_T (as CpuFold does).  Returns the per-step
@@ -364,15 +385,19 @@ class GpuFold:
         acc.close()
         return recs, final
 
+    def close(self):
+        self.dev_W = self.pin_W = self.pin_np = self.dev_ptr = None
+        self.acc.close(); self.shape.close(); self.ck.close(); self.eng.close()
+
     def h2d_bytes(self):
         return (self.sh.num_vars + self.sh.num_io + 1 + 1) * 32
 
     def cross_term_bytes(self):
-        """Algorithmic HBM bytes of one k_cross_term_stream<CACHED> launch: (col, value-index) per non-zero, three row
-        pointer arrays, one pass over z2, the cached (Az1, Bz1, Cz1) read and (Az2, Bz2, Cz2) written, T written, and the
-        recoded digit array of T written for the MSM that follows."""
+        """Algorithmic HBM bytes of the cross term of one step (k_matvec_stream + k_cross_finish): (col, value-index) per
+        non-zero, three row pointer arrays, one pass over z2, (Az2, Bz2, Cz2) written then read, the cached (Az1, Bz1, Cz1)
+        read, T written, and the recoded digit array of T written for the MSM that follows."""
         sh = self.sh
-        return (sh.nnz * 8 + 3 * (sh.num_cons + 1) * 4 + (sh.num_vars + 1 + sh.num_io) * 32 + 6 * sh.num_cons * 32 + sh.num_cons * 32
+        return (sh.nnz * 8 + 3 * (sh.num_cons + 1) * 4 + (sh.num_vars + 1 + sh.num_io) * 32 + 9 * sh.num_cons * 32 + sh.num_cons * 32
                 + sh.num_cons * self.ck.num_windows * 4)
 
 
@@ -382,12 +407,12 @@ class GpuFoldSharded:
     the step's only collective is the NCCL all-gather of the two partial commitments.  Every rank builds the same
     problem (same seed) and keeps W replicated."""
 
-    def __init__(self, curve_name, circuit, seed, device, torch, dist, rank, world):
+    def __init__(self, curve_name, circuit, seed, device, torch, dist, rank, world, comm=None, num_witnesses=0):
         import vimz_b200
         from vimz_b200 import CommitmentKey
-        from vimz_b200.sharding import FoldShard, ShardedFoldAccumulator
+        from vimz_b200.sharding import Comm, FoldShard, ShardedFoldAccumulator
         self.torch, self.dist, self.rank = torch, dist, rank
-        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed)
+        self.cv, self.sh, self.wits = build_problem(curve_name, circuit, seed, num_witnesses)
         self.eng = eng = vimz_b200.Engine(curve_name, device)
         self.dev = f"cuda:{device}"
         sh = self.sh
@@ -398,34 +423,37 @@ class GpuFoldSharded:
             return CommitmentKey.from_device(eng, d.data_ptr(), count)
 
         self.shard = FoldShard(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, make_ck, rank, world)
-        self.acc = ShardedFoldAccumulator(dist, self.shard, eng.point_sum, device=self.dev)
+        # the exchange runs inside libvimz_gpu.so: its own NCCL communicator, collectives on the context's stream
+        self.comm = comm if comm is not None else Comm.from_torch_dist(dist, device)
+        self.acc = ShardedFoldAccumulator(dist, self.shard, eng.point_sum, device=self.dev, comm=self.comm)
         self.dev_W = [torch.from_numpy(w.view(np.int64)).to(self.dev) for w, _ in self.wits]
-        self.pin_W = [torch.from_numpy(w.view(np.int64).copy()).pin_memory() for w, _ in self.wits] if rank == 0 else None
-        self.stage = torch.empty_like(self.dev_W[0])
+        self.pin_np = None
+        if rank == 0:
+            self.pin_W = [torch.from_numpy(w.view(np.int64).copy()).pin_memory() for w, _ in self.wits]
+            self.pin_np = [t.numpy().view(np.uint64).reshape(-1, 4) for t in self.pin_W]
+        self.X2_bytes = [np.ascontiguousarray(x, dtype=np.uint64).tobytes() for _, x in self.wits]
         self.q = self.cv.scalar_modulus
 
     def step(self, k: int, resident: bool):
-        from vimz_host.field import ints_to_mont
         i = k % len(self.wits)
-        X2 = self.wits[i][1]
+        X2 = self.X2_bytes[i]
         if resident:
             cw, ct = self.acc.step_begin_dev(self.dev_W[i].data_ptr(), X2)
-        else:  # the fresh witness exists on rank 0's host only: H2D there, NCCL broadcast to the other ranks
-            if self.rank == 0:
-                self.stage.copy_(self.pin_W[i], non_blocking=True)
-            self.dist.broadcast(self.stage, src=0)
-            self.torch.cuda.current_stream().synchronize()
-            cw, ct = self.acc.step_begin_dev(self.stage.data_ptr(), X2)
-        r = ints_to_mont([challenge_from(ct.tobytes(), k)], self.q)
-        self.acc.step_end(r)
+        else:  # the fresh witness exists on rank 0's host only: H2D there + NCCL broadcast + step, all inside the library call
+            cw, ct = self.acc.step_begin_root(self.pin_np[i] if self.rank == 0 else None, X2, root=0)
+        self.acc.step_end(((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little"))
         return ct
 
 
-def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup):
-    """Strong-scaling leg of an N > 1 run: the same grayscale (or --circuit) proof folded by all ranks together."""
-    prim = GpuFoldSharded(CYCLES[args.cycle][0], args.circuit, SEED, local_rank, torch, dist, rank, world)
+def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup, circuit=None, prefold=None, num_witnesses=0, expect=None,
+                       comm=None):
+    """Strong-scaling leg of an N > 1 run: the same grayscale (or `circuit`) proof folded by all ranks together."""
+    circuit = circuit or args.circuit
+    prefold = PREFOLD if prefold is None else prefold
+    prim = GpuFoldSharded(CYCLES[args.cycle][0], circuit, SEED, local_rank, torch, dist, rank, world, comm=comm, num_witnesses=num_witnesses)
     if os.environ.get("VIMZ_SHARD_SECONDARY", "1") == "1":   # the secondary curve's 10.5k rows are sharded the same way
-        sec = GpuFoldSharded(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch, dist, rank, world)
+        sec = GpuFoldSharded(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch, dist, rank, world, comm=prim.comm,
+                             num_witnesses=num_witnesses)
     else:
         sec = GpuFold(CYCLES[args.cycle][1], "secondary", SEED + 1, local_rank, torch)
     engines = [prim.eng, sec.eng]
@@ -437,26 +465,119 @@ def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup
     def step_e2e(k):
         sec.step(k, False); last["ct"] = prim.step(k, False)
 
-    for k in range(PREFOLD + warmup):
+    for k in range(prefold + warmup):
         step_resident(k)
     for k in range(2):
         step_e2e(k)
-    ms, _ = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + k), steps, dist)
-    ms_e2e, _ = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
+    ms, _ = timed_region(torch, engines, lambda k: step_resident(prefold + warmup + k), steps, dist)
+    ms_e2e, _ = timed_region(torch, engines, lambda k: step_e2e(prefold + warmup + steps + k), steps, dist)
     # every rank must have derived the same transcript: compare the last comm_T across ranks
     t = torch.from_numpy(last["ct"].view(np.int64).copy()).to(f"cuda:{local_rank}")
     parts = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(parts, t)
     same = all(bool((p == parts[0]).all()) for p in parts)
-    res = {"steps_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_steps_per_s": steps / (ms_e2e * 1e-3),
+    # parity of the sharded path: the first folds of the proof again, from the default instance, with the challenge derived
+    # from canonical coordinates -- every full commitment must equal the one-GPU fold of the same witnesses (`expect`, rank 0's
+    # replica replayed through the plain entry points, itself checked against the CPU oracle at N = 1)
+    equals_unsharded = None
+    if expect is not None and isinstance(sec, GpuFoldSharded):
+        ok = True
+        for f, exp in ((sec, expect[0]), (prim, expect[1])):
+            f.shard.acc.reset()
+            for k, (ew, et) in enumerate(exp):
+                i = k % len(f.wits)
+                cw, ct = f.acc.step_begin_dev(f.dev_W[i].data_ptr(), f.X2_bytes[i])
+                aw, at = f.eng.to_affine(cw).tobytes(), f.eng.to_affine(ct).tobytes()
+                ok = ok and aw == ew and at == et
+                f.acc.step_end(((challenge_from(at, k) << 256) % f.q).to_bytes(32, "little"))
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        equals_unsharded = bool(int(flag[0]))
+    res = {"circuit": circuit, "equals_one_gpu_fold": equals_unsharded, "steps_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_steps_per_s": steps / (ms_e2e * 1e-3),
            "e2e_ms_per_step": ms_e2e / steps, "scaling": "strong", "ranks_agree_on_comm_T": same,
            "rows_per_rank": prim.shard.m_local, "vars_per_rank": prim.shard.var_count,
-           "exchange": "NCCL all-gather of 2 partial commitments (192 B per rank) per step; e2e adds the NCCL broadcast of W2 "
-                       f"({prim.sh.num_vars * 32} B) from rank 0",
+           "exchange": "inside libvimz_gpu.so (vimz_acc_step_begin_sharded*): NCCL all-gather of 2 partial commitments (192 B per rank) on the "
+                       "context stream + k_point_sum_batch, one host wait per curve; e2e adds rank 0's H2D copy and the NCCL broadcast of W2 "
+                       f"({prim.sh.num_vars * 32} B) in the same call",
            "parallelism": f"rows / E / T / ck of {'both curves' if isinstance(sec, GpuFoldSharded) else 'the primary curve (secondary replicated)'} "
                           f"sharded x{world} by constraint-row range, W replicated"}
     prim.shard.close()
+    if isinstance(sec, GpuFoldSharded):
+        sec.shard.close()
     return res
+
+
+CONFIG_CIRCUITS = ["brightness", "contrast", "resize", "crop", "blur4k", "sharpness4k"]   # BASELINE.json configs 2-4 at N = 1
+CONFIG_SHARDED = ["resize", "crop", "blur4k", "sharpness4k"]                                # configs 3-4: one proof over N GPUs
+CONFIG_MIXED = ["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash"]  # config 5: one transformation per GPU
+CONFIG_STEPS, CONFIG_PREFOLD, CONFIG_WITNESSES = 10, 8, 3
+
+
+def run_configs(args, torch, dist, rank, world, local_rank, sec, peaks, comm):
+    """The remaining BASELINE.json configurations, bounded (10 timed steps each after 8 pre-folds, 3 distinct witnesses): sizes from
+    /root/reference/circuits/nova_snark/circuit_parameters.csv:2-9 (+ Nova's augmented circuit); blur4k / sharpness4k are the x3-width
+    estimates of SURVEY.md section 8 (the 4K circuits do not exist in the reference).  N = 1: every step circuit on one GPU plus the
+    MSM sweep.  N > 1: resize / crop / blur4k / sharpness4k as ONE proof sharded over the N GPUs, the 2^24 MSM sharded by point
+    range, and N DIFFERENT transformations folded concurrently, one per GPU (the analogue of /root/reference/benchmark.sh:25-58)."""
+    prim_curve = CYCLES[args.cycle][0]
+    out = {"steps_each": CONFIG_STEPS, "prefold": CONFIG_PREFOLD}
+    iters = 3
+    if world == 1:
+        circuits = []
+        for circ in CONFIG_CIRCUITS:
+            f = GpuFold(prim_curve, circ, SEED, local_rank, torch, num_witnesses=CONFIG_WITNESSES)
+            engines = [f.eng, sec.eng]
+
+            def sr(k, f=f):
+                sec.step(k, True); f.step(k, True)
+
+            def se(k, f=f):
+                sec.step(k, False); f.step(k, False)
+
+            for k in range(CONFIG_PREFOLD + 3):
+                sr(k)
+            se(0)
+            ms, _ = timed_region(torch, engines, lambda k: sr(100 + k), CONFIG_STEPS, None)
+            ms_e, _ = timed_region(torch, engines, lambda k: se(200 + k), CONFIG_STEPS, None)
+            circuits.append({"circuit": circ, "num_cons": f.sh.num_cons, "num_vars": f.sh.num_vars, "nnz": f.sh.nnz, "ck_log2": (len(f.ck) - 1).bit_length(),
+                             "window_bits": f.ck.window_bits, "steps_per_s": CONFIG_STEPS / (ms * 1e-3), "ms_per_step": ms / CONFIG_STEPS,
+                             "e2e_steps_per_s": CONFIG_STEPS / (ms_e * 1e-3), "proof_steps": {"resize": 240, "blur4k": 2160, "sharpness4k": 2160}.get(circ, 720)})
+            f.close()
+        out["circuits"] = circuits
+        out["msm"] = [msm_bench(torch, local_rank, rank, world, dist, lg, iters, peaks, "uniform") for lg in (16, 24)]
+        return out
+    sharded = []
+    for circ in CONFIG_SHARDED:
+        sharded.append(sharded_step_bench(args, torch, dist, rank, world, local_rank, CONFIG_STEPS, 3, circuit=circ, prefold=CONFIG_PREFOLD,
+                                          num_witnesses=CONFIG_WITNESSES, comm=comm))
+    out["sharded_step"] = sharded
+    out["msm"] = [msm_bench(torch, local_rank, rank, world, dist, 24, iters, peaks, "uniform", comm=comm)]
+    # N different transformations, one per GPU, concurrently (no collective on the data path)
+    circ = CONFIG_MIXED[rank % len(CONFIG_MIXED)]
+    f = GpuFold(prim_curve, circ, SEED + 100 * rank, local_rank, torch, num_witnesses=CONFIG_WITNESSES)
+
+    def sr(k):
+        sec.step(k, True); f.step(k, True)
+
+    for k in range(CONFIG_PREFOLD + 3):
+        sr(k)
+    stream = torch.cuda.ExternalStream(f.eng.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f.eng.sync(); sec.eng.sync(); torch.cuda.synchronize()
+    dist.barrier()
+    e0.record(stream)
+    for k in range(CONFIG_STEPS):
+        sr(100 + k)
+    f.eng.sync(); sec.eng.sync()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    mine = {"rank": rank, "circuit": circ, "num_cons": f.sh.num_cons, "steps_per_s": CONFIG_STEPS / (e0.elapsed_time(e1) * 1e-3)}
+    f.close()
+    allr = [None] * world
+    dist.all_gather_object(allr, mine)
+    out["mixed_transformations"] = {"per_gpu": allr, "aggregate_steps_per_s": sum(r["steps_per_s"] for r in allr),
+                                    "note": "N different step circuits folded concurrently, one prover context per GPU (benchmark.sh:25-58)"}
+    return out
 
 
 def timed_region(torch, engines, fn, steps, dist):
@@ -485,9 +606,10 @@ def timed_region(torch, engines, fn, steps, dist):
     return ms, wall
 
 
-def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist="uniform", check=True):
+def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist="uniform", check=True, comm=None):
     """Pallas MSM over 2^log2n resident points, uniform full-width scalars resident in HBM.  world > 1: point-range
-    shards, per-rank partial sums all-gathered over NCCL and added on the GPU."""
+    shards (the window is chosen per rank-local key length); the per-rank partial sums are all-gathered by NCCL on the
+    context's stream and added on the GPU inside ONE library call (vimz_msm_sharded_dev), one host wait per MSM."""
     import vimz_b200
     from vimz_b200 import CommitmentEngine, CommitmentKey
     from vimz_host import synthetic as S
@@ -517,13 +639,9 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
     stream = torch.cuda.ExternalStream(eng.stream)
 
     def one(j):
-        CommitmentEngine.commit_async_dev(ck, sc[j % 2].data_ptr(), per, d_out.data_ptr())
         if world > 1:
-            eng.sync()
-            parts = [torch.empty_like(d_out) for _ in range(world)]
-            dist.all_gather(parts, d_out)
-            pts = torch.stack(parts).cpu().numpy().view(np.uint64)
-            return eng.point_sum(pts)
+            return comm.commit_dev(ck, sc[j % 2].data_ptr(), per, 0)
+        CommitmentEngine.commit_async_dev(ck, sc[j % 2].data_ptr(), per, d_out.data_ptr())
         return None
 
     for j in range(3):
@@ -543,7 +661,7 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
     e1.record(stream)
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    ms = max(e0.elapsed_time(e1), wall_ms if world > 1 else 0.0)
+    ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -560,7 +678,11 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
         local = CommitmentEngine.commit_dev(ck, sc[0].data_ptr(), per)
         exp = P.scalar_mul(c, closed_form_log(sc[0].cpu().numpy().view(np.uint64).reshape(-1, 4), K0, DK, q, first), P.generator(c))
         verified = bool(eng.to_affine_ints(local) == exp)
-        if world > 1:   # every rank's shard must check out
+        if world > 1:   # every rank's shard must check out, and so must the gathered sum: the logs of all shards add up
+            full = comm.commit_dev(ck, sc[0].data_ptr(), per, 0)
+            logs = [None] * world
+            dist.all_gather_object(logs, closed_form_log(sc[0].cpu().numpy().view(np.uint64).reshape(-1, 4), K0, DK, q, first))
+            verified = verified and bool(eng.to_affine_ints(full) == P.scalar_mul(c, sum(logs) % q, P.generator(c)))
             t = torch.tensor([1 if verified else 0], dtype=torch.int64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             verified = bool(int(t[0]))
@@ -642,6 +764,13 @@ def main_gpu(args, rank, world, local_rank):
     launches = sum(e.launch_count for e in engines) - launches0
     ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
 
+    def step_staged(k):     # pipelined e2e: the Circom part of the primary witness travels while the secondary curve is folded
+        prim.stage(k); sec.step(k, False); prim.step_staged(k)
+
+    for k in range(2):
+        step_staged(k)
+    ms_staged, _ = timed_region(torch, engines, lambda k: step_staged(PREFOLD + warmup + 4 * steps + k), steps, dist)
+
     def step_pageable(k):   # W2 in plain (pageable) host memory, as a Rust Vec<Scalar> would be
         sec.step(k, "pageable"); prim.step(k, "pageable")
 
@@ -713,20 +842,34 @@ def main_gpu(args, rank, world, local_rank):
     ct_ms, ct_calls = prof["cross_term"]
     ct_bytes = prim.cross_term_bytes()
     ct_gbs = ct_bytes * ct_calls / (ct_ms * 1e-3) / 1e9 if ct_ms > 0 else None
-    roofline_hbm = {"kernel": "k_cross_term_stream<CACHED> (3 mat-vecs with z2 + cached products of z1 + T + digit recoding of T fused; scalar field of %s)" % prim.cv.name, "bound": "hbm", "achieved": ct_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roofline_hbm = {"kernel": "k_matvec_stream + k_cross_finish (3 mat-vecs with z2: TMA bulk copy of the chunk's index stream, cp.async z gathers; then T "
+                              "from the cached products of z1 + digit recoding of T; scalar field of %s)" % prim.cv.name,
+                    "bound": "hbm", "achieved": ct_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": (ct_gbs / peaks["hbm_gbs"]) if ct_gbs else None, "traffic": None, "peak_source": peaks["hbm_src"],
-                    "algorithmic": f"{ct_bytes} B per launch = nnz*8 (col + coefficient index) + 3(m+1)*4 + (n+3)*32 (z2) + 6*m*32 (cached Az1,Bz1,Cz1 in, Az2,Bz2,Cz2 out) + m*32 (T) + m*W*4 (digits of T)"}
+                    "us_per_step": (ct_ms * 1e3 / ct_calls) if ct_calls else None,
+                    "algorithmic": f"{ct_bytes} B per step = nnz*8 (col + coefficient index) + 3(m+1)*4 + (n+3)*32 (z2) + 9*m*32 (Az2,Bz2,Cz2 out and in, cached Az1,Bz1,Cz1 in) + m*32 (T) + m*W*4 (digits of T)",
+                    "note": "gather-latency / occupancy bound, not bandwidth bound: z2 (4 MB) and the products live in the 126 MB L2, the two kernels "
+                            "run ~45 us against ~7 us of pure HBM time (profiles/r2_timeline_fold_step.txt, DESIGN.md section 5)"}
     phases = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof.items() if k != "msm_entries"}
     phases_sec = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof_sec.items() if k != "msm_entries"}
 
     # Pallas MSM throughput (second half of the metric)
+    comm = None
+    if world > 1:
+        from vimz_b200.sharding import Comm
+        comm = Comm.from_torch_dist(dist, local_rank)   # NCCL communicator inside libvimz_gpu.so (collectives on the context streams)
     msm = []
     for lg in args.msm_log2:
-        msm.append(msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks, args.msm_dist))
+        msm.append(msm_bench(torch, local_rank, rank, world, dist, lg, max(3, min(steps, 10)), peaks, args.msm_dist, comm=comm))
 
     sharded = None
     if world > 1 and not args.no_sharded_step:
-        sharded = sharded_step_bench(args, torch, dist, rank, world, local_rank, min(steps, 100), warmup)
+        # what the sharded fold must reproduce: rank 0's replica (same seed as the sharded problem) replayed on ONE GPU
+        expect = [None]
+        if rank == 0:
+            expect = [(sec.replay_from_zero(3)[0], prim.replay_from_zero(3)[0])]
+        dist.broadcast_object_list(expect, src=0)
+        sharded = sharded_step_bench(args, torch, dist, rank, world, local_rank, min(steps, 100), warmup, expect=expect[0], comm=comm)
 
     # CPU restatement on the host cores: the reported baseline AND the checker of the parity replay -- the same K = 3 (+1
     # warm-up) steps from the default relaxed instance are folded by both arms on the same witnesses and compared value by value
@@ -748,6 +891,10 @@ def main_gpu(args, rank, world, local_rank):
                               "comm_W, comm_E on both curves; GPU through the host-pointer C ABI vs oracle/nova_cpu.c",
                   "commitments_equal": bool(commit_eq), "folded_instances_equal": bool(final_eq)}
 
+    configs = None
+    if not args.no_configs:
+        configs = run_configs(args, torch, dist, rank, world, local_rank, sec, peaks, comm)
+
     if rank == 0:
         bad = [r for r in clocks["reasons"] if r != "sw_power_cap"]
         line = {"metric": "nova_fold_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -755,8 +902,14 @@ def main_gpu(args, rank, world, local_rank):
                 "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
                 "config": workload_config(prim.sh, cycle=args.cycle, extra={"parallelism": f"replicas x{world} (one transformation per GPU)",
                                                                    "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows}),
-                "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
-                        "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_e2e / steps,
+                "e2e": {"value": world * steps / (ms_staged * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
+                        "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_staged / steps,
+                        "api": "vimz_acc_stage_fresh + vimz_acc_step_begin_staged (primary), vimz_acc_step_begin (secondary), vimz_acc_step_end: every "
+                               "step copies its whole fresh witness host -> device inside the timed region; the fold-independent rows of the "
+                               f"primary witness ({prim.staged_split()} of {prim.sh.num_vars}: the Circom step circuit's variables) are enqueued before the "
+                               "secondary curve's step so the copy overlaps it, the augmented circuit's ~10 k variables go up inside step_begin",
+                        "plain_call_value": e2e_value, "plain_call_ms_per_step": ms_e2e / steps,
+                        "plain_call_note": "same steps through vimz_acc_step_begin alone (whole W2 copied inside the call, nothing overlapped)",
                         "host_buffers": "pinned (cudaHostAlloc)", "pageable_value": world * steps / (ms_page * 1e-3),
                         "pageable_ms_per_step": ms_page / steps,
                         "pageable_note": "same call with W2 in ordinary pageable memory (what a Rust Vec<Scalar> is): the driver stages the copy",
@@ -766,7 +919,7 @@ def main_gpu(args, rank, world, local_rank):
                 "clocks": clocks, "clock_verdict": "rejected: " + ",".join(bad) if bad else "ok",
                 "phases_primary": phases, "phases_secondary": phases_sec,
                 "wall_ms_per_step": wall * 1e3 / steps, "profiled_pass_ms_per_step": ms_prof / steps,
-                "msm": msm, "sharded_step": sharded, "published_reference": "README-derived >= 2.99 steps/s end-to-end on a Ryzen 9 (BASELINE.md section 1), other hardware"}
+                "msm": msm, "sharded_step": sharded, "configs": configs, "published_reference": "README-derived >= 2.99 steps/s end-to-end on a Ryzen 9 (BASELINE.md section 1), other hardware"}
         emit(line)
     if dist is not None:
         dist.barrier()
@@ -798,6 +951,7 @@ def main():
     ap.add_argument("--msm-dist", default="uniform", choices=["uniform", "witness", "edge"],
                     help="scalar distribution of the MSM sweep (SURVEY.md section 8d: U / B / Z)")
     ap.add_argument("--no-sharded-step", action="store_true", help="N > 1: skip the strong-scaling leg (one proof folded by all ranks)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the bounded block of the other BASELINE configurations (other circuits, MSM sweep, sharded / mixed legs)")
     ap.add_argument("--msm-only", action="store_true", help="skip the fold-step measurement (window sweeps)")
     ap.add_argument("--circuit", default="grayscale", choices=["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash", "blur4k", "sharpness4k"],
                     help="step circuit whose published size the primary shape takes (BASELINE metric: grayscale; the others are the "

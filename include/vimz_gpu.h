@@ -61,7 +61,8 @@ int vimz_ctx_sync(vimz_ctx* ctx);
 /* Tunables: "msm_window" (c bits, 0 = auto), "msm_acc_blocks" (accumulation blocks per SM, 1..8), "msm_seg_min" (shortest accumulation segment, 1..4096),
  * "msm_direct_c" (digit width of that table, 0 = by key length: 10 up to 16 384 points, else 8),
  * "msm_direct_max" (keys uploaded afterwards with at most this many points keep ALL digit multiples resident -- 256 KB per point at c = 8 --
- * and commit without buckets; default 32768, 0 = always the bucket pipeline; a forced msm_window also selects buckets), "cross_cache" (0/1, default 1:
+ * and commit without buckets; default 32768, 0 = always the bucket pipeline; a forced msm_window also selects buckets), "msm_defer_giants" (0/1, default 1: buckets cut into hundreds of segments are summed beside
+ * the bucket reduction instead of in front of it), "spin_wait" (0/1, default 1: step_begin polls its stream instead of a blocking wait), "cross_cache" (0/1, default 1:
  * accumulators created afterwards keep (Az1, Bz1, Cz1) of the running instance resident and fold them in step_end instead of
  * recomputing them in every step_begin), "aux_lane" (0/1), "profile" (0/1), "graph" (0/1: replay a fold step's launch
  * sequence as a CUDA graph, default 1).  Unknown keys -> VIMZ_ERR_ARG. */
@@ -161,6 +162,8 @@ int vimz_acc_init_sharded(vimz_ctx* ctx, const vimz_shape* s_rows, const vimz_ck
  * step_combine_dev adds them on the GPU, copies the two full commitments back and synchronises once. */
 int vimz_acc_step_begin_dev_async(vimz_acc* acc, const void* d_W2, const vimz_fr* X2, void** d_partials);
 int vimz_acc_step_combine_dev(vimz_acc* acc, const void* d_gathered, size_t world, vimz_point* comm_W2, vimz_point* comm_T);
+/* Back to the default relaxed instance (a new proof over the same shape and key). */
+int vimz_acc_reset(vimz_acc* acc);
 int vimz_acc_load(vimz_acc* acc, const vimz_fr* W, const vimz_fr* E, const vimz_fr* u, const vimz_fr* X,
                   const vimz_point* comm_W, const vimz_point* comm_E);
 int vimz_acc_step_begin(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);
@@ -173,11 +176,47 @@ int vimz_acc_step_begin_dev(vimz_acc* acc, const void* d_W2, const vimz_fr* X2, 
 int vimz_acc_commit_fresh(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2);
 int vimz_acc_cross_begin(vimz_acc* acc, vimz_point* comm_T);
 int vimz_acc_fresh_witness(vimz_acc* acc, vimz_fr* W2, vimz_fr* X2);
+/* Streaming upload of the fresh witness: vimz_acc_stage_fresh enqueues an H2D copy of W2[first .. first + count) behind the
+ * previous step_end and returns at once (the host buffer must stay valid until the next step_begin* returns); the part of a
+ * witness that does not depend on the previous fold (the Circom step circuit's variables) can so travel while the other curve
+ * is being folded.  vimz_acc_step_begin_staged uploads the remaining range and runs the step. */
+int vimz_acc_stage_fresh(vimz_acc* acc, const vimz_fr* W2_part, size_t first, size_t count);
+int vimz_acc_step_begin_staged(vimz_acc* acc, const vimz_fr* W2_rest, size_t first, size_t count, const vimz_fr* X2, vimz_point* comm_W2,
+                               vimz_point* comm_T);
 int vimz_acc_step_end(vimz_acc* acc, const vimz_fr* r);
 int vimz_acc_download(vimz_acc* acc, vimz_fr* W, vimz_fr* E, vimz_fr* u, vimz_fr* X, vimz_point* comm_W, vimz_point* comm_E);
 /* T of the last step_begin (m elements), for callers that keep nova-snark's (T, comm_T) pair. */
 int vimz_acc_last_T(vimz_acc* acc, vimz_fr* T);
 void vimz_acc_destroy(vimz_acc* acc);
+
+/* ---- several GPUs of one node ------------------------------------------ */
+/* One process (or thread) per GPU.  A communicator wraps an NCCL communicator bound at run time (dlopen of libnccl.so.2 on
+ * first use -- single-GPU users never load NCCL); rank 0 makes the 128-byte id and hands it to the other ranks over any
+ * channel the host has.  Collectives are enqueued on the stream of the context / accumulator they are called with, so the
+ * exchange is ordered with the kernels and the host waits once per call.  The reference has no counterpart: its
+ * parallelism is rayon inside one process; these entry points are what a multi-GPU build of the
+ * provider selected at /root/reference/vimz/src/nova_snark_backend/mod.rs:19-20 would call instead of vimz_msm /
+ * vimz_acc_step_begin. */
+typedef struct vimz_comm vimz_comm;
+#define VIMZ_COMM_ID_BYTES 128
+int vimz_comm_unique_id(uint8_t id[VIMZ_COMM_ID_BYTES]);
+int vimz_comm_create(int device, const uint8_t id[VIMZ_COMM_ID_BYTES], int rank, int world, vimz_comm** out);
+void vimz_comm_destroy(vimz_comm* comm);
+int vimz_comm_rank(const vimz_comm* comm);
+int vimz_comm_world(const vimz_comm* comm);
+int vimz_comm_nccl_version(void);
+/* NCCL broadcast of `bytes` of device memory from rank `root`, on the context's stream. */
+int vimz_comm_broadcast_dev(vimz_ctx* ctx, vimz_comm* comm, void* d_buf, size_t bytes, int root);
+/* commit(ck, v) with ck / v split by point range across the ranks: this rank passes its slice (first, d_scalars, n) of a key
+ * shard it uploaded; the 96-byte partial sums are all-gathered and added on the GPU, every rank gets the full commitment. */
+int vimz_msm_sharded_dev(vimz_ctx* ctx, vimz_comm* comm, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, vimz_point* out);
+/* One fold step of a row-range shard (vimz_acc_init_sharded): enqueue, all-gather the partial (comm_W2, comm_T) pairs,
+ * add them on the GPU, wait once; every rank returns the FULL commitments (and then derives the same challenge).
+ * _dev: W2 is device memory on every rank.  Host variant: W2 is host memory on rank `root` (NULL elsewhere); the root
+ * copies it to its GPU and NCCL broadcasts it into every rank's accumulator before the step runs. */
+int vimz_acc_step_begin_sharded_dev(vimz_acc* acc, vimz_comm* comm, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T);
+int vimz_acc_step_begin_sharded(vimz_acc* acc, vimz_comm* comm, const vimz_fr* W2, int root, const vimz_fr* X2, vimz_point* comm_W2,
+                                vimz_point* comm_T);
 
 /* ---- test / bench utilities (device-side generators; not part of the reference interface) ---- */
 /* bases[i] = (k0 + i*dk) * G written as n affine points to device memory d_out (64*n bytes). */

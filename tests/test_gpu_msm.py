@@ -335,3 +335,24 @@ def test_concurrent_commits_on_one_context(engines, coracle):
     for t in range(len(vecs)):
         assert got[t] == [expect[t]] * 4
     ck.close()
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+def test_endomorphism_identity_on_gpu_commitments(name, engines):
+    """Implementation-independent pin (see tests/test_oracle.py::check_endomorphism): commit(ck, lambda * v) must be
+    (zeta * x, y) of commit(ck, v) for primitive cube roots of unity lambda (scalar field) and zeta (base field), with the
+    SAME pairing of lambda and zeta for every key and vector -- on device-generated bases, for a short key (direct table)
+    and a 2^15-point key (bucket pipeline), without any oracle group arithmetic."""
+    import torch
+    from test_oracle import check_endomorphism
+    c, eng = P.CURVES[name], engines[name]
+    rng = random.Random(5 + c.curve_id)
+    seen = set()
+    for n in (700, 1 << 15):
+        d_bases = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+        vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(eng._h, 1000 + n, 987654321, n, d_bases.data_ptr()))
+        ck = CommitmentKey.from_device(eng, d_bases.data_ptr(), n)
+        sc = [rng.randrange(c.q) if rng.random() < 0.5 else rng.randrange(1 << 130) for _ in range(n)]
+        seen.add(check_endomorphism(c, lambda v: gpu_commit_affine(eng, ck, ints_to_mont(v, c.q)), sc))
+        ck.close()
+    assert len(seen) == 1

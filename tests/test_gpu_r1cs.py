@@ -521,6 +521,51 @@ def test_row_sharded_fold_matches_unsharded_chain(name, world, engines, coracle)
     shape.close(); small.close()
 
 
+def test_library_level_sharded_step_and_msm_world1(engines, coracle):
+    """The multi-GPU entry points with the exchange inside the library (vimz_comm_* / vimz_acc_step_begin_sharded* /
+    vimz_msm_sharded_dev; NCCL bound with dlopen) on a one-rank communicator: same values as the plain entry points and as
+    the CPU chain.  (N > 1 runs the same code under torchrun: bench.py's sharded_step / msm legs check it there.)"""
+    import torch
+    from vimz_b200.sharding import Comm, FoldShard, ShardedFoldAccumulator
+    eng, c = engines["pallas"], P.PALLAS
+    q = c.q
+    assert vimz_b200.lib.vimz_comm_nccl_version() >= 20000
+    comm = Comm(0, 0, 1, Comm.unique_id())
+    assert (comm.rank, comm.world) == (0, 1)
+    sh = S.synthetic_shape(CURVES["pallas"], "grayscale", seed=45, scale=0.012)
+    bases, logs = make_bases(c, max(sh.num_cons, sh.num_vars), seed=45)
+    Bm = affine_to_mont(bases, c.p)
+    rng = random.Random(18)
+    wit = []
+    for k in range(3):
+        Wi, Xi = S.synthetic_witness(sh, 400 + k)
+        wit.append((ints_to_mont(Wi, q), ints_to_mont(Xi, q)))
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(3)]
+    ref = _oracle_fold_chain(coracle, c, sh, Bm, wit, chal)
+    shard = FoldShard(eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C, lambda f, n: CommitmentKey.from_bases(eng, Bm[f:f + n]), 0, 1)
+    acc = ShardedFoldAccumulator(None, shard, eng.point_sum, device="cuda", comm=comm)
+    d_W = [torch.from_numpy(w.view(np.int64)).cuda() for w, _ in wit]
+    for k in range(3):
+        if k == 1:   # witness in host memory on the root: H2D + (one-rank) broadcast inside the call
+            cw, ct = acc.step_begin_root(wit[k][0], wit[k][1], root=0)
+        else:
+            cw, ct = acc.step_begin_dev(d_W[k].data_ptr(), wit[k][1])
+        assert eng.to_affine_ints(cw) == _affine(coracle, c, ref[k]["comm_W2"]) and eng.to_affine_ints(ct) == _affine(coracle, c, ref[k]["comm_T"])
+        acc.step_end(chal[k])
+    U, W = shard.download()
+    assert np.array_equal(W.W, ref[-1]["W"]) and np.array_equal(W.E, ref[-1]["E"])
+    assert eng.to_affine_ints(U.comm_E) == _affine(coracle, c, ref[-1]["cE"])
+    with pytest.raises(vimz_b200.VimzError):
+        shard.step_begin_sharded(comm, None, wit[0][1], root=0)        # the root must pass the witness
+    # sharded commit through the same communicator
+    n = len(bases)
+    sc = [rng.randrange(q) for _ in range(n)]
+    d_S = torch.from_numpy(ints_to_mont(sc, q).view(np.int64)).cuda()
+    got = comm.commit_dev(shard.ck_rows, d_S.data_ptr(), sh.num_cons, 0)
+    assert eng.to_affine_ints(got) == P.scalar_mul(c, sum(s_ * k_ for s_, k_ in zip(sc[:sh.num_cons], logs)) % q, P.generator(c))
+    shard.close(); comm.close()
+
+
 def test_commit_T_on_shape_without_rows(engines):
     """num_cons = 0 (what a row shard beyond the last constraint looks like): T is empty and comm_T the identity, whatever
     an earlier commit left in the workspace."""

@@ -163,3 +163,46 @@ def test_full_hd_grayscale_proof_720_steps(coracle):
     for h in (pp.shape_primary, pp.shape_secondary, ck1, ck2):
         h.close()
     e1.close(); e2.close()
+
+
+def test_sonobe_call_sequence_bn254_grumpkin(coracle):
+    """the fold step of the Sonobe backend (/root/reference/vimz/src/sonobe_backend/folding.rs:52-65 -- Nova + CycleFold
+    over BN254 / Grumpkin) in its own call order: NIFS on G1 with the pair committed by the previous step, two CycleFold folds
+    on G2, commit of the next fresh witness.  Checked against the CPU chain in the same order and by Nova::verify's
+    satisfiability checks."""
+    from vimz_b200 import SonobeNova
+    c1, c2 = P.BN254, P.GRUMPKIN
+    e1, e2 = vimz_b200.Engine("bn254", 0), vimz_b200.Engine("grumpkin", 0)
+    sh1 = S.synthetic_shape(CURVES["bn254"], "grayscale", seed=91, scale=0.012)
+    sh2 = S.synthetic_shape(CURVES["grumpkin"], "secondary", seed=92, scale=0.14)      # ~1.5 k rows: the size of a CycleFold circuit
+    ck1, B1 = _key(e1, c1, coracle, max(sh1.num_cons, sh1.num_vars))
+    ck2, B2 = _key(e2, c2, coracle, max(sh2.num_cons, sh2.num_vars))
+    s1 = R1CSShape(e1, sh1.num_cons, sh1.num_vars, sh1.num_io, sh1.A, sh1.B, sh1.C)
+    s2 = R1CSShape(e2, sh2.num_cons, sh2.num_vars, sh2.num_io, sh2.A, sh2.B, sh2.C)
+    w1, w2 = _witnesses(sh1, c1.q, 5, 1700), _witnesses(sh2, c2.q, 7, 1800)
+    digest = 0x50B0
+    nova = SonobeNova(s1, ck1, s2, ck2, w1[0], digest=digest)
+    cpu1, cpu2 = CpuCurve(coracle, c1, sh1, B1, digest), CpuCurve(coracle, c2, sh2, B2, digest)
+    fresh = w1[0]
+    fresh_cw = cpu1.commit(fresh[0])
+    steps = 12
+    for k in range(steps):
+        nxt, cfW, cfE = w1[(k + 1) % 5], w2[(2 * k) % 7], w2[(2 * k + 1) % 7]
+        nova.prove_step(nxt, cfW, cfE)
+        ct1 = cpu1.nifs(fresh[0], fresh[1], fresh_cw)                                   # (a)
+        ctW = cpu2.nifs(cfW[0], cfW[1], cpu2.commit(cfW[0]))                            # (b)
+        ctE = cpu2.nifs(cfE[0], cfE[1], cpu2.commit(cfE[0]))                            # (c)
+        fresh, fresh_cw = nxt, cpu1.commit(nxt[0])                                      # (d)
+        assert e1.to_affine_ints(nova.cmT) == cpu1.aff(ct1), k
+        assert e2.to_affine_ints(nova.cf_cmT[0]) == cpu2.aff(ctW) and e2.to_affine_ints(nova.cf_cmT[1]) == cpu2.aff(ctE), k
+        assert e1.to_affine_ints(nova.u_i.comm_W) == cpu1.aff(fresh_cw)
+    for acc, cpu, eng in ((nova.acc, cpu1, e1), (nova.cf_acc, cpu2, e2)):
+        U, W = acc.download()
+        assert np.array_equal(W.W, cpu.W) and np.array_equal(W.E, cpu.E) and np.array_equal(U.u, cpu.u) and np.array_equal(U.X, cpu.X)
+        assert eng.to_affine_ints(U.comm_W) == cpu.aff(cpu.cW) and eng.to_affine_ints(U.comm_E) == cpu.aff(cpu.cE)
+    assert nova.i == steps
+    nova.verify()
+    nova.close()
+    for h in (s1, s2, ck1, ck2):
+        h.close()
+    e1.close(); e2.close()

@@ -275,3 +275,58 @@ def test_synthetic_step_shapes_are_satisfied(circuit, coracle):
         assert sum(1 for w in Wi if w < 2) / len(Wi) > 0.6
     full = S.STEP_CIRCUITS[circuit]
     assert sh.num_cons == int((full[0] + S.NOVA_AUGMENTED) * (0.01 if circuit != "hash" else 0.2))
+
+
+# ---- implementation-independent pin of the Pasta (and BN254 / Grumpkin) group law: the GLV endomorphism ------------------
+# All four curves have j-invariant 0 (y^2 = x^3 + b), so phi(x, y) = (zeta * x, y) with zeta a primitive cube root of unity of
+# the BASE field is an endomorphism and acts as multiplication by a primitive cube root of unity lambda of the SCALAR field:
+# phi(P) = [lambda] P.  Hence for ANY correct commit(): commit(ck, lambda * v) has the same y as commit(ck, v) and x multiplied
+# by a non-trivial cube root of unity -- a statement about field elements that needs no second implementation of the group law
+# (a wrong scalar multiplication lands on such a point with probability ~2^-254).  zeta and lambda come from modular
+# exponentiation alone.  The Pasta curves have no published vectors that could be restated here; this identity
+# pins the metric's curves independently of oracle/pyref.py's own addition formulas.
+def cube_roots_of_unity(modulus):
+    g = 2
+    while pow(g, (modulus - 1) // 3, modulus) == 1:
+        g += 1
+    z = pow(g, (modulus - 1) // 3, modulus)
+    assert z != 1 and pow(z, 3, modulus) == 1
+    return z, z * z % modulus
+
+
+def check_endomorphism(c, commit_affine, scalars):
+    """commit_affine(list of canonical scalars) -> affine (x, y) or None.  Returns the zeta the implementation pairs with
+    lambda_1 (so callers can check that it is the same for every input)."""
+    lam1, lam2 = cube_roots_of_unity(c.q)
+    zetas = cube_roots_of_unity(c.p)
+    base = commit_affine(scalars)
+    assert base is not None
+    seen = []
+    for lam in (lam1, lam2):
+        pt = commit_affine([s * lam % c.q for s in scalars])
+        assert pt is not None and pt[1] == base[1], "phi keeps y"
+        ratio = pt[0] * pow(base[0], -1, c.p) % c.p
+        assert ratio in zetas, "x must be multiplied by a primitive cube root of unity"
+        seen.append(ratio)
+    assert seen[0] != seen[1] and seen[0] * seen[1] % c.p == 1      # lambda^2 <-> zeta^2
+    return seen[0]
+
+
+@pytest.mark.parametrize("name", list(P.CURVES))
+def test_endomorphism_identity_pins_the_oracles(name, coracle):
+    c = P.CURVES[name]
+    rng = random.Random(31 + c.curve_id)
+    G = P.generator(c)
+    # python oracle: single point
+    z0 = check_endomorphism(c, lambda sc: P.scalar_mul(c, sc[0], G), [rng.randrange(1, c.q)])
+    # C oracle: a 200-point MSM, same pairing of lambda and zeta
+    n = 200
+    bases = [P.scalar_mul(c, rng.randrange(1, c.q), G) for _ in range(8)]
+    bases = [bases[i % 8] if i < 8 else P.aff_add(c, bases[i % 8], bases[(i * 5 + 1) % 8]) for i in range(n)]
+    Bm = affine_to_mont(bases, c.p)
+
+    def c_commit(sc):
+        return mont_to_affine(coracle.to_affine(c.curve_id, coracle.msm(c.curve_id, ints_to_mont(sc, c.q), Bm, 2)), c.p)[0]
+
+    z1 = check_endomorphism(c, c_commit, [rng.randrange(c.q) for _ in range(n)])
+    assert z0 == z1

@@ -1,26 +1,28 @@
 #!/usr/bin/env python3
-"""Wall-clock breakdown of one fold step on the host side (where does the non-kernel time go?)."""
+"""Wall-clock breakdown of one fold step on the host side at the fold index bench.py times (PREFOLD 260): latency of
+step_begin per curve (graph launch -> both lanes -> result on the host), the stand-in RO, step_end.
+usage: python tools/host_breakdown.py [prefold]   (VIMZ_WINDOW_PALLAS etc. are honoured through bench.GpuFold)"""
 import os, sys, time
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from vimz_b200.field import ints_to_mont
 
+prefold = int(sys.argv[1]) if len(sys.argv) > 1 else 260
 prim = bench.GpuFold("pallas", "grayscale", bench.SEED, 0, torch)
 sec = bench.GpuFold("vesta", "secondary", bench.SEED + 1, 0, torch)
-for k in range(40):
+for k in range(prefold):
     sec.step(k, True); prim.step(k, True)
 acc = {"begin_p": 0.0, "ro_p": 0.0, "end_p": 0.0, "begin_s": 0.0, "ro_s": 0.0, "end_s": 0.0}
-N = 50
+N = 100
 t_all = time.perf_counter()
-for k in range(40, 40 + N):
+for k in range(prefold, prefold + N):
     for tag, f in (("s", sec), ("p", prim)):
-        i = k % bench.NUM_WITNESSES
+        i = k % len(f.wits)
         t0 = time.perf_counter()
-        cw, ct = f.acc.step_begin_dev(f.dev_W[i].data_ptr(), f.wits[i][1])
+        cw, ct = f.acc.step_begin_dev(f.dev_ptr[i], f.X2_bytes[i])
         t1 = time.perf_counter()
-        r = ints_to_mont([bench.challenge_from(ct.tobytes(), k)], f.q)
+        r = ((bench.challenge_from(ct.tobytes(), k) << 256) % f.q).to_bytes(32, "little")
         t2 = time.perf_counter()
         f.acc.step_end(r)
         t3 = time.perf_counter()

@@ -2,13 +2,81 @@
 // Measures, per SM per clock: IMAD (32-bit), IMAD.HI.U32, IMAD.WIDE.U32, carry-chained IMAD.WIDE.U32.X,
 // IADD3.X, an IMAD.WIDE/IADD3 mix, and field multiplications/s of vimz_b200/csrc/fp.cuh.  The result is
 // the denominator of the MSM roofline ("IMAD peak must be measured").
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Ivimz_b200/csrc -o tools/int_peak tools/int_peak.cu
+// Every test also records the NVML SM clock (median of the samples taken while it ran), the board power (max) and the
+// clock-event reasons seen: the IMAD loop is POWER-limited on this part (sw_power_cap, ~1.2 GHz), which is why the measured
+// peak, not the nominal one, is the roofline denominator of bench.py.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Ivimz_b200/csrc -o tools/int_peak tools/int_peak.cu -ldl
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <time.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <string>
+#include <vector>
 #include "fp.cuh"
 using namespace vimz;
+
+// ---- NVML (bound at run time): SM clock, board power and clock-event reasons sampled WHILE each test runs, so the
+// measured peak carries the conditions it was measured under (a multiplier-bound loop is power-limited on this part).
+struct Nvml {
+  void* h = nullptr;
+  void* dev = nullptr;
+  int (*Init)() = nullptr;
+  int (*GetHandle)(unsigned, void**) = nullptr;
+  int (*Clock)(void*, int, unsigned*) = nullptr;
+  int (*Power)(void*, unsigned*) = nullptr;
+  int (*Reasons)(void*, unsigned long long*) = nullptr;
+  bool ok = false;
+  Nvml() {
+    h = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+    if (!h) return;
+    Init = (int (*)())dlsym(h, "nvmlInit_v2");
+    GetHandle = (int (*)(unsigned, void**))dlsym(h, "nvmlDeviceGetHandleByIndex_v2");
+    Clock = (int (*)(void*, int, unsigned*))dlsym(h, "nvmlDeviceGetClockInfo");
+    Power = (int (*)(void*, unsigned*))dlsym(h, "nvmlDeviceGetPowerUsage");
+    Reasons = (int (*)(void*, unsigned long long*))dlsym(h, "nvmlDeviceGetCurrentClocksEventReasons");
+    if (!Reasons) Reasons = (int (*)(void*, unsigned long long*))dlsym(h, "nvmlDeviceGetCurrentClocksThrottleReasons");
+    if (!Init || !GetHandle || !Clock || !Power || !Reasons) return;
+    if (Init() != 0 || GetHandle(0, &dev) != 0) return;
+    ok = true;
+  }
+};
+struct NvmlSamples {
+  std::vector<unsigned> mhz;
+  unsigned power_mw_max = 0;
+  unsigned long long reasons = 0;
+  void reset() { mhz.clear(); power_mw_max = 0; reasons = 0; }
+  void sample(Nvml& n) {
+    if (!n.ok) return;
+    unsigned c = 0, p = 0;
+    unsigned long long r = 0;
+    if (n.Clock(n.dev, 1 /* NVML_CLOCK_SM */, &c) == 0) mhz.push_back(c);
+    if (n.Power(n.dev, &p) == 0) power_mw_max = std::max(power_mw_max, p);
+    if (n.Reasons(n.dev, &r) == 0) reasons |= r;
+  }
+  std::string json() {
+    if (mhz.empty()) return "";
+    std::sort(mhz.begin(), mhz.end());
+    std::string names;
+    const struct { unsigned long long bit; const char* name; } R[] = {{0x1, "gpu_idle"}, {0x2, "app_clocks"}, {0x4, "sw_power_cap"}, {0x8, "hw_slowdown"},
+                                                                       {0x20, "sw_thermal_slowdown"}, {0x40, "hw_thermal_slowdown"}, {0x80, "hw_power_brake"}};
+    for (auto& r : R)
+      if (reasons & r.bit) names += std::string(names.empty() ? "" : "|") + r.name;
+    char buf[256];
+    snprintf(buf, sizeof(buf), ", \"nvml_sm_mhz\": %u, \"nvml_power_w\": %.0f, \"nvml_reasons\": \"%s\", \"nvml_samples\": %zu", mhz[mhz.size() / 2],
+             power_mw_max / 1000.0, names.empty() ? "none" : names.c_str(), mhz.size());
+    return buf;
+  }
+};
+static Nvml g_nvml;
+static NvmlSamples g_samples;
+// wait for an event while sampling NVML (instead of a blocking synchronise)
+static cudaError_t wait_sampling(cudaEvent_t e) {
+  cudaError_t r;
+  while ((r = cudaEventQuery(e)) == cudaErrorNotReady) g_samples.sample(g_nvml);
+  return r;
+}
 
 #define ITERS 65536
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
@@ -204,8 +272,8 @@ int main() {
     avg /= blocks;
     double per_sm_clk = ops_per_thread * threads * bps / avg;  // thread-ops / clk / SM (blocks co-resident)
     double total = ops_per_thread * threads * (double)blocks;
-    printf("  {\"name\": \"%s\", \"ops_per_clk_per_sm\": %.2f, \"Gops_per_s\": %.1f, \"ms\": %.3f, \"eff_clock_mhz\": %.0f}%s\n", name,
-           per_sm_clk, total / (ms * 1e6), ms, avg / (ms * 1e3), last ? "" : ",");
+    printf("  {\"name\": \"%s\", \"ops_per_clk_per_sm\": %.2f, \"Gops_per_s\": %.1f, \"ms\": %.3f, \"eff_clock_mhz\": %.0f%s}%s\n", name,
+           per_sm_clk, total / (ms * 1e6), ms, avg / (ms * 1e3), g_samples.json().c_str(), last ? "" : ",");
   };
 // warm up for ~150 ms so the SM clock has ramped, then time 20 back-to-back launches
 #define RUN(NAME, OPS, LAUNCH, LAST)              \
@@ -218,10 +286,11 @@ int main() {
       CK(cudaEventSynchronize(e1));               \
       cudaEventElapsedTime(&wms, e0, e1);         \
     }                                             \
+    g_samples.reset();                            \
     cudaEventRecord(e0);                          \
     for (int w = 0; w < 5; w++) { LAUNCH; }       \
     cudaEventRecord(e1);                          \
-    CK(cudaEventSynchronize(e1));                 \
+    CK(wait_sampling(e1));                        \
     float ms;                                     \
     cudaEventElapsedTime(&ms, e0, e1);            \
     report(NAME, OPS, ms / 5.f, LAST);           \
@@ -263,6 +332,7 @@ int main() {
 #define BURST(NAME, OPS, LAUNCH, LAST)                                         \
   do {                                                                         \
     float best = 1e30f;                                                        \
+    g_samples.reset();                                                         \
     for (int r = 0; r < 8; r++) {                                              \
       CK(cudaDeviceSynchronize());                                             \
       struct timespec ts = {0, 30 * 1000 * 1000};                              \
@@ -270,7 +340,7 @@ int main() {
       cudaEventRecord(e0);                                                     \
       LAUNCH;                                                                  \
       cudaEventRecord(e1);                                                     \
-      CK(cudaEventSynchronize(e1));                                            \
+      CK(wait_sampling(e1));                                                   \
       float ms;                                                                \
       cudaEventElapsedTime(&ms, e0, e1);                                       \
       if (ms < best) best = ms;                                                \

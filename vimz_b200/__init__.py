@@ -23,5 +23,6 @@ from .nova import (  # noqa: F401
 )
 
 from .recursive import PublicParams, RecursiveSNARK, fold_input, verify_folded_proof  # noqa: F401
+from .sonobe import SonobeNova  # noqa: F401
 
 __version__ = "0.2.0"

@@ -79,16 +79,29 @@ def _load() -> C.CDLL:
         "vimz_acc_init_sharded": (i32, [vp, vp, vp, vp, sz, sz, pp]),
         "vimz_acc_step_begin_dev_async": (i32, [vp, vp, vp, pp]),
         "vimz_acc_step_combine_dev": (i32, [vp, vp, sz, vp, vp]),
+        "vimz_acc_reset": (i32, [vp]),
         "vimz_acc_load": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "vimz_acc_step_begin": (i32, [vp, vp, vp, vp, vp]),
         "vimz_acc_step_begin_dev": (i32, [vp, vp, vp, vp, vp]),
         "vimz_acc_commit_fresh": (i32, [vp, vp, vp, vp]),
         "vimz_acc_cross_begin": (i32, [vp, vp]),
         "vimz_acc_fresh_witness": (i32, [vp, vp, vp]),
+        "vimz_acc_stage_fresh": (i32, [vp, vp, sz, sz]),
+        "vimz_acc_step_begin_staged": (i32, [vp, vp, sz, sz, vp, vp, vp]),
         "vimz_acc_step_end": (i32, [vp, vp]),
         "vimz_acc_download": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "vimz_acc_last_T": (i32, [vp, vp]),
         "vimz_acc_destroy": (None, [vp]),
+        "vimz_comm_unique_id": (i32, [vp]),
+        "vimz_comm_create": (i32, [i32, vp, i32, i32, pp]),
+        "vimz_comm_destroy": (None, [vp]),
+        "vimz_comm_rank": (i32, [vp]),
+        "vimz_comm_world": (i32, [vp]),
+        "vimz_comm_nccl_version": (i32, []),
+        "vimz_comm_broadcast_dev": (i32, [vp, vp, vp, sz, i32]),
+        "vimz_msm_sharded_dev": (i32, [vp, vp, vp, sz, vp, sz, vp]),
+        "vimz_acc_step_begin_sharded_dev": (i32, [vp, vp, vp, vp, vp, vp]),
+        "vimz_acc_step_begin_sharded": (i32, [vp, vp, vp, i32, vp, vp, vp]),
         "vimz_gen_bases_dev": (i32, [vp, u64, u64, sz, vp]),
         "vimz_field_op": (i32, [vp, i32, i32, vp, vp, sz, vp]),
     }

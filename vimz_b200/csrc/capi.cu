@@ -166,10 +166,10 @@ static void shape_release(vimz_shape* s) {
       if (s->rowptr[k]) cudaFree(s->rowptr[k]);
       if (s->col[k]) cudaFree(s->col[k]);
       if (s->val[k]) cudaFree(s->val[k]);
-      if (s->vidx[k]) cudaFree(s->vidx[k]);
     }
     if (s->dict) cudaFree(s->dict);
-    if (s->chunk_start) cudaFree(s->chunk_start);
+    if (s->chunk_stream) cudaFree(s->chunk_stream);
+    if (s->chunk_desc) cudaFree(s->chunk_desc);
     if (s->long_rows) cudaFree(s->long_rows);
     if (s->mid_rows) cudaFree(s->mid_rows);
     delete s;
@@ -202,9 +202,16 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
   ctx->curve = curve_id;
   ctx->device = device;
   auto init = [&]() -> int {
-    VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
-    VIMZ_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    // The main stream carries the critical lane of a fold step (cross term -> commit(T)); the aux lane (commit(W2)) and the
+    // side stream (commitment folds) have slack, so they get the lowest priority: when both lanes have a grid pending, the
+    // block scheduler serves the critical one first.  VIMZ_STREAM_PRIORITY=0 disables it (A/B).
+    int prio_lo = 0, prio_hi = 0;
+    VIMZ_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // lo = numerically greatest = least urgent
+    const char* pe = getenv("VIMZ_STREAM_PRIORITY");
+    if (pe && atoi(pe) == 0) prio_hi = prio_lo;
+    VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+    VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
+    VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_lo));
     VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
     VIMZ_TRY(ctx->ws.result.reserve(4096));
@@ -304,6 +311,15 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     ctx->opt_graph = value != 0;
     return VIMZ_OK;
   }
+  if (strcmp(key, "msm_defer_giants") == 0) {
+    ctx->opt_defer_giants = value != 0;
+    alloc_epoch()++;
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "spin_wait") == 0) {
+    ctx->opt_spin_wait = value != 0;
+    return VIMZ_OK;
+  }
   return set_error(VIMZ_ERR_ARG, std::string("unknown option: ") + key);
 }
 
@@ -343,11 +359,11 @@ int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* call
     const char* what = name + 6;
     uint32_t v = 0;
     const uint32_t* src = nullptr;
-    if (ws.last_M && ws.cls.ptr && ws.offsets.ptr) {
+    if (ws.last_M && ws.counts.ptr && ws.offsets.ptr) {  // the control block sits in front of the histogram
       if (strcmp(what, "entries") == 0) src = ws.offsets.as<uint32_t>() + ws.last_M;
-      else if (strcmp(what, "nmid") == 0) src = ws.cls.as<uint32_t>() + CTRL_NMID;
-      else if (strcmp(what, "ngiant") == 0) src = ws.cls.as<uint32_t>() + CTRL_NGIANT;
-      else if (strcmp(what, "nchunk") == 0) src = ws.cls.as<uint32_t>() + CTRL_NCHUNK;
+      else if (strcmp(what, "nmid") == 0) src = ws.counts.as<uint32_t>() + CTRL_NMID;
+      else if (strcmp(what, "ngiant") == 0) src = ws.counts.as<uint32_t>() + CTRL_NGIANT;
+      else if (strcmp(what, "nchunk") == 0) src = ws.counts.as<uint32_t>() + CTRL_NCHUNK;
     }
     if (src) {
       VIMZ_CUDA(cudaMemcpy(&v, src, 4, cudaMemcpyDeviceToHost));
@@ -548,7 +564,7 @@ struct ValueDict {
 
 static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row, const uint32_t* col, const vimz_fr* val, size_t nnz,
                       uint32_t** d_rowptr, uint32_t** d_col, void** d_val, std::vector<uint32_t>& row_nnz, ValueDict& dict,
-                      uint32_t** d_vidx) {
+                      std::vector<uint32_t>& h_rowptr, std::vector<uint32_t>& h_col, std::vector<uint32_t>& h_vidx) {
   std::vector<uint32_t> rowptr(m + 1, 0);
   for (size_t k = 0; k < nnz; k++) {
     if (row[k] >= m || col[k] >= ncols) return set_error(VIMZ_ERR_INDEX, "vimz_shape_upload: entry out of range (InvalidIndex)");
@@ -563,10 +579,8 @@ static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row
     ccol[p] = col[k];
     cval[p] = val[k];
   }
-  std::vector<uint32_t> vidx(nnz);
-  for (size_t k = 0; k < nnz; k++) vidx[k] = dict.lookup(cval[k]);
-  VIMZ_CUDA(cudaMalloc(d_vidx, std::max<size_t>(nnz * 4, 4)));
-  VIMZ_CUDA(cudaMemcpyAsync(*d_vidx, vidx.data(), nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+  h_vidx.resize(nnz);
+  for (size_t k = 0; k < nnz; k++) h_vidx[k] = dict.lookup(cval[k]);
   VIMZ_CUDA(cudaMalloc(d_rowptr, (m + 1) * 4));
   VIMZ_CUDA(cudaMalloc(d_col, std::max<size_t>(nnz * 4, 4)));
   VIMZ_CUDA(cudaMalloc(d_val, std::max<size_t>(nnz * 32, 32)));
@@ -574,6 +588,8 @@ static int coo_to_csr(vimz_ctx* ctx, size_t m, size_t ncols, const uint32_t* row
   VIMZ_CUDA(cudaMemcpyAsync(*d_col, ccol.data(), nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
   VIMZ_CUDA(cudaMemcpyAsync(*d_val, cval.data(), nnz * 32, cudaMemcpyHostToDevice, ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  h_rowptr.swap(rowptr);
+  h_col.swap(ccol);
   return VIMZ_OK;
 }
 
@@ -618,10 +634,11 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
     dict.lookup(one);
     dict.lookup(minus_one);
   }
+  std::vector<uint32_t> h_rowptr[3], h_col[3], h_vidx[3];
   for (int k = 0; k < 3; k++) {
     s->nnz[k] = nnz[k];
     int rc = coo_to_csr(ctx, num_cons, ncols, rows[k], cols[k], vals[k], nnz[k], &s->rowptr[k], &s->col[k], &s->val[k], row_nnz, dict,
-                        &s->vidx[k]);
+                        h_rowptr[k], h_col[k], h_vidx[k]);
     if (rc != VIMZ_OK) {
       vimz_shape_destroy(s);
       return rc;
@@ -644,28 +661,48 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
     e = cudaMalloc(&s->mid_rows, s->n_mid * 4);
     if (e == cudaSuccess) e = cudaMemcpy(s->mid_rows, mid_rows.data(), s->n_mid * 4, cudaMemcpyHostToDevice);
   }
-  // streamed cross term: consecutive rows are grouped into chunks of <= CROSS_CHUNK_NNZ non-zeros (A+B+C) and
-  // <= CROSS_CHUNK_ROWS rows; a row above CROSS_ROW_MAX non-zeros is a chunk of its own, handled by one warp
-  std::vector<uint32_t> chunk_start;
+  // streamed mat-vec: consecutive rows are grouped into chunks of <= CROSS_CHUNK_NNZ non-zeros (A+B+C) and
+  // <= CROSS_CHUNK_ROWS rows; a row above CROSS_ROW_MAX non-zeros is a chunk of its own, walked by one warp in global memory.
+  // Every other chunk gets its (col, vidx) pairs packed contiguously -- A's entries, then B's, then C's, each in CSR order --
+  // starting at an even pair index (16-byte aligned: the kernel fetches the stream with one TMA bulk copy).
+  std::vector<ChunkDesc> desc;
+  std::vector<uint2> stream;
   {
     size_t i = 0;
     while (i < num_cons) {
+      ChunkDesc d{};
       if (row_nnz[i] > CROSS_ROW_MAX) {
-        chunk_start.push_back((uint32_t)i | 0x80000000u);
+        d.off = CHUNK_LONG_ROW; d.r0 = (uint32_t)i; d.nrows = 1;
+        desc.push_back(d);
         i++;
         continue;
       }
-      chunk_start.push_back((uint32_t)i);
       size_t acc = 0, j = i;
       while (j < num_cons && j - i < CROSS_CHUNK_ROWS && row_nnz[j] <= CROSS_ROW_MAX && acc + row_nnz[j] <= CROSS_CHUNK_NNZ) acc += row_nnz[j++];
+      if (stream.size() & 1) stream.push_back(make_uint2(0, 0));
+      d.off = (uint32_t)stream.size(); d.r0 = (uint32_t)i; d.nrows = (uint32_t)(j - i);
+      uint32_t* cnt[3] = {&d.nA, &d.nB, &d.nC};
+      for (int k = 0; k < 3; k++) {
+        const uint32_t b = h_rowptr[k][i], e2 = h_rowptr[k][j];
+        *cnt[k] = e2 - b;
+        for (uint32_t t = b; t < e2; t++) stream.push_back(make_uint2(h_col[k][t], h_vidx[k][t]));
+      }
+      desc.push_back(d);
       i = j;
     }
-    s->n_chunks = chunk_start.size();
-    chunk_start.push_back((uint32_t)num_cons);
+    s->n_chunks = desc.size();
+    stream.push_back(make_uint2(0, 0));  // the bulk copy rounds a chunk's byte count up to 16
+    stream.push_back(make_uint2(0, 0));
+    if (stream.size() >= (1ull << 32)) {
+      vimz_shape_destroy(s);
+      return set_error(VIMZ_ERR_ARG, "vimz_shape_upload: shape too large (packed index stream)");
+    }
   }
   s->n_dict = dict.values.size();
-  if (e == cudaSuccess) e = cudaMalloc(&s->chunk_start, chunk_start.size() * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(s->chunk_start, chunk_start.data(), chunk_start.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&s->chunk_stream, stream.size() * sizeof(uint2));
+  if (e == cudaSuccess) e = cudaMemcpy(s->chunk_stream, stream.data(), stream.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&s->chunk_desc, std::max<size_t>(desc.size(), 1) * sizeof(ChunkDesc));
+  if (e == cudaSuccess && !desc.empty()) e = cudaMemcpy(s->chunk_desc, desc.data(), desc.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&s->dict, s->n_dict * 32);
   if (e == cudaSuccess) e = cudaMemcpy(s->dict, dict.values.data(), s->n_dict * 32, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -837,6 +874,17 @@ int vimz_acc_init_sharded(vimz_ctx* ctx, const vimz_shape* s_rows, const vimz_ck
   return acc_create(ctx, s_rows, ck_rows, ck_vars, var_first, var_count, out);
 }
 
+// The host side of a fold step waits for ~200 bytes that the stream produces 0.2 - 0.6 ms after the launch: polling the
+// stream returns within a few microseconds of completion, a blocking cudaStreamSynchronize adds the wake-up latency of the
+// driver's sleeping wait to every step (option "spin_wait", default 1).
+static cudaError_t wait_stream(vimz_ctx* ctx, cudaStream_t st) {
+  if (!ctx->opt_spin_wait) return cudaStreamSynchronize(st);
+  cudaError_t e;
+  while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+  }
+  return e;
+}
+
 // main stream waits for the commitment folds still running on the side stream
 static int acc_wait_side(vimz_acc* a) {
   for (int k = 0; k < 2; k++)
@@ -870,6 +918,30 @@ int vimz_acc_load(vimz_acc* a, const vimz_fr* W, const vimz_fr* E, const vimz_fr
   return VIMZ_OK;
 }
 
+// Back to the default relaxed instance (all zero, u = 0), as after vimz_acc_init: a new proof on the same shape / key.
+int vimz_acc_reset(vimz_acc* a) {
+  CHECK_ARG(a, "vimz_acc_reset: null argument");
+  vimz_ctx* ctx = a->ctx;
+  CtxGuard g(ctx);
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
+  a->side_pending[0] = a->side_pending[1] = false;
+  const vimz_shape* s = a->shape;
+  cudaStream_t st = ctx->stream;
+  const size_t nb = std::max<size_t>(s->n * 32, 32), mb = std::max<size_t>(s->m * 32, 32), tb = (1 + s->io) * 32;
+  VIMZ_CUDA(cudaMemsetAsync(a->W1, 0, nb, st));
+  VIMZ_CUDA(cudaMemsetAsync(a->E1, 0, mb, st));
+  VIMZ_CUDA(cudaMemsetAsync(a->tail1, 0, tb, st));
+  VIMZ_CUDA(cudaMemsetAsync(a->comms, 0, 6 * 96 + 2 * 32, st));
+  if (a->cache1) VIMZ_CUDA(cudaMemsetAsync(a->cache1, 0, 3 * mb, st));
+  VIMZ_CUDA(cudaStreamSynchronize(st));
+  a->half_open = false;
+  a->step_enqueued = false;
+  a->fresh_complete = false;
+  return VIMZ_OK;
+}
+
 // The stream work of step_begin after W2 is resident: everything here has fixed addresses, so it can be captured.
 static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   vimz_ctx* ctx = a->ctx;
@@ -877,22 +949,26 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
   VIMZ_CUDA(cudaMemcpyAsync(a->tail2, a->pinned + ACC_PIN_STAGE, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
-  // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) -- independent of T, so it runs on the aux
-  // stream with its own workspace while the main stream does the cross term and commit(T).
+  // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) is independent of T, so it runs on the aux stream with its own
+  // workspace while the main stream does the cross term and commit(T).  The main lane is the critical one and is enqueued
+  // FIRST: a captured graph dispatches its nodes in creation order, a few microseconds apart, and with the aux lane in
+  // front the first cross-term kernel started ~20 us late.
   const bool two_lanes = ctx->opt_aux_lane;
   if (two_lanes) {
     VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
     VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
-    VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
-    VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
   } else {  // one lane (used by the profiled pass so kernel times are not inflated by the other lane)
     VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
   }
-  // T = cross term (six mat-vecs fused), comm_T = commit(ck, T)      (commit_T)
+  // T = cross term (mat-vecs with z2 + element-wise combination), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2));  // also histograms T's digits
   // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
   // so nothing recoded T: the commit then does its own, empty, digit pass)
   VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
+  if (two_lanes) {
+    VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
+    VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
+  }
   if (two_lanes) VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   return VIMZ_OK;
@@ -959,7 +1035,7 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
   a->fresh_complete = false;
   a->step_enqueued = true;
   if (!sync) return VIMZ_OK;
-  VIMZ_CUDA(cudaStreamSynchronize(st));
+  VIMZ_CUDA(wait_stream(ctx, st));
   a->fresh_complete = true;
   memcpy(comm_W2, a->pinned + ACC_PIN_FRESH, 96);
   memcpy(comm_T, a->pinned + ACC_PIN_FRESH + 96, 96);
@@ -969,7 +1045,8 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
 int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* X2, void** d_partials) {
   CHECK_ARG(a && d_partials && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev_async: null argument");
   CtxGuard g(a->ctx);
-  VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
+  if (d_W2 != a->W2)  // (the sharded entry points broadcast the witness straight into the accumulator)
+    VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
   VIMZ_TRY(acc_step_begin_common(a, X2, nullptr, nullptr, false));
   *d_partials = (char*)a->comms + (2 + 2 * a->parity) * 96;
   return VIMZ_OK;
@@ -994,6 +1071,28 @@ int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_
   CHECK_ARG(a && comm_W2 && comm_T && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin: null argument");
   CtxGuard g(a->ctx);
   VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  return acc_step_begin_common(a, X2, comm_W2, comm_T);
+}
+
+// Streaming upload of the fresh witness.  Most of a step's witness (the Circom part: 118 k of grayscale's 128 k variables) does
+// not depend on the previous fold -- the witness generator can run ahead -- so the host may hand it over as soon as the previous
+// step_end has been issued: the copy is enqueued on the context's stream behind that step_end (whose axpy is the last reader of
+// the buffer) and runs while the host and the GPU work on the OTHER curve.  step_begin_staged then uploads only the rest.
+int vimz_acc_stage_fresh(vimz_acc* a, const vimz_fr* W2_part, size_t first, size_t count) {
+  CHECK_ARG(a && (W2_part || count == 0), "vimz_acc_stage_fresh: null argument");
+  if (first > a->shape->n || count > a->shape->n - first) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_stage_fresh: range outside the witness");
+  CtxGuard g(a->ctx);
+  if (a->half_open) return set_error(VIMZ_ERR_ARG, "vimz_acc_stage_fresh: a step is open (commit_fresh without cross_begin)");
+  if (count) VIMZ_CUDA(cudaMemcpyAsync((char*)a->W2 + first * 32, W2_part, count * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  return VIMZ_OK;
+}
+
+int vimz_acc_step_begin_staged(vimz_acc* a, const vimz_fr* W2_rest, size_t first, size_t count, const vimz_fr* X2, vimz_point* comm_W2,
+                               vimz_point* comm_T) {
+  CHECK_ARG(a && comm_W2 && comm_T && (W2_rest || count == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_staged: null argument");
+  if (first > a->shape->n || count > a->shape->n - first) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_step_begin_staged: range outside the witness");
+  CtxGuard g(a->ctx);
+  if (count) VIMZ_CUDA(cudaMemcpyAsync((char*)a->W2 + first * 32, W2_rest, count * 32, cudaMemcpyHostToDevice, a->ctx->stream));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 

@@ -82,13 +82,14 @@ struct MsmWorkspace {
   vimz::DevBuf chunkL;     // [T] XYZZ chunk weighted sums
   vimz::DevBuf bitsums;    // [(nb+1) * G] XYZZ
   vimz::DevBuf scaled;     // [nb+1] XYZZ
+  vimz::DevBuf deferred;   // [max_giants] XYZZ: weighted sums of the giant buckets kept out of the bucket array
   vimz::DevBuf scal;       // staged scalars (host-pointer entry points)
   vimz::DevBuf result;     // Jacobian results (device)
   uint32_t last_M = 0;     // buckets of the last MSM run on this workspace (statistics: vimz_ctx_profile "laneK_*")
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release(); digits.release();
     cls.release(); biglist.release(); partials.release(); buckets.release();
-    chunkA.release(); chunkL.release(); bitsums.release(); scaled.release(); scal.release(); result.release();
+    chunkA.release(); chunkL.release(); bitsums.release(); scaled.release(); deferred.release(); scal.release(); result.release();
   }
 };
 
@@ -123,13 +124,15 @@ struct vimz_ctx {
   int sm_count = 148;
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
+  bool opt_defer_giants = true; // giant buckets are summed beside the bucket reduction (k_reduce_tail) instead of in front of it
+  bool opt_spin_wait = true; // step_begin polls the stream for its result instead of a blocking synchronise
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
   bool opt_cross_stream = true; // cross term: chunked CSR streaming through shared memory (false: row-class kernel)
   bool opt_cross_cache = true;  // accumulators created from now on keep (Az1, Bz1, Cz1) resident instead of recomputing them
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
   long opt_direct_c = 0;       // digit width of the direct table (0 = chosen by key length)
-  long opt_direct_bps = 4;     // k_msm_direct blocks per SM (1..4)
+  long opt_direct_bps = 3;     // k_msm_direct blocks per SM (1..4): at 2 the two commits of a fold step (two stream lanes) are resident together
   long opt_direct_max = 32768; // keys up to this many points get the direct multiples table (256 KB per point); 0 = never
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
@@ -183,11 +186,12 @@ struct vimz_shape {
   uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};  // [m+1]
   uint32_t* col[3] = {nullptr, nullptr, nullptr};     // [nnz]
   void* val[3] = {nullptr, nullptr, nullptr};         // [nnz] Montgomery scalars
-  // streamed cross term: coefficient dictionary + per-non-zero index, rows cut into chunks of bounded non-zeros
-  uint32_t* vidx[3] = {nullptr, nullptr, nullptr};    // [nnz] index into dict (0: +1, 1: -1, no multiplication)
-  void* dict = nullptr;                               // [n_dict] distinct Montgomery coefficients of A, B, C
+  // streamed mat-vec (r1cs.cuh, k_matvec_stream): rows cut into chunks of bounded non-zeros; every chunk's (column,
+  // coefficient-dictionary index) pairs packed contiguously (A's, then B's, then C's) and 16-byte aligned for the TMA bulk copy
+  void* dict = nullptr;                               // [n_dict] distinct Montgomery coefficients of A, B, C (0: +1, 1: -1, no multiplication)
   size_t n_dict = 0;
-  uint32_t* chunk_start = nullptr;                    // [n_chunks + 1] first row of every chunk; bit 31: a single long row
+  void* chunk_stream = nullptr;                       // uint2 (col, vidx) pairs
+  void* chunk_desc = nullptr;                         // [n_chunks] ChunkDesc
   size_t n_chunks = 0;
   uint32_t* long_rows = nullptr;                      // rows with > R1CS_LONG_ROW non-zeros over A+B+C (warp each)
   size_t n_long = 0;

@@ -53,14 +53,13 @@ const CurveVTable* curve_vtable(int curve_id);
 
 inline uint32_t ceil_div(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 
-constexpr size_t CROSS_SMEM_CACHED = (size_t)CROSS_CHUNK_NNZ * 32, CROSS_SMEM_UNCACHED = (size_t)CROSS_CHUNK_NNZ * 64;
+constexpr size_t MATVEC_SMEM = (size_t)CROSS_CHUNK_NNZ * (8 + 32);  // index stream + product slots of one chunk
 
 // Per-DEVICE kernel attributes (cudaFuncSetAttribute applies to the current device only): called by vimz_ctx_create
 // for every context, so a process driving several GPUs gets the > 48 KB shared-memory opt-in on each of them.
 template <class C>
 int impl_init_device(vimz_ctx*) {
-  VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CROSS_SMEM_CACHED));
-  VIMZ_CUDA(cudaFuncSetAttribute(k_cross_term_stream<typename C::Fs, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CROSS_SMEM_UNCACHED));
+  VIMZ_CUDA(cudaFuncSetAttribute(k_matvec_stream<typename C::Fs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATVEC_SMEM));
   return VIMZ_OK;
 }
 
@@ -110,6 +109,18 @@ int impl_msm_direct(vimz_ctx* ctx, cudaStream_t st, MsmWorkspace& ws, const vimz
   return VIMZ_OK;
 }
 
+// Geometry shared by the bucket pipeline and the fused cross term: accumulation threads, capacity of the giant lists,
+// and the control block, which lives IN FRONT of the bucket histogram so one memset node clears both.
+inline uint32_t msm_nthreads(const vimz_ctx* ctx) { return (uint32_t)ctx->sm_count * (uint32_t)ctx->opt_acc_blocks * 128; }
+inline uint32_t msm_max_giants(const vimz_ctx* ctx) { return 2 * msm_nthreads(ctx) / COMBINE_MID + 2; }
+inline uint32_t msm_ctrl_words(const vimz_ctx* ctx) { return (CTRL_GIANT_DONE + msm_max_giants(ctx) + 3) & ~3u; }  // keeps counts[] 16-byte aligned
+inline int msm_zero_control(vimz_ctx* ctx, MsmWorkspace& ws, uint32_t M, cudaStream_t st) {
+  const size_t bytes = ((size_t)msm_ctrl_words(ctx) + M) * 4;
+  VIMZ_TRY(ws.counts.reserve(bytes));
+  VIMZ_CUDA(cudaMemsetAsync(ws.counts.ptr, 0, bytes, st));
+  return VIMZ_OK;
+}
+
 template <class C>
 int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted) {
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
@@ -126,24 +137,26 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   int nb = 0;
   while ((1u << nb) < T) nb++;
   // second level: 32 quads per block, ~2 chunk sums per quad: the tree depth, not the work, sets the time
-  const int G = (int)std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 2), 1), 64);
+  // (G * (nb + 1) blocks of 128 threads must stay resident together -- 4 per SM -- or the last-arriving hand-offs wait for a
+  // second wave: with 32 768 buckets and G = 64 the tail took 1.5 waves and ~50 us longer)
+  const uint32_t g_fit = std::max<uint32_t>(((uint32_t)ctx->sm_count * 4) / (uint32_t)(nb + 2), 1);
+  const int G = (int)std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 2), 1), 64), g_fit);
   // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
-  const uint32_t nthreads = (uint32_t)ctx->sm_count * (uint32_t)ctx->opt_acc_blocks * 128;
+  const uint32_t nthreads = msm_nthreads(ctx);
   const uint32_t seg_min = (uint32_t)ctx->opt_seg_min;
   // capacity bounds: a bucket cut into p pieces overlaps p segments and every segment boundary cuts at most one
   // bucket, so sum(pieces) <= 2 * nthreads; a giant has > COMBINE_MID pieces and ceil(p / GIANT_CHUNK) chunks
-  const uint32_t max_giants = 2 * nthreads / COMBINE_MID + 2;
+  const uint32_t max_giants = msm_max_giants(ctx);
   const uint32_t max_chunks = 2 * nthreads / GIANT_CHUNK + max_giants + 2;
+  const uint32_t ctrl_words = msm_ctrl_words(ctx);
 
-  VIMZ_TRY(ws.counts.reserve((size_t)M * 4));
+  VIMZ_TRY(ws.counts.reserve(((size_t)ctrl_words + M) * 4));
   VIMZ_TRY(ws.offsets.reserve(((size_t)M + 1) * 4));
   VIMZ_TRY(ws.cursor.reserve((size_t)M * 4));
   uint32_t scan_blocks = ceil_div(M, SCAN_THREADS * SCAN_ITEMS);
   VIMZ_TRY(ws.blocksums.reserve(((size_t)scan_blocks + 2) * 4));
   VIMZ_TRY(ws.sorted.reserve(E * 4));
   VIMZ_TRY(ws.digits.reserve(E * 4));
-  const size_t ctrl_words = CTRL_GIANT_DONE + max_giants;
-  VIMZ_TRY(ws.cls.reserve(ctrl_words * 4));
   VIMZ_TRY(ws.biglist.reserve(((size_t)3 * max_giants + (size_t)2 * max_chunks + (size_t)M + 4) * 4));
   VIMZ_TRY(ws.partials.reserve(((size_t)2 * nthreads + max_chunks) * 128));
   VIMZ_TRY(ws.buckets.reserve((size_t)M * 128));
@@ -151,14 +164,16 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   VIMZ_TRY(ws.chunkL.reserve((size_t)T * 128));
   VIMZ_TRY(ws.bitsums.reserve((size_t)(nb + 1) * G * 128));
   VIMZ_TRY(ws.scaled.reserve((size_t)(nb + 1) * 128));
+  const bool defer = ctx->opt_defer_giants;
+  if (defer) VIMZ_TRY(ws.deferred.reserve((size_t)max_giants * 128));
 
-  uint32_t* counts = ws.counts.as<uint32_t>();
+  uint32_t* counts = ws.counts.as<uint32_t>() + ctrl_words;
   uint32_t* offsets = ws.offsets.as<uint32_t>();
   uint32_t* cursor = ws.cursor.as<uint32_t>();
   uint32_t* blocksums = ws.blocksums.as<uint32_t>();
   uint32_t* sorted = ws.sorted.as<uint32_t>();
   MsmCombine cb;
-  cb.ctrl = ws.cls.as<uint32_t>();
+  cb.ctrl = ws.counts.as<uint32_t>();
   cb.giants = ws.biglist.as<uint32_t>();
   cb.chunk_rec = cb.giants + (size_t)3 * max_giants;
   cb.mids = cb.chunk_rec + (size_t)2 * max_chunks;
@@ -167,8 +182,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   cb.max_chunks = max_chunks;
 
   ws.last_M = M;
-  if (!counted) VIMZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
-  VIMZ_CUDA(cudaMemsetAsync(cb.ctrl, 0, ctrl_words * 4, st));
+  if (!counted) VIMZ_TRY(msm_zero_control(ctx, ws, M, st));  // (counted: the fused cross term cleared control block + histogram)
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
   {
@@ -210,17 +224,19 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
     }
     VIMZ_LAUNCH_CHECK(ctx);
     // pieces of cut buckets: giants (blocks per chunk + last-arrival fold), mids (a warp each), the rest (a quad each)
-    const uint32_t nb_big = (uint32_t)ctx->sm_count * VIMZ_BIG_BLOCKS_PER_SM, nb_mid = (uint32_t)ctx->sm_count * 4,
+    // (with deferred giants the giant role moves into k_reduce_tail, off the chain accumulate -> combine -> reduce)
+    const uint32_t nb_big = defer ? 0u : (uint32_t)ctx->sm_count * VIMZ_BIG_BLOCKS_PER_SM, nb_mid = (uint32_t)ctx->sm_count * 4,
                    nb_small = ceil_div((size_t)M * 4, 128);
     k_msm_combine_all<C><<<nb_big + nb_mid + nb_small, 128, 0, st>>>(offsets, M, nthreads, seg_min, nb_big, nb_mid, ws.partials.ptr,
-                                                                     ws.buckets.ptr, cb);
+                                                                     ws.buckets.ptr, cb, defer);
     VIMZ_LAUNCH_CHECK(ctx);
   }
   ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);
   k_reduce_chunks<C><<<ceil_div((size_t)T * 4, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
-  k_reduce_tail<C><<<dim3(G, nb + 1), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, logK, ws.bitsums.ptr, ws.scaled.ptr,
-                                                    cb.ctrl + CTRL_REDUCE, d_out);
+  k_reduce_tail<C><<<dim3(G, nb + 1 + (defer ? 1 : 0)), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, logK, ws.bitsums.ptr, ws.scaled.ptr,
+                                                                      cb.ctrl + CTRL_REDUCE, d_out, offsets, M, nthreads, seg_min, ws.partials.ptr, cb,
+                                                                      defer ? ws.deferred.ptr : nullptr);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -296,9 +312,8 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
     dc.digits = ctx->ws.digits.as<uint32_t>();
     dc.stride = s->m;
     if (!fuse_ck->dtable) {  // a direct-table key has no buckets: digits only
-      VIMZ_TRY(ctx->ws.counts.reserve((size_t)M * 4));
-      VIMZ_CUDA(cudaMemsetAsync(ctx->ws.counts.ptr, 0, (size_t)M * 4, ctx->stream));
-      dc.counts = ctx->ws.counts.as<uint32_t>();
+      VIMZ_TRY(msm_zero_control(ctx, ctx->ws, M, ctx->stream));
+      dc.counts = ctx->ws.counts.as<uint32_t>() + msm_ctrl_words(ctx);
     }
     dc.c = fuse_ck->c;
     dc.nwin = fuse_ck->nwin;
@@ -309,19 +324,28 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
   ca.m = (uint32_t)s->m; ca.n = (uint32_t)s->n;
   ca.W1 = d_W1; ca.tail1 = d_tail1; ca.W2 = d_W2; ca.tail2 = d_tail2; ca.T = d_T; ca.dc = dc;
   if (ctx->opt_cross_stream && s->n_chunks) {
-    CrossStreamArgs sa;
-    sa.a = ca;
-    sa.vidx[0] = s->vidx[0]; sa.vidx[1] = s->vidx[1]; sa.vidx[2] = s->vidx[2];
-    sa.dict = s->dict;
-    sa.chunk_start = s->chunk_start;
-    sa.cache1 = cache1;
-    sa.cache2 = cache2;
-    // (the dynamic shared memory opt-in of both variants is made per device in impl_init_device)
-    if (cache1 && cache2) {
-      k_cross_term_stream<typename C::Fs, true><<<(uint32_t)s->n_chunks, 256, CROSS_SMEM_CACHED, ctx->stream>>>(sa);
-    } else {
-      k_cross_term_stream<typename C::Fs, false><<<(uint32_t)s->n_chunks, 256, CROSS_SMEM_UNCACHED, ctx->stream>>>(sa);
+    MatvecStreamArgs ma;
+    ma.A = ca.A; ma.B = ca.B; ma.Cm = ca.Cm;
+    ma.m = ca.m; ma.n = ca.n;
+    ma.stream = reinterpret_cast<const uint2*>(s->chunk_stream);
+    ma.desc = reinterpret_cast<const ChunkDesc*>(s->chunk_desc);
+    ma.dict = s->dict;
+    const void* p1 = cache1;
+    void* p2 = cache2;
+    if (!(cache1 && cache2)) {  // stand-alone commit_T: both product triples are computed here, into context scratch
+      const size_t mb3 = (size_t)3 * s->m * 32;
+      VIMZ_TRY(ctx->tmp4.reserve(mb3));
+      VIMZ_TRY(ctx->tmp5.reserve(mb3));
+      ma.W = d_W1; ma.tail = d_tail1; ma.out = ctx->tmp4.ptr;
+      k_matvec_stream<typename C::Fs><<<(uint32_t)s->n_chunks, 256, MATVEC_SMEM, ctx->stream>>>(ma);
+      VIMZ_LAUNCH_CHECK(ctx);
+      p1 = ctx->tmp4.ptr;
+      p2 = ctx->tmp5.ptr;
     }
+    ma.W = d_W2; ma.tail = d_tail2; ma.out = p2;
+    k_matvec_stream<typename C::Fs><<<(uint32_t)s->n_chunks, 256, MATVEC_SMEM, ctx->stream>>>(ma);
+    VIMZ_LAUNCH_CHECK(ctx);
+    k_cross_finish<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(p1, p2, d_tail1, (uint32_t)s->m, d_T, dc);
     VIMZ_LAUNCH_CHECK(ctx);
     return VIMZ_OK;
   }

@@ -368,6 +368,112 @@ __device__ __forceinline__ QPoint<C> q_block_reduce_128(QPoint<C> acc, uint32_t*
   return acc;
 }
 
+// Last stage of the bucket reduction, shared by its two kinds of producers (k_reduce_tail): the nb + 1 scaled bit-plane
+// sums and the deferred giant buckets each announce themselves on one counter; whoever arrives last adds them all and
+// writes the Jacobian result.  Called by warp 0 of a block (all 32 lanes).
+struct TailFinal {
+  void* scaled;          // [nsums] XYZZ
+  int nsums;
+  void* deferred;        // [ngiant] XYZZ, already multiplied by the bucket weight
+  const uint32_t* ngiant_p;
+  uint32_t max_giants;
+  uint32_t* cnt;         // arrival counter
+  void* out_jac;
+};
+template <class C>
+__device__ __forceinline__ void reduce_arrive_final(const TailFinal& f) {
+  const uint32_t ngiant = f.deferred ? min(*f.ngiant_p, f.max_giants) : 0u;
+  uint32_t done = 0;
+  if ((threadIdx.x & 31) == 0) done = atomicAdd(f.cnt, 1u) + 1;
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done != (uint32_t)f.nsums + ngiant) return;
+  __threadfence();
+  const uint32_t q8 = (threadIdx.x & 31) >> 2, total = (uint32_t)f.nsums + ngiant;
+  QPoint<C> acc = QPoint<C>::identity();
+#pragma unroll 1
+  for (uint32_t it = 0; it < (total + 7) / 8; it++) {
+    const uint32_t g = it * 8 + q8;
+    const char* src = g < (uint32_t)f.nsums ? reinterpret_cast<const char*>(f.scaled) + (size_t)g * 128
+                                            : reinterpret_cast<const char*>(f.deferred) + (size_t)(g - f.nsums) * 128;
+    QPoint<C> p = g < total ? QPoint<C>::load_cg(src) : QPoint<C>::identity();
+    acc = q_add<C>(acc, p);
+  }
+  acc = q_warp_reduce<C>(acc);
+  q_store_jacobian<C>(acc, f.out_jac, (threadIdx.x & 31) < 4);
+}
+
+// Giant buckets (cut into more than COMBINE_MID pieces: the 0/1 bucket of a witness vector, the one- or two-bit top window of
+// the cross term late in a proof).  Blocks `block`, `block + nblocks`, ... each sum one chunk of GIANT_CHUNK pieces (32 quads);
+// the block that finishes the last chunk of a giant also folds its chunk sums.  Two uses:
+//   * inside k_msm_combine_all (deferred == nullptr): the giant's sum goes to buckets[b] like every other bucket;
+//   * inside k_reduce_tail (deferred != nullptr): the giant was left OUT of the bucket array (identity there), its sum is
+//     scaled by its weight b + 1 here and handed to the final stage -- a ~19-addition chain that then runs beside the
+//     bucket reduction instead of in front of it.
+template <class C>
+__device__ __forceinline__ void giant_role(const uint32_t* __restrict__ offsets, uint32_t L, uint32_t block, uint32_t nblocks,
+                                           const void* __restrict__ partials, const MsmCombine& cb, uint32_t* smem, uint32_t* last_flag_p,
+                                           void* __restrict__ buckets, const TailFinal* fin) {
+  void* deferred = fin ? fin->deferred : nullptr;
+  const char* parts = reinterpret_cast<const char*>(partials);
+  const uint32_t nchunks = min(cb.ctrl[CTRL_NCHUNK], cb.max_chunks);
+  const uint32_t quad = threadIdx.x >> 2;
+  for (uint32_t j = block; j < nchunks; j += nblocks) {
+    const uint32_t g = cb.chunk_rec[2 * j], idx = cb.chunk_rec[2 * j + 1];
+    const uint32_t b = cb.giants[3 * g], gbase = cb.giants[3 * g + 1], nch = cb.giants[3 * g + 2];
+    const uint32_t s = offsets[b], e = offsets[b + 1];
+    const uint32_t t0 = s / L, t1 = (e - 1) / L;
+    const uint32_t first = t0 + idx * GIANT_CHUNK, last = min(t1, first + GIANT_CHUNK - 1);
+    QPoint<C> acc = QPoint<C>::identity();
+#pragma unroll 1
+    for (uint32_t it = 0; it < GIANT_CHUNK / 32; it++) {  // uniform trip count: every lane joins the shuffles
+      uint32_t t = first + it * 32 + quad;
+      QPoint<C> p = t <= last ? QPoint<C>::load(parts + seg_partial_index(t, t0, s, L) * 128) : QPoint<C>::identity();
+      acc = q_add<C>(acc, p);
+    }
+    acc = q_block_reduce_128<C>(acc, smem);
+    if (threadIdx.x < 4) {
+      acc.store(reinterpret_cast<char*>(cb.chunk_sums) + (size_t)j * 128);
+      __threadfence();  // publish the chunk sum before announcing it
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *last_flag_p = (atomicAdd(&cb.ctrl[CTRL_GIANT_DONE + g], 1u) + 1 == nch) ? 1u : 0u;
+    __syncthreads();
+    if (*last_flag_p && threadIdx.x < 32) {  // last chunk of giant g: one warp folds all its chunk sums (read through L2)
+      __threadfence();
+      const uint32_t q8 = threadIdx.x >> 2;
+      QPoint<C> tot = QPoint<C>::identity();
+      const uint32_t iters = (nch + 7) / 8;
+#pragma unroll 1
+      for (uint32_t it = 0; it < iters; it++) {
+        uint32_t jj = it * 8 + q8;
+        QPoint<C> p = jj < nch ? QPoint<C>::load_cg(reinterpret_cast<const char*>(cb.chunk_sums) + (size_t)(gbase + jj) * 128)
+                               : QPoint<C>::identity();
+        tot = q_add<C>(tot, p);
+      }
+      tot = q_warp_reduce<C>(tot);
+      if (!deferred) {
+        if (threadIdx.x < 4) tot.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+      } else {
+        // weight of bucket b in sum_k (k+1) B_k: (b + 1) * tot by double-and-add (warp-uniform: b is)
+        const uint32_t w = b + 1;
+        QPoint<C> sc = QPoint<C>::identity();
+#pragma unroll 1
+        for (int bit = 31 - __clz(w); bit >= 0; bit--) {
+          sc = q_dbl<C>(sc);
+          if ((w >> bit) & 1) sc = q_add<C>(sc, tot);
+        }
+        if (threadIdx.x < 4) {
+          sc.store(reinterpret_cast<char*>(deferred) + (size_t)g * 128);
+          __threadfence();
+        }
+        __syncwarp();
+        reduce_arrive_final<C>(*fin);  // the last arrival -- a bit-plane sum or a giant -- adds everything up
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // All pieces of cut buckets are added in ONE launch after the accumulation; the block index selects the role
 // (longest chains first so they start first):
 //   blocks [0, nb_big)            giant buckets: a block (32 quads) per chunk of GIANT_CHUNK pieces; the block that
@@ -379,52 +485,13 @@ __device__ __forceinline__ QPoint<C> q_block_reduce_128(QPoint<C> acc, uint32_t*
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_combine_all(const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min,
                                                          uint32_t nb_big, uint32_t nb_mid, const void* __restrict__ partials,
-                                                         void* __restrict__ buckets, MsmCombine cb) {
+                                                         void* __restrict__ buckets, MsmCombine cb, bool defer_giants) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
   __shared__ uint32_t last_flag;
   const uint32_t E = offsets[M], L = seg_len(E, nthreads, seg_min);
   const char* parts = reinterpret_cast<const char*>(partials);
   if (blockIdx.x < nb_big) {
-    const uint32_t nchunks = min(cb.ctrl[CTRL_NCHUNK], cb.max_chunks);
-    const uint32_t quad = threadIdx.x >> 2;
-    for (uint32_t j = blockIdx.x; j < nchunks; j += nb_big) {
-      const uint32_t g = cb.chunk_rec[2 * j], idx = cb.chunk_rec[2 * j + 1];
-      const uint32_t b = cb.giants[3 * g], gbase = cb.giants[3 * g + 1], nch = cb.giants[3 * g + 2];
-      const uint32_t s = offsets[b], e = offsets[b + 1];
-      const uint32_t t0 = s / L, t1 = (e - 1) / L;
-      const uint32_t first = t0 + idx * GIANT_CHUNK, last = min(t1, first + GIANT_CHUNK - 1);
-      QPoint<C> acc = QPoint<C>::identity();
-#pragma unroll 1
-      for (uint32_t it = 0; it < GIANT_CHUNK / 32; it++) {  // uniform trip count: every lane joins the shuffles
-        uint32_t t = first + it * 32 + quad;
-        QPoint<C> p = t <= last ? QPoint<C>::load(parts + seg_partial_index(t, t0, s, L) * 128) : QPoint<C>::identity();
-        acc = q_add<C>(acc, p);
-      }
-      acc = q_block_reduce_128<C>(acc, smem);
-      if (threadIdx.x < 4) {
-        acc.store(reinterpret_cast<char*>(cb.chunk_sums) + (size_t)j * 128);
-        __threadfence();  // publish the chunk sum before announcing it
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) last_flag = (atomicAdd(&cb.ctrl[CTRL_GIANT_DONE + g], 1u) + 1 == nch) ? 1u : 0u;
-      __syncthreads();
-      if (last_flag && threadIdx.x < 32) {  // last chunk of giant g: one warp folds all its chunk sums (read through L2)
-        __threadfence();
-        const uint32_t q8 = threadIdx.x >> 2;
-        QPoint<C> tot = QPoint<C>::identity();
-        const uint32_t iters = (nch + 7) / 8;
-#pragma unroll 1
-        for (uint32_t it = 0; it < iters; it++) {
-          uint32_t jj = it * 8 + q8;
-          QPoint<C> p = jj < nch ? QPoint<C>::load_cg(reinterpret_cast<const char*>(cb.chunk_sums) + (size_t)(gbase + jj) * 128)
-                                 : QPoint<C>::identity();
-          tot = q_add<C>(tot, p);
-        }
-        tot = q_warp_reduce<C>(tot);
-        if (threadIdx.x < 4) tot.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
-      }
-      __syncthreads();
-    }
+    giant_role<C>(offsets, L, blockIdx.x, nb_big, partials, cb, smem, &last_flag, buckets, nullptr);
     return;
   }
   if (blockIdx.x < nb_big + nb_mid) {
@@ -467,7 +534,8 @@ __global__ void __launch_bounds__(128) k_msm_combine_all(const uint32_t* __restr
     nxt = i + 1 < mine ? QPoint<C>::load(parts + seg_partial_index(t0 + i + 1, t0, s, L) * 128) : QPoint<C>::identity();
     acc = q_add<C>(acc, q);
   }
-  if (empty || mine) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
+  // a deferred giant stays out of the bucket array (identity here): k_reduce_tail adds its weighted sum at the very end
+  if (empty || mine || (defer_giants && pieces > COMBINE_MID)) acc.store(reinterpret_cast<char*>(buckets) + (size_t)b * 128);
 }
 
 // ---- bucket reduction: sum_{k=0}^{M-1} (k+1) * B_k ------------------------------------------
@@ -506,10 +574,22 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb, int logK,
                                                      void* __restrict__ bitsums, void* __restrict__ scaled, uint32_t* __restrict__ cnt,
-                                                     void* __restrict__ out_jac) {
+                                                     void* __restrict__ out_jac,
+                                                     // deferred giants (deferred == nullptr: none): row nb + 1 of the grid sums them
+                                                     const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min,
+                                                     const void* __restrict__ partials, MsmCombine cb, void* __restrict__ deferred) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
   __shared__ uint32_t flag;
   const int s = blockIdx.y, G = gridDim.x;
+  TailFinal fin;
+  fin.scaled = scaled; fin.nsums = nb + 1; fin.deferred = deferred; fin.ngiant_p = cb.ctrl + CTRL_NGIANT; fin.max_giants = cb.max_giants;
+  fin.cnt = cnt + nb + 1; fin.out_jac = out_jac;
+  if (s == nb + 1) {  // giant role (only launched when giants are deferred)
+    if (cb.ctrl[CTRL_NGIANT] == 0) return;
+    const uint32_t L = seg_len(offsets[M], nthreads, seg_min);
+    giant_role<C>(offsets, L, blockIdx.x, (uint32_t)G, partials, cb, smem, &flag, nullptr, &fin);
+    return;
+  }
   // s < nb: enumerate exactly the indices with bit s set so every quad is busy; s == nb: all of chunkL
   const bool plain = (s == nb);
   const uint32_t count = plain ? T : (T >> 1), lowmask = plain ? 0u : ((1u << s) - 1);
@@ -547,27 +627,13 @@ __global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ ch
   const int ndbl = s < nb ? s + logK : 0;  // warp-uniform
 #pragma unroll 1
   for (int k = 0; k < ndbl; k++) acc = q_dbl<C>(acc);
-  uint32_t done = 0;
   if (threadIdx.x < 4) {
     acc.store(reinterpret_cast<char*>(scaled) + (size_t)s * 128);
     __threadfence();
   }
   __syncwarp();
-  if (threadIdx.x == 0) done = atomicAdd(&cnt[nb + 1], 1u) + 1;
-  done = __shfl_sync(0xffffffffu, done, 0);
-  if (done != (uint32_t)(nb + 1)) return;
-  // ---- last sum finished: add the nb+1 (<= 32) scaled sums, convert to Jacobian
-  __threadfence();
-  const int nsums = nb + 1;
-  acc = QPoint<C>::identity();
-#pragma unroll 1
-  for (int it = 0; it < (nsums + 7) / 8; it++) {
-    int g = it * 8 + q8;
-    QPoint<C> p = g < nsums ? QPoint<C>::load_cg(reinterpret_cast<const char*>(scaled) + (size_t)g * 128) : QPoint<C>::identity();
-    acc = q_add<C>(acc, p);
-  }
-  acc = q_warp_reduce<C>(acc);
-  q_store_jacobian<C>(acc, out_jac, threadIdx.x < 4);
+  // ---- the last arrival (a sum or a deferred giant) adds the nb + 1 scaled sums and the giants, converts to Jacobian
+  reduce_arrive_final<C>(fin);
 }
 
 // ---- window-table expansion (once per commitment key) ---------------------------------------

@@ -188,168 +188,182 @@ __global__ void __launch_bounds__(128) k_cross_term(CrossArgs a, const uint32_t*
   }
 }
 
-// ---- streamed cross term (default) -------------------------------------------------------------------------
-// The row-class kernel above is bound by dependent loads (rowptr -> col/val -> z) of threads that own whole rows.
-// Here a 256-thread block owns a CHUNK of consecutive rows holding <= CROSS_CHUNK_NNZ non-zeros over A+B+C:
-//   phase 1: the threads stride the chunk's non-zeros of A, then B, then C -- coalesced (col, value-index) reads,
-//            independent z1/z2 gathers (L2), products v*z1, v*z2 written to shared memory;
-//   phase 2: one thread per row sums its products out of shared memory and forms T (rows above CROSS_ROW_COOP
-//            non-zeros are summed by a warp with shuffles instead).
-// Coefficients come from the shape's value dictionary (4 B per non-zero instead of 32 B; +1 / -1 need no product).
+// ---- streamed mat-vec triple + element-wise cross term (default) -------------------------------------------
+// The row-class kernel above is bound by dependent loads (rowptr -> col/val -> z) of threads that own whole rows, and a
+// single fused kernel (mat-vecs + T + digit recoding, 122 registers, two blocks per SM) spent its time in three waves of
+// latency-bound blocks (round 1: 67 us for 130 k rows, 11 % of the HBM roofline).  Now two launches:
+//
+//   k_matvec_stream   one 256-thread block per CHUNK of consecutive rows (<= CROSS_CHUNK_NNZ non-zeros over A+B+C,
+//                     <= CROSS_CHUNK_ROWS rows).  The chunk's (column, coefficient-index) pairs were packed into ONE
+//                     contiguous, 16-byte aligned stream when the shape was uploaded:
+//                       1. one thread issues a TMA bulk copy (cp.async.bulk, mbarrier complete_tx) of that stream into shared
+//                          memory -- no rowptr -> col dependent loads, no per-thread index traffic;
+//                       2. every thread issues its z gathers as cp.async (LDGSTS) 2 x 16 B straight into the product slots:
+//                          all of a chunk's gathers are in flight at once, without holding registers;
+//                       3. coefficients: +1 / -1 need no product, the others come from the shape's value dictionary;
+//                       4. one thread per row sums its slots (a warp for rows above CROSS_ROW_COOP non-zeros) and writes
+//                          (Az, Bz, Cz)[row].
+//                     ~60 registers: four to five blocks per SM instead of two.
+//   k_cross_finish    one thread per row, perfectly coalesced: T = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1, plus the signed-digit
+//                     recoding and bucket histogram of T for the commit that follows.
+// The resident accumulator keeps (Az1, Bz1, Cz1) folded (A (z1 + r z2) = A z1 + r A z2), so a step runs the mat-vec
+// kernel once, on z2; the stand-alone commit_T runs it twice.
 #ifndef VIMZ_CROSS_CHUNK_NNZ
 #define VIMZ_CROSS_CHUNK_NNZ 1024
 #endif
-constexpr uint32_t CROSS_CHUNK_NNZ = VIMZ_CROSS_CHUNK_NNZ;  // products per chunk: 64 B of shared memory each
+constexpr uint32_t CROSS_CHUNK_NNZ = VIMZ_CROSS_CHUNK_NNZ;  // products per chunk: 8 B of index stream + 32 B of product slot each
 constexpr uint32_t CROSS_CHUNK_ROWS = 256;  // = block size
 constexpr uint32_t CROSS_ROW_MAX = CROSS_CHUNK_NNZ < 512 ? CROSS_CHUNK_NNZ : 512;     // longer rows are chunks of their own (a warp walks them in global memory)
-constexpr uint32_t CROSS_ROW_COOP = 32;     // rows above this are summed by a warp in phase 2
+constexpr uint32_t CROSS_ROW_COOP = 32;     // rows above this are summed by a warp
+constexpr uint32_t CHUNK_LONG_ROW = 0xffffffffu;
 
-struct CrossStreamArgs {
-  CrossArgs a;
-  const uint32_t* vidx[3];
-  const void* dict;
-  const uint32_t* chunk_start;
-  // CACHED variant (the resident accumulator): the products with the running z1 are linear in the fold,
-  //   A (z1 + r z2) = A z1 + r A z2,
-  // so the accumulator keeps (Az1, Bz1, Cz1) = cache1[3][m] resident and folds them in step_end with the
-  // (Az2, Bz2, Cz2) = cache2[3][m] written here: no z1 gather, no z1 product, half the shared memory.
-  const void* cache1;
-  void* cache2;
+struct ChunkDesc {        // 32 bytes, one per chunk
+  uint32_t off;           // first (col, vidx) pair of the chunk in the packed stream (even => 16-byte aligned); CHUNK_LONG_ROW: a single long row
+  uint32_t nA, nB, nC;    // non-zeros of the chunk per matrix; the stream holds A's, then B's, then C's, in CSR order
+  uint32_t r0, nrows;
+  uint32_t pad0, pad1;
 };
 
-#ifndef VIMZ_CROSS_MINB
-#define VIMZ_CROSS_MINB 2
-#endif
-template <class F, bool CACHED>
-__global__ void __launch_bounds__(256, CACHED ? VIMZ_CROSS_MINB : 2) k_cross_term_stream(CrossStreamArgs s) {
-  extern __shared__ __align__(32) unsigned char cross_smem[];
-  char* P1 = reinterpret_cast<char*>(cross_smem);
-  char* P2 = CACHED ? P1 : P1 + (size_t)CROSS_CHUNK_NNZ * 32;  // CACHED: only the z2 products are staged
+struct MatvecStreamArgs {
+  CsrView A, B, Cm;       // row pointers (and, for long rows, columns / values)
+  uint32_t m, n;
+  const void *W, *tail;   // z = (W || tail)
+  const uint2* stream;    // packed (col, vidx) pairs
+  const ChunkDesc* desc;
+  const void* dict;
+  void* out;              // (Az, Bz, Cz)[3][m]
+};
+
+VIMZ_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <class F>
+__global__ void __launch_bounds__(256, 4) k_matvec_stream(MatvecStreamArgs s) {
+  extern __shared__ __align__(128) unsigned char mv_smem[];
+  uint2* idx = reinterpret_cast<uint2*>(mv_smem);                       // [CROSS_CHUNK_NNZ]
+  char* P = reinterpret_cast<char*>(mv_smem) + (size_t)CROSS_CHUNK_NNZ * 8;  // [CROSS_CHUNK_NNZ][32]
+  __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t big_rows[32];
   __shared__ uint32_t nbig;
-  const CrossArgs& a = s.a;
-  const uint32_t cs = s.chunk_start[blockIdx.x], ce = s.chunk_start[blockIdx.x + 1];
-  const uint32_t r0 = cs & 0x7fffffffu, r1 = ce & 0x7fffffffu;
-  const size_t m32 = (size_t)a.m * 32;
-  auto keep2 = [&](uint32_t row_, const Fp<F>& a2_, const Fp<F>& b2_, const Fp<F>& c2_) {  // (Az2, Bz2, Cz2)[row] for step_end
-    char* c2p = reinterpret_cast<char*>(s.cache2) + (size_t)row_ * 32;
-    a2_.store(c2p); b2_.store(c2p + m32); c2_.store(c2p + 2 * m32);
-  };
-  if (cs >> 31) {  // a single row longer than CROSS_ROW_MAX: a warp walks it in global memory (both z: rare)
+  const uint4* dp = reinterpret_cast<const uint4*>(s.desc + blockIdx.x);
+  const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+  const uint32_t off = d0.x, nA = d0.y, nB = d0.z, nC = d0.w, r0 = d1.x, nrows = d1.y;
+  const size_t m32 = (size_t)s.m * 32;
+  char* out = reinterpret_cast<char*>(s.out);
+  if (off == CHUNK_LONG_ROW) {  // a single row longer than CROSS_ROW_MAX: a warp walks it in global memory (rare)
     if (threadIdx.x < 32) {
-      if (!CACHED) {
-        cross_term_grouped_row<F, 32>(a, r0, true);
-      } else {
-        const uint32_t lane = threadIdx.x;
-        Fp<F> a1, a2, b1, b2, c1, c2;
-        row_dot2<F>(a.A, a.A.rowptr[r0] + lane, a.A.rowptr[r0 + 1], 32, a.n, a.W1, a.tail1, a.W2, a.tail2, a1, a2);
-        row_dot2<F>(a.B, a.B.rowptr[r0] + lane, a.B.rowptr[r0 + 1], 32, a.n, a.W1, a.tail1, a.W2, a.tail2, b1, b2);
-        row_dot2<F>(a.Cm, a.Cm.rowptr[r0] + lane, a.Cm.rowptr[r0 + 1], 32, a.n, a.W1, a.tail1, a.W2, a.tail2, c1, c2);
-        a1 = group_sum_fp<F, 32>(a1); a2 = group_sum_fp<F, 32>(a2);
-        b1 = group_sum_fp<F, 32>(b1); b2 = group_sum_fp<F, 32>(b2);
-        c1 = group_sum_fp<F, 32>(c1); c2 = group_sum_fp<F, 32>(c2);
-        if (lane == 0) {
-          cross_term_finish<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(a.tail1), a.T, r0, a.dc);
-          keep2(r0, a2, b2, c2);
+      const uint32_t lane = threadIdx.x;
+      Fp<F> acc[3];
+      const CsrView* M[3] = {&s.A, &s.B, &s.Cm};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        acc[k] = Fp<F>::zero();
+        for (uint32_t e = M[k]->rowptr[r0] + lane; e < M[k]->rowptr[r0 + 1]; e += 32) {
+          Fp<F> v = Fp<F>::load_nc(reinterpret_cast<const char*>(M[k]->val) + (size_t)e * 32);
+          acc[k] = fp_add(acc[k], coeff_mul(v, load_z<F>(s.W, s.tail, s.n, __ldg(M[k]->col + e))));
         }
+        acc[k] = group_sum_fp<F, 32>(acc[k]);
+      }
+      if (lane == 0) {
+        acc[0].store(out + (size_t)r0 * 32); acc[1].store(out + m32 + (size_t)r0 * 32); acc[2].store(out + 2 * m32 + (size_t)r0 * 32);
       }
     }
     return;
   }
-  if (threadIdx.x == 0) nbig = 0;
-  const uint32_t begA = a.A.rowptr[r0], begB = a.B.rowptr[r0], begC = a.Cm.rowptr[r0];
-  const uint32_t nA = a.A.rowptr[r1] - begA, nB = a.B.rowptr[r1] - begB, nC = a.Cm.rowptr[r1] - begC;
   const uint32_t total = nA + nB + nC;
-  // this thread's row bounds for phase 2, fetched now so their latency hides behind phase 1
-  const uint32_t row = r0 + threadIdx.x;
-  const bool have_row = row < r1;
-  uint32_t ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0, rc0 = 0, rc1 = 0;
-  if (have_row) {
-    ra0 = a.A.rowptr[row]; ra1 = a.A.rowptr[row + 1];
-    rb0 = a.B.rowptr[row]; rb1 = a.B.rowptr[row + 1];
-    rc0 = a.Cm.rowptr[row]; rc1 = a.Cm.rowptr[row + 1];
-  }
-  const Fp<F> u1 = Fp<F>::load(a.tail1);
-  auto entry = [&](uint32_t k, uint32_t& col, uint32_t& vi) {
-    if (k < nA) { col = __ldg(a.A.col + begA + k); vi = __ldg(s.vidx[0] + begA + k); }
-    else if (k < nA + nB) { col = __ldg(a.B.col + begB + (k - nA)); vi = __ldg(s.vidx[1] + begB + (k - nA)); }
-    else { col = __ldg(a.Cm.col + begC + (k - nA - nB)); vi = __ldg(s.vidx[2] + begC + (k - nA - nB)); }
-  };
-  auto product = [&](uint32_t k, uint32_t vi, Fp<F> z1, Fp<F> z2) {
-    if (vi >= 2) {
-      Fp<F> v = Fp<F>::load_nc(reinterpret_cast<const char*>(s.dict) + (size_t)vi * 32);
-      if (!CACHED) z1 = fp_mul_noinline<F>(v, z1);
-      z2 = fp_mul_noinline<F>(v, z2);
-    } else if (vi == 1) {
-      if (!CACHED) z1 = fp_neg(z1);
-      z2 = fp_neg(z2);
-    }
-    if (!CACHED) z1.store(P1 + (size_t)k * 32);
-    z2.store(P2 + (size_t)k * 32);
-  };
-  for (uint32_t k = threadIdx.x; k < total; k += 512) {  // two entries in flight per thread
-    const uint32_t k2 = k + 256;
-    const bool two = k2 < total;
-    uint32_t c0, v0, c1 = 0, v1 = 0;
-    entry(k, c0, v0);
-    if (two) entry(k2, c1, v1);
-    Fp<F> x1 = Fp<F>::zero(), y1 = Fp<F>::zero(), y2 = Fp<F>::zero();
-    if (!CACHED) x1 = load_z<F>(a.W1, a.tail1, a.n, c0);
-    Fp<F> x2 = load_z<F>(a.W2, a.tail2, a.n, c0);
-    if (two) {
-      if (!CACHED) y1 = load_z<F>(a.W1, a.tail1, a.n, c1);
-      y2 = load_z<F>(a.W2, a.tail2, a.n, c1);
-    }
-    product(k, v0, x1, x2);
-    if (two) product(k2, v1, y1, y2);
+  const uint32_t mb = smem_u32(&mbar);
+  if (threadIdx.x == 0) {
+    nbig = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto sum2 = [&](uint32_t first, uint32_t count, uint32_t start, uint32_t stride, Fp<F>& d1, Fp<F>& d2) {
-    d1 = Fp<F>::zero();
-    d2 = Fp<F>::zero();
-    for (uint32_t j = start; j < count; j += stride) {
-      if (!CACHED) d1 = fp_add(d1, Fp<F>::load(P1 + (size_t)(first + j) * 32));
-      d2 = fp_add(d2, Fp<F>::load(P2 + (size_t)(first + j) * 32));
+  if (threadIdx.x == 0 && total) {  // 1. TMA bulk copy of the chunk's index stream (16-byte granules; the stream is padded)
+    const uint32_t bytes = (total * 8 + 15) & ~15u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(idx)),
+                 "l"(s.stream + off), "r"(bytes), "r"(mb)
+                 : "memory");
+  }
+  // this thread's row bounds for step 4, fetched now so their latency hides behind steps 1-3
+  const uint32_t row = r0 + threadIdx.x;
+  const bool have_row = threadIdx.x < nrows;
+  const uint32_t begA = __ldg(s.A.rowptr + r0), begB = __ldg(s.B.rowptr + r0), begC = __ldg(s.Cm.rowptr + r0);
+  uint32_t ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0, rc0 = 0, rc1 = 0;
+  if (have_row) {
+    ra0 = __ldg(s.A.rowptr + row); ra1 = __ldg(s.A.rowptr + row + 1);
+    rb0 = __ldg(s.B.rowptr + row); rb1 = __ldg(s.B.rowptr + row + 1);
+    rc0 = __ldg(s.Cm.rowptr + row); rc1 = __ldg(s.Cm.rowptr + row + 1);
+  }
+  if (total) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mb) : "memory");
     }
-  };
-  auto cached1 = [&](uint32_t row_, Fp<F>& a1_, Fp<F>& b1_, Fp<F>& c1_) {  // (Az1, Bz1, Cz1)[row] kept by the accumulator
-    const char* c1p = reinterpret_cast<const char*>(s.cache1) + (size_t)row_ * 32;
-    a1_ = Fp<F>::load(c1p); b1_ = Fp<F>::load(c1p + m32); c1_ = Fp<F>::load(c1p + 2 * m32);
+  }
+  // 2. z gathers: cp.async straight into the product slots, all in flight at once
+  for (uint32_t k = threadIdx.x; k < total; k += 256) {
+    const uint32_t col = idx[k].x;
+    const char* src = col < s.n ? reinterpret_cast<const char*>(s.W) + (size_t)col * 32 : reinterpret_cast<const char*>(s.tail) + (size_t)(col - s.n) * 32;
+    const uint32_t dst = smem_u32(P + (size_t)k * 32);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // 3. coefficients (own slots only: no barrier needed before, one after)
+  for (uint32_t k = threadIdx.x; k < total; k += 256) {
+    const uint32_t vi = idx[k].y;
+    if (vi == 0) continue;
+    Fp<F> z = Fp<F>::load(P + (size_t)k * 32);
+    if (vi == 1) z = fp_neg(z);
+    else z = fp_mul_noinline<F>(Fp<F>::load_nc(reinterpret_cast<const char*>(s.dict) + (size_t)vi * 32), z);
+    z.store(P + (size_t)k * 32);
+  }
+  __syncthreads();
+  // 4. row sums
+  auto sum = [&](uint32_t first, uint32_t count, uint32_t start, uint32_t stride) {
+    Fp<F> d = Fp<F>::zero();
+    for (uint32_t j = start; j < count; j += stride) d = fp_add(d, Fp<F>::load(P + (size_t)(first + j) * 32));
+    return d;
   };
   if (have_row) {
     const uint32_t cnt = (ra1 - ra0) + (rb1 - rb0) + (rc1 - rc0);
     if (cnt > CROSS_ROW_COOP) {
       big_rows[atomicAdd(&nbig, 1u)] = threadIdx.x;  // at most CROSS_CHUNK_NNZ / (CROSS_ROW_COOP + 1) = 31 per chunk
     } else {
-      Fp<F> a1, a2, b1, b2, c1, c2;
-      sum2(ra0 - begA, ra1 - ra0, 0, 1, a1, a2);
-      sum2(nA + (rb0 - begB), rb1 - rb0, 0, 1, b1, b2);
-      sum2(nA + nB + (rc0 - begC), rc1 - rc0, 0, 1, c1, c2);
-      if (CACHED) cached1(row, a1, b1, c1);
-      cross_term_finish<F>(a1, a2, b1, b2, c1, c2, u1, a.T, row, a.dc);
-      if (CACHED) keep2(row, a2, b2, c2);
+      sum(ra0 - begA, ra1 - ra0, 0, 1).store(out + (size_t)row * 32);
+      sum(nA + (rb0 - begB), rb1 - rb0, 0, 1).store(out + m32 + (size_t)row * 32);
+      sum(nA + nB + (rc0 - begC), rc1 - rc0, 0, 1).store(out + 2 * m32 + (size_t)row * 32);
     }
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x >> 5; i < nbig; i += 8) {  // warp-uniform
     const uint32_t br = r0 + big_rows[i];
-    const uint32_t qa0 = a.A.rowptr[br], qa1 = a.A.rowptr[br + 1], qb0 = a.B.rowptr[br], qb1 = a.B.rowptr[br + 1];
-    const uint32_t qc0 = a.Cm.rowptr[br], qc1 = a.Cm.rowptr[br + 1];
-    Fp<F> a1, a2, b1, b2, c1, c2;
-    sum2(qa0 - begA, qa1 - qa0, lane, 32, a1, a2);
-    sum2(nA + (qb0 - begB), qb1 - qb0, lane, 32, b1, b2);
-    sum2(nA + nB + (qc0 - begC), qc1 - qc0, lane, 32, c1, c2);
-    if (!CACHED) { a1 = group_sum_fp<F, 32>(a1); b1 = group_sum_fp<F, 32>(b1); c1 = group_sum_fp<F, 32>(c1); }
-    a2 = group_sum_fp<F, 32>(a2);
-    b2 = group_sum_fp<F, 32>(b2);
-    c2 = group_sum_fp<F, 32>(c2);
+    const uint32_t qa0 = s.A.rowptr[br], qa1 = s.A.rowptr[br + 1], qb0 = s.B.rowptr[br], qb1 = s.B.rowptr[br + 1];
+    const uint32_t qc0 = s.Cm.rowptr[br], qc1 = s.Cm.rowptr[br + 1];
+    Fp<F> a = group_sum_fp<F, 32>(sum(qa0 - begA, qa1 - qa0, lane, 32));
+    Fp<F> b = group_sum_fp<F, 32>(sum(nA + (qb0 - begB), qb1 - qb0, lane, 32));
+    Fp<F> c = group_sum_fp<F, 32>(sum(nA + nB + (qc0 - begC), qc1 - qc0, lane, 32));
     if (lane == 0) {
-      if (CACHED) cached1(br, a1, b1, c1);
-      cross_term_finish<F>(a1, a2, b1, b2, c1, c2, u1, a.T, br, a.dc);
-      if (CACHED) keep2(br, a2, b2, c2);
+      a.store(out + (size_t)br * 32); b.store(out + m32 + (size_t)br * 32); c.store(out + 2 * m32 + (size_t)br * 32);
     }
   }
+}
+
+// T[row] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1 from the two product triples p1 = (Az1, Bz1, Cz1)[3][m], p2 = (Az2, Bz2, Cz2)[3][m];
+// recodes / histograms T's digits for the commit that follows (dc.digits != nullptr).
+template <class F>
+__global__ void __launch_bounds__(256) k_cross_finish(const void* __restrict__ p1, const void* __restrict__ p2, const void* __restrict__ tail1,
+                                                      uint32_t m, void* __restrict__ T, DigitCount dc) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;  // (the warp-aggregated histogram matches the lanes that are still converged)
+  const size_t m32 = (size_t)m * 32;
+  const char* q1 = reinterpret_cast<const char*>(p1) + (size_t)row * 32;
+  const char* q2 = reinterpret_cast<const char*>(p2) + (size_t)row * 32;
+  Fp<F> a1 = Fp<F>::load(q1), b1 = Fp<F>::load(q1 + m32), c1 = Fp<F>::load(q1 + 2 * m32);
+  Fp<F> a2 = Fp<F>::load(q2), b2 = Fp<F>::load(q2 + m32), c2 = Fp<F>::load(q2 + 2 * m32);
+  cross_term_finish<F>(a1, a2, b1, b2, c1, c2, Fp<F>::load(tail1), T, row, dc);
 }
 
 // out[i] = a[i] + r * b[i]

@@ -429,6 +429,10 @@ class FoldAccumulator:
         except Exception:
             pass
 
+    def reset(self):
+        """Back to RelaxedR1CSInstance::default / RelaxedR1CSWitness::default (a new proof on the same shape and key)."""
+        check(lib.vimz_acc_reset(self._h))
+
     def load(self, U: RelaxedR1CSInstance, W: RelaxedR1CSWitness):
         s = self.shape
         Wv, E = as_fr(W.W, s.num_vars), as_fr(W.E, s.num_cons)
@@ -466,6 +470,20 @@ class FoldAccumulator:
         X2, px = self._fr_ptr(X2, s.num_io)
         out, pw, pt = self._io()
         check(lib.vimz_acc_step_begin(self._h, C.c_void_p(W2.__array_interface__["data"][0]), px, pw, pt))
+        return out[:12].copy(), out[12:].copy()
+
+    def stage_fresh(self, W2: np.ndarray, first: int, count: int) -> None:
+        """Enqueue the H2D copy of W2[first : first + count] (rows of the full (n, 4) host array `W2`) behind the previous
+        step_end and return at once; `W2` must stay alive and unchanged until the next step_begin_staged returns."""
+        base = W2.__array_interface__["data"][0] + 32 * first
+        check(lib.vimz_acc_stage_fresh(self._h, C.c_void_p(base), first, count))
+
+    def step_begin_staged(self, W2: np.ndarray, first: int, count: int, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Upload the remaining rows W2[first : first + count] and run the step on the staged witness -> (comm_W2, comm_T)."""
+        X2, px = self._fr_ptr(X2, self.shape.num_io)
+        out, pw, pt = self._io()
+        base = W2.__array_interface__["data"][0] + 32 * first
+        check(lib.vimz_acc_step_begin_staged(self._h, C.c_void_p(base), first, count, px, pw, pt))
         return out[:12].copy(), out[12:].copy()
 
     def step_begin_dev(self, d_W2: int, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

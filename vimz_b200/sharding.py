@@ -47,6 +47,62 @@ def sharded_commit(dist, n: int, local_commit: Callable[[int, int], np.ndarray],
 # ------------------------------------------------------------------------------------------------------------
 # One fold step sharded by constraint-row range ("SpMV / cross-term / E-fold")
 # ------------------------------------------------------------------------------------------------------------
+class Comm:
+    """`vimz_comm`: the NCCL communicator INSIDE libvimz_gpu.so (bound at run time with dlopen), so the exchange of a
+    sharded step / MSM is enqueued by the library on its own stream -- no torch tensor, no Python between the kernels and
+    the collective.  Rank 0 creates the 128-byte id; `from_torch_dist` ships it over an existing torch.distributed group
+    (any backend), a non-Python host would use its own channel."""
+
+    def __init__(self, device: int, rank: int, world: int, unique_id: bytes):
+        import ctypes as C
+        from ._lib import check, lib
+        if len(unique_id) != 128:
+            raise ValueError("NCCL unique id is 128 bytes")
+        h = C.c_void_p()
+        check(lib.vimz_comm_create(device, unique_id, rank, world, C.byref(h)))
+        self._h, self.rank, self.world, self.device = h, rank, world, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from ._lib import check, lib
+        buf = (C.c_uint8 * 128)()
+        check(lib.vimz_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch_dist(cls, dist, device: int) -> "Comm":
+        box = [cls.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(device, dist.get_rank(), dist.get_world_size(), box[0])
+
+    def broadcast_dev(self, engine, d_buf: int, nbytes: int, root: int = 0) -> None:
+        import ctypes as C
+        from ._lib import check, lib
+        check(lib.vimz_comm_broadcast_dev(engine._h, self._h, C.c_void_p(d_buf), nbytes, root))
+
+    def commit_dev(self, ck, d_scalars: int, n: int, first: int = 0) -> np.ndarray:
+        """commit over a key split by point range: this rank's slice; the partial sums are all-gathered and added on the
+        GPU inside the call; every rank returns the same full commitment (vimz_msm_sharded_dev)."""
+        import ctypes as C
+        from ._lib import check, lib
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib.vimz_msm_sharded_dev(ck.engine._h, self._h, ck._h, first, C.c_void_p(d_scalars), n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            from ._lib import lib
+            lib.vimz_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def shard_matrix(M, first: int, count: int):
     """Rows [first, first+count) of a COO matrix (rows, cols, vals), re-based to row 0; entry order preserved."""
     rows, cols, vals = M
@@ -113,6 +169,34 @@ class FoldShard:
                                             ct.ctypes.data_as(C.c_void_p)))
         return cw, ct
 
+    def step_begin_sharded_dev(self, comm: "Comm", d_W2: int, X2: np.ndarray):
+        """The whole sharded step inside the library: enqueue, NCCL all-gather of the partial pairs on the context stream, add
+        on the GPU, one host wait -> FULL (comm_W2, comm_T) on every rank (vimz_acc_step_begin_sharded_dev)."""
+        import ctypes as C
+        from ._lib import check, lib
+        X2, px = self.acc._fr_ptr(X2, self.num_io)
+        out, pw, pt = self.acc._io()
+        check(lib.vimz_acc_step_begin_sharded_dev(self.acc._h, comm._h, C.c_void_p(d_W2), px, pw, pt))
+        return out[:12].copy(), out[12:].copy()
+
+    def step_begin_sharded(self, comm: "Comm", W2, X2: np.ndarray, root: int = 0):
+        """Same with the fresh witness in host memory on `root` only (None elsewhere): H2D on the root, NCCL broadcast into
+        every rank's accumulator, then the step (vimz_acc_step_begin_sharded)."""
+        import ctypes as C
+        from ._lib import check, lib
+        from .field import as_fr
+        X2, px = self.acc._fr_ptr(X2, self.num_io)
+        pw2 = None
+        if W2 is not None:
+            W2 = W2 if (type(W2) is np.ndarray and W2.dtype == np.uint64 and W2.ndim == 2 and W2.flags.c_contiguous) else as_fr(W2)
+            if W2.shape != (self.num_vars, 4):
+                from ._lib import VIMZ_ERR_LENGTH, InvalidWitnessLength
+                raise InvalidWitnessLength(VIMZ_ERR_LENGTH, "step_begin_sharded: witness length != num_vars")
+            pw2 = C.c_void_p(W2.__array_interface__["data"][0])
+        out, pw, pt = self.acc._io()
+        check(lib.vimz_acc_step_begin_sharded(self.acc._h, comm._h, pw2, root, px, pw, pt))
+        return out[:12].copy(), out[12:].copy()
+
     def step_end(self, r: np.ndarray):
         self.acc.step_end(r)
 
@@ -137,8 +221,10 @@ class ShardedFoldAccumulator:
     step/download methods and `point_sum` any callable adding (k, 12) Jacobian points (tests/test_dist.py drives
     this logic over gloo with CPU stand-ins)."""
 
-    def __init__(self, dist, shard, point_sum: Callable[[np.ndarray], np.ndarray], device=None):
-        self.dist, self.shard, self.point_sum, self.device = dist, shard, point_sum, device
+    def __init__(self, dist, shard, point_sum: Callable[[np.ndarray], np.ndarray], device=None, comm: "Comm" = None):
+        """comm != None: the exchange runs inside libvimz_gpu.so (vimz_acc_step_begin_sharded*); torch.distributed is then only
+        used by download().  comm == None: the all-gather goes through torch.distributed (any backend; the CPU tests use gloo)."""
+        self.dist, self.shard, self.point_sum, self.device, self.comm = dist, shard, point_sum, device, comm
 
     def _combine(self, cw: np.ndarray, ct: np.ndarray):
         both = np.concatenate([np.asarray(cw, np.uint64).reshape(12), np.asarray(ct, np.uint64).reshape(12)])
@@ -155,7 +241,15 @@ class ShardedFoldAccumulator:
     def step_begin(self, W2: np.ndarray, X2: np.ndarray):
         return self._combine(*self.shard.step_begin(W2, X2))
 
+    def step_begin_root(self, W2, X2: np.ndarray, root: int = 0):
+        """The fresh witness exists in host memory on `root` only (library path: H2D there + NCCL broadcast + step)."""
+        if self.comm is None:
+            raise RuntimeError("step_begin_root needs a vimz_b200.sharding.Comm")
+        return self.shard.step_begin_sharded(self.comm, W2, X2, root)
+
     def step_begin_dev(self, d_W2: int, X2: np.ndarray):
+        if self.comm is not None:
+            return self.shard.step_begin_sharded_dev(self.comm, d_W2, X2)
         if self.device is not None and hasattr(self.shard, "step_begin_dev_async"):
             return self._step_begin_on_stream(d_W2, X2)
         return self._combine(*self.shard.step_begin_dev(d_W2, X2))
