@@ -510,11 +510,13 @@ def sharded_step_bench(args, torch, dist, rank, world, local_rank, steps, warmup
 CONFIG_CIRCUITS = ["brightness", "contrast", "resize", "crop", "blur4k", "sharpness4k"]   # BASELINE.json configs 2-4 at N = 1
 CONFIG_SHARDED = ["resize", "crop", "blur4k", "sharpness4k"]                                # configs 3-4: one proof over N GPUs
 CONFIG_MIXED = ["grayscale", "brightness", "contrast", "resize", "crop", "blur", "sharpness", "hash"]  # config 5: one transformation per GPU
-CONFIG_STEPS, CONFIG_PREFOLD, CONFIG_WITNESSES = 10, 8, 3
+# (few distinct witnesses make T degenerate -- with 3 of them every bit row of T takes one of 4 values and the buckets collapse into
+# giants: 540 instead of 760 steps/s for brightness -- so the running instance is mixed from 24 rows first)
+CONFIG_STEPS, CONFIG_PREFOLD, CONFIG_WITNESSES = 10, 30, 24
 
 
 def run_configs(args, torch, dist, rank, world, local_rank, sec, peaks, comm):
-    """The remaining BASELINE.json configurations, bounded (10 timed steps each after 8 pre-folds, 3 distinct witnesses): sizes from
+    """The remaining BASELINE.json configurations, bounded (10 timed steps each after 30 pre-folds over 24 distinct witnesses): sizes from
     /root/reference/circuits/nova_snark/circuit_parameters.csv:2-9 (+ Nova's augmented circuit); blur4k / sharpness4k are the x3-width
     estimates of SURVEY.md section 8 (the 4K circuits do not exist in the reference).  N = 1: every step circuit on one GPU plus the
     MSM sweep.  N > 1: resize / crop / blur4k / sharpness4k as ONE proof sharded over the N GPUs, the 2^24 MSM sharded by point

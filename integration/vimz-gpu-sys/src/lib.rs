@@ -35,6 +35,7 @@ pub struct Point { pub x: [u64; 4], pub y: [u64; 4], pub z: [u64; 4] }
 #[repr(C)] pub struct vimz_ck { _p: [u8; 0] }
 #[repr(C)] pub struct vimz_shape { _p: [u8; 0] }
 #[repr(C)] pub struct vimz_acc { _p: [u8; 0] }
+#[repr(C)] pub struct vimz_comm { _p: [u8; 0] }
 
 extern "C" {
     pub fn vimz_last_error() -> *const c_char;
@@ -78,6 +79,26 @@ extern "C" {
     pub fn vimz_point_scale_add(ctx: *mut vimz_ctx, a: *const Point, r: *const Scalar, b: *const Point, out: *mut Point) -> c_int;
     #[allow(dead_code)]
     fn vimz_ctx_sync(ctx: *mut vimz_ctx) -> c_int;
+    // prove_step order on the secondary curve: commit at the end of step i, fold at the start of step i + 1
+    pub fn vimz_acc_commit_fresh(acc: *mut vimz_acc, w2: *const Scalar, x2: *const Scalar, comm_w2: *mut Point) -> c_int;
+    pub fn vimz_acc_cross_begin(acc: *mut vimz_acc, comm_t: *mut Point) -> c_int;
+    pub fn vimz_acc_fresh_witness(acc: *mut vimz_acc, w2: *mut Scalar, x2: *mut Scalar) -> c_int;
+    pub fn vimz_acc_reset(acc: *mut vimz_acc) -> c_int;
+    // streaming upload of the fold-independent part of a witness
+    pub fn vimz_acc_stage_fresh(acc: *mut vimz_acc, w2_part: *const Scalar, first: usize, count: usize) -> c_int;
+    pub fn vimz_acc_step_begin_staged(acc: *mut vimz_acc, w2_rest: *const Scalar, first: usize, count: usize, x2: *const Scalar,
+        comm_w2: *mut Point, comm_t: *mut Point) -> c_int;
+    // several GPUs of one node: NCCL inside the library (bound with dlopen), one process / thread per GPU
+    pub fn vimz_comm_unique_id(id: *mut u8 /* [u8; 128] */) -> c_int;
+    pub fn vimz_comm_create(device: c_int, id: *const u8, rank: c_int, world: c_int, out: *mut *mut vimz_comm) -> c_int;
+    pub fn vimz_comm_destroy(comm: *mut vimz_comm);
+    pub fn vimz_comm_broadcast_dev(ctx: *mut vimz_ctx, comm: *mut vimz_comm, d_buf: *mut core::ffi::c_void, bytes: usize, root: c_int) -> c_int;
+    pub fn vimz_msm_sharded_dev(ctx: *mut vimz_ctx, comm: *mut vimz_comm, ck: *const vimz_ck, first: usize,
+        d_scalars: *const core::ffi::c_void, n: usize, out: *mut Point) -> c_int;
+    pub fn vimz_acc_step_begin_sharded_dev(acc: *mut vimz_acc, comm: *mut vimz_comm, d_w2: *const core::ffi::c_void, x2: *const Scalar,
+        comm_w2: *mut Point, comm_t: *mut Point) -> c_int;
+    pub fn vimz_acc_step_begin_sharded(acc: *mut vimz_acc, comm: *mut vimz_comm, w2: *const Scalar /* NULL off the root */, root: c_int,
+        x2: *const Scalar, comm_w2: *mut Point, comm_t: *mut Point) -> c_int;
 }
 
 #[derive(Debug)]
@@ -139,5 +160,27 @@ impl Accumulator {
         Ok((cw, ct))
     }
     pub fn step_end(&mut self, r: &Scalar) -> Result<(), GpuError> { check(unsafe { vimz_acc_step_end(self.raw, r) }) }
+    /// r1cs_instance_and_witness on the secondary curve: commit now, fold at the start of the next prove_step.
+    pub fn commit_fresh(&mut self, w2: &[Scalar], x2: &[Scalar]) -> Result<Point, GpuError> {
+        let mut cw = Point::default();
+        check(unsafe { vimz_acc_commit_fresh(self.raw, w2.as_ptr(), x2.as_ptr(), &mut cw) })?;
+        Ok(cw)
+    }
+    pub fn cross_begin(&mut self) -> Result<Point, GpuError> {
+        let mut ct = Point::default();
+        check(unsafe { vimz_acc_cross_begin(self.raw, &mut ct) })?;
+        Ok(ct)
+    }
+    /// Hand over the rows of the witness that do not depend on the previous fold while the other curve is being folded.
+    /// # Safety: `part` must stay alive and unchanged until the next `step_begin_staged` returns.
+    pub unsafe fn stage_fresh(&mut self, part: &[Scalar], first: usize) -> Result<(), GpuError> {
+        check(vimz_acc_stage_fresh(self.raw, part.as_ptr(), first, part.len()))
+    }
+    pub fn step_begin_staged(&mut self, rest: &[Scalar], first: usize, x2: &[Scalar]) -> Result<(Point, Point), GpuError> {
+        let (mut cw, mut ct) = (Point::default(), Point::default());
+        check(unsafe { vimz_acc_step_begin_staged(self.raw, rest.as_ptr(), first, rest.len(), x2.as_ptr(), &mut cw, &mut ct) })?;
+        Ok((cw, ct))
+    }
+    pub fn raw(&self) -> *mut vimz_acc { self.raw }
 }
 impl Drop for Accumulator { fn drop(&mut self) { unsafe { vimz_acc_destroy(self.raw) } } }

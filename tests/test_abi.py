@@ -76,3 +76,25 @@ def test_dev_words_exposes_cuda_array_interface():
     w = _DevWords(0x7F0000001000, 24)
     cai = w.__cuda_array_interface__
     assert cai["shape"] == (24,) and cai["typestr"] == "<i8" and cai["data"] == (0x7F0000001000, False)
+
+
+def test_rust_sys_crate_binds_only_exported_symbols():
+    """integration/vimz-gpu-sys (uncompiled source: no Rust toolchain here) must not declare anything the library lacks, and its
+    argument COUNTS must match the header (a drifted FFI block would only show up at link / run time on the reference side)."""
+    src = open(os.path.join(ROOT, "integration", "vimz-gpu-sys", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    decls = re.findall(r"fn (vimz_[a-zA-Z0-9_]+)\s*\((.*?)\)\s*(?:->|;)", block, flags=re.S)
+    assert len(decls) >= 35
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vimz_gpu.h")).read(), flags=re.S)
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+
+    def nargs(arglist):
+        arglist = re.sub(r"/\*.*?\*/", "", arglist, flags=re.S).strip()
+        return 0 if arglist in ("", "void") else arglist.count(",") + 1
+
+    for name, args in decls:
+        assert hasattr(raw, name), f"{name} bound by the -sys crate but not exported"
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", hdr, flags=re.S)
+        assert m, f"{name} not declared in include/vimz_gpu.h"
+        assert nargs(m.group(1)) == nargs(args), f"{name}: {nargs(args)} arguments in lib.rs, {nargs(m.group(1))} in the header"

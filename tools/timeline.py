@@ -2,7 +2,7 @@
 """Per-kernel timeline of one fold step as it really runs (both stream lanes concurrent, CUDA-graph replay), from CUPTI
 through torch.profiler -- the image has no nsys.  Prints, for the last profiled step, every kernel / memcpy with its
 stream, start offset and duration, and the host-side latency of the two step_begin calls.
-usage: python tools/timeline.py [prefold] [e2e]"""
+usage: python tools/timeline.py [prefold] [resident|e2e|staged]"""
 import json, os, sys, time, tempfile
 import numpy as np
 import torch
@@ -11,20 +11,33 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 
 prefold = int(sys.argv[1]) if len(sys.argv) > 1 else 260
-resident = not (len(sys.argv) > 2 and sys.argv[2] == "e2e")
+mode = sys.argv[2] if len(sys.argv) > 2 else "resident"
+resident = mode == "resident"
+
+
+def one(k):
+    if mode == "staged":
+        prim.stage(k); sec.step(k, False); prim.step_staged(k)
+    else:
+        sec.step(k, resident); prim.step(k, resident)
 prim = bench.GpuFold("pallas", "grayscale", bench.SEED, 0, torch)
 sec = bench.GpuFold("vesta", "secondary", bench.SEED + 1, 0, torch)
 for k in range(prefold):
     sec.step(k, True); prim.step(k, True)
 for k in range(prefold, prefold + 4):
-    sec.step(k, resident); prim.step(k, resident)
+    one(k)
 marks = []
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for k in range(prefold + 4, prefold + 7):
         t0 = time.perf_counter_ns()
+        if mode == "staged":
+            prim.stage(k)
         sec.step(k, resident)
         t1 = time.perf_counter_ns()
-        prim.step(k, resident)
+        if mode == "staged":
+            prim.step_staged(k)
+        else:
+            prim.step(k, resident)
         t2 = time.perf_counter_ns()
         marks.append((t0, t1, t2))
     prim.eng.sync(); sec.eng.sync()
