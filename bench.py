@@ -767,7 +767,13 @@ def main_gpu(args, rank, world, local_rank):
     ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
 
     def step_staged(k):     # pipelined e2e: the Circom part of the primary witness travels while the secondary curve is folded
-        prim.stage(k); sec.step(k, False); prim.step_staged(k)
+        # (H2D copies share a copy engine in issue order: the secondary's own witness is enqueued first, then the staged rows)
+        i = k % len(sec.wits)
+        sec.acc.step_begin_async(sec.pin_np[i], sec.X2_bytes[i])
+        prim.stage(k)
+        cw, ct = sec.acc.step_wait()
+        sec.acc.step_end(((challenge_from(ct.tobytes(), k) << 256) % sec.q).to_bytes(32, "little"))
+        prim.step_staged(k)
 
     for k in range(2):
         step_staged(k)
@@ -906,7 +912,7 @@ def main_gpu(args, rank, world, local_rank):
                                                                    "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows}),
                 "e2e": {"value": world * steps / (ms_staged * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
                         "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_staged / steps,
-                        "api": "vimz_acc_stage_fresh + vimz_acc_step_begin_staged (primary), vimz_acc_step_begin (secondary), vimz_acc_step_end: every "
+                        "api": "vimz_acc_stage_fresh + vimz_acc_step_begin_staged (primary), vimz_acc_step_begin_async / _wait (secondary), vimz_acc_step_end: every "
                                "step copies its whole fresh witness host -> device inside the timed region; the fold-independent rows of the "
                                f"primary witness ({prim.staged_split()} of {prim.sh.num_vars}: the Circom step circuit's variables) are enqueued before the "
                                "secondary curve's step so the copy overlaps it, the augmented circuit's ~10 k variables go up inside step_begin",

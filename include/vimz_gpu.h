@@ -181,6 +181,12 @@ int vimz_acc_fresh_witness(vimz_acc* acc, vimz_fr* W2, vimz_fr* X2);
  * witness that does not depend on the previous fold (the Circom step circuit's variables) can so travel while the other curve
  * is being folded.  vimz_acc_step_begin_staged uploads the remaining range and runs the step. */
 int vimz_acc_stage_fresh(vimz_acc* acc, const vimz_fr* W2_part, size_t first, size_t count);
+/* vimz_acc_step_begin in two halves: _async copies W2 / X2 and enqueues the step (the host buffers must stay valid until _wait
+ * returns), _wait blocks for the commitments.  Host-to-device copies of different accumulators share one copy engine in issue
+ * order: a host that stages the NEXT primary witness while the secondary curve folds issues secondary _async, primary
+ * stage_fresh, secondary _wait -- the small secondary witness goes first and the large staged copy hides behind its kernels. */
+int vimz_acc_step_begin_async(vimz_acc* acc, const vimz_fr* W2, const vimz_fr* X2);
+int vimz_acc_step_wait(vimz_acc* acc, vimz_point* comm_W2, vimz_point* comm_T);
 int vimz_acc_step_begin_staged(vimz_acc* acc, const vimz_fr* W2_rest, size_t first, size_t count, const vimz_fr* X2, vimz_point* comm_W2,
                                vimz_point* comm_T);
 int vimz_acc_step_end(vimz_acc* acc, const vimz_fr* r);

@@ -86,6 +86,8 @@ extern "C" {
     pub fn vimz_acc_reset(acc: *mut vimz_acc) -> c_int;
     // streaming upload of the fold-independent part of a witness
     pub fn vimz_acc_stage_fresh(acc: *mut vimz_acc, w2_part: *const Scalar, first: usize, count: usize) -> c_int;
+    pub fn vimz_acc_step_begin_async(acc: *mut vimz_acc, w2: *const Scalar, x2: *const Scalar) -> c_int;
+    pub fn vimz_acc_step_wait(acc: *mut vimz_acc, comm_w2: *mut Point, comm_t: *mut Point) -> c_int;
     pub fn vimz_acc_step_begin_staged(acc: *mut vimz_acc, w2_rest: *const Scalar, first: usize, count: usize, x2: *const Scalar,
         comm_w2: *mut Point, comm_t: *mut Point) -> c_int;
     // several GPUs of one node: NCCL inside the library (bound with dlopen), one process / thread per GPU

@@ -17,7 +17,12 @@ resident = mode == "resident"
 
 def one(k):
     if mode == "staged":
-        prim.stage(k); sec.step(k, False); prim.step_staged(k)
+        i = k % len(sec.wits)
+        sec.acc.step_begin_async(sec.pin_np[i], sec.X2_bytes[i])
+        prim.stage(k)
+        cw, ct = sec.acc.step_wait()
+        sec.acc.step_end(((bench.challenge_from(ct.tobytes(), k) << 256) % sec.q).to_bytes(32, "little"))
+        prim.step_staged(k)
     else:
         sec.step(k, resident); prim.step(k, resident)
 prim = bench.GpuFold("pallas", "grayscale", bench.SEED, 0, torch)
@@ -31,8 +36,13 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for k in range(prefold + 4, prefold + 7):
         t0 = time.perf_counter_ns()
         if mode == "staged":
+            i = k % len(sec.wits)
+            sec.acc.step_begin_async(sec.pin_np[i], sec.X2_bytes[i])
             prim.stage(k)
-        sec.step(k, resident)
+            cw, ct = sec.acc.step_wait()
+            sec.acc.step_end(((bench.challenge_from(ct.tobytes(), k) << 256) % sec.q).to_bytes(32, "little"))
+        else:
+            sec.step(k, resident)
         t1 = time.perf_counter_ns()
         if mode == "staged":
             prim.step_staged(k)

@@ -87,6 +87,8 @@ def _load() -> C.CDLL:
         "vimz_acc_cross_begin": (i32, [vp, vp]),
         "vimz_acc_fresh_witness": (i32, [vp, vp, vp]),
         "vimz_acc_stage_fresh": (i32, [vp, vp, sz, sz]),
+        "vimz_acc_step_begin_async": (i32, [vp, vp, vp]),
+        "vimz_acc_step_wait": (i32, [vp, vp, vp]),
         "vimz_acc_step_begin_staged": (i32, [vp, vp, sz, sz, vp, vp, vp]),
         "vimz_acc_step_end": (i32, [vp, vp]),
         "vimz_acc_download": (i32, [vp, vp, vp, vp, vp, vp, vp]),

@@ -1096,6 +1096,27 @@ int vimz_acc_step_begin_staged(vimz_acc* a, const vimz_fr* W2_rest, size_t first
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
+// step_begin in two halves for a host that has something to enqueue in between (another accumulator's staged upload, its
+// own work): _async copies W2 / X2 and enqueues the step, _wait blocks for the two commitments.
+int vimz_acc_step_begin_async(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2) {
+  CHECK_ARG(a && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_async: null argument");
+  CtxGuard g(a->ctx);
+  VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  return acc_step_begin_common(a, X2, nullptr, nullptr, false);
+}
+
+int vimz_acc_step_wait(vimz_acc* a, vimz_point* comm_W2, vimz_point* comm_T) {
+  CHECK_ARG(a && comm_W2 && comm_T, "vimz_acc_step_wait: null argument");
+  vimz_ctx* ctx = a->ctx;
+  CtxGuard g(ctx);
+  if (!a->step_enqueued || a->half_open) return set_error(VIMZ_ERR_ARG, "vimz_acc_step_wait: no enqueued step");
+  VIMZ_CUDA(wait_stream(ctx, ctx->stream));
+  a->fresh_complete = true;
+  memcpy(comm_W2, a->pinned + ACC_PIN_FRESH, 96);
+  memcpy(comm_T, a->pinned + ACC_PIN_FRESH + 96, 96);
+  return VIMZ_OK;
+}
+
 int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
   CtxGuard g(a->ctx);

@@ -486,6 +486,23 @@ class FoldAccumulator:
         check(lib.vimz_acc_step_begin_staged(self._h, C.c_void_p(base), first, count, px, pw, pt))
         return out[:12].copy(), out[12:].copy()
 
+    def step_begin_async(self, W2: np.ndarray, X2) -> None:
+        """Enqueue a step (W2 / X2 host buffers must stay alive until step_wait returns)."""
+        s = self.shape
+        if not (type(W2) is np.ndarray and W2.dtype == np.uint64 and W2.ndim == 2 and W2.flags.c_contiguous):
+            W2 = as_fr(W2)
+        if W2.shape[0] != s.num_vars or W2.shape[1] != 4:
+            raise InvalidWitnessLength(_lib.VIMZ_ERR_LENGTH, "step_begin_async: witness length != num_vars")
+        X2, px = self._fr_ptr(X2, s.num_io)
+        self._pending = (W2, X2)
+        check(lib.vimz_acc_step_begin_async(self._h, C.c_void_p(W2.__array_interface__["data"][0]), px))
+
+    def step_wait(self) -> Tuple[np.ndarray, np.ndarray]:
+        out, pw, pt = self._io()
+        check(lib.vimz_acc_step_wait(self._h, pw, pt))
+        self._pending = None
+        return out[:12].copy(), out[12:].copy()
+
     def step_begin_dev(self, d_W2: int, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         X2, px = self._fr_ptr(X2, self.shape.num_io)
         out, pw, pt = self._io()
