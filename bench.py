@@ -830,10 +830,23 @@ def main_gpu(args, rank, world, local_rank):
             except Exception:
                 traffic = None
     modmul_per_s = entries * MODMUL_PER_MADD / (acc_ms * 1e-3) if acc_ms > 0 else None
+    # the two launch classes of a step separately: commit(T) (1.3 M insertions, fills the GPU) and commit(W2) (0.29 M insertions of a
+    # 93 % 0/1 vector: 4 per thread, latency-bound whatever the kernel does)
+    accT_ms, accT_calls = prof.get("msm_accumulate_kernel_T", (0.0, 0))
+    entries_T = prof.get("msm_entries_T", (0, 0))[1]
+    per_class = None
+    if accT_ms > 0 and acc_calls > accT_calls:
+        tT = entries_T * MODMUL_PER_MADD * IMAD_PER_MODMUL / (accT_ms * 1e-3) / 1e12
+        tW = (entries - entries_T) * MODMUL_PER_MADD * IMAD_PER_MODMUL / ((acc_ms - accT_ms) * 1e-3) / 1e12
+        per_class = {"commit_T": {"insertions_per_launch": entries_T / accT_calls, "launch_us": accT_ms * 1e3 / accT_calls, "timad_per_s": tT,
+                                  "frac": tT / peaks["imad_tops"]},
+                     "commit_W2": {"insertions_per_launch": (entries - entries_T) / (acc_calls - accT_calls),
+                                   "launch_us": (acc_ms - accT_ms) * 1e3 / (acc_calls - accT_calls), "timad_per_s": tW, "frac": tW / peaks["imad_tops"]}}
     roofline = {"kernel": "k_msm_accumulate<%s>" % prim.cv.name, "bound": "imad", "achieved": achieved, "peak": peaks["imad_tops"],
                 "unit": "TIMAD/s", "frac": (achieved / peaks["imad_tops"]) if achieved else None, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peaks["imad_src"],
+                "per_launch_class": per_class,
                 "modmul_per_s": modmul_per_s, "modmul_peak_per_s": peaks.get("modmul_peak"),
                 "modmul_frac": (modmul_per_s / peaks["modmul_peak"]) if modmul_per_s and peaks.get("modmul_peak") else None,
                 "algorithmic": f"{entries} bucket insertions x {MODMUL_PER_MADD} modmul x {IMAD_PER_MODMUL} IMAD over {acc_calls} launches "
@@ -858,8 +871,8 @@ def main_gpu(args, rank, world, local_rank):
                     "algorithmic": f"{ct_bytes} B per step = nnz*8 (col + coefficient index) + 3(m+1)*4 + (n+3)*32 (z2) + 9*m*32 (Az2,Bz2,Cz2 out and in, cached Az1,Bz1,Cz1 in) + m*32 (T) + m*W*4 (digits of T)",
                     "note": "gather-latency / occupancy bound, not bandwidth bound: z2 (4 MB) and the products live in the 126 MB L2, the two kernels "
                             "run ~45 us against ~7 us of pure HBM time (profiles/r2_timeline_fold_step.txt, DESIGN.md section 5)"}
-    phases = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof.items() if k != "msm_entries"}
-    phases_sec = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof_sec.items() if k != "msm_entries"}
+    phases = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof.items() if not k.startswith("msm_entries")}
+    phases_sec = {k: {"ms_per_step": v[0] / steps, "calls": v[1]} for k, v in prof_sec.items() if not k.startswith("msm_entries")}
 
     # Pallas MSM throughput (second half of the metric)
     comm = None

@@ -68,7 +68,7 @@ int vimz_ctx_sync(vimz_ctx* ctx);
  * sequence as a CUDA graph, default 1).  Unknown keys -> VIMZ_ERR_ARG. */
 int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value);
 /* Device-side phase timers, enabled with vimz_ctx_set_option(ctx, "profile", 1): accumulated CUDA-event
- * milliseconds and call counts for "msm_sort", "msm_accumulate" (kernel + combine), "msm_accumulate_kernel",
+ * milliseconds and call counts for "msm_sort", "msm_accumulate" (kernel + combine), "msm_accumulate_kernel", "msm_accumulate_kernel_T" (the commit(T) launches alone; "msm_entries_T" their insertions),
  * "msm_reduce", "cross_term", "axpy", "spmv"; name "msm_entries" returns the number of bucket insertions in *calls.  Synchronises the stream. */
 int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset);
 /* The context's CUDA stream (cudaStream_t as void*), so a caller can time on it with events. */

@@ -323,7 +323,8 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   return set_error(VIMZ_ERR_ARG, std::string("unknown option: ") + key);
 }
 
-static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_reduce", "cross_term", "axpy", "spmv", "msm_accumulate_kernel"};
+static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_reduce", "cross_term", "axpy", "spmv", "msm_accumulate_kernel",
+                                             "msm_accumulate_kernel_T"};
 
 int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset) {
   CHECK_ARG(ctx && name, "vimz_ctx_profile: null argument");
@@ -341,15 +342,23 @@ int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* call
     p.pool.push_back(s.b);
   }
   p.open.clear();
-  for (uint32_t* slot : p.entry_slots) {
+  for (size_t k = 0; k < p.entry_slots.size(); k++) {
+    uint32_t* slot = p.entry_slots[k];
     p.msm_entries += *slot;
+    if (k < p.entry_fused.size() && p.entry_fused[k]) p.msm_entries_fused += *slot;
     p.entry_pool.push_back(slot);
   }
   p.entry_slots.clear();
+  p.entry_fused.clear();
   int rc = VIMZ_ERR_ARG;
   if (strcmp(name, "msm_entries") == 0) {
     if (ms) *ms = 0;
     if (calls) *calls = p.msm_entries;
+    rc = VIMZ_OK;
+  }
+  if (strcmp(name, "msm_entries_T") == 0) {  // insertions of the commit(T) launches alone
+    if (ms) *ms = 0;
+    if (calls) *calls = p.msm_entries_fused;
     rc = VIMZ_OK;
   }
   // statistics of the last MSM of a lane: "lane0_entries" (bucket insertions), "lane0_nmid" / "lane0_ngiant" /
@@ -381,6 +390,7 @@ int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* call
   if (reset) {
     for (int k = 0; k < PROF_COUNT; k++) { p.ms[k] = 0; p.calls[k] = 0; }
     p.msm_entries = 0;
+    p.msm_entries_fused = 0;
   }
   return rc == VIMZ_OK ? rc : set_error(VIMZ_ERR_ARG, std::string("unknown profile timer: ") + name);
 }
@@ -954,23 +964,30 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   // FIRST: a captured graph dispatches its nodes in creation order, a few microseconds apart, and with the aux lane in
   // front the first cross-term kernel started ~20 us late.
   const bool two_lanes = ctx->opt_aux_lane;
+  // Both final kernels also write their result into this accumulator's pinned block (mapped host memory): no D2H copy node.
+  struct HostOut {  // cleared on every exit path
+    vimz_ctx* c;
+    ~HostOut() { c->ws.host_out = nullptr; c->ws_aux.host_out = nullptr; }
+  } host_out_guard{ctx};
   if (two_lanes) {
     VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
     VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
   } else {  // one lane (used by the profiled pass so kernel times are not inflated by the other lane)
+    ctx->ws.host_out = a->pinned + ACC_PIN_FRESH;
     VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
   }
   // T = cross term (mat-vecs with z2 + element-wise combination), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2));  // also histograms T's digits
   // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
   // so nothing recoded T: the commit then does its own, empty, digit pass)
+  ctx->ws.host_out = a->pinned + ACC_PIN_FRESH + 96;
   VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
   if (two_lanes) {
+    ctx->ws_aux.host_out = a->pinned + ACC_PIN_FRESH;
     VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
     VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
+    VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   }
-  if (two_lanes) VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
-  VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH, fresh, 2 * 96, cudaMemcpyDeviceToHost, st));
   return VIMZ_OK;
 }
 

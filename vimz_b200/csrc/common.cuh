@@ -85,6 +85,9 @@ struct MsmWorkspace {
   vimz::DevBuf deferred;   // [max_giants] XYZZ: weighted sums of the giant buckets kept out of the bucket array
   vimz::DevBuf scal;       // staged scalars (host-pointer entry points)
   vimz::DevBuf result;     // Jacobian results (device)
+  // set by a caller around ONE msm launch sequence: the final kernel also writes its Jacobian result here -- mapped page-locked
+  // host memory the host reads after the stream completes (saves the D2H copy node of a fold step and its dispatch gap)
+  void* host_out = nullptr;
   uint32_t last_M = 0;     // buckets of the last MSM run on this workspace (statistics: vimz_ctx_profile "laneK_*")
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release(); digits.release();
@@ -95,7 +98,9 @@ struct MsmWorkspace {
 
 // Optional per-phase device timers (vimz_ctx_set_option("profile", 1)): event pairs are recorded on the
 // context stream around a phase and resolved when vimz_ctx_profile() is called.
-enum ProfTimer { PROF_MSM_SORT = 0, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_CROSS_TERM, PROF_AXPY, PROF_SPMV, PROF_MSM_ACC_KERNEL, PROF_COUNT };
+enum ProfTimer { PROF_MSM_SORT = 0, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_CROSS_TERM, PROF_AXPY, PROF_SPMV, PROF_MSM_ACC_KERNEL,
+                 PROF_MSM_ACC_KERNEL_FUSED,  // the accumulation launches whose digits came from the fused cross term: commit(T)
+                 PROF_COUNT };
 struct ProfSpan { cudaEvent_t a, b; int timer; };
 struct Profiler {
   bool on = false;
@@ -104,7 +109,9 @@ struct Profiler {
   double ms[PROF_COUNT] = {0};
   uint64_t calls[PROF_COUNT] = {0};
   uint64_t msm_entries = 0;            // bucket insertions (non-zero digits) seen by profiled MSMs
+  uint64_t msm_entries_fused = 0;      // ... of which in commit(T) launches (digits recoded by the cross term)
   std::vector<uint32_t*> entry_slots;  // pinned words receiving each MSM's entry total
+  std::vector<bool> entry_fused;       // parallel to entry_slots
   std::vector<uint32_t*> entry_pool;
 };
 
@@ -132,7 +139,7 @@ struct vimz_ctx {
   bool opt_cross_cache = true;  // accumulators created from now on keep (Az1, Bz1, Cz1) resident instead of recomputing them
   bool opt_aux_lane = true; // fold step: commit(W2) on the aux stream beside cross term + commit(T)
   long opt_direct_c = 0;       // digit width of the direct table (0 = chosen by key length)
-  long opt_direct_bps = 3;     // k_msm_direct blocks per SM (1..4): at 2 the two commits of a fold step (two stream lanes) are resident together
+  long opt_direct_bps = 2;     // k_msm_direct blocks per SM (1..4): at 2 the two commits of a fold step (two stream lanes) are resident together
   long opt_direct_max = 32768; // keys up to this many points get the direct multiples table (256 KB per point); 0 = never
   uint64_t launches = 0;
   MsmWorkspace ws, ws_aux;
@@ -147,7 +154,7 @@ struct ProfScope {
   ProfSpan span;
   bool active;
   cudaStream_t st;
-  ProfScope(vimz_ctx* c, int timer, cudaStream_t stream) : ctx(c), active(c->prof.on), st(stream) {
+  ProfScope(vimz_ctx* c, int timer, cudaStream_t stream) : ctx(c), active(c && c->prof.on), st(stream) {
     if (!active) return;
     auto get = [&]() {
       cudaEvent_t e;

@@ -104,7 +104,7 @@ int impl_msm_direct(vimz_ctx* ctx, cudaStream_t st, MsmWorkspace& ws, const vimz
   ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
   ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
   k_msm_direct<C><<<blocks, 128, 0, st>>>(ws.digits.as<uint32_t>(), (uint32_t)n, nwin, (uint32_t)ck->n, (uint32_t)first, c - 1, ck->dtable,
-                                          ws.partials.ptr, ws.cls.as<uint32_t>(), d_out);
+                                          ws.partials.ptr, ws.cls.as<uint32_t>(), d_out, ws.host_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -215,11 +215,13 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
     else VIMZ_CUDA(cudaMallocHost(&slot, 4));
     VIMZ_CUDA(cudaMemcpyAsync(slot, offsets + M, 4, cudaMemcpyDeviceToHost, st));
     ctx->prof.entry_slots.push_back(slot);
+    ctx->prof.entry_fused.push_back(counted);
   }
   {
     ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
     {
       ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
+      ProfScope prof_fused(counted ? ctx : nullptr, PROF_MSM_ACC_KERNEL_FUSED, st);
       k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, seg_min, ws.buckets.ptr, ws.partials.ptr);
     }
     VIMZ_LAUNCH_CHECK(ctx);
@@ -235,7 +237,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   k_reduce_chunks<C><<<ceil_div((size_t)T * 4, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
   k_reduce_tail<C><<<dim3(G, nb + 1 + (defer ? 1 : 0)), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, logK, ws.bitsums.ptr, ws.scaled.ptr,
-                                                                      cb.ctrl + CTRL_REDUCE, d_out, offsets, M, nthreads, seg_min, ws.partials.ptr, cb,
+                                                                      cb.ctrl + CTRL_REDUCE, d_out, ws.host_out, offsets, M, nthreads, seg_min, ws.partials.ptr, cb,
                                                                       defer ? ws.deferred.ptr : nullptr);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
@@ -345,7 +347,7 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
     ma.W = d_W2; ma.tail = d_tail2; ma.out = p2;
     k_matvec_stream<typename C::Fs><<<(uint32_t)s->n_chunks, 256, MATVEC_SMEM, ctx->stream>>>(ma);
     VIMZ_LAUNCH_CHECK(ctx);
-    k_cross_finish<typename C::Fs><<<ceil_div(s->m, 256), 256, 0, ctx->stream>>>(p1, p2, d_tail1, (uint32_t)s->m, d_T, dc);
+    k_cross_finish<typename C::Fs><<<ceil_div(s->m, CROSS_FINISH_THREADS), CROSS_FINISH_THREADS, 0, ctx->stream>>>(p1, p2, d_tail1, (uint32_t)s->m, d_T, dc);
     VIMZ_LAUNCH_CHECK(ctx);
     return VIMZ_OK;
   }

@@ -47,6 +47,7 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, in
 // (digit 1 of window 0) and T's top window lands in a few dozen buckets: same-address atomics serialise in L2 and
 // made the histogram atomics-bound (k_msm_scatter aggregates its returning atomics the same way).  The lanes that are converged here and target the same counter
 // are matched (MATCH.ANY); one of them adds the group's size.
+constexpr uint32_t AGG_MAX_DIGIT = 16;  // digits up to this magnitude take the warp-aggregated path
 __device__ __forceinline__ void warp_count_add(uint32_t* counter) {
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
@@ -70,7 +71,11 @@ __device__ __forceinline__ void recode_scalar(const Fp<F>& mont, int c, int nwin
     digits[(size_t)j * stride + i] = mag | ((neg != flip) ? 0x80000000u : 0u);
     next = j + 1;
     if (counts) {  // nullptr: digits only (direct-table keys have no buckets to size)
-      if (AGG) warp_count_add(&counts[mag - 1]);
+      // Only SMALL digits are shared by many lanes (the 0/1 wires of a witness: digit 1 of window 0; the one- or two-bit top
+      // window of the cross term): those are matched and added once per group.  The other windows hold uniform c-bit digits,
+      // for which MATCH.ANY found nothing to merge and cost more than the atomics it saved (k_cross_finish: 45 % of its stall
+      // samples were the short scoreboard of the match unit, 52 us for 131 k rows) -- they go out as plain reductions.
+      if (AGG && mag <= AGG_MAX_DIGIT) warp_count_add(&counts[mag - 1]);
       else atomicAdd(&counts[mag - 1], 1u);
     }
   });

@@ -161,7 +161,7 @@ __device__ __noinline__ QPoint<C> q_add(QPoint<C> p1, QPoint<C> p2) { return q_a
 
 // acc (quad) -> Jacobian {X*ZZ^4, Y*ZZZ^4, ZZ*ZZZ}; identity -> (0, R, 0).  Writes 96 bytes from the quad.
 template <class C>
-VIMZ_DI void q_store_jacobian(const QPoint<C>& p, void* out, bool do_store = true) {
+VIMZ_DI void q_store_jacobian(const QPoint<C>& p, void* out, bool do_store = true, void* out2 = nullptr) {
   using F = Fp<typename C::Fb>;
   const int role = threadIdx.x & 3;
   const bool ident = p.is_identity();
@@ -172,7 +172,10 @@ VIMZ_DI void q_store_jacobian(const QPoint<C>& p, void* out, bool do_store = tru
   F other = role == 2 ? zzz : p.c;                        // L0: X, L1: Y, L2: ZZZ
   F res = fp_mul_call<typename C::Fb>(role == 2 ? zz : q4, other);  // L0: X*ZZ^4, L1: Y*ZZZ^4, L2: ZZ*ZZZ
   if (ident) res = role == 1 ? F::one() : F::zero();
-  if (role < 3 && do_store) res.store(reinterpret_cast<char*>(out) + 32 * role);
+  if (role < 3 && do_store) {
+    res.store(reinterpret_cast<char*>(out) + 32 * role);
+    if (out2) res.store(reinterpret_cast<char*>(out2) + 32 * role);  // second copy: page-locked host memory the caller polls for
+  }
 }
 
 // Jacobian {X, Y, Z} (96 bytes) -> quad XYZZ (ZZ = Z^2, ZZZ = Z^3); Z = 0 -> identity

@@ -129,14 +129,21 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __re
   for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
     const uint32_t i = base + lane;
     const uint32_t d = i < n ? __ldg(row + i) : 0u;
-    const unsigned active = __ballot_sync(0xffffffffu, d != 0);
-    if (d != 0) {
-      const uint32_t b = (d & 0x7fffffffu) - 1;
-      const unsigned peers = __match_any_sync(active, b);
+    const uint32_t b = (d & 0x7fffffffu) - 1;
+    // only small digits are shared by many lanes (see recode_scalar): they claim their slots per group of equal digits,
+    // everything else takes its slot with a plain returning atomic (uniform digits: nothing to merge, and the match unit
+    // was this kernel's top stall)
+    const bool small = d != 0 && b < AGG_MAX_DIGIT;
+    const unsigned smask = __ballot_sync(0xffffffffu, small);
+    if (small) {
+      const unsigned peers = __match_any_sync(smask, b);
       const int leader = __ffs(peers) - 1;
       uint32_t slot = 0;
       if ((int)lane == leader) slot = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
       slot = __shfl_sync(peers, slot, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      sorted[slot] = (j * table_stride + first + i) | (d & 0x80000000u);
+    } else if (d != 0) {
+      const uint32_t slot = atomicAdd(&cursor[b], 1u);
       sorted[slot] = (j * table_stride + first + i) | (d & 0x80000000u);
     }
   }
@@ -379,6 +386,7 @@ struct TailFinal {
   uint32_t max_giants;
   uint32_t* cnt;         // arrival counter
   void* out_jac;
+  void* out_host;        // optional second copy of the result in mapped page-locked host memory (nullptr: none)
 };
 template <class C>
 __device__ __forceinline__ void reduce_arrive_final(const TailFinal& f) {
@@ -399,7 +407,7 @@ __device__ __forceinline__ void reduce_arrive_final(const TailFinal& f) {
     acc = q_add<C>(acc, p);
   }
   acc = q_warp_reduce<C>(acc);
-  q_store_jacobian<C>(acc, f.out_jac, (threadIdx.x & 31) < 4);
+  q_store_jacobian<C>(acc, f.out_jac, (threadIdx.x & 31) < 4, f.out_host);
 }
 
 // Giant buckets (cut into more than COMBINE_MID pieces: the 0/1 bucket of a witness vector, the one- or two-bit top window of
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb, int logK,
                                                      void* __restrict__ bitsums, void* __restrict__ scaled, uint32_t* __restrict__ cnt,
-                                                     void* __restrict__ out_jac,
+                                                     void* __restrict__ out_jac, void* __restrict__ out_host,
                                                      // deferred giants (deferred == nullptr: none): row nb + 1 of the grid sums them
                                                      const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min,
                                                      const void* __restrict__ partials, MsmCombine cb, void* __restrict__ deferred) {
@@ -583,7 +591,7 @@ __global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ ch
   const int s = blockIdx.y, G = gridDim.x;
   TailFinal fin;
   fin.scaled = scaled; fin.nsums = nb + 1; fin.deferred = deferred; fin.ngiant_p = cb.ctrl + CTRL_NGIANT; fin.max_giants = cb.max_giants;
-  fin.cnt = cnt + nb + 1; fin.out_jac = out_jac;
+  fin.cnt = cnt + nb + 1; fin.out_jac = out_jac; fin.out_host = out_host;
   if (s == nb + 1) {  // giant role (only launched when giants are deferred)
     if (cb.ctrl[CTRL_NGIANT] == 0) return;
     const uint32_t L = seg_len(offsets[M], nthreads, seg_min);
@@ -738,7 +746,7 @@ __global__ void __launch_bounds__(128) k_precompute_direct(const void* __restric
 template <class C>
 __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restrict__ digits, uint32_t n, int nwin, uint32_t ck_n, uint32_t first,
                                                        int cshift, const void* __restrict__ dtable, void* __restrict__ partials,
-                                                       uint32_t* __restrict__ ctrl, void* __restrict__ out_jac) {
+                                                       uint32_t* __restrict__ ctrl, void* __restrict__ out_jac, void* __restrict__ out_host) {
   __shared__ __align__(16) uint32_t smem[4 * 32];
   __shared__ uint32_t flag;
   const uint32_t nthreads = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -796,7 +804,7 @@ __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restric
   __threadfence();
   q = quad < ngroups ? QPoint<C>::load_cg(parts + (size_t)(nblocks + quad) * 128) : QPoint<C>::identity();
   q = q_block_reduce_128<C>(q, smem);
-  if (threadIdx.x < 32) q_store_jacobian<C>(q, out_jac, threadIdx.x < 4);
+  if (threadIdx.x < 32) q_store_jacobian<C>(q, out_jac, threadIdx.x < 4, out_host);
 }
 
 // ---- small single-thread group kernels ---------------------------------------------------------

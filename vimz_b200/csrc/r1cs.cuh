@@ -353,8 +353,11 @@ __global__ void __launch_bounds__(256, 4) k_matvec_stream(MatvecStreamArgs s) {
 
 // T[row] = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1 from the two product triples p1 = (Az1, Bz1, Cz1)[3][m], p2 = (Az2, Bz2, Cz2)[3][m];
 // recodes / histograms T's digits for the commit that follows (dc.digits != nullptr).
+// 128-thread blocks (10 K registers each): on the secondary curve this kernel must find room on SMs whose register files
+// already hold three k_msm_direct blocks of the other lane -- with 256-thread blocks it waited ~60 us for them to drain.
+constexpr int CROSS_FINISH_THREADS = 128;
 template <class F>
-__global__ void __launch_bounds__(256) k_cross_finish(const void* __restrict__ p1, const void* __restrict__ p2, const void* __restrict__ tail1,
+__global__ void __launch_bounds__(CROSS_FINISH_THREADS) k_cross_finish(const void* __restrict__ p1, const void* __restrict__ p2, const void* __restrict__ tail1,
                                                       uint32_t m, void* __restrict__ T, DigitCount dc) {
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= m) return;  // (the warp-aggregated histogram matches the lanes that are still converged)

@@ -61,7 +61,8 @@ class Engine:
     def profile(self, reset: bool = False) -> dict:
         """Device-side phase timers (enable with set_option("profile", 1)): name -> (ms, calls)."""
         out = {}
-        names = ["msm_sort", "msm_accumulate", "msm_accumulate_kernel", "msm_reduce", "cross_term", "axpy", "spmv", "msm_entries"]
+        names = ["msm_sort", "msm_accumulate", "msm_accumulate_kernel", "msm_accumulate_kernel_T", "msm_reduce", "cross_term", "axpy", "spmv",
+                 "msm_entries_T", "msm_entries"]
         for i, name in enumerate(names):
             ms, calls = C.c_double(0), C.c_uint64(0)
             check(lib.vimz_ctx_profile(self._h, name.encode(), C.byref(ms), C.byref(calls), 1 if (reset and i == len(names) - 1) else 0))
