@@ -311,6 +311,9 @@ class GpuFold:
             self.eng.set_option("spin_wait", int(os.environ["VIMZ_SPIN_WAIT"]))
         if os.environ.get("VIMZ_ACC_BLOCKS"):
             self.eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
+        for kv in filter(None, os.environ.get("VIMZ_OPTS", "").split(",")):   # A/B experiments: VIMZ_OPTS=bitrow_fold=0,graph=1
+            key, val = kv.split("=")
+            self.eng.set_option(key, int(val))
         sh = self.sh
         self.shape = R1CSShape(self.eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
         nck = max(sh.num_cons, sh.num_vars)

@@ -62,7 +62,9 @@ int vimz_ctx_sync(vimz_ctx* ctx);
  * "msm_direct_c" (digit width of that table, 0 = by key length: 10 up to 16 384 points, else 8),
  * "msm_direct_max" (keys uploaded afterwards with at most this many points keep ALL digit multiples resident -- 256 KB per point at c = 8 --
  * and commit without buckets; default 32768, 0 = always the bucket pipeline; a forced msm_window also selects buckets), "msm_defer_giants" (0/1, default 1: buckets cut into hundreds of segments are summed beside
- * the bucket reduction instead of in front of it), "spin_wait" (0/1, default 1: step_begin polls its stream instead of a blocking wait), "cross_cache" (0/1, default 1:
+ * the bucket reduction instead of in front of it), "bitrow_fold" (0/1, default 1: accumulators created afterwards
+ * on shapes with many booleanity rows b*(b-1)=0 keep K_S = sum over those rows of (A z1)_i ck_i and commit T + [row] A z1 instead of T -- half
+ * of those rows then insert nothing; same comm_T), "spin_wait" (0/1, default 1: step_begin polls its stream instead of a blocking wait), "cross_cache" (0/1, default 1:
  * accumulators created afterwards keep (Az1, Bz1, Cz1) of the running instance resident and fold them in step_end instead of
  * recomputing them in every step_begin), "aux_lane" (0/1), "profile" (0/1), "graph" (0/1: replay a fold step's launch
  * sequence as a CUDA graph, default 1).  Unknown keys -> VIMZ_ERR_ARG. */

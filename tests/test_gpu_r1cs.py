@@ -354,8 +354,8 @@ def test_full_size_grayscale_fold_bit_exact_vs_c_oracle(coracle):
         spill = sum(1 for t in mont_to_ints(T, q) if 135 <= min(t, q - t).bit_length() <= 150)
         assert spill > 10_000, "T must reach into the tenth 15-bit window like the mid-proof steps bench.py times"
         stats = eng.lane_stats()
-        # (copy rows have T = 0 and insert nothing; the others carry ten or more digits)
-        assert stats["lane0_entries"] > 7 * sh.num_cons and stats["lane0_ngiant"] >= 1, stats
+        # (with the booleanity-row fold the rows whose fresh bit is 0 insert nothing; the others carry ten or more digits)
+        assert stats["lane0_entries"] > 4 * sh.num_cons and stats["lane0_ngiant"] >= 1, stats
         assert np.array_equal(acc.last_T(), T), f"T differs at step {k}"
         exp_T, exp_W2 = coracle.msm(cid, T, Bm, 8), coracle.msm(cid, W2, Bm, 8)
         assert eng.to_affine_ints(comm_T) == _affine(coracle, c, exp_T), f"comm_T differs at step {k}"
@@ -371,6 +371,58 @@ def test_full_size_grayscale_fold_bit_exact_vs_c_oracle(coracle):
     assert eng.to_affine_ints(U.comm_W) == _affine(coracle, c, cW) and eng.to_affine_ints(U.comm_E) == _affine(coracle, c, cE)
     vimz_b200.is_sat_relaxed(shape, ck, U, W)       # and the folded instance verifies (folding.rs:53-55)
     acc.close(); shape.close(); ck.close(); eng.close()
+
+
+@pytest.mark.parametrize("fold_on", [1, 0])
+def test_booleanity_row_fold_is_exact(fold_on, coracle):
+    """The accumulator's K_S trick (option bitrow_fold, default on: commit T + [booleanity row] Az1 and subtract the running
+    K_S = sum over those rows of (A z1)_i ck_i) must give the SAME comm_T, T and folded pairs as the plain path and as the CPU
+    chain -- from a loaded mid-proof instance (K_S initialised by a general MSM), over several steps (K_S folded on the side
+    stream), and for a witness that VIOLATES a booleanity constraint (a fresh wire that is neither 0 nor 1: the exact slow path
+    of k_masked_base_sum), since commit_T is defined for any vectors."""
+    c = P.PALLAS
+    q = c.q
+    eng = vimz_b200.Engine("pallas", 0)
+    eng.set_option("bitrow_fold", fold_on)
+    eng.set_option("msm_direct_max", 0)            # the fold lives on the bucket pipeline
+    sh, shape, ck, Bm = _setup(eng, c, 0.02, seed=81)
+    assert sh.nbits * 8 >= sh.num_cons              # most rows of this shape are booleanity rows
+    rng = random.Random(13)
+    wit = []
+    for k in range(6):
+        Wi, Xi = S.synthetic_witness(sh, 600 + k)
+        if k == 3:                                   # break three booleanity constraints: wires that are not bits
+            Wi[0], Wi[5], Wi[sh.nbits - 1] = 2, rng.randrange(q), q - 1
+        wit.append((ints_to_mont(Wi, q), ints_to_mont(Xi, q)))
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(6)]
+    ref = _oracle_fold_chain(coracle, c, sh, Bm, wit, chal)
+    acc = FoldAccumulator(shape, ck)
+    st = ref[1]                                      # start from the CPU's state after two folds
+    acc.load(RelaxedR1CSInstance(st["cW"], st["cE"], st["X"], st["u"]), RelaxedR1CSWitness(st["W"], st["E"]))
+    for k in range(2, 6):
+        comm_W2, comm_T = acc.step_begin(*wit[k])
+        assert eng.to_affine_ints(comm_T) == _affine(coracle, c, ref[k]["comm_T"]), (fold_on, k)
+        assert eng.to_affine_ints(comm_W2) == _affine(coracle, c, ref[k]["comm_W2"])
+        assert np.array_equal(acc.last_T(), ref[k]["T"])                 # the stored T is the true one, not the shifted one
+        acc.step_end(chal[k])
+    U, W = acc.download()
+    assert np.array_equal(W.W, ref[5]["W"]) and np.array_equal(W.E, ref[5]["E"]) and np.array_equal(U.u, ref[5]["u"])
+    assert eng.to_affine_ints(U.comm_E) == _affine(coracle, c, ref[5]["cE"]) and eng.to_affine_ints(U.comm_W) == _affine(coracle, c, ref[5]["cW"])
+    # the fold must actually have been in use: with it, a step's commit(T) inserts far fewer digits
+    entries = eng.lane_stats()["lane0_entries"]
+    acc.reset()
+    for k in range(2):
+        comm_W2, comm_T = acc.step_begin(*wit[k])
+        assert eng.to_affine_ints(comm_T) == _affine(coracle, c, ref[k]["comm_T"])
+        acc.step_end(chal[k])
+    acc.close(); shape.close(); ck.close(); eng.close()
+    test_booleanity_row_fold_is_exact.entries[fold_on] = entries
+    if len(test_booleanity_row_fold_is_exact.entries) == 2:
+        on, off = test_booleanity_row_fold_is_exact.entries[1], test_booleanity_row_fold_is_exact.entries[0]
+        assert on < 0.75 * off, (on, off)
+
+
+test_booleanity_row_fold_is_exact.entries = {}
 
 
 def test_fold_from_r1cs_and_wtns_files_bn254(tmp_path, engines, coracle):

@@ -172,6 +172,7 @@ static void shape_release(vimz_shape* s) {
     if (s->chunk_desc) cudaFree(s->chunk_desc);
     if (s->long_rows) cudaFree(s->long_rows);
     if (s->mid_rows) cudaFree(s->mid_rows);
+    if (s->rowflag) cudaFree(s->rowflag);
     delete s;
   }
   ctx_release(ctx);
@@ -314,6 +315,10 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   if (strcmp(key, "msm_defer_giants") == 0) {
     ctx->opt_defer_giants = value != 0;
     alloc_epoch()++;
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "bitrow_fold") == 0) {  // applies to accumulators created afterwards
+    ctx->opt_bitrow_fold = value != 0;
     return VIMZ_OK;
   }
   if (strcmp(key, "spin_wait") == 0) {
@@ -708,11 +713,28 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
       return set_error(VIMZ_ERR_ARG, "vimz_shape_upload: shape too large (packed index stream)");
     }
   }
+  // booleanity rows b * (b - 1) = 0: A = {(b, +1)}, B = {(b, +1), (one, -1)} in either order, C = {} -- `one` is column num_vars
+  // (the u slot of z = (W, u, X)); dictionary slots 0 / 1 are +1 / -1.  See k_cross_finish for what the accumulator does with them.
+  std::vector<uint8_t> rowflag(num_cons, 0);
+  for (size_t i = 0; i < num_cons; i++) {
+    const uint32_t a0 = h_rowptr[0][i], a1 = h_rowptr[0][i + 1], b0 = h_rowptr[1][i], b1 = h_rowptr[1][i + 1];
+    if (a1 - a0 != 1 || b1 - b0 != 2 || h_rowptr[2][i + 1] != h_rowptr[2][i]) continue;
+    const uint32_t bcol = h_col[0][a0];
+    if (bcol >= num_vars || h_vidx[0][a0] != 0) continue;
+    bool ok = false;
+    for (int k = 0; k < 2 && !ok; k++) {
+      const uint32_t p = b0 + k, q2 = b0 + 1 - k;
+      ok = h_col[1][p] == bcol && h_vidx[1][p] == 0 && h_col[1][q2] == (uint32_t)num_vars && h_vidx[1][q2] == 1;
+    }
+    if (ok) { rowflag[i] = 1; s->n_bitrows++; }
+  }
   s->n_dict = dict.values.size();
   if (e == cudaSuccess) e = cudaMalloc(&s->chunk_stream, stream.size() * sizeof(uint2));
   if (e == cudaSuccess) e = cudaMemcpy(s->chunk_stream, stream.data(), stream.size() * sizeof(uint2), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&s->chunk_desc, std::max<size_t>(desc.size(), 1) * sizeof(ChunkDesc));
   if (e == cudaSuccess && !desc.empty()) e = cudaMemcpy(s->chunk_desc, desc.data(), desc.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && num_cons) e = cudaMalloc(&s->rowflag, num_cons);
+  if (e == cudaSuccess && num_cons) e = cudaMemcpy(s->rowflag, rowflag.data(), num_cons, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&s->dict, s->n_dict * 32);
   if (e == cudaSuccess) e = cudaMemcpy(s->dict, dict.values.data(), s->n_dict * 32, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -766,7 +788,7 @@ int vimz_commit_T(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck,
     VIMZ_CUDA(cudaMemcpyAsync(t1 + 32, X1, s->io * 32, cudaMemcpyHostToDevice, st));
     VIMZ_CUDA(cudaMemcpyAsync(t2 + 32, X2, s->io * 32, cudaMemcpyHostToDevice, st));
   }
-  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr, ck, nullptr, nullptr));
+  VIMZ_TRY(vt->cross_term(ctx, s, ctx->tmp0.ptr, t1, ctx->tmp1.ptr, t2, ctx->tmp3.ptr, ck, nullptr, nullptr, nullptr));
   if (T_out) VIMZ_CUDA(cudaMemcpyAsync(T_out, ctx->tmp3.ptr, s->m * 32, cudaMemcpyDeviceToHost, st));
   VIMZ_TRY(vt->msm(ctx, 0, ck, 0, ctx->tmp3.ptr, s->m, ctx->ws.result.ptr, s->m > 0));  // no rows: no cross term ran, nothing was recoded
   return fetch_points(ctx, ctx->ws.result.ptr, comm_T, 96);
@@ -796,6 +818,10 @@ int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r, const vimz_fr* W1, const 
 
 // ---- device-resident running instance --------------------------------------------------------------
 constexpr size_t ACC_PIN_FRESH = 0, ACC_PIN_COMBINED = 256, ACC_PIN_STAGE = 512;  // layout of vimz_acc::pinned
+// vimz_acc::comms, in Jacobian points: the running triple (comm_W, comm_E, K_S), then one (comm_W2, comm_T, P_S) triple per parity
+// slot -- step_end folds the three pairs with one launch: running[k] += r * fresh[k]
+constexpr size_t ACC_SLOT_KS = 2, ACC_SLOTS = 9;
+static inline char* acc_fresh(const vimz_acc* a, int parity) { return (char*)a->comms + (3 + 3 * parity) * 96; }
 void vimz_acc_destroy(vimz_acc* a) {
   if (!a) return;
   vimz_ctx* ctx = a->ctx;
@@ -804,7 +830,7 @@ void vimz_acc_destroy(vimz_acc* a) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     cudaStreamSynchronize(ctx->aux);
-    void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2};
+    void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2, a->ksum_scratch};
     for (void* b : bufs)
       if (b) cudaFree(b);
     if (a->pinned) cudaFreeHost(a->pinned);
@@ -813,6 +839,7 @@ void vimz_acc_destroy(vimz_acc* a) {
     if (a->ev_main) cudaEventDestroy(a->ev_main);
     if (a->ev_w2) cudaEventDestroy(a->ev_w2);
     if (a->ev_aux) cudaEventDestroy(a->ev_aux);
+    if (a->ev_ksum) cudaEventDestroy(a->ev_ksum);
     for (int k = 0; k < 2; k++)
       if (a->ev_side[k]) cudaEventDestroy(a->ev_side[k]);
   }
@@ -846,11 +873,18 @@ static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, con
     if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, ctx->stream);
   };
   alloc0(&a->W1, nb); alloc0(&a->W2, nb); alloc0(&a->E1, mb); alloc0(&a->T, mb);
-  alloc0(&a->tail1, tb); alloc0(&a->tail2, tb); alloc0(&a->comms, 6 * 96 + 2 * 32);
+  alloc0(&a->tail1, tb); alloc0(&a->tail2, tb); alloc0(&a->comms, ACC_SLOTS * 96);
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&a->pinned), ACC_PIN_STAGE + tb);
   if (ctx->opt_cross_cache) {  // the default instance is all zero, and so are its products
     alloc0(&a->cache1, 3 * mb);
     alloc0(&a->cache2, 3 * mb);
+  }
+  // booleanity-row fold: worth it when a good share of the rows qualifies; needs the cached products (K_S folds like them) and
+  // the bucket pipeline (a direct-table key has no final stage that subtracts K_S -- and the shapes it serves have no such rows)
+  a->use_ks = ctx->opt_bitrow_fold && a->cache1 && !ck->dtable && s->rowflag && s->n_bitrows * 8 >= s->m && s->n_bitrows >= 32;
+  if (a->use_ks) {
+    alloc0(&a->ksum_scratch, masked_sum_scratch_bytes(ctx));  // (the arrival counters reset themselves afterwards)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_ksum, cudaEventDisableTiming);  // "(A z2) is complete" inside a step
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_w2, cudaEventDisableTiming);
@@ -924,6 +958,12 @@ int vimz_acc_load(vimz_acc* a, const vimz_fr* W, const vimz_fr* E, const vimz_fr
     char* c1 = (char*)a->cache1;
     VIMZ_TRY(curve_vtable(ctx->curve)->spmv3(ctx, s, a->W1, a->tail1, c1, c1 + s->m * 32, c1 + 2 * s->m * 32));
   }
+  if (a->use_ks && s->m) {  // K_S of the loaded instance: commit of (A z1) restricted to the booleanity rows, once (general MSM)
+    const CurveVTable* vt = curve_vtable(ctx->curve);
+    VIMZ_TRY(ctx->tmp5.reserve(std::max<size_t>(s->m * 32, 32)));
+    VIMZ_TRY(vt->mask_rows(ctx, st, a->cache1, s->rowflag, s->m, ctx->tmp5.ptr));
+    VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, ctx->tmp5.ptr, s->m, (char*)a->comms + ACC_SLOT_KS * 96, false));
+  }
   VIMZ_CUDA(cudaStreamSynchronize(st));
   return VIMZ_OK;
 }
@@ -943,13 +983,45 @@ int vimz_acc_reset(vimz_acc* a) {
   VIMZ_CUDA(cudaMemsetAsync(a->W1, 0, nb, st));
   VIMZ_CUDA(cudaMemsetAsync(a->E1, 0, mb, st));
   VIMZ_CUDA(cudaMemsetAsync(a->tail1, 0, tb, st));
-  VIMZ_CUDA(cudaMemsetAsync(a->comms, 0, 6 * 96 + 2 * 32, st));
+  VIMZ_CUDA(cudaMemsetAsync(a->comms, 0, ACC_SLOTS * 96, st));
   if (a->cache1) VIMZ_CUDA(cudaMemsetAsync(a->cache1, 0, 3 * mb, st));
   VIMZ_CUDA(cudaStreamSynchronize(st));
   a->half_open = false;
   a->step_enqueued = false;
   a->fresh_complete = false;
   return VIMZ_OK;
+}
+
+// Cross term + commit(T) on the main lane.  With the booleanity-row fold (vimz_acc::use_ks) the streamed kernels recode the digits
+// of T' = T + [bit row] Az1 and the final kernel of the MSM subtracts K_S, so `d_comm_T` receives the true commit(T).  K_S is folded
+// by the PREVIOUS step_end on the side stream (its scalar multiplication takes ~0.4 ms and was issued a whole step of the other
+// curve ago): the final kernel -- only that one -- waits for that event.
+static int enqueue_cross_commit_T(vimz_acc* a, void* d_comm_T, void* host_out) {
+  vimz_ctx* ctx = a->ctx;
+  const vimz_shape* s = a->shape;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  const bool shifted = a->use_ks && ctx->opt_cross_stream && s->n_chunks > 0 && s->m > 0;
+  struct Reset {
+    vimz_ctx* c;
+    ~Reset() { c->ws.host_out = nullptr; c->ws.sub_jac = nullptr; c->ws.sub_event = nullptr; }
+  } reset{ctx};
+  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2, shifted ? s->rowflag : nullptr));
+  if (a->use_ks) VIMZ_CUDA(cudaEventRecord(a->ev_ksum, ctx->stream));  // (A z2) is complete: the aux lane may sum P_S
+  ctx->ws.host_out = host_out;
+  if (shifted) {
+    ctx->ws.sub_jac = (char*)a->comms + ACC_SLOT_KS * 96;
+    ctx->ws.sub_event = a->ev_side[a->parity ^ 1];
+  }
+  // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
+  // so nothing recoded T: the commit then does its own, empty, digit pass)
+  return vt->msm(ctx, 0, a->ck, 0, a->T, s->m, d_comm_T, s->m > 0);
+}
+
+// P_S = sum over the booleanity rows of (A z2)_i ck_i (what K_S gains, times r, in step_end): a plain sum of the ~55 k bases whose
+// fresh wire is 1, into the third slot of the step's fresh triple.  Needs the mat-vec of the step; off the critical lane.
+static int enqueue_ps(vimz_acc* a, cudaStream_t st, char* fresh) {
+  if (!(a->use_ks && a->shape->m)) return VIMZ_OK;
+  return curve_vtable(a->ctx->curve)->masked_base_sum(a->ctx, st, a->cache2, a->shape->rowflag, a->shape->m, a->ck, a->ksum_scratch, fresh + 2 * 96);
 }
 
 // The stream work of step_begin after W2 is resident: everything here has fixed addresses, so it can be captured.
@@ -977,14 +1049,15 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
     VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
   }
   // T = cross term (mat-vecs with z2 + element-wise combination), comm_T = commit(ck, T)      (commit_T)
-  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2));  // also histograms T's digits
-  // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
-  // so nothing recoded T: the commit then does its own, empty, digit pass)
-  ctx->ws.host_out = a->pinned + ACC_PIN_FRESH + 96;
-  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
+  VIMZ_TRY(enqueue_cross_commit_T(a, fresh + 96, a->pinned + ACC_PIN_FRESH + 96));
+  if (!two_lanes) VIMZ_TRY(enqueue_ps(a, st, fresh));
   if (two_lanes) {
     ctx->ws_aux.host_out = a->pinned + ACC_PIN_FRESH;
     VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
+    if (a->use_ks && s->m) {  // P_S on the aux lane, behind commit(W2): it has the slack (the mat-vec it reads finished long before)
+      VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_ksum, 0));
+      VIMZ_TRY(enqueue_ps(a, ctx->aux, fresh));
+    }
     VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
     VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   }
@@ -1005,7 +1078,7 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
     VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_side[p], 0));
     a->side_pending[p] = false;
   }
-  char* fresh = (char*)a->comms + (2 + 2 * p) * 96;
+  char* fresh = acc_fresh(a, p);
   // tail2 = (1, X2) staged in this accumulator's pinned block (read by the copy when the stream reaches it).  A step that
   // was only enqueued (sharded fold) may still have that copy pending: wait for it before overwriting the block.
   if (a->step_enqueued && !a->fresh_complete) VIMZ_CUDA(cudaStreamSynchronize(st));
@@ -1065,7 +1138,7 @@ int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* 
   if (d_W2 != a->W2)  // (the sharded entry points broadcast the witness straight into the accumulator)
     VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
   VIMZ_TRY(acc_step_begin_common(a, X2, nullptr, nullptr, false));
-  *d_partials = (char*)a->comms + (2 + 2 * a->parity) * 96;
+  *d_partials = acc_fresh(a, a->parity);
   return VIMZ_OK;
 }
 
@@ -1161,7 +1234,7 @@ int vimz_acc_commit_fresh(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vim
     VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_side[p], 0));
     a->side_pending[p] = false;
   }
-  char* fresh = (char*)a->comms + (2 + 2 * p) * 96;
+  char* fresh = acc_fresh(a, p);
   uint8_t* stage = a->pinned + ACC_PIN_STAGE;
   memcpy(stage, vt->scalar_one_mont, 32);
   if (s->io) memcpy(stage + 32, X2, s->io * 32);
@@ -1185,9 +1258,9 @@ int vimz_acc_cross_begin(vimz_acc* a, vimz_point* comm_T) {
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
-  char* fresh = (char*)a->comms + (2 + 2 * a->parity) * 96;
-  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2));
-  VIMZ_TRY(vt->msm(ctx, 0, a->ck, 0, a->T, s->m, fresh + 96, s->m > 0));
+  char* fresh = acc_fresh(a, a->parity);
+  VIMZ_TRY(enqueue_cross_commit_T(a, fresh + 96, nullptr));
+  VIMZ_TRY(enqueue_ps(a, st, fresh));
   VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH + 96, fresh + 96, 96, cudaMemcpyDeviceToHost, st));
   VIMZ_CUDA(cudaStreamSynchronize(st));
   a->half_open = false;
@@ -1219,7 +1292,7 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
   char* comms = (char*)a->comms;
-  char* fresh = comms + (2 + 2 * a->parity) * 96;
+  char* fresh = acc_fresh(a, a->parity);
   // r travels by value in both launches: W1 += r*W2, E1 += r*T, (u1, X1) += r*(1, X2) on the main stream ...
   AxpySeg segs[4] = {{a->W1, a->W2, s->n}, {a->E1, a->T, s->m}, {a->tail1, a->tail2, 1 + s->io}, {a->cache1, a->cache2, a->cache1 ? 3 * s->m : 0}};
   VIMZ_TRY(vt->axpyn(ctx, segs, 4, r));
@@ -1231,7 +1304,8 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
     VIMZ_CUDA(cudaEventRecord(a->ev_main, st));
     VIMZ_CUDA(cudaStreamWaitEvent(ctx->side, a->ev_main, 0));
   }
-  VIMZ_TRY(vt->point_scale_add_val(ctx, ctx->side, comms, r, fresh, comms, 2));
+  // (with the booleanity-row fold a third pair rides along: K_S += r * P_S, P_S made by step_begin)
+  VIMZ_TRY(vt->point_scale_add_val(ctx, ctx->side, comms, r, fresh, comms, (a->use_ks && s->m) ? 3 : 2));
   VIMZ_CUDA(cudaEventRecord(a->ev_side[a->parity], ctx->side));
   a->side_pending[a->parity] = true;
   return VIMZ_OK;

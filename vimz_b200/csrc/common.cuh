@@ -88,6 +88,10 @@ struct MsmWorkspace {
   // set by a caller around ONE msm launch sequence: the final kernel also writes its Jacobian result here -- mapped page-locked
   // host memory the host reads after the stream completes (saves the D2H copy node of a fold step and its dispatch gap)
   void* host_out = nullptr;
+  // same protocol: a Jacobian point the final kernel subtracts from the sum (the accumulator's K_S), and the event after which
+  // it is valid (waited for right in front of the final kernel only)
+  const void* sub_jac = nullptr;
+  cudaEvent_t sub_event = nullptr;
   uint32_t last_M = 0;     // buckets of the last MSM run on this workspace (statistics: vimz_ctx_profile "laneK_*")
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release(); digits.release();
@@ -132,6 +136,7 @@ struct vimz_ctx {
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
   bool opt_defer_giants = true; // giant buckets are summed beside the bucket reduction (k_reduce_tail) instead of in front of it
+  bool opt_bitrow_fold = true;  // accumulators created from now on keep K_S and commit T + [bit row] Az1 (r1cs.cuh, k_cross_finish)
   bool opt_spin_wait = true; // step_begin polls the stream for its result instead of a blocking synchronise
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
@@ -204,6 +209,8 @@ struct vimz_shape {
   size_t n_long = 0;
   uint32_t* mid_rows = nullptr;                       // rows with R1CS_SHORT_ROW+1 .. R1CS_LONG_ROW non-zeros (8 lanes each)
   size_t n_mid = 0;
+  uint8_t* rowflag = nullptr;                         // [m] 1 = booleanity row b*(b-1)=0 (A = {(b,1)}, B = {(b,1),(one,-1)}, C = {}), see k_cross_finish
+  size_t n_bitrows = 0;
 };
 
 struct vimz_acc {
@@ -219,8 +226,14 @@ struct vimz_acc {
   // cached products (option "cross_cache", fixed when the accumulator is created): cache1 = (Az1, Bz1, Cz1)[3][m] of the
   // running instance, folded in step_end with cache2 = (Az2, Bz2, Cz2)[3][m] of the fresh one -- linear, so exact
   void *cache1 = nullptr, *cache2 = nullptr;
-  // Jacobian points comm_W1, comm_E1, then two alternating (comm_W2, comm_T) pairs, then two r slots
+  // Jacobian points comm_W1, comm_E1, K_S, then two alternating (comm_W2, comm_T, P_S) triples (ACC_SLOTS, capi.cu)
   void* comms = nullptr;
+  // Booleanity-row fold (r1cs.cuh, k_cross_finish): K_S = sum_{i in S} (A z1)_i ck_i of the running instance lives in the third
+  // commitment slot and folds with the other two (K_S += r * P_S, P_S = the same sum for the step's fresh z2, made by
+  // k_masked_base_sum on the side stream).  Fixed when the accumulator is created.
+  bool use_ks = false;
+  void* ksum_scratch = nullptr;  // block / group sums + self-resetting arrival counters of k_masked_base_sum
+  cudaEvent_t ev_ksum = nullptr;
   // pinned host block of THIS accumulator (several accumulators may share a context and have steps in flight at once):
   // [0, 192) the step's (comm_W2, comm_T) as copied back by the stream, [256, 448) the combined pair of a sharded step,
   // [512, ..) the staged (1, X2) tail that the step's H2D copy reads when the stream reaches it

@@ -23,6 +23,7 @@ struct CurveVTable {
   // dtable[((j*n + i) << (c-1)) + k-1] = k * table[j][i]  (direct-table keys)
   int (*precompute_direct)(vimz_ctx*, const void* table, size_t n, int c, int nwin, void* dtable);
   // lane 0 = context stream + main workspace, lane 1 = aux stream + second workspace (runs concurrently)
+  // (MsmWorkspace::host_out / sub_jac / sub_event, set by the caller around one call, reach the final kernel)
   // counted = true: the bucket histogram of the scalars is already in the lane's `counts` buffer (fused cross term)
   int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted);
   int (*point_sum)(vimz_ctx*, const void* d_pts, size_t k, void* d_out);
@@ -35,8 +36,12 @@ struct CurveVTable {
   // fuse_ck != nullptr: also histogram T's digits for the commit(fuse_ck, T) that follows on lane 0
   // cache1 / cache2 != nullptr (resident accumulator): (Az1, Bz1, Cz1) are READ from cache1[3][m] instead of being
   // recomputed and (Az2, Bz2, Cz2) are written to cache2[3][m] for the fold in step_end
+  // rowflag != nullptr: the digits recoded for fuse_ck are those of T + [rowflag] Az1 (the caller subtracts K_S from the commitment)
   int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
-                    const vimz_ck* fuse_ck, const void* cache1, void* cache2);
+                    const vimz_ck* fuse_ck, const void* cache1, void* cache2, const uint8_t* rowflag);
+  int (*mask_rows)(vimz_ctx*, cudaStream_t, const void* d_v, const uint8_t* rowflag, size_t m, void* d_out);
+  // d_out = sum over the flagged rows of vals[i] * ck_i (bases = row 0 of the key's window table); scratch: MASKED_SUM_SCRATCH bytes, zeroed once
+  int (*masked_base_sum)(vimz_ctx*, cudaStream_t, const void* d_vals, const uint8_t* rowflag, size_t m, const vimz_ck*, void* scratch, void* d_out);
   int (*axpy)(vimz_ctx*, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out);
   // up to AXPY_MAX_SEGS in-place folds a_k += r * b_k in one launch (witness fold W, E, the (u, X) tail, cached products)
   int (*axpyn)(vimz_ctx*, const vimz::AxpySeg* segs, int count, const vimz_fr* r);
@@ -125,7 +130,10 @@ template <class C>
 int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted) {
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
   MsmWorkspace& ws = lane == 0 ? ctx->ws : ctx->ws_aux;
-  if (ck->dtable) return impl_msm_direct<C>(ctx, st, ws, ck, first, d_scalars, n, d_out, counted);
+  if (ck->dtable) {
+    if (ws.sub_jac) return set_error(VIMZ_ERR_ARG, "msm: a subtracted point is only supported on the bucket pipeline");
+    return impl_msm_direct<C>(ctx, st, ws, ck, first, d_scalars, n, d_out, counted);
+  }
   const int c = ck->c, nwin = ck->nwin;
   const uint32_t M = 1u << (c - 1);
   const size_t E = std::max<size_t>(n * (size_t)nwin, 1);
@@ -236,8 +244,15 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   ProfScope prof_red(ctx, PROF_MSM_REDUCE, st);
   k_reduce_chunks<C><<<ceil_div((size_t)T * 4, 128), 128, 0, st>>>(ws.buckets.ptr, T, K, ws.chunkA.ptr, ws.chunkL.ptr);
   VIMZ_LAUNCH_CHECK(ctx);
+  // (the subtracted point is produced by another stream long before: inside a captured graph an EXTERNAL event wait, so that it
+  // stays a wait on the event object and does not pull that stream into the capture)
+  if (ws.sub_jac && ws.sub_event) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    VIMZ_CUDA(cudaStreamIsCapturing(st, &cs));
+    VIMZ_CUDA(cudaStreamWaitEvent(st, ws.sub_event, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault));
+  }
   k_reduce_tail<C><<<dim3(G, nb + 1 + (defer ? 1 : 0)), 128, 0, st>>>(ws.chunkA.ptr, ws.chunkL.ptr, T, nb, logK, ws.bitsums.ptr, ws.scaled.ptr,
-                                                                      cb.ctrl + CTRL_REDUCE, d_out, ws.host_out, offsets, M, nthreads, seg_min, ws.partials.ptr, cb,
+                                                                      cb.ctrl + CTRL_REDUCE, d_out, ws.host_out, ws.sub_jac, offsets, M, nthreads, seg_min, ws.partials.ptr, cb,
                                                                       defer ? ws.deferred.ptr : nullptr);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
@@ -305,7 +320,7 @@ int impl_spmv3(vimz_ctx* ctx, const vimz_shape* s, const void* d_W, const void* 
 }
 template <class C>
 int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
-                    const vimz_ck* fuse_ck, const void* cache1, void* cache2) {
+                    const vimz_ck* fuse_ck, const void* cache1, void* cache2, const uint8_t* rowflag) {
   if (s->m == 0) return VIMZ_OK;
   DigitCount dc{nullptr, 0, 0, nullptr, 0};
   if (fuse_ck) {  // zero lane 0's histogram, then let the cross-term kernels fill it and the digit array
@@ -347,10 +362,11 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
     ma.W = d_W2; ma.tail = d_tail2; ma.out = p2;
     k_matvec_stream<typename C::Fs><<<(uint32_t)s->n_chunks, 256, MATVEC_SMEM, ctx->stream>>>(ma);
     VIMZ_LAUNCH_CHECK(ctx);
-    k_cross_finish<typename C::Fs><<<ceil_div(s->m, CROSS_FINISH_THREADS), CROSS_FINISH_THREADS, 0, ctx->stream>>>(p1, p2, d_tail1, (uint32_t)s->m, d_T, dc);
+    k_cross_finish<typename C::Fs><<<ceil_div(s->m, CROSS_FINISH_THREADS), CROSS_FINISH_THREADS, 0, ctx->stream>>>(p1, p2, d_tail1, (uint32_t)s->m, d_T, dc, rowflag);
     VIMZ_LAUNCH_CHECK(ctx);
     return VIMZ_OK;
   }
+  if (rowflag) return set_error(VIMZ_ERR_ARG, "cross_term: the booleanity-row shift needs the streamed kernels (cross_stream = 1)");
   const uint32_t nb_long = ceil_div(s->n_long * 32, 128), nb_mid = ceil_div(s->n_mid * 8, 128), nb_short = ceil_div(s->m, 128);
   k_cross_term<typename C::Fs><<<nb_long + nb_mid + nb_short, 128, 0, ctx->stream>>>(ca, s->long_rows, (uint32_t)s->n_long, nb_long,
                                                                                      s->mid_rows, (uint32_t)s->n_mid, nb_mid);
@@ -361,6 +377,28 @@ int impl_cross_term(vimz_ctx* ctx, const vimz_shape* s, const void* d_W1, const 
         csr_view(s, 0), csr_view(s, 1), csr_view(s, 2), (uint32_t)s->m, (uint32_t)s->n, d_W2, d_tail2, c2, c2 + s->m * 32, c2 + 2 * s->m * 32);
     VIMZ_LAUNCH_CHECK(ctx);
   }
+  return VIMZ_OK;
+}
+template <class C>
+int impl_mask_rows(vimz_ctx* ctx, cudaStream_t st, const void* d_v, const uint8_t* rowflag, size_t m, void* d_out) {
+  if (m == 0) return VIMZ_OK;
+  k_mask_rows<typename C::Fs><<<ceil_div(m, 256), 256, 0, st>>>(d_v, rowflag, (uint32_t)m, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+constexpr uint32_t MASKED_SUM_BLOCKS_PER_SM = 2;
+inline size_t masked_sum_scratch_bytes(const vimz_ctx* ctx) {
+  const uint32_t blocks = (uint32_t)ctx->sm_count * MASKED_SUM_BLOCKS_PER_SM;
+  return ((size_t)blocks + ceil_div(blocks, DIRECT_GROUP)) * 128 + 64 * 4;  // block sums, group sums, then the counters
+}
+template <class C>
+int impl_masked_base_sum(vimz_ctx* ctx, cudaStream_t st, const void* d_vals, const uint8_t* rowflag, size_t m, const vimz_ck* ck, void* scratch,
+                         void* d_out) {
+  const uint32_t blocks = std::min<uint32_t>((uint32_t)ctx->sm_count * MASKED_SUM_BLOCKS_PER_SM, DIRECT_MAX_BLOCKS);
+  char* sc = reinterpret_cast<char*>(scratch);
+  uint32_t* ctrl = reinterpret_cast<uint32_t*>(sc + masked_sum_scratch_bytes(ctx) - 64 * 4);
+  k_masked_base_sum<C><<<blocks, 128, 0, st>>>(d_vals, rowflag, (uint32_t)m, ck->table, sc, ctrl, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
 template <class C>
@@ -426,6 +464,8 @@ CurveVTable make_vtable(const char* name) {
   t.gen_bases = &impl_gen_bases<C>;
   t.spmv3 = &impl_spmv3<C>;
   t.cross_term = &impl_cross_term<C>;
+  t.mask_rows = &impl_mask_rows<C>;
+  t.masked_base_sum = &impl_masked_base_sum<C>;
   t.axpy = &impl_axpy<C>;
   t.axpyn = &impl_axpyn<C>;
   t.field_op = &impl_field_op<C>;

@@ -387,6 +387,7 @@ struct TailFinal {
   uint32_t* cnt;         // arrival counter
   void* out_jac;
   void* out_host;        // optional second copy of the result in mapped page-locked host memory (nullptr: none)
+  const void* sub_jac;   // optional Jacobian point SUBTRACTED from the sum before it is written (the accumulator's K_S, r1cs.cuh)
 };
 template <class C>
 __device__ __forceinline__ void reduce_arrive_final(const TailFinal& f) {
@@ -407,6 +408,11 @@ __device__ __forceinline__ void reduce_arrive_final(const TailFinal& f) {
     acc = q_add<C>(acc, p);
   }
   acc = q_warp_reduce<C>(acc);
+  if (f.sub_jac) {  // warp-uniform
+    QPoint<C> k = q_load_jacobian<C>(f.sub_jac);
+    if ((threadIdx.x & 3) == 1) k.c = fp_neg(k.c);  // -(X, Y, ZZ, ZZZ) = (X, -Y, ZZ, ZZZ)
+    acc = q_add<C>(acc, k);
+  }
   q_store_jacobian<C>(acc, f.out_jac, (threadIdx.x & 31) < 4, f.out_host);
 }
 
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
 template <class C>
 __global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ chunkA, const void* __restrict__ chunkL, uint32_t T, int nb, int logK,
                                                      void* __restrict__ bitsums, void* __restrict__ scaled, uint32_t* __restrict__ cnt,
-                                                     void* __restrict__ out_jac, void* __restrict__ out_host,
+                                                     void* __restrict__ out_jac, void* __restrict__ out_host, const void* __restrict__ sub_jac,
                                                      // deferred giants (deferred == nullptr: none): row nb + 1 of the grid sums them
                                                      const uint32_t* __restrict__ offsets, uint32_t M, uint32_t nthreads, uint32_t seg_min,
                                                      const void* __restrict__ partials, MsmCombine cb, void* __restrict__ deferred) {
@@ -591,7 +597,7 @@ __global__ void __launch_bounds__(128) k_reduce_tail(const void* __restrict__ ch
   const int s = blockIdx.y, G = gridDim.x;
   TailFinal fin;
   fin.scaled = scaled; fin.nsums = nb + 1; fin.deferred = deferred; fin.ngiant_p = cb.ctrl + CTRL_NGIANT; fin.max_giants = cb.max_giants;
-  fin.cnt = cnt + nb + 1; fin.out_jac = out_jac; fin.out_host = out_host;
+  fin.cnt = cnt + nb + 1; fin.out_jac = out_jac; fin.out_host = out_host; fin.sub_jac = sub_jac;
   if (s == nb + 1) {  // giant role (only launched when giants are deferred)
     if (cb.ctrl[CTRL_NGIANT] == 0) return;
     const uint32_t L = seg_len(offsets[M], nthreads, seg_min);
@@ -743,6 +749,52 @@ __global__ void __launch_bounds__(128) k_precompute_direct(const void* __restric
   }
 }
 
+// Tree shared by k_msm_direct and k_masked_base_sum: every thread holds an XYZZ sum; thread sums -> one point per quad -> block
+// sum -> the last-arriving block of each group of DIRECT_GROUP blocks adds the group's block sums -> the last-arriving group adds
+// the group sums and writes the Jacobian result.  `self_reset`: the final block zeroes the arrival counters for the next launch.
+template <class C>
+__device__ __forceinline__ void direct_tree(const Xyzz<C>& acc, uint32_t* smem, uint32_t* flag_p, void* __restrict__ partials,
+                                            uint32_t* __restrict__ ctrl, void* __restrict__ out_jac, void* __restrict__ out_host, bool self_reset) {
+  QPoint<C> q = q_from_lane<C>(acc, 0);
+#pragma unroll 1
+  for (int j = 1; j < 4; j++) q = q_add<C>(q, q_from_lane<C>(acc, j));
+  q = q_block_reduce_128<C>(q, smem);
+  char* parts = reinterpret_cast<char*>(partials);
+  const uint32_t nblocks = gridDim.x, ngroups = (nblocks + DIRECT_GROUP - 1) / DIRECT_GROUP;
+  const uint32_t g = blockIdx.x / DIRECT_GROUP;
+  const uint32_t gsize = min(DIRECT_GROUP, nblocks - g * DIRECT_GROUP);
+  if (threadIdx.x < 4) {
+    q.store(parts + (size_t)blockIdx.x * 128);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *flag_p = (atomicAdd(&ctrl[g], 1u) + 1 == gsize) ? 1u : 0u;
+  __syncthreads();
+  if (!*flag_p) return;
+  // last block of group g: its 32 quads fetch the group's block sums (through L2) and add them
+  __threadfence();
+  const uint32_t quad = threadIdx.x >> 2;
+  q = quad < gsize ? QPoint<C>::load_cg(parts + (size_t)(g * DIRECT_GROUP + quad) * 128) : QPoint<C>::identity();
+  q = q_block_reduce_128<C>(q, smem);
+  if (threadIdx.x < 4) {
+    q.store(parts + (size_t)(nblocks + g) * 128);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (self_reset) ctrl[g] = 0;
+    *flag_p = (atomicAdd(&ctrl[DIRECT_CTRL_FINAL], 1u) + 1 == ngroups) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!*flag_p) return;
+  // last group: add the <= 32 group sums, write the Jacobian result
+  __threadfence();
+  q = quad < ngroups ? QPoint<C>::load_cg(parts + (size_t)(nblocks + quad) * 128) : QPoint<C>::identity();
+  q = q_block_reduce_128<C>(q, smem);
+  if (threadIdx.x < 32) q_store_jacobian<C>(q, out_jac, threadIdx.x < 4, out_host);
+  if (self_reset && threadIdx.x == 0) ctrl[DIRECT_CTRL_FINAL] = 0;
+}
+
 template <class C>
 __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restrict__ digits, uint32_t n, int nwin, uint32_t ck_n, uint32_t first,
                                                        int cshift, const void* __restrict__ dtable, void* __restrict__ partials,
@@ -770,41 +822,40 @@ __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restric
     e = en;
     d = dn;
   }
-  // thread sums -> one point per quad -> block sum
-  QPoint<C> q = q_from_lane<C>(acc, 0);
-#pragma unroll 1
-  for (int j = 1; j < 4; j++) q = q_add<C>(q, q_from_lane<C>(acc, j));
-  q = q_block_reduce_128<C>(q, smem);
-  char* parts = reinterpret_cast<char*>(partials);
-  const uint32_t nblocks = gridDim.x, ngroups = (nblocks + DIRECT_GROUP - 1) / DIRECT_GROUP;
-  const uint32_t g = blockIdx.x / DIRECT_GROUP;
-  const uint32_t gsize = min(DIRECT_GROUP, nblocks - g * DIRECT_GROUP);
-  if (threadIdx.x < 4) {
-    q.store(parts + (size_t)blockIdx.x * 128);
-    __threadfence();
+  direct_tree<C>(acc, smem, &flag, partials, ctrl, out_jac, out_host, false);
+}
+
+// sum_{i < m, rowflag[i]} vals[i] * bases[i] for a vector `vals` whose flagged entries are (almost always) 0 or 1: the fresh
+// (A z2) on the booleanity rows of a step (r1cs.cuh, k_cross_finish; a satisfying witness cannot hold anything else there).
+// An entry equal to one is ONE mixed addition; any other non-zero value -- only an unsatisfying witness has them -- is multiplied
+// out bit by bit so that the result stays exact.  Same tree as k_msm_direct; the arrival counters reset themselves.
+template <class C>
+__global__ void __launch_bounds__(128, 4) k_masked_base_sum(const void* __restrict__ vals, const uint8_t* __restrict__ rowflag, uint32_t m,
+                                                            const void* __restrict__ bases, void* __restrict__ partials,
+                                                            uint32_t* __restrict__ ctrl, void* __restrict__ out_jac) {
+  using Fs = Fp<typename C::Fs>;
+  __shared__ __align__(16) uint32_t smem[4 * 32];
+  __shared__ uint32_t flag;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  Xyzz<C> acc = Xyzz<C>::identity();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += nthreads) {
+    if (!rowflag[i]) continue;
+    const Fs v = Fs::load_nc(reinterpret_cast<const char*>(vals) + (size_t)i * 32);
+    if (v.is_zero()) continue;
+    const Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
+    if (v == Fs::one()) {
+      xyzz_madd<C, VIMZ_DIRECT_MUL>(acc, p, false);
+    } else {  // rare, slow, exact: v * p by double-and-add
+      const Fs raw = fp_from_mont(v);
+      Xyzz<C> t = Xyzz<C>::identity();
+      for (int bit = 255; bit >= 0; bit--) {
+        xyzz_dbl_call<C>(t);
+        if ((raw.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd_call<C>(t, p, false);
+      }
+      xyzz_add_call<C>(acc, t);
+    }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) flag = (atomicAdd(&ctrl[g], 1u) + 1 == gsize) ? 1u : 0u;
-  __syncthreads();
-  if (!flag) return;
-  // last block of group g: its 32 quads fetch the group's block sums (through L2) and add them
-  __threadfence();
-  const uint32_t quad = threadIdx.x >> 2;
-  q = quad < gsize ? QPoint<C>::load_cg(parts + (size_t)(g * DIRECT_GROUP + quad) * 128) : QPoint<C>::identity();
-  q = q_block_reduce_128<C>(q, smem);
-  if (threadIdx.x < 4) {
-    q.store(parts + (size_t)(nblocks + g) * 128);
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) flag = (atomicAdd(&ctrl[DIRECT_CTRL_FINAL], 1u) + 1 == ngroups) ? 1u : 0u;
-  __syncthreads();
-  if (!flag) return;
-  // last group: add the <= 32 group sums, write the Jacobian result
-  __threadfence();
-  q = quad < ngroups ? QPoint<C>::load_cg(parts + (size_t)(nblocks + quad) * 128) : QPoint<C>::identity();
-  q = q_block_reduce_128<C>(q, smem);
-  if (threadIdx.x < 32) q_store_jacobian<C>(q, out_jac, threadIdx.x < 4, out_host);
+  direct_tree<C>(acc, smem, &flag, partials, ctrl, out_jac, nullptr, true);
 }
 
 // ---- small single-thread group kernels ---------------------------------------------------------
