@@ -126,6 +126,8 @@ static void ctx_free(vimz_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->side);
   cudaStreamSynchronize(ctx->aux);
+  cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
   ctx->ws.release();
   ctx->ws_aux.release();
   ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
@@ -138,6 +140,8 @@ static void ctx_free(vimz_ctx* ctx) {
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->side);
   cudaStreamDestroy(ctx->aux);
+  cudaStreamDestroy(ctx->ps);
+  cudaStreamDestroy(ctx->ks);
   delete ctx;
 }
 static void ctx_release(vimz_ctx* ctx) {
@@ -150,6 +154,11 @@ static void ck_release(vimz_ck* ck) {
     CtxGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->aux);
+  cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
+    cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
+    cudaStreamSynchronize(ctx->ks);
     if (ck->table) cudaFree(ck->table);
     if (ck->dtable) cudaFree(ck->dtable);
     delete ck;
@@ -173,6 +182,7 @@ static void shape_release(vimz_shape* s) {
     if (s->long_rows) cudaFree(s->long_rows);
     if (s->mid_rows) cudaFree(s->mid_rows);
     if (s->rowflag) cudaFree(s->rowflag);
+    if (s->bitcol) cudaFree(s->bitcol);
     delete s;
   }
   ctx_release(ctx);
@@ -213,6 +223,8 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
     VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
     VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
     VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_lo));
+    VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->ps, cudaStreamNonBlocking, prio_lo));
+    VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->ks, cudaStreamNonBlocking, prio_hi));
     VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
     VIMZ_TRY(ctx->ws.result.reserve(4096));
@@ -224,6 +236,8 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->ps) cudaStreamDestroy(ctx->ps);
+    if (ctx->ks) cudaStreamDestroy(ctx->ks);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     ctx->ws.release();
     delete ctx;
@@ -241,6 +255,11 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     cudaStreamSynchronize(ctx->aux);
+  cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
+    cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
+    cudaStreamSynchronize(ctx->ks);
   }
   ctx_release(ctx);  // freed now, or when the last key / shape / accumulator created on it is destroyed
 }
@@ -251,6 +270,8 @@ int vimz_ctx_sync(vimz_ctx* ctx) {
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->ps));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->ks));
   return VIMZ_OK;
 }
 
@@ -336,6 +357,8 @@ int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* call
   CtxGuard g(ctx);
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->ps));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->ks));
   Profiler& p = ctx->prof;
   for (ProfSpan& s : p.open) {
     float t = 0;
@@ -716,6 +739,7 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   // booleanity rows b * (b - 1) = 0: A = {(b, +1)}, B = {(b, +1), (one, -1)} in either order, C = {} -- `one` is column num_vars
   // (the u slot of z = (W, u, X)); dictionary slots 0 / 1 are +1 / -1.  See k_cross_finish for what the accumulator does with them.
   std::vector<uint8_t> rowflag(num_cons, 0);
+  std::vector<uint32_t> bitcol(num_cons, 0xffffffffu);
   for (size_t i = 0; i < num_cons; i++) {
     const uint32_t a0 = h_rowptr[0][i], a1 = h_rowptr[0][i + 1], b0 = h_rowptr[1][i], b1 = h_rowptr[1][i + 1];
     if (a1 - a0 != 1 || b1 - b0 != 2 || h_rowptr[2][i + 1] != h_rowptr[2][i]) continue;
@@ -726,7 +750,7 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
       const uint32_t p = b0 + k, q2 = b0 + 1 - k;
       ok = h_col[1][p] == bcol && h_vidx[1][p] == 0 && h_col[1][q2] == (uint32_t)num_vars && h_vidx[1][q2] == 1;
     }
-    if (ok) { rowflag[i] = 1; s->n_bitrows++; }
+    if (ok) { rowflag[i] = 1; bitcol[i] = bcol; s->n_bitrows++; }
   }
   s->n_dict = dict.values.size();
   if (e == cudaSuccess) e = cudaMalloc(&s->chunk_stream, stream.size() * sizeof(uint2));
@@ -735,6 +759,8 @@ int vimz_shape_upload(vimz_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   if (e == cudaSuccess && !desc.empty()) e = cudaMemcpy(s->chunk_desc, desc.data(), desc.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && num_cons) e = cudaMalloc(&s->rowflag, num_cons);
   if (e == cudaSuccess && num_cons) e = cudaMemcpy(s->rowflag, rowflag.data(), num_cons, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && num_cons) e = cudaMalloc(&s->bitcol, num_cons * sizeof(uint32_t));
+  if (e == cudaSuccess && num_cons) e = cudaMemcpy(s->bitcol, bitcol.data(), num_cons * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&s->dict, s->n_dict * 32);
   if (e == cudaSuccess) e = cudaMemcpy(s->dict, dict.values.data(), s->n_dict * 32, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -830,7 +856,12 @@ void vimz_acc_destroy(vimz_acc* a) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     cudaStreamSynchronize(ctx->aux);
-    void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2, a->ksum_scratch};
+  cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
+    cudaStreamSynchronize(ctx->ps);
+  cudaStreamSynchronize(ctx->ks);
+    cudaStreamSynchronize(ctx->ks);
+    void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2, a->ksum_scratch, a->ps_parts};
     for (void* b : bufs)
       if (b) cudaFree(b);
     if (a->pinned) cudaFreeHost(a->pinned);
@@ -839,7 +870,8 @@ void vimz_acc_destroy(vimz_acc* a) {
     if (a->ev_main) cudaEventDestroy(a->ev_main);
     if (a->ev_w2) cudaEventDestroy(a->ev_w2);
     if (a->ev_aux) cudaEventDestroy(a->ev_aux);
-    if (a->ev_ksum) cudaEventDestroy(a->ev_ksum);
+    for (cudaEvent_t ev : {a->ev_ps_fork, a->ev_ps_join, a->ev_ks[0], a->ev_ks[1]})
+      if (ev) cudaEventDestroy(ev);
     for (int k = 0; k < 2; k++)
       if (a->ev_side[k]) cudaEventDestroy(a->ev_side[k]);
   }
@@ -884,7 +916,9 @@ static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, con
   a->use_ks = ctx->opt_bitrow_fold && a->cache1 && !ck->dtable && s->rowflag && s->n_bitrows * 8 >= s->m && s->n_bitrows >= 32;
   if (a->use_ks) {
     alloc0(&a->ksum_scratch, masked_sum_scratch_bytes(ctx));  // (the arrival counters reset themselves afterwards)
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_ksum, cudaEventDisableTiming);  // "(A z2) is complete" inside a step
+    alloc0(&a->ps_parts, 2 * SCALE_PARTS * 128);
+    for (cudaEvent_t* ev : {&a->ev_ps_fork, &a->ev_ps_join, &a->ev_ks[0], &a->ev_ks[1]})
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_w2, cudaEventDisableTiming);
@@ -936,6 +970,8 @@ static int acc_wait_side(vimz_acc* a) {
       VIMZ_CUDA(cudaStreamWaitEvent(a->ctx->stream, a->ev_side[k], 0));
       a->side_pending[k] = false;
     }
+  if (a->use_ks)  // (an event that was never recorded counts as complete)
+    for (int k = 0; k < 2; k++) VIMZ_CUDA(cudaStreamWaitEvent(a->ctx->stream, a->ev_ks[k], 0));
   return VIMZ_OK;
 }
 
@@ -975,6 +1011,8 @@ int vimz_acc_reset(vimz_acc* a) {
   CtxGuard g(ctx);
   VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->ps));
+  VIMZ_CUDA(cudaStreamSynchronize(ctx->ks));
   VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
   a->side_pending[0] = a->side_pending[1] = false;
   const vimz_shape* s = a->shape;
@@ -1006,11 +1044,10 @@ static int enqueue_cross_commit_T(vimz_acc* a, void* d_comm_T, void* host_out) {
     ~Reset() { c->ws.host_out = nullptr; c->ws.sub_jac = nullptr; c->ws.sub_event = nullptr; }
   } reset{ctx};
   VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2, shifted ? s->rowflag : nullptr));
-  if (a->use_ks) VIMZ_CUDA(cudaEventRecord(a->ev_ksum, ctx->stream));  // (A z2) is complete: the aux lane may sum P_S
   ctx->ws.host_out = host_out;
   if (shifted) {
     ctx->ws.sub_jac = (char*)a->comms + ACC_SLOT_KS * 96;
-    ctx->ws.sub_event = a->ev_side[a->parity ^ 1];
+    ctx->ws.sub_event = a->ev_ks[a->parity ^ 1];
   }
   // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
   // so nothing recoded T: the commit then does its own, empty, digit pass)
@@ -1018,10 +1055,47 @@ static int enqueue_cross_commit_T(vimz_acc* a, void* d_comm_T, void* host_out) {
 }
 
 // P_S = sum over the booleanity rows of (A z2)_i ck_i (what K_S gains, times r, in step_end): a plain sum of the ~55 k bases whose
-// fresh wire is 1, into the third slot of the step's fresh triple.  Needs the mat-vec of the step; off the critical lane.
-static int enqueue_ps(vimz_acc* a, cudaStream_t st, char* fresh) {
+// fresh wire is 1 -- (A z2)_i is that wire, so only W2 is needed -- into the third slot of the step's fresh triple, then its multiples
+// 2^(64 j) P_S (64 doublings by one quad) so that step_end's r * P_S is two half-length chains.  A third branch of the step (stream
+// vimz_ctx::ps) forked from `st` where fork_ps_branch was called and complete at ev_ps_join, which the caller makes `st` wait for
+// before the step ends: ~0.1 ms + ~0.2 ms of latency beside ~0.5 ms of commitments.  Its nodes are created AFTER those of the main
+// lane: in front of them the mat-vec (160 KB of shared memory per SM) waited ~35 us for the SMs to drain this kernel's blocks.
+static inline char* acc_ps_parts(const vimz_acc* a, int parity) { return (char*)a->ps_parts + (size_t)parity * SCALE_PARTS * 128; }
+static int fork_ps_branch(vimz_acc* a, cudaStream_t st) {  // the point of `st` after which W2 is resident
   if (!(a->use_ks && a->shape->m)) return VIMZ_OK;
-  return curve_vtable(a->ctx->curve)->masked_base_sum(a->ctx, st, a->cache2, a->shape->rowflag, a->shape->m, a->ck, a->ksum_scratch, fresh + 2 * 96);
+  VIMZ_CUDA(cudaEventRecord(a->ev_ps_fork, st));
+  return VIMZ_OK;
+}
+static int enqueue_ps_branch(vimz_acc* a, char* fresh) {
+  if (!(a->use_ks && a->shape->m)) return VIMZ_OK;
+  vimz_ctx* ctx = a->ctx;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  VIMZ_CUDA(cudaStreamWaitEvent(ctx->ps, a->ev_ps_fork, 0));
+  VIMZ_TRY(vt->masked_base_sum(ctx, ctx->ps, a->W2, a->shape->bitcol, a->shape->m, a->ck, a->ksum_scratch, fresh + 2 * 96));
+  VIMZ_TRY(vt->point_pow2_parts(ctx, ctx->ps, fresh + 2 * 96, acc_ps_parts(a, a->parity)));
+  VIMZ_CUDA(cudaEventRecord(a->ev_ps_join, ctx->ps));
+  return VIMZ_OK;
+}
+static int join_ps_branch(vimz_acc* a, cudaStream_t st) {
+  if (!(a->use_ks && a->shape->m)) return VIMZ_OK;
+  VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_ps_join, 0));
+  return VIMZ_OK;
+}
+
+__global__ void __launch_bounds__(256) k_copy16(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int copy_dev(vimz_ctx* ctx, void* dst, const void* src, size_t bytes) {  // bytes: a multiple of 32, both 16-byte aligned
+  if (bytes == 0 || dst == src) return VIMZ_OK;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) {
+    VIMZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return VIMZ_OK;
+  }
+  const size_t n16 = bytes / 16;
+  k_copy16<<<(unsigned)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+      reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n16);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
 }
 
 // The stream work of step_begin after W2 is resident: everything here has fixed addresses, so it can be captured.
@@ -1030,7 +1104,14 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
-  VIMZ_CUDA(cudaMemcpyAsync(a->tail2, a->pinned + ACC_PIN_STAGE, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  VIMZ_TRY(fork_ps_branch(a, st));
+  // tail2 = the staged (1, X2): copied by the kernel that clears commit(T)'s histogram when there is one (one node instead of two)
+  const bool fused_tail = ctx->opt_cross_stream && s->n_chunks > 0 && s->m > 0 && !a->ck->dtable;
+  if (fused_tail) {
+    ctx->ws.pro_src = a->pinned + ACC_PIN_STAGE; ctx->ws.pro_dst = a->tail2; ctx->ws.pro_bytes = (1 + s->io) * 32;
+  } else {
+    VIMZ_CUDA(cudaMemcpyAsync(a->tail2, a->pinned + ACC_PIN_STAGE, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  }
   // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) is independent of T, so it runs on the aux stream with its own
   // workspace while the main stream does the cross term and commit(T).  The main lane is the critical one and is enqueued
   // FIRST: a captured graph dispatches its nodes in creation order, a few microseconds apart, and with the aux lane in
@@ -1039,7 +1120,7 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   // Both final kernels also write their result into this accumulator's pinned block (mapped host memory): no D2H copy node.
   struct HostOut {  // cleared on every exit path
     vimz_ctx* c;
-    ~HostOut() { c->ws.host_out = nullptr; c->ws_aux.host_out = nullptr; }
+    ~HostOut() { c->ws.host_out = nullptr; c->ws_aux.host_out = nullptr; c->ws.pro_bytes = 0; }
   } host_out_guard{ctx};
   if (two_lanes) {
     VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
@@ -1050,18 +1131,14 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   }
   // T = cross term (mat-vecs with z2 + element-wise combination), comm_T = commit(ck, T)      (commit_T)
   VIMZ_TRY(enqueue_cross_commit_T(a, fresh + 96, a->pinned + ACC_PIN_FRESH + 96));
-  if (!two_lanes) VIMZ_TRY(enqueue_ps(a, st, fresh));
+  VIMZ_TRY(enqueue_ps_branch(a, fresh));
   if (two_lanes) {
     ctx->ws_aux.host_out = a->pinned + ACC_PIN_FRESH;
     VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
-    if (a->use_ks && s->m) {  // P_S on the aux lane, behind commit(W2): it has the slack (the mat-vec it reads finished long before)
-      VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_ksum, 0));
-      VIMZ_TRY(enqueue_ps(a, ctx->aux, fresh));
-    }
     VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
     VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   }
-  return VIMZ_OK;
+  return join_ps_branch(a, st);
 }
 
 // sync = false: enqueue only (sharded fold: the partial commitments stay on the device for the all-gather)
@@ -1210,8 +1287,8 @@ int vimz_acc_step_wait(vimz_acc* a, vimz_point* comm_W2, vimz_point* comm_T) {
 int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
   CtxGuard g(a->ctx);
-  // keep W2 resident for step_end
-  VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
+  // keep W2 resident for step_end (a copy kernel: a copy-engine node in front of the step's graph costs ~10 us of hand-over)
+  VIMZ_TRY(copy_dev(a->ctx, a->W2, d_W2, a->shape->n * 32));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
@@ -1259,8 +1336,10 @@ int vimz_acc_cross_begin(vimz_acc* a, vimz_point* comm_T) {
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
   char* fresh = acc_fresh(a, a->parity);
+  VIMZ_TRY(fork_ps_branch(a, st));
   VIMZ_TRY(enqueue_cross_commit_T(a, fresh + 96, nullptr));
-  VIMZ_TRY(enqueue_ps(a, st, fresh));
+  VIMZ_TRY(enqueue_ps_branch(a, fresh));
+  VIMZ_TRY(join_ps_branch(a, st));
   VIMZ_CUDA(cudaMemcpyAsync(a->pinned + ACC_PIN_FRESH + 96, fresh + 96, 96, cudaMemcpyDeviceToHost, st));
   VIMZ_CUDA(cudaStreamSynchronize(st));
   a->half_open = false;
@@ -1300,12 +1379,21 @@ int vimz_acc_step_end(vimz_acc* a, const vimz_fr* r) {
   // latency-bound, overlapping the next step's MSMs.  Their inputs (the step's fresh pair) were complete when
   // step_begin returned, and the running pair is only touched on the side stream, so no cross-stream wait is needed
   // (unless the step was only enqueued and never waited for: then the side stream waits for the main stream).
+  const bool ks = a->use_ks && s->m;
   if (!a->fresh_complete) {
     VIMZ_CUDA(cudaEventRecord(a->ev_main, st));
     VIMZ_CUDA(cudaStreamWaitEvent(ctx->side, a->ev_main, 0));
+    if (ks) VIMZ_CUDA(cudaStreamWaitEvent(ctx->ks, a->ev_main, 0));
   }
-  // (with the booleanity-row fold a third pair rides along: K_S += r * P_S, P_S made by step_begin)
-  VIMZ_TRY(vt->point_scale_add_val(ctx, ctx->side, comms, r, fresh, comms, (a->use_ks && s->m) ? 3 : 2));
+  // With the booleanity-row fold K_S += r * P_S goes by itself on its own stream: the next step of this accumulator subtracts K_S in
+  // the final kernel of its commit(T), ~0.6 ms from now, while the lone warp of a 128-bit scalar multiplication takes 0.4 - 0.65 ms
+  // beside busy SMs (and behind the other two on one stream the folds of a step took longer than the step).  step_begin left the
+  // multiples 2^(64 j) P_S, so this one is two 64-bit pieces (~0.25 ms).
+  if (ks) {
+    VIMZ_TRY(vt->point_scale_add_parts(ctx, ctx->ks, comms + ACC_SLOT_KS * 96, r, acc_ps_parts(a, a->parity), comms + ACC_SLOT_KS * 96));
+    VIMZ_CUDA(cudaEventRecord(a->ev_ks[a->parity], ctx->ks));
+  }
+  VIMZ_TRY(vt->point_scale_add_val(ctx, ctx->side, comms, r, fresh, comms, 2));
   VIMZ_CUDA(cudaEventRecord(a->ev_side[a->parity], ctx->side));
   a->side_pending[a->parity] = true;
   return VIMZ_OK;

@@ -92,6 +92,12 @@ struct MsmWorkspace {
   // it is valid (waited for right in front of the final kernel only)
   const void* sub_jac = nullptr;
   cudaEvent_t sub_event = nullptr;
+  // same protocol: a small host -> device copy (the accumulator's staged (1, X2) tail, in mapped page-locked memory) that the kernel
+  // clearing the control block + histogram performs as well -- one graph node instead of a copy node and a memset node in front of
+  // the first kernel of the critical lane (each costs ~8 us of dispatch there)
+  const void* pro_src = nullptr;
+  void* pro_dst = nullptr;
+  size_t pro_bytes = 0;    // multiple of 16
   uint32_t last_M = 0;     // buckets of the last MSM run on this workspace (statistics: vimz_ctx_profile "laneK_*")
   void release() {
     counts.release(); offsets.release(); cursor.release(); blocksums.release(); sorted.release(); digits.release();
@@ -132,6 +138,9 @@ struct vimz_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // instance-fold scalar multiplications overlap the next step here
   cudaStream_t aux = nullptr;   // second MSM lane: commit(W2) runs beside cross-term + commit(T)
+  cudaStream_t ps = nullptr;    // third branch of a step: P_S of the booleanity-row fold and its 2^(64 j) multiples (vimz_acc::use_ks)
+  cudaStream_t ks = nullptr;    // K_S += r * P_S of step_end: a lone warp with a deadline (the next commit(T) of the accumulator), kept apart
+                                // from the comm_W / comm_E folds on `side`, which have none
   int sm_count = 148;
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
@@ -210,6 +219,7 @@ struct vimz_shape {
   uint32_t* mid_rows = nullptr;                       // rows with R1CS_SHORT_ROW+1 .. R1CS_LONG_ROW non-zeros (8 lanes each)
   size_t n_mid = 0;
   uint8_t* rowflag = nullptr;                         // [m] 1 = booleanity row b*(b-1)=0 (A = {(b,1)}, B = {(b,1),(one,-1)}, C = {}), see k_cross_finish
+  uint32_t* bitcol = nullptr;                         // [m] the column b of such a row (a variable of W), ~0 for every other row
   size_t n_bitrows = 0;
 };
 
@@ -233,7 +243,9 @@ struct vimz_acc {
   // k_masked_base_sum on the side stream).  Fixed when the accumulator is created.
   bool use_ks = false;
   void* ksum_scratch = nullptr;  // block / group sums + self-resetting arrival counters of k_masked_base_sum
-  cudaEvent_t ev_ksum = nullptr;
+  void* ps_parts = nullptr;      // [2 parities][SCALE_PARTS] XYZZ records 2^(32 j) P_S (k_point_pow2_parts), read by step_end
+  cudaEvent_t ev_ps_fork = nullptr, ev_ps_join = nullptr;  // the P_S branch of a step (stream vimz_ctx::ps)
+  cudaEvent_t ev_ks[2] = {nullptr, nullptr};               // "K_S has absorbed the step of this parity" (side stream)
   // pinned host block of THIS accumulator (several accumulators may share a context and have steps in flight at once):
   // [0, 192) the step's (comm_W2, comm_T) as copied back by the stream, [256, 448) the combined pair of a sharded step,
   // [512, ..) the staged (1, X2) tail that the step's H2D copy reads when the stream reaches it

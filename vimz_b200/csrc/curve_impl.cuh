@@ -40,8 +40,12 @@ struct CurveVTable {
   int (*cross_term)(vimz_ctx*, const vimz_shape*, const void* d_W1, const void* d_tail1, const void* d_W2, const void* d_tail2, void* d_T,
                     const vimz_ck* fuse_ck, const void* cache1, void* cache2, const uint8_t* rowflag);
   int (*mask_rows)(vimz_ctx*, cudaStream_t, const void* d_v, const uint8_t* rowflag, size_t m, void* d_out);
-  // d_out = sum over the flagged rows of vals[i] * ck_i (bases = row 0 of the key's window table); scratch: MASKED_SUM_SCRATCH bytes, zeroed once
-  int (*masked_base_sum)(vimz_ctx*, cudaStream_t, const void* d_vals, const uint8_t* rowflag, size_t m, const vimz_ck*, void* scratch, void* d_out);
+  // d_out = sum over the booleanity rows i of vals[bitcol[i]] * ck_i (bases = row 0 of the key's window table; vals = the fresh W2);
+  // scratch: masked_sum_scratch_bytes(), zeroed once
+  int (*masked_base_sum)(vimz_ctx*, cudaStream_t, const void* d_vals, const uint32_t* bitcol, size_t m, const vimz_ck*, void* scratch, void* d_out);
+  // d_parts[j] = 2^(32 j) * (Jacobian) d_pt as XYZZ records, j < SCALE_PARTS; then d_out = d_a + r * d_pt from those parts
+  int (*point_pow2_parts)(vimz_ctx*, cudaStream_t, const void* d_pt, void* d_parts);
+  int (*point_scale_add_parts)(vimz_ctx*, cudaStream_t, const void* d_a, const vimz_fr* r, const void* d_parts, void* d_out);
   int (*axpy)(vimz_ctx*, const void* d_a, const void* d_b, const vimz_fr* r, size_t len, void* d_out);
   // up to AXPY_MAX_SEGS in-place folds a_k += r * b_k in one launch (witness fold W, E, the (u, X) tail, cached products)
   int (*axpyn)(vimz_ctx*, const vimz::AxpySeg* segs, int count, const vimz_fr* r);
@@ -119,9 +123,23 @@ int impl_msm_direct(vimz_ctx* ctx, cudaStream_t st, MsmWorkspace& ws, const vimz
 inline uint32_t msm_nthreads(const vimz_ctx* ctx) { return (uint32_t)ctx->sm_count * (uint32_t)ctx->opt_acc_blocks * 128; }
 inline uint32_t msm_max_giants(const vimz_ctx* ctx) { return 2 * msm_nthreads(ctx) / COMBINE_MID + 2; }
 inline uint32_t msm_ctrl_words(const vimz_ctx* ctx) { return (CTRL_GIANT_DONE + msm_max_giants(ctx) + 3) & ~3u; }  // keeps counts[] 16-byte aligned
+// zero `nz` 16-byte words at `z`, and copy `nc` 16-byte words src -> dst (src: mapped page-locked host memory)
+static __global__ void __launch_bounds__(256) k_zero_and_copy(uint4* __restrict__ z, uint32_t nz, const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t nc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nc) dst[i] = src[i];
+  if (i < nz) z[i] = make_uint4(0, 0, 0, 0);
+}
 inline int msm_zero_control(vimz_ctx* ctx, MsmWorkspace& ws, uint32_t M, cudaStream_t st) {
-  const size_t bytes = ((size_t)msm_ctrl_words(ctx) + M) * 4;
-  VIMZ_TRY(ws.counts.reserve(bytes));
+  const size_t bytes = ((size_t)msm_ctrl_words(ctx) + M) * 4;  // (a multiple of 16: msm_ctrl_words is a multiple of 4, M a power of two >= 4 or ...)
+  VIMZ_TRY(ws.counts.reserve((bytes + 15) & ~(size_t)15));
+  if (ws.pro_bytes) {  // the caller's small host -> device copy rides along (MsmWorkspace::pro_*): one node instead of two
+    const uint32_t nz = (uint32_t)((bytes + 15) / 16), nc = (uint32_t)(ws.pro_bytes / 16);
+    k_zero_and_copy<<<ceil_div(std::max(nz, nc), 256u), 256, 0, st>>>(reinterpret_cast<uint4*>(ws.counts.ptr), nz,
+                                                                      reinterpret_cast<const uint4*>(ws.pro_src), reinterpret_cast<uint4*>(ws.pro_dst), nc);
+    VIMZ_LAUNCH_CHECK(ctx);
+    ws.pro_bytes = 0;  // consumed
+    return VIMZ_OK;
+  }
   VIMZ_CUDA(cudaMemsetAsync(ws.counts.ptr, 0, bytes, st));
   return VIMZ_OK;
 }
@@ -386,18 +404,34 @@ int impl_mask_rows(vimz_ctx* ctx, cudaStream_t st, const void* d_v, const uint8_
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
-constexpr uint32_t MASKED_SUM_BLOCKS_PER_SM = 2;
+// One 128-thread block on every second SM: ~55 k additions are ~6 per thread (~25 us) plus the tree, and a grid this thin leaves the
+// kernels of the critical lane, which run beside it, their SMs (two blocks on every SM made k_cross_finish and k_msm_scatter 2x slower).
+inline uint32_t masked_sum_blocks(const vimz_ctx* ctx) { return std::min<uint32_t>(std::max<uint32_t>((uint32_t)ctx->sm_count / 2, 1), DIRECT_MAX_BLOCKS); }
 inline size_t masked_sum_scratch_bytes(const vimz_ctx* ctx) {
-  const uint32_t blocks = (uint32_t)ctx->sm_count * MASKED_SUM_BLOCKS_PER_SM;
+  const uint32_t blocks = masked_sum_blocks(ctx);
   return ((size_t)blocks + ceil_div(blocks, DIRECT_GROUP)) * 128 + 64 * 4;  // block sums, group sums, then the counters
 }
 template <class C>
-int impl_masked_base_sum(vimz_ctx* ctx, cudaStream_t st, const void* d_vals, const uint8_t* rowflag, size_t m, const vimz_ck* ck, void* scratch,
+int impl_masked_base_sum(vimz_ctx* ctx, cudaStream_t st, const void* d_vals, const uint32_t* bitcol, size_t m, const vimz_ck* ck, void* scratch,
                          void* d_out) {
-  const uint32_t blocks = std::min<uint32_t>((uint32_t)ctx->sm_count * MASKED_SUM_BLOCKS_PER_SM, DIRECT_MAX_BLOCKS);
+  const uint32_t blocks = masked_sum_blocks(ctx);
   char* sc = reinterpret_cast<char*>(scratch);
   uint32_t* ctrl = reinterpret_cast<uint32_t*>(sc + masked_sum_scratch_bytes(ctx) - 64 * 4);
-  k_masked_base_sum<C><<<blocks, 128, 0, st>>>(d_vals, rowflag, (uint32_t)m, ck->table, sc, ctrl, d_out);
+  k_masked_base_sum<C><<<blocks, 128, 0, st>>>(d_vals, bitcol, (uint32_t)m, ck->table, sc, ctrl, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_point_pow2_parts(vimz_ctx* ctx, cudaStream_t st, const void* d_pt, void* d_parts) {
+  k_point_pow2_parts<C><<<1, 32, 0, st>>>(d_pt, d_parts);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_point_scale_add_parts(vimz_ctx* ctx, cudaStream_t st, const void* d_a, const vimz_fr* r, const void* d_parts, void* d_out) {
+  Fp<typename C::Fs> rr;
+  memcpy(rr.v, r, 32);
+  k_point_scale_add_parts<C><<<1, 32 * SCALE_PARTS, 0, st>>>(d_a, rr, d_parts, d_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -466,6 +500,8 @@ CurveVTable make_vtable(const char* name) {
   t.cross_term = &impl_cross_term<C>;
   t.mask_rows = &impl_mask_rows<C>;
   t.masked_base_sum = &impl_masked_base_sum<C>;
+  t.point_pow2_parts = &impl_point_pow2_parts<C>;
+  t.point_scale_add_parts = &impl_point_scale_add_parts<C>;
   t.axpy = &impl_axpy<C>;
   t.axpyn = &impl_axpyn<C>;
   t.field_op = &impl_field_op<C>;

@@ -825,12 +825,13 @@ __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restric
   direct_tree<C>(acc, smem, &flag, partials, ctrl, out_jac, out_host, false);
 }
 
-// sum_{i < m, rowflag[i]} vals[i] * bases[i] for a vector `vals` whose flagged entries are (almost always) 0 or 1: the fresh
-// (A z2) on the booleanity rows of a step (r1cs.cuh, k_cross_finish; a satisfying witness cannot hold anything else there).
+// sum over the booleanity rows i (bitcol[i] != ~0) of vals[bitcol[i]] * bases[i] for a vector `vals` whose entries there are
+// (almost always) 0 or 1: the fresh witness W2 of a step -- on such a row (A z2)_i IS the wire W2[bitcol[i]] (r1cs.cuh,
+// k_cross_finish; a satisfying witness cannot hold anything else there), so this sum needs no mat-vec and starts with the step.
 // An entry equal to one is ONE mixed addition; any other non-zero value -- only an unsatisfying witness has them -- is multiplied
 // out bit by bit so that the result stays exact.  Same tree as k_msm_direct; the arrival counters reset themselves.
 template <class C>
-__global__ void __launch_bounds__(128, 4) k_masked_base_sum(const void* __restrict__ vals, const uint8_t* __restrict__ rowflag, uint32_t m,
+__global__ void __launch_bounds__(128, 4) k_masked_base_sum(const void* __restrict__ vals, const uint32_t* __restrict__ bitcol, uint32_t m,
                                                             const void* __restrict__ bases, void* __restrict__ partials,
                                                             uint32_t* __restrict__ ctrl, void* __restrict__ out_jac) {
   using Fs = Fp<typename C::Fs>;
@@ -839,8 +840,9 @@ __global__ void __launch_bounds__(128, 4) k_masked_base_sum(const void* __restri
   const uint32_t nthreads = gridDim.x * blockDim.x;
   Xyzz<C> acc = Xyzz<C>::identity();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += nthreads) {
-    if (!rowflag[i]) continue;
-    const Fs v = Fs::load_nc(reinterpret_cast<const char*>(vals) + (size_t)i * 32);
+    const uint32_t col = __ldg(bitcol + i);
+    if (col == 0xffffffffu) continue;
+    const Fs v = Fs::load(reinterpret_cast<const char*>(vals) + (size_t)col * 32);
     if (v.is_zero()) continue;
     const Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
     if (v == Fs::one()) {
@@ -936,6 +938,56 @@ template <class C>
 __global__ void __launch_bounds__(32) k_point_scale_add_val(const void* __restrict__ a, Fp<typename C::Fs> r_mont, const void* __restrict__ b,
                                                             void* __restrict__ out, int count) {
   point_scale_add_body<C>(a, r_mont, b, out, count);
+}
+
+// parts[j] = 2^(PART_BITS j) * P, j = 0 .. SCALE_PARTS-1, as XYZZ records (128 B each), from a Jacobian P: one quad walks the doublings.
+// Runs inside step_begin beside the commitments (P = the step's P_S is known ~0.15 ms into the step, r only after it), so that the
+// scalar multiplication r * P_S in step_end is SCALE_PARTS independent PART_BITS-bit pieces instead of one 128-bit chain.
+constexpr int SCALE_PARTS = 2, PART_BITS = 64;
+template <class C>
+__global__ void __launch_bounds__(32) k_point_pow2_parts(const void* __restrict__ jac, void* __restrict__ parts) {
+  QPoint<C> p = q_load_jacobian<C>(jac);
+  if (threadIdx.x < 4) p.store(parts);
+#pragma unroll 1
+  for (int j = 1; j < SCALE_PARTS; j++) {
+#pragma unroll 1
+    for (int b = 0; b < PART_BITS; b++) p = q_dbl<C>(p);
+    if (threadIdx.x < 4) p.store(reinterpret_cast<char*>(parts) + (size_t)j * 128);
+  }
+}
+
+// out = a + r * P given parts[j] = 2^(PART_BITS j) P (k_point_pow2_parts): warp j multiplies parts[j] by bits [PART_BITS j, PART_BITS (j + 1))
+// of r, warp 0 adds the pieces and `a`.  A 128-bit r (Nova's challenge) is 64 doublings + ~32 additions deep instead of 128 + ~64; a
+// wider r takes the plain chain on warp 0 (exact for any field element).  One block of SCALE_PARTS warps; every quad of a warp does
+// the same work.
+template <class C>
+__global__ void __launch_bounds__(32 * SCALE_PARTS) k_point_scale_add_parts(const void* __restrict__ a, Fp<typename C::Fs> r_mont,
+                                                                           const void* __restrict__ parts, void* __restrict__ out) {
+  using Fs = Fp<typename C::Fs>;
+  static_assert(SCALE_PARTS * PART_BITS == 128 && PART_BITS % 32 == 0 && SCALE_PARTS <= 8, "pieces of a 128-bit challenge");
+  __shared__ __align__(16) uint32_t smem[SCALE_PARTS * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Fs r = fp_from_mont(r_mont);
+  const bool wide = (r.v[4] | r.v[5] | r.v[6] | r.v[7]) != 0;  // block-uniform
+  QPoint<C> acc = QPoint<C>::identity();
+  if (!wide || warp == 0) {
+    const QPoint<C> base = QPoint<C>::load(reinterpret_cast<const char*>(parts) + (size_t)warp * 128);
+    int top = wide ? 255 : PART_BITS * (warp + 1) - 1;
+    const int low = wide ? 0 : PART_BITS * warp;
+    while (top >= low && !((r.v[top >> 5] >> (top & 31)) & 1)) top--;
+#pragma unroll 1
+    for (int bit = top; bit >= low; bit--) {  // warp-uniform trip count and branch
+      acc = q_dbl<C>(acc);
+      if ((r.v[bit >> 5] >> (bit & 31)) & 1) acc = q_add<C>(acc, base);
+    }
+  }
+  if (lane < 4) acc.store(smem + warp * 32);
+  __syncthreads();
+  if (warp != 0) return;
+  acc = lane < 4 * SCALE_PARTS ? QPoint<C>::load(smem + (lane >> 2) * 32) : QPoint<C>::identity();
+  acc = q_warp_reduce<C>(acc, SCALE_PARTS > 4 ? 4 : (SCALE_PARTS > 2 ? 2 : 1));
+  acc = q_add<C>(acc, q_load_jacobian<C>(a));
+  q_store_jacobian<C>(acc, out, lane < 4);
 }
 
 // bases[i] = (k0 + i*dk) * G ; each thread walks a run of GEN_RUN consecutive multiples.
