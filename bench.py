@@ -360,14 +360,22 @@ class GpuFold:
         n = self.sh.num_vars
         return max(0, n - NOVA_AUGMENTED) if n > 2 * NOVA_AUGMENTED else 0
 
-    def stage(self, k: int):
+    def stage(self, k: int, resident=False):
         i = k % len(self.wits)
-        self.acc.stage_fresh(self.pin_np[i], 0, self.staged_split())
+        self.acc.stage_fresh(self.dev_ptr[i] if resident else self.pin_np[i], 0, self.staged_split())
 
-    def step_staged(self, k: int):
+    def step_staged(self, k: int, resident=False):
         i = k % len(self.wits)
         e = self.staged_split()
-        cw, ct = self.acc.step_begin_staged(self.pin_np[i], e, self.sh.num_vars - e, self.X2_bytes[i])
+        cw, ct = self.acc.step_begin_staged(self.dev_ptr[i] if resident else self.pin_np[i], e, self.sh.num_vars - e, self.X2_bytes[i])
+        self.acc.step_end(((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little"))
+
+    def begin_async(self, k: int, resident=False):
+        i = k % len(self.wits)
+        self.acc.step_begin_async(self.dev_ptr[i] if resident else self.pin_np[i], self.X2_bytes[i])
+
+    def finish_async(self, k: int):
+        cw, ct = self.acc.step_wait()
         self.acc.step_end(((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little"))
 
     def replay_from_zero(self, nsteps: int):

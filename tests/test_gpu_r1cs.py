@@ -427,6 +427,65 @@ def test_booleanity_row_fold_is_exact(fold_on, coracle):
 test_booleanity_row_fold_is_exact.entries = {}
 
 
+@pytest.mark.parametrize("opts", [{}, {"stage_commit": 1}, {"acc_order": 1}, {"stage_commit": 1, "bitrow_fold": 0}])
+def test_staged_async_and_resident_entry_points_match_cpu_chain(opts, coracle):
+    """Every way a step's witness can reach the accumulator gives the CPU chain's commitments and folded pair: the plain host call,
+    stage_fresh (prefix / suffix, host or device memory) + step_begin_staged -- with the early commitment of the staged range
+    (option stage_commit) and without --, step_begin_async + step_wait, and step_begin_dev (whose copy is a patched graph node);
+    graph replays included (each variant runs more than twice), with the accumulations ordered (acc_order) or not.  A staged range
+    that is re-uploaded by step_begin_staged must fall back to a full commitment."""
+    import torch
+    c = P.PALLAS
+    q = c.q
+    eng = vimz_b200.Engine("pallas", 0)
+    eng.set_option("msm_direct_max", 0)            # bucket pipeline: the paths these options shape
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    sh, shape, ck, Bm = _setup(eng, c, 0.02, seed=91)
+    n = sh.num_vars
+    rng = random.Random(17)
+    nsteps = 14
+    wit = []
+    for k in range(nsteps):
+        Wi, Xi = S.synthetic_witness(sh, 900 + k)
+        wit.append((ints_to_mont(Wi, q), ints_to_mont(Xi, q)))
+    chal = [ints_to_mont([rng.randrange(1 << 128)], q) for _ in range(nsteps)]
+    ref = _oracle_fold_chain(coracle, c, sh, Bm, wit, chal)
+    dev = [torch.from_numpy(w.view(np.int64)).to("cuda:0") for w, _ in wit]
+    acc = FoldAccumulator(shape, ck)
+    split = n - 1100                                 # the staged prefix is long enough for an early commitment (>= 1024 rows)
+    for k in range(nsteps):
+        W2, X2 = wit[k]
+        mode = k % 7
+        if mode == 0:
+            cw, ct = acc.step_begin(W2, X2)
+        elif mode == 1:                              # prefix staged from the host, rest in the step
+            acc.stage_fresh(W2, 0, split)
+            cw, ct = acc.step_begin_staged(W2, split, n - split, X2)
+        elif mode == 2:                              # the same from device memory
+            acc.stage_fresh(dev[k].data_ptr(), 0, split)
+            cw, ct = acc.step_begin_staged(dev[k].data_ptr(), split, n - split, X2)
+        elif mode == 3:                              # suffix staged, prefix in the step
+            acc.stage_fresh(W2, n - split, split)
+            cw, ct = acc.step_begin_staged(W2, 0, n - split, X2)
+        elif mode == 4:
+            acc.step_begin_async(dev[k].data_ptr(), X2)
+            cw, ct = acc.step_wait()
+        elif mode == 5:
+            cw, ct = acc.step_begin_dev(dev[k].data_ptr(), X2)
+        else:                                        # a WRONG prefix staged first, then everything re-uploaded: the early commitment is void
+            acc.stage_fresh(wit[(k + 1) % nsteps][0], 0, split)
+            cw, ct = acc.step_begin_staged(W2, 0, n, X2)
+        assert eng.to_affine_ints(cw) == _affine(coracle, c, ref[k]["comm_W2"]), (opts, k, mode)
+        assert eng.to_affine_ints(ct) == _affine(coracle, c, ref[k]["comm_T"]), (opts, k, mode)
+        acc.step_end(chal[k])
+    U, W = acc.download()
+    last = ref[-1]
+    assert np.array_equal(W.W, last["W"]) and np.array_equal(W.E, last["E"]) and np.array_equal(U.u, last["u"]) and np.array_equal(U.X, last["X"])
+    assert eng.to_affine_ints(U.comm_W) == _affine(coracle, c, last["cW"]) and eng.to_affine_ints(U.comm_E) == _affine(coracle, c, last["cE"])
+    acc.close(); shape.close(); ck.close(); eng.close()
+
+
 def test_fold_from_r1cs_and_wtns_files_bn254(tmp_path, engines, coracle):
     """Real-artifact ingestion: an iden3 .r1cs + two .wtns files (circom's bn128 prime) are read,
     uploaded and folded on the BN254 engine; result == CPU chain and the folded instance is satisfied."""

@@ -117,19 +117,27 @@ struct CtxGuard {
   explicit CtxGuard(vimz_ctx* ctx) : lock(ctx->mu), dev(ctx->device) {}
 };
 
+// every stream of a context: main, commitment folds, aux MSM lane, P_S branch, K_S update, early commitments
+static cudaError_t sync_all_streams(vimz_ctx* ctx) {
+  cudaError_t first = cudaSuccess;
+  for (cudaStream_t st : {ctx->stream, ctx->side, ctx->aux, ctx->ps, ctx->ks, ctx->early})
+    if (st) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (first == cudaSuccess) first = e;
+    }
+  return first;
+}
+
 // ---- handle lifetimes ----------------------------------------------------------------------------------
 // Children (keys, shapes, accumulators) hold a reference on their context, accumulators also on their shape and keys.
 // A *_destroy call on a parent that still has children only drops the owner's reference: the object is freed when the
 // last child goes, so destruction order on the host side (Drop order in Rust, garbage collection in Python) is free.
 static void ctx_free(vimz_ctx* ctx) {
   DeviceGuard dg(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->side);
-  cudaStreamSynchronize(ctx->aux);
-  cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
+  sync_all_streams(ctx);
   ctx->ws.release();
   ctx->ws_aux.release();
+  ctx->ws_early.release();
   ctx->tmp0.release(); ctx->tmp1.release(); ctx->tmp2.release();
   ctx->tmp3.release(); ctx->tmp4.release(); ctx->tmp5.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -142,6 +150,7 @@ static void ctx_free(vimz_ctx* ctx) {
   cudaStreamDestroy(ctx->aux);
   cudaStreamDestroy(ctx->ps);
   cudaStreamDestroy(ctx->ks);
+  cudaStreamDestroy(ctx->early);
   delete ctx;
 }
 static void ctx_release(vimz_ctx* ctx) {
@@ -152,13 +161,7 @@ static void ck_release(vimz_ck* ck) {
   vimz_ctx* ctx = ck->ctx;
   {
     CtxGuard g(ctx);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->aux);
-  cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
-    cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
-    cudaStreamSynchronize(ctx->ks);
+    sync_all_streams(ctx);
     if (ck->table) cudaFree(ck->table);
     if (ck->dtable) cudaFree(ck->dtable);
     delete ck;
@@ -225,6 +228,7 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
     VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_lo));
     VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->ps, cudaStreamNonBlocking, prio_lo));
     VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->ks, cudaStreamNonBlocking, prio_hi));
+    VIMZ_CUDA(cudaStreamCreateWithPriority(&ctx->early, cudaStreamNonBlocking, prio_lo));
     VIMZ_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     VIMZ_CUDA(cudaMallocHost(&ctx->pinned, 4096));
     VIMZ_TRY(ctx->ws.result.reserve(4096));
@@ -238,6 +242,7 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out) {
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ps) cudaStreamDestroy(ctx->ps);
     if (ctx->ks) cudaStreamDestroy(ctx->ks);
+    if (ctx->early) cudaStreamDestroy(ctx->early);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     ctx->ws.release();
     delete ctx;
@@ -252,14 +257,7 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
   if (!ctx) return;
   {  // wait for a call still running on another thread, then for the streams
     CtxGuard g(ctx);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->side);
-    cudaStreamSynchronize(ctx->aux);
-  cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
-    cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
-    cudaStreamSynchronize(ctx->ks);
+    sync_all_streams(ctx);
   }
   ctx_release(ctx);  // freed now, or when the last key / shape / accumulator created on it is destroyed
 }
@@ -267,11 +265,7 @@ void vimz_ctx_destroy(vimz_ctx* ctx) {
 int vimz_ctx_sync(vimz_ctx* ctx) {
   CHECK_ARG(ctx, "vimz_ctx_sync: null ctx");
   CtxGuard g(ctx);
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->ps));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->ks));
+  VIMZ_CUDA(sync_all_streams(ctx));
   return VIMZ_OK;
 }
 
@@ -338,6 +332,15 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     alloc_epoch()++;
     return VIMZ_OK;
   }
+  if (strcmp(key, "acc_order") == 0) {
+    ctx->opt_acc_order = value != 0;
+    alloc_epoch()++;  // (shapes the captured launch sequence)
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "stage_commit") == 0) {
+    ctx->opt_stage_commit = value != 0;
+    return VIMZ_OK;
+  }
   if (strcmp(key, "bitrow_fold") == 0) {  // applies to accumulators created afterwards
     ctx->opt_bitrow_fold = value != 0;
     return VIMZ_OK;
@@ -355,10 +358,7 @@ static const char* PROF_NAMES[PROF_COUNT] = {"msm_sort", "msm_accumulate", "msm_
 int vimz_ctx_profile(vimz_ctx* ctx, const char* name, double* ms, uint64_t* calls, int reset) {
   CHECK_ARG(ctx && name, "vimz_ctx_profile: null argument");
   CtxGuard g(ctx);
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->ps));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->ks));
+  VIMZ_CUDA(sync_all_streams(ctx));
   Profiler& p = ctx->prof;
   for (ProfSpan& s : p.open) {
     float t = 0;
@@ -846,27 +846,26 @@ int vimz_fold_witness(vimz_ctx* ctx, const vimz_fr* r, const vimz_fr* W1, const 
 constexpr size_t ACC_PIN_FRESH = 0, ACC_PIN_COMBINED = 256, ACC_PIN_STAGE = 512;  // layout of vimz_acc::pinned
 // vimz_acc::comms, in Jacobian points: the running triple (comm_W, comm_E, K_S), then one (comm_W2, comm_T, P_S) triple per parity
 // slot -- step_end folds the three pairs with one launch: running[k] += r * fresh[k]
-constexpr size_t ACC_SLOT_KS = 2, ACC_SLOTS = 9;
+// ... then the early commitment of a staged witness range and the commitment of the rest (vimz_acc_stage_fresh)
+constexpr size_t ACC_SLOT_KS = 2, ACC_SLOT_EARLY = 9, ACC_SLOT_REST = 10, ACC_SLOTS = 11;
 static inline char* acc_fresh(const vimz_acc* a, int parity) { return (char*)a->comms + (3 + 3 * parity) * 96; }
 void vimz_acc_destroy(vimz_acc* a) {
   if (!a) return;
   vimz_ctx* ctx = a->ctx;
   {
     CtxGuard g(ctx);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->side);
-    cudaStreamSynchronize(ctx->aux);
-  cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
-    cudaStreamSynchronize(ctx->ps);
-  cudaStreamSynchronize(ctx->ks);
-    cudaStreamSynchronize(ctx->ks);
+    sync_all_streams(ctx);
     void* bufs[] = {a->W1, a->E1, a->W2, a->T, a->tail1, a->tail2, a->comms, a->cache1, a->cache2, a->ksum_scratch, a->ps_parts};
     for (void* b : bufs)
       if (b) cudaFree(b);
     if (a->pinned) cudaFreeHost(a->pinned);
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 8; k++) {
       if (a->graph[k]) cudaGraphExecDestroy(a->graph[k]);
+      if (a->graph_src[k]) cudaGraphDestroy(a->graph_src[k]);
+    }
+    if (a->ev_stage) cudaEventDestroy(a->ev_stage);
+    if (a->ev_auxacc) cudaEventDestroy(a->ev_auxacc);
+    if (a->ev_early) cudaEventDestroy(a->ev_early);
     if (a->ev_main) cudaEventDestroy(a->ev_main);
     if (a->ev_w2) cudaEventDestroy(a->ev_w2);
     if (a->ev_aux) cudaEventDestroy(a->ev_aux);
@@ -920,6 +919,9 @@ static int acc_create(vimz_ctx* ctx, const vimz_shape* s, const vimz_ck* ck, con
     for (cudaEvent_t* ev : {&a->ev_ps_fork, &a->ev_ps_join, &a->ev_ks[0], &a->ev_ks[1]})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_stage, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_auxacc, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_early, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_w2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_aux, cudaEventDisableTiming);
@@ -1009,11 +1011,7 @@ int vimz_acc_reset(vimz_acc* a) {
   CHECK_ARG(a, "vimz_acc_reset: null argument");
   vimz_ctx* ctx = a->ctx;
   CtxGuard g(ctx);
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->stream));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->aux));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->ps));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->ks));
-  VIMZ_CUDA(cudaStreamSynchronize(ctx->side));
+  VIMZ_CUDA(sync_all_streams(ctx));
   a->side_pending[0] = a->side_pending[1] = false;
   const vimz_shape* s = a->shape;
   cudaStream_t st = ctx->stream;
@@ -1034,17 +1032,26 @@ int vimz_acc_reset(vimz_acc* a) {
 // of T' = T + [bit row] Az1 and the final kernel of the MSM subtracts K_S, so `d_comm_T` receives the true commit(T).  K_S is folded
 // by the PREVIOUS step_end on the side stream (its scalar multiplication takes ~0.4 ms and was issued a whole step of the other
 // curve ago): the final kernel -- only that one -- waits for that event.
-static int enqueue_cross_commit_T(vimz_acc* a, void* d_comm_T, void* host_out) {
+static inline bool acc_shifted(const vimz_acc* a) {
+  return a->use_ks && a->ctx->opt_cross_stream && a->shape->n_chunks > 0 && a->shape->m > 0;
+}
+static int enqueue_cross(vimz_acc* a) {
+  const vimz_shape* s = a->shape;
+  return curve_vtable(a->ctx->curve)->cross_term(a->ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2,
+                                                acc_shifted(a) ? s->rowflag : nullptr);
+}
+// acc_wait: an event commit(T)'s accumulation kernel waits for (nullptr: none)
+static int enqueue_commit_T(vimz_acc* a, void* d_comm_T, void* host_out, cudaEvent_t acc_wait = nullptr) {
   vimz_ctx* ctx = a->ctx;
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
-  const bool shifted = a->use_ks && ctx->opt_cross_stream && s->n_chunks > 0 && s->m > 0;
+  const bool shifted = acc_shifted(a);
   struct Reset {
     vimz_ctx* c;
-    ~Reset() { c->ws.host_out = nullptr; c->ws.sub_jac = nullptr; c->ws.sub_event = nullptr; }
+    ~Reset() { c->ws.host_out = nullptr; c->ws.sub_jac = nullptr; c->ws.sub_event = nullptr; c->ws.acc_wait = nullptr; }
   } reset{ctx};
-  VIMZ_TRY(vt->cross_term(ctx, s, a->W1, a->tail1, a->W2, a->tail2, a->T, a->ck, a->cache1, a->cache2, shifted ? s->rowflag : nullptr));
   ctx->ws.host_out = host_out;
+  ctx->ws.acc_wait = acc_wait;
   if (shifted) {
     ctx->ws.sub_jac = (char*)a->comms + ACC_SLOT_KS * 96;
     ctx->ws.sub_event = a->ev_ks[a->parity ^ 1];
@@ -1052,6 +1059,10 @@ static int enqueue_cross_commit_T(vimz_acc* a, void* d_comm_T, void* host_out) {
   // (an accumulator without rows -- a shard of a fold spread over more ranks than constraints -- ran no cross term,
   // so nothing recoded T: the commit then does its own, empty, digit pass)
   return vt->msm(ctx, 0, a->ck, 0, a->T, s->m, d_comm_T, s->m > 0);
+}
+static int enqueue_cross_commit_T(vimz_acc* a, void* d_comm_T, void* host_out) {
+  VIMZ_TRY(enqueue_cross(a));
+  return enqueue_commit_T(a, d_comm_T, host_out);
 }
 
 // P_S = sum over the booleanity rows of (A z2)_i ck_i (what K_S gains, times r, in step_end): a plain sum of the ~55 k bases whose
@@ -1085,6 +1096,20 @@ static int join_ps_branch(vimz_acc* a, cudaStream_t st) {
 __global__ void __launch_bounds__(256) k_copy16(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
+struct CopyNode {
+  uint4* dst;
+  const uint4* src;
+  size_t n16;
+  unsigned grid;
+};
+static CopyNode copy_node_params(const vimz_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CopyNode c;
+  c.dst = reinterpret_cast<uint4*>(dst);
+  c.src = reinterpret_cast<const uint4*>(src);
+  c.n16 = bytes / 16;
+  c.grid = (unsigned)std::min<size_t>((c.n16 + 255) / 256, (size_t)ctx->sm_count * 8);
+  return c;
+}
 static int copy_dev(vimz_ctx* ctx, void* dst, const void* src, size_t bytes) {  // bytes: a multiple of 32, both 16-byte aligned
   if (bytes == 0 || dst == src) return VIMZ_OK;
   if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) {
@@ -1098,19 +1123,78 @@ static int copy_dev(vimz_ctx* ctx, void* dst, const void* src, size_t bytes) {  
   return VIMZ_OK;
 }
 
+// comm_W2 = commit(ck_w, W2[w_first .. w_first + w_count)) on MSM lane `lane`, result in `fresh` and in the pinned block.  With an early
+// commitment of a staged range (vimz_acc_stage_fresh, lane 2, possibly still running: it started a whole step of the other curve
+// ago) only the complement is committed here, and one more kernel adds the two -- that one waits for the early lane.
+// phase 1 / 2: only the front / back half of the pipeline (MsmWorkspace::phase), the front half recording `acc_record` behind its
+// accumulation kernel
+static int enqueue_commit_W2(vimz_acc* a, int lane, char* fresh, int phase = 0, cudaEvent_t acc_record = nullptr) {
+  vimz_ctx* ctx = a->ctx;
+  const CurveVTable* vt = curve_vtable(ctx->curve);
+  MsmWorkspace& ws = lane == 0 ? ctx->ws : ctx->ws_aux;
+  cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
+  if (!a->early_valid) {
+    ws.host_out = a->pinned + ACC_PIN_FRESH;
+    ws.phase = phase;
+    ws.acc_record = acc_record;
+    int rc = vt->msm(ctx, lane, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, lane == 1 && a->w2_counted);
+    ws.host_out = nullptr;
+    ws.phase = 0;
+    ws.acc_record = nullptr;
+    return rc;
+  }
+  // the staged range is a prefix or a suffix of the committed variables (checked by vimz_acc_stage_fresh): the rest is one range
+  const size_t rest_first = a->early_first == a->w_first ? a->early_first + a->early_count : a->w_first;
+  const size_t rest_count = a->w_count - a->early_count;
+  char* comms = (char*)a->comms;
+  ws.host_out = nullptr;
+  VIMZ_TRY(vt->msm(ctx, lane, a->ck_w, rest_first - a->w_first, (const char*)a->W2 + rest_first * 32, rest_count, comms + ACC_SLOT_REST * 96, false));
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  VIMZ_CUDA(cudaStreamIsCapturing(st, &cs));  // (inside a captured graph an EXTERNAL wait: the early lane is not part of the capture)
+  VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_early, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault));
+  return vt->point_add2(ctx, st, comms + ACC_SLOT_EARLY * 96, comms + ACC_SLOT_REST * 96, fresh, a->pinned + ACC_PIN_FRESH);
+}
+
+// A witness (range) handed over through a host-pointer entry point: an H2D copy -- unless the pointer is device memory (unified
+// addressing tells), which the resident-witness callers of the staged entry points pass: then the copy kernel.
+static int copy_in(vimz_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return VIMZ_OK;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeDevice) return copy_dev(ctx, dst, src, bytes);
+  cudaGetLastError();  // (an unregistered host pointer may leave an error behind on old drivers)
+  VIMZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return VIMZ_OK;
+}
+
 // The stream work of step_begin after W2 is resident: everything here has fixed addresses, so it can be captured.
 static int enqueue_step_begin(vimz_acc* a, char* fresh) {
   vimz_ctx* ctx = a->ctx;
   const vimz_shape* s = a->shape;
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
+  if (a->w2_mailbox && s->n) {  // step_begin_dev: the resident witness is copied by the step's own first node, whose source
+    // parameter is patched before every replay (copy_node_params; reading the address from a mapped host word instead cost 0.8 us per
+    // BLOCK: sysmem reads are served one at a time)
+    CopyNode cn = copy_node_params(ctx, a->W2, a->w2_src, s->n * 32);
+    k_copy16<<<cn.grid, 256, 0, st>>>(cn.dst, cn.src, cn.n16);
+    VIMZ_LAUNCH_CHECK(ctx);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaGraph_t cg = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    VIMZ_CUDA(cudaStreamGetCaptureInfo_v2(st, &cs, nullptr, &cg, &deps, &ndeps));
+    a->cap_copy_node = (cs == cudaStreamCaptureStatusActive && ndeps == 1) ? deps[0] : nullptr;
+  }
   VIMZ_TRY(fork_ps_branch(a, st));
   // tail2 = the staged (1, X2): copied by the kernel that clears commit(T)'s histogram when there is one (one node instead of two)
   const bool fused_tail = ctx->opt_cross_stream && s->n_chunks > 0 && s->m > 0 && !a->ck->dtable;
   if (fused_tail) {
     ctx->ws.pro_src = a->pinned + ACC_PIN_STAGE; ctx->ws.pro_dst = a->tail2; ctx->ws.pro_bytes = (1 + s->io) * 32;
-  } else {
-    VIMZ_CUDA(cudaMemcpyAsync(a->tail2, a->pinned + ACC_PIN_STAGE, (1 + s->io) * 32, cudaMemcpyHostToDevice, st));
+  } else {  // (a kernel that reads the mapped block: a copy-engine node costs more dispatch than it moves)
+    const uint32_t nc = (uint32_t)((1 + s->io) * 2);
+    k_zero_and_copy<<<(nc + 255) / 256, 256, 0, st>>>(nullptr, 0, reinterpret_cast<const uint4*>(a->pinned + ACC_PIN_STAGE),
+                                                      reinterpret_cast<uint4*>(a->tail2), nc);
+    VIMZ_LAUNCH_CHECK(ctx);
   }
   // comm_W2 = commit(ck, W2)   (r1cs_instance_and_witness) is independent of T, so it runs on the aux stream with its own
   // workspace while the main stream does the cross term and commit(T).  The main lane is the critical one and is enqueued
@@ -1122,19 +1206,29 @@ static int enqueue_step_begin(vimz_acc* a, char* fresh) {
     vimz_ctx* c;
     ~HostOut() { c->ws.host_out = nullptr; c->ws_aux.host_out = nullptr; c->ws.pro_bytes = 0; }
   } host_out_guard{ctx};
+  a->w2_counted = false;
   if (two_lanes) {
     VIMZ_CUDA(cudaEventRecord(a->ev_w2, st));
     VIMZ_CUDA(cudaStreamWaitEvent(ctx->aux, a->ev_w2, 0));
+    // the aux lane's first two nodes (clear + digit pass) are created HERE, ahead of the main lane's: a graph dispatches its root
+    // nodes in creation order, and created last the aux lane started ~25 us into the step -- its accumulation then ran beside the
+    // main lane's scatter and accumulation instead of beside the (light) cross term
+    if (!a->early_valid)
+      VIMZ_TRY(vt->msm_digits(ctx, 1, a->ck_w, (const char*)a->W2 + a->w_first * 32, a->w_count, &a->w2_counted));
   } else {  // one lane (used by the profiled pass so kernel times are not inflated by the other lane)
-    ctx->ws.host_out = a->pinned + ACC_PIN_FRESH;
-    VIMZ_TRY(vt->msm(ctx, 0, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
+    VIMZ_TRY(enqueue_commit_W2(a, 0, fresh));
   }
   // T = cross term (mat-vecs with z2 + element-wise combination), comm_T = commit(ck, T)      (commit_T)
-  VIMZ_TRY(enqueue_cross_commit_T(a, fresh + 96, a->pinned + ACC_PIN_FRESH + 96));
+  // Ordered accumulations (option acc_order): the two accumulation kernels are throughput-bound and gain nothing from sharing the SMs,
+  // while everything behind each of them is a latency chain -- so commit(W2)'s (the short one, ready first) runs alone, commit(T)'s
+  // starts when it has finished, and the tails of the aux lane are well under way when those of the main lane begin.
+  const bool ordered = two_lanes && ctx->opt_acc_order && !a->early_valid && a->w2_counted && !a->ck->dtable && s->m > 0 && !ctx->prof.on;
+  VIMZ_TRY(enqueue_cross(a));
+  if (ordered) VIMZ_TRY(enqueue_commit_W2(a, 1, fresh, 1, a->ev_auxacc));
+  VIMZ_TRY(enqueue_commit_T(a, fresh + 96, a->pinned + ACC_PIN_FRESH + 96, ordered ? a->ev_auxacc : nullptr));
   VIMZ_TRY(enqueue_ps_branch(a, fresh));
   if (two_lanes) {
-    ctx->ws_aux.host_out = a->pinned + ACC_PIN_FRESH;
-    VIMZ_TRY(vt->msm(ctx, 1, a->ck_w, 0, (const char*)a->W2 + a->w_first * 32, a->w_count, fresh, false));
+    VIMZ_TRY(enqueue_commit_W2(a, 1, fresh, ordered ? 2 : 0));
     VIMZ_CUDA(cudaEventRecord(a->ev_aux, ctx->aux));
     VIMZ_CUDA(cudaStreamWaitEvent(st, a->ev_aux, 0));
   }
@@ -1163,14 +1257,18 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
   memcpy(stage, vt->scalar_one_mont, 32);
   if (s->io) memcpy(stage + 32, X2, s->io * 32);
 
-  bool use_graph = ctx->opt_graph && !ctx->prof.on && a->warm[p];
-  if (use_graph && a->graph[p] && a->graph_epoch[p] != alloc_epoch()) {  // a workspace moved: rebuild
-    cudaGraphExecDestroy(a->graph[p]);
-    a->graph[p] = nullptr;
+  // a step with an early commitment / with the witness copy inside has its own launch sequence
+  const int gi = p + (a->early_valid ? 2 : 0) + (a->w2_mailbox ? 4 : 0);
+  bool use_graph = ctx->opt_graph && !ctx->prof.on && a->warm[gi];
+  if (use_graph && a->graph[gi] &&
+      (a->graph_epoch[gi] != alloc_epoch() ||  // a workspace moved: rebuild
+       (a->early_valid && (a->graph_early[gi][0] != a->early_first || a->graph_early[gi][1] != a->early_count)))) {
+    cudaGraphExecDestroy(a->graph[gi]);
+    a->graph[gi] = nullptr;
     use_graph = false;  // one eager run re-validates the buffers first
   }
   if (use_graph) {
-    if (!a->graph[p]) {
+    if (!a->graph[gi]) {
       uint64_t l0 = ctx->launches, e0 = alloc_epoch();
       VIMZ_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
       int rc = enqueue_step_begin(a, fresh);
@@ -1183,22 +1281,40 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
         if (rc == VIMZ_OK) rc = enqueue_step_begin(a, fresh);
         if (rc != VIMZ_OK) return rc;
       } else {
-        a->graph_launches[p] = ctx->launches - l0;
+        a->graph_launches[gi] = ctx->launches - l0;
         ctx->launches = l0;
-        e = cudaGraphInstantiate(&a->graph[p], g, 0);
-        cudaGraphDestroy(g);
+        e = cudaGraphInstantiate(&a->graph[gi], g, 0);
+        if (a->graph_src[gi]) cudaGraphDestroy(a->graph_src[gi]);
+        a->graph_src[gi] = nullptr;
+        if (e == cudaSuccess && a->w2_mailbox) a->graph_src[gi] = g;  // the copy node's handle lives in the source graph
+        else cudaGraphDestroy(g);
         if (e != cudaSuccess) return set_error(VIMZ_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-        a->graph_epoch[p] = e0;
+        a->graph_epoch[gi] = e0;
+        a->graph_early[gi][0] = a->early_first; a->graph_early[gi][1] = a->early_count;
+        a->copy_node[gi] = a->cap_copy_node;
+        if (a->w2_mailbox && !a->copy_node[gi]) return set_error(VIMZ_ERR_CUDA, "step_begin_dev: the captured copy node was not found");
       }
     }
-    if (a->graph[p]) {
-      VIMZ_CUDA(cudaGraphLaunch(a->graph[p], st));
-      ctx->launches += a->graph_launches[p];
+    if (a->graph[gi]) {
+      if (a->w2_mailbox && s->n) {  // this replay's witness
+        CopyNode cn = copy_node_params(ctx, a->W2, a->w2_src, s->n * 32);
+        void* kargs[3] = {&cn.dst, &cn.src, &cn.n16};
+        cudaKernelNodeParams kp = {};
+        kp.func = reinterpret_cast<void*>(k_copy16);
+        kp.gridDim = dim3(cn.grid);
+        kp.blockDim = dim3(256);
+        kp.kernelParams = kargs;
+        VIMZ_CUDA(cudaGraphExecKernelNodeSetParams(a->graph[gi], a->copy_node[gi], &kp));
+      }
+      VIMZ_CUDA(cudaGraphLaunch(a->graph[gi], st));
+      ctx->launches += a->graph_launches[gi];
     }
   } else {
     VIMZ_TRY(enqueue_step_begin(a, fresh));
-    a->warm[p] = true;
+    a->warm[gi] = true;
   }
+  a->early_valid = false;  // consumed
+  a->w2_mailbox = false;
   a->fresh_complete = false;
   a->step_enqueued = true;
   if (!sync) return VIMZ_OK;
@@ -1212,6 +1328,7 @@ static int acc_step_begin_common(vimz_acc* a, const vimz_fr* X2, vimz_point* com
 int vimz_acc_step_begin_dev_async(vimz_acc* a, const void* d_W2, const vimz_fr* X2, void** d_partials) {
   CHECK_ARG(a && d_partials && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev_async: null argument");
   CtxGuard g(a->ctx);
+  a->early_valid = false;  // the whole witness is replaced: an early commitment of a staged range is void
   if (d_W2 != a->W2)  // (the sharded entry points broadcast the witness straight into the accumulator)
     VIMZ_CUDA(cudaMemcpyAsync(a->W2, d_W2, a->shape->n * 32, cudaMemcpyDeviceToDevice, a->ctx->stream));
   VIMZ_TRY(acc_step_begin_common(a, X2, nullptr, nullptr, false));
@@ -1237,7 +1354,8 @@ int vimz_acc_step_combine_dev(vimz_acc* a, const void* d_gathered, size_t world,
 int vimz_acc_step_begin(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vimz_point* comm_W2, vimz_point* comm_T) {
   CHECK_ARG(a && comm_W2 && comm_T && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin: null argument");
   CtxGuard g(a->ctx);
-  VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  a->early_valid = false;
+  VIMZ_TRY(copy_in(a->ctx, a->W2, W2, a->shape->n * 32));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
@@ -1250,7 +1368,25 @@ int vimz_acc_stage_fresh(vimz_acc* a, const vimz_fr* W2_part, size_t first, size
   if (first > a->shape->n || count > a->shape->n - first) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_stage_fresh: range outside the witness");
   CtxGuard g(a->ctx);
   if (a->half_open) return set_error(VIMZ_ERR_ARG, "vimz_acc_stage_fresh: a step is open (commit_fresh without cross_begin)");
-  if (count) VIMZ_CUDA(cudaMemcpyAsync((char*)a->W2 + first * 32, W2_part, count * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  vimz_ctx* ctx = a->ctx;
+  a->early_valid = false;
+  VIMZ_TRY(copy_in(ctx, (char*)a->W2 + first * 32, W2_part, count * 32));
+  // Early commitment: the staged range is final, so its share of comm_W2 = commit(ck, W2) can be computed NOW, on a lane of its
+  // own, while the GPU folds the other curve (whose step leaves most of the SMs idle) -- the step then commits only the rest and
+  // its throughput phase no longer shares the SMs with commit(T).  Only for a prefix / suffix of the committed variables (the rest
+  // must be one range), a key on the bucket pipeline, and a range worth a pipeline of its own.
+  const bool edge = first == a->w_first || first + count == a->w_first + a->w_count;
+  if (ctx->opt_stage_commit && count >= 1024 && first >= a->w_first && first + count <= a->w_first + a->w_count && edge && !a->ck_w->dtable &&
+      (a->fresh_complete || !a->step_enqueued)) {
+    VIMZ_CUDA(cudaEventRecord(a->ev_stage, ctx->stream));
+    VIMZ_CUDA(cudaStreamWaitEvent(ctx->early, a->ev_stage, 0));
+    VIMZ_TRY(curve_vtable(ctx->curve)->msm(ctx, 2, a->ck_w, first - a->w_first, (const char*)a->W2 + first * 32, count,
+                                          (char*)a->comms + ACC_SLOT_EARLY * 96, false));
+    VIMZ_CUDA(cudaEventRecord(a->ev_early, ctx->early));
+    a->early_valid = true;
+    a->early_first = first;
+    a->early_count = count;
+  }
   return VIMZ_OK;
 }
 
@@ -1259,7 +1395,9 @@ int vimz_acc_step_begin_staged(vimz_acc* a, const vimz_fr* W2_rest, size_t first
   CHECK_ARG(a && comm_W2 && comm_T && (W2_rest || count == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_staged: null argument");
   if (first > a->shape->n || count > a->shape->n - first) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_step_begin_staged: range outside the witness");
   CtxGuard g(a->ctx);
-  if (count) VIMZ_CUDA(cudaMemcpyAsync((char*)a->W2 + first * 32, W2_rest, count * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  if (a->early_valid && count && first < a->early_first + a->early_count && a->early_first < first + count)
+    a->early_valid = false;  // the range committed early is being overwritten: commit everything in the step
+  VIMZ_TRY(copy_in(a->ctx, (char*)a->W2 + first * 32, W2_rest, count * 32));
   return acc_step_begin_common(a, X2, comm_W2, comm_T);
 }
 
@@ -1268,7 +1406,8 @@ int vimz_acc_step_begin_staged(vimz_acc* a, const vimz_fr* W2_rest, size_t first
 int vimz_acc_step_begin_async(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2) {
   CHECK_ARG(a && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_async: null argument");
   CtxGuard g(a->ctx);
-  VIMZ_CUDA(cudaMemcpyAsync(a->W2, W2, a->shape->n * 32, cudaMemcpyHostToDevice, a->ctx->stream));
+  a->early_valid = false;
+  VIMZ_TRY(copy_in(a->ctx, a->W2, W2, a->shape->n * 32));
   return acc_step_begin_common(a, X2, nullptr, nullptr, false);
 }
 
@@ -1288,8 +1427,16 @@ int vimz_acc_step_begin_dev(vimz_acc* a, const void* d_W2, const vimz_fr* X2, vi
   CHECK_ARG(a && comm_W2 && comm_T && (d_W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_dev: null argument");
   CtxGuard g(a->ctx);
   // keep W2 resident for step_end (a copy kernel: a copy-engine node in front of the step's graph costs ~10 us of hand-over)
-  VIMZ_TRY(copy_dev(a->ctx, a->W2, d_W2, a->shape->n * 32));
-  return acc_step_begin_common(a, X2, comm_W2, comm_T);
+  a->early_valid = false;
+  if ((reinterpret_cast<uintptr_t>(d_W2) & 15) == 0 && d_W2 != a->W2) {
+    a->w2_mailbox = true;
+    a->w2_src = d_W2;
+  } else {
+    VIMZ_TRY(copy_dev(a->ctx, a->W2, d_W2, a->shape->n * 32));
+  }
+  int rc = acc_step_begin_common(a, X2, comm_W2, comm_T);
+  a->w2_mailbox = false;  // (also on an error path)
+  return rc;
 }
 
 // ---- the two halves of step_begin as separate calls (strict prove_step order on the secondary curve) --------------
@@ -1305,6 +1452,7 @@ int vimz_acc_commit_fresh(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2, vim
   const CurveVTable* vt = curve_vtable(ctx->curve);
   cudaStream_t st = ctx->stream;
   if (a->step_enqueued && !a->fresh_complete) VIMZ_CUDA(cudaStreamSynchronize(st));
+  a->early_valid = false;
   a->parity ^= 1;
   const int p = a->parity;
   if (a->side_pending[p]) {

@@ -95,6 +95,11 @@ struct MsmWorkspace {
   // same protocol: a small host -> device copy (the accumulator's staged (1, X2) tail, in mapped page-locked memory) that the kernel
   // clearing the control block + histogram performs as well -- one graph node instead of a copy node and a memset node in front of
   // the first kernel of the critical lane (each costs ~8 us of dispatch there)
+  // same protocol: run only the FRONT half of the bucket pipeline (1: clear / digits / scan / scatter / accumulate) or only the BACK
+  // half (2: combine / reduce), so that a caller can create the nodes of two lanes in an order of its choice; and events around the
+  // accumulation kernel -- waited for right in front of it / recorded right behind it -- to order the accumulations of two lanes
+  int phase = 0;
+  cudaEvent_t acc_wait = nullptr, acc_record = nullptr;
   const void* pro_src = nullptr;
   void* pro_dst = nullptr;
   size_t pro_bytes = 0;    // multiple of 16
@@ -139,12 +144,15 @@ struct vimz_ctx {
   cudaStream_t side = nullptr;  // instance-fold scalar multiplications overlap the next step here
   cudaStream_t aux = nullptr;   // second MSM lane: commit(W2) runs beside cross-term + commit(T)
   cudaStream_t ps = nullptr;    // third branch of a step: P_S of the booleanity-row fold and its 2^(64 j) multiples (vimz_acc::use_ks)
+  cudaStream_t early = nullptr; // lane 2: the commitment of a witness range staged ahead of its step (vimz_acc_stage_fresh), beside the OTHER curve's step
   cudaStream_t ks = nullptr;    // K_S += r * P_S of step_end: a lone warp with a deadline (the next commit(T) of the accumulator), kept apart
                                 // from the comm_W / comm_E folds on `side`, which have none
   int sm_count = 148;
   long opt_window = 0;  // 0 = auto
   bool opt_graph = true; // replay the fixed launch sequence of a fold step as a CUDA graph
   bool opt_defer_giants = true; // giant buckets are summed beside the bucket reduction (k_reduce_tail) instead of in front of it
+  bool opt_acc_order = false;   // fold step: commit(T)'s accumulation starts when commit(W2)'s has finished instead of sharing the SMs with it (measured: +33 us per step)
+  bool opt_stage_commit = false; // vimz_acc_stage_fresh also commits the staged range at once (lane 2); step_begin_staged commits only the rest
   bool opt_bitrow_fold = true;  // accumulators created from now on keep K_S and commit T + [bit row] Az1 (r1cs.cuh, k_cross_finish)
   bool opt_spin_wait = true; // step_begin polls the stream for its result instead of a blocking synchronise
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
@@ -156,7 +164,7 @@ struct vimz_ctx {
   long opt_direct_bps = 2;     // k_msm_direct blocks per SM (1..4): at 2 the two commits of a fold step (two stream lanes) are resident together
   long opt_direct_max = 32768; // keys up to this many points get the direct multiples table (256 KB per point); 0 = never
   uint64_t launches = 0;
-  MsmWorkspace ws, ws_aux;
+  MsmWorkspace ws, ws_aux, ws_early;  // lanes 0 / 1 / 2 (vimz_ctx::stream / aux / early)
   vimz::DevBuf tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;  // R1CS staging for host-pointer entry points
   void* pinned = nullptr;                      // small pinned staging block for results
   Profiler prof;
@@ -258,8 +266,24 @@ struct vimz_acc {
   int parity = 0;
   // step_begin's launch sequence (cross term + both MSMs, ~35 kernels on two streams) captured once per
   // parity slot and replayed: the step is latency-bound and stream launches cost more than the small kernels
-  cudaGraphExec_t graph[2] = {nullptr, nullptr};
-  uint64_t graph_epoch[2] = {0, 0};
-  uint64_t graph_launches[2] = {0, 0};
-  bool warm[2] = {false, false};
+  // (index = parity + 2 * [the step has an early commitment of a staged range: it commits only the rest of W2] + 4 * [the copy
+  // of a resident witness is the first node])
+  cudaGraphExec_t graph[8] = {};
+  uint64_t graph_epoch[8] = {};
+  uint64_t graph_launches[8] = {};
+  bool warm[8] = {};
+  size_t graph_early[8][2] = {};  // the staged range a graph with an early commitment was captured for
+  // Early commitment (option "stage_commit"): vimz_acc_stage_fresh committed W2[early_first .. + early_count) on lane 2 into the
+  // EARLY slot of `comms`; the next step_begin_staged commits the complement and adds the two.  Consumed by that step.
+  bool w2_counted = false;  // inside enqueue_step_begin: the aux lane's digit pass was created ahead of the main lane's nodes
+  // W2 of a step_begin_dev call: the copy of the resident witness is the FIRST NODE of the step's graph, its source parameter patched
+  // before every replay (a separate copy launch in front of the graph costs ~10 us of dispatch)
+  bool w2_mailbox = false;
+  const void* w2_src = nullptr;
+  cudaGraphNode_t cap_copy_node = nullptr, copy_node[8] = {};
+  cudaGraph_t graph_src[8] = {};  // kept alive for the graphs that have a copy node (its handle belongs to the source graph)
+  bool early_valid = false;
+  size_t early_first = 0, early_count = 0;
+  cudaEvent_t ev_stage = nullptr, ev_early = nullptr;
+  cudaEvent_t ev_auxacc = nullptr;  // "commit(W2)'s accumulation kernel has finished" inside a step (option acc_order)
 };

@@ -22,12 +22,16 @@ struct CurveVTable {
   int (*precompute)(vimz_ctx*, const void* d_bases, size_t n, int c, int nwin, void* table);
   // dtable[((j*n + i) << (c-1)) + k-1] = k * table[j][i]  (direct-table keys)
   int (*precompute_direct)(vimz_ctx*, const void* table, size_t n, int c, int nwin, void* dtable);
-  // lane 0 = context stream + main workspace, lane 1 = aux stream + second workspace (runs concurrently)
+  // lane 0 = context stream + main workspace, lane 1 = aux stream + second workspace (runs concurrently), lane 2 = early stream +
+  // third workspace (early commitment of a staged witness range, beside another context's step)
   // (MsmWorkspace::host_out / sub_jac / sub_event, set by the caller around one call, reach the final kernel)
   // counted = true: the bucket histogram of the scalars is already in the lane's `counts` buffer (fused cross term)
   int (*msm)(vimz_ctx*, int lane, const vimz_ck*, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted);
+  int (*msm_digits)(vimz_ctx*, int lane, const vimz_ck*, const void* d_scalars, size_t n, bool* done);
   int (*point_sum)(vimz_ctx*, const void* d_pts, size_t k, void* d_out);
   int (*point_sum_batch)(vimz_ctx*, const void* d_pts, size_t k, size_t sets, void* d_out);
+  // d_out = d_a + d_b (Jacobian), also written to `host_out` (mapped page-locked host memory) when given
+  int (*point_add2)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_b, void* d_out, void* host_out);
   int (*point_to_affine)(vimz_ctx*, const void* d_pt, void* d_out);
   int (*point_scale_add)(vimz_ctx*, cudaStream_t, const void* d_a, const void* d_r, const void* d_b, void* d_out, int count);
   int (*point_scale_add_val)(vimz_ctx*, cudaStream_t, const void* d_a, const vimz_fr* r, const void* d_b, void* d_out, int count);
@@ -99,10 +103,12 @@ int impl_msm_direct(vimz_ctx* ctx, cudaStream_t st, MsmWorkspace& ws, const vimz
   const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(ceil_div(E, 128 * 2), max_blocks));
   const uint32_t ngroups = ceil_div(blocks, DIRECT_GROUP);
   VIMZ_TRY(ws.digits.reserve(E * 4));
-  VIMZ_TRY(ws.cls.reserve(64 * 4));
+  if (ws.cls.cap < 64 * 4) {  // arrival counters: zeroed once, the last block of every launch leaves them zero again (no memset node per commit)
+    VIMZ_TRY(ws.cls.reserve(64 * 4));
+    VIMZ_CUDA(cudaMemsetAsync(ws.cls.ptr, 0, 64 * 4, st));
+  }
   VIMZ_TRY(ws.partials.reserve(((size_t)blocks + ngroups) * 128));
   ws.last_M = 0;
-  VIMZ_CUDA(cudaMemsetAsync(ws.cls.ptr, 0, 64 * 4, st));
   if (n > 0 && !digits_ready) {
     ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
     const int grid_n = (int)std::min<size_t>(ceil_div(n, 256), (size_t)ctx->sm_count * 8);
@@ -144,10 +150,32 @@ inline int msm_zero_control(vimz_ctx* ctx, MsmWorkspace& ws, uint32_t M, cudaStr
   return VIMZ_OK;
 }
 
+// The first two nodes of a bucket-pipeline commit -- clear control block + histogram, recode the scalars -- by themselves, so that a
+// caller can create them ahead of another lane's nodes; the commit proper follows as msm(..., counted = true).  Returns
+// VIMZ_OK without doing anything for a direct-table key or an empty range (msm is then called with counted = false).
+template <class C>
+int impl_msm_digits(vimz_ctx* ctx, int lane, const vimz_ck* ck, const void* d_scalars, size_t n, bool* done) {
+  *done = false;
+  if (ck->dtable || n == 0) return VIMZ_OK;
+  cudaStream_t st = lane == 0 ? ctx->stream : (lane == 1 ? ctx->aux : ctx->early);
+  MsmWorkspace& ws = lane == 0 ? ctx->ws : (lane == 1 ? ctx->ws_aux : ctx->ws_early);
+  const int c = ck->c, nwin = ck->nwin;
+  const uint32_t M = 1u << (c - 1);
+  VIMZ_TRY(ws.digits.reserve(std::max<size_t>(n * (size_t)nwin, 1) * 4));
+  VIMZ_TRY(msm_zero_control(ctx, ws, M, st));
+  ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
+  const int grid_n = (int)std::min<size_t>(ceil_div(n, 256), (size_t)ctx->sm_count * 8);
+  k_msm_digits<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin,
+                                          ws.counts.as<uint32_t>() + msm_ctrl_words(ctx), ws.digits.as<uint32_t>());
+  VIMZ_LAUNCH_CHECK(ctx);
+  *done = true;
+  return VIMZ_OK;
+}
+
 template <class C>
 int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const void* d_scalars, size_t n, void* d_out, bool counted) {
-  cudaStream_t st = lane == 0 ? ctx->stream : ctx->aux;
-  MsmWorkspace& ws = lane == 0 ? ctx->ws : ctx->ws_aux;
+  cudaStream_t st = lane == 0 ? ctx->stream : (lane == 1 ? ctx->aux : ctx->early);
+  MsmWorkspace& ws = lane == 0 ? ctx->ws : (lane == 1 ? ctx->ws_aux : ctx->ws_early);
   if (ck->dtable) {
     if (ws.sub_jac) return set_error(VIMZ_ERR_ARG, "msm: a subtracted point is only supported on the bucket pipeline");
     return impl_msm_direct<C>(ctx, st, ws, ck, first, d_scalars, n, d_out, counted);
@@ -208,10 +236,11 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   cb.max_chunks = max_chunks;
 
   ws.last_M = M;
-  if (!counted) VIMZ_TRY(msm_zero_control(ctx, ws, M, st));  // (counted: the fused cross term cleared control block + histogram)
+  const int phase = ws.phase;  // 0: everything, 1: up to the accumulation, 2: from the combine on (MsmWorkspace::phase)
+  if (phase != 2 && !counted) VIMZ_TRY(msm_zero_control(ctx, ws, M, st));  // (counted: the fused cross term cleared control block + histogram)
 
   const int grid_n = (int)std::min<size_t>(ceil_div(std::max<size_t>(n, 1), 256), (size_t)ctx->sm_count * 8);
-  {
+  if (phase != 2) {
     ProfScope prof_sort(ctx, PROF_MSM_SORT, st);
     if (n > 0 && !counted) {
       k_msm_digits<C><<<grid_n, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), (uint32_t)n, c, nwin, counts,
@@ -235,7 +264,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
       VIMZ_LAUNCH_CHECK(ctx);
     }
   }
-  if (ctx->prof.on) {  // total bucket insertions of this MSM = offsets[M]
+  if (ctx->prof.on && phase != 2) {  // total bucket insertions of this MSM = offsets[M]
     uint32_t* slot;
     if (!ctx->prof.entry_pool.empty()) { slot = ctx->prof.entry_pool.back(); ctx->prof.entry_pool.pop_back(); }
     else VIMZ_CUDA(cudaMallocHost(&slot, 4));
@@ -245,12 +274,17 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   }
   {
     ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, st);
-    {
-      ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
-      ProfScope prof_fused(counted ? ctx : nullptr, PROF_MSM_ACC_KERNEL_FUSED, st);
-      k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, seg_min, ws.buckets.ptr, ws.partials.ptr);
+    if (phase != 2) {
+      if (ws.acc_wait) VIMZ_CUDA(cudaStreamWaitEvent(st, ws.acc_wait, 0));
+      {
+        ProfScope prof_kernel(ctx, PROF_MSM_ACC_KERNEL, st);
+        ProfScope prof_fused(counted ? ctx : nullptr, PROF_MSM_ACC_KERNEL_FUSED, st);
+        k_msm_accumulate<C><<<nthreads / 128, 128, 0, st>>>(offsets, sorted, ck->table, M, nthreads, seg_min, ws.buckets.ptr, ws.partials.ptr);
+      }
+      VIMZ_LAUNCH_CHECK(ctx);
+      if (ws.acc_record) VIMZ_CUDA(cudaEventRecord(ws.acc_record, st));
     }
-    VIMZ_LAUNCH_CHECK(ctx);
+    if (phase == 1) return VIMZ_OK;
     // pieces of cut buckets: giants (blocks per chunk + last-arrival fold), mids (a warp each), the rest (a quad each)
     // (with deferred giants the giant role moves into k_reduce_tail, off the chain accumulate -> combine -> reduce)
     const uint32_t nb_big = defer ? 0u : (uint32_t)ctx->sm_count * VIMZ_BIG_BLOCKS_PER_SM, nb_mid = (uint32_t)ctx->sm_count * 4,
@@ -279,6 +313,12 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
 template <class C>
 int impl_point_sum(vimz_ctx* ctx, const void* d_pts, size_t k, void* d_out) {
   k_point_sum<C><<<1, 32, 0, ctx->stream>>>(d_pts, (uint32_t)k, d_out);
+  VIMZ_LAUNCH_CHECK(ctx);
+  return VIMZ_OK;
+}
+template <class C>
+int impl_point_add2(vimz_ctx* ctx, cudaStream_t st, const void* d_a, const void* d_b, void* d_out, void* host_out) {
+  k_point_add2<C><<<1, 32, 0, st>>>(d_a, d_b, d_out, host_out);
   VIMZ_LAUNCH_CHECK(ctx);
   return VIMZ_OK;
 }
@@ -492,6 +532,8 @@ CurveVTable make_vtable(const char* name) {
   t.msm = &impl_msm<C>;
   t.point_sum = &impl_point_sum<C>;
   t.point_sum_batch = &impl_point_sum_batch<C>;
+  t.point_add2 = &impl_point_add2<C>;
+  t.msm_digits = &impl_msm_digits<C>;
   t.point_to_affine = &impl_point_to_affine<C>;
   t.point_scale_add = &impl_point_scale_add<C>;
   t.point_scale_add_val = &impl_point_scale_add_val<C>;

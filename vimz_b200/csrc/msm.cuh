@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restric
     e = en;
     d = dn;
   }
-  direct_tree<C>(acc, smem, &flag, partials, ctrl, out_jac, out_host, false);
+  direct_tree<C>(acc, smem, &flag, partials, ctrl, out_jac, out_host, true);
 }
 
 // sum over the booleanity rows i (bitcol[i] != ~0) of vals[bitcol[i]] * bases[i] for a vector `vals` whose entries there are
@@ -902,6 +902,13 @@ __global__ void __launch_bounds__(32) k_point_sum_batch(const void* __restrict__
   }
   acc = q_warp_reduce<C>(acc);
   q_store_jacobian<C>(acc, reinterpret_cast<char*>(out) + (size_t)s * 96, threadIdx.x < 4);
+}
+
+// out = a + b for two Jacobian points (the early and the in-step share of comm_W2), second copy to mapped host memory
+template <class C>
+__global__ void __launch_bounds__(32) k_point_add2(const void* __restrict__ a, const void* __restrict__ b, void* __restrict__ out, void* __restrict__ out_host) {
+  QPoint<C> acc = q_add<C>(q_load_jacobian<C>(a), q_load_jacobian<C>(b));
+  q_store_jacobian<C>(acc, out, threadIdx.x < 4, out_host);
 }
 
 // out[t] = a[t] + r * b[t] for count <= 8 independent pairs, one QUAD each (one warp in total); r is a

@@ -473,30 +473,37 @@ class FoldAccumulator:
         check(lib.vimz_acc_step_begin(self._h, C.c_void_p(W2.__array_interface__["data"][0]), px, pw, pt))
         return out[:12].copy(), out[12:].copy()
 
-    def stage_fresh(self, W2: np.ndarray, first: int, count: int) -> None:
-        """Enqueue the H2D copy of W2[first : first + count] (rows of the full (n, 4) host array `W2`) behind the previous
-        step_end and return at once; `W2` must stay alive and unchanged until the next step_begin_staged returns."""
-        base = W2.__array_interface__["data"][0] + 32 * first
-        check(lib.vimz_acc_stage_fresh(self._h, C.c_void_p(base), first, count))
+    @staticmethod
+    def _row_ptr(W2, first: int) -> int:
+        """Address of row `first` of a full (n, 4) witness: a host array, or an int = device address of its first row."""
+        return (W2 if isinstance(W2, int) else W2.__array_interface__["data"][0]) + 32 * first
+
+    def stage_fresh(self, W2, first: int, count: int) -> None:
+        """Enqueue the copy of W2[first : first + count] (rows of the full (n, 4) host array `W2`, or of the device buffer at
+        address `W2`) behind the previous step_end and return at once; `W2` must stay alive and unchanged until the next
+        step_begin_staged returns.  With the engine option "stage_commit" (default) a prefix / suffix range is also committed
+        at once, beside whatever the GPU is doing for the other curve."""
+        check(lib.vimz_acc_stage_fresh(self._h, C.c_void_p(self._row_ptr(W2, first)), first, count))
 
     def step_begin_staged(self, W2: np.ndarray, first: int, count: int, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """Upload the remaining rows W2[first : first + count] and run the step on the staged witness -> (comm_W2, comm_T)."""
         X2, px = self._fr_ptr(X2, self.shape.num_io)
         out, pw, pt = self._io()
-        base = W2.__array_interface__["data"][0] + 32 * first
-        check(lib.vimz_acc_step_begin_staged(self._h, C.c_void_p(base), first, count, px, pw, pt))
+        check(lib.vimz_acc_step_begin_staged(self._h, C.c_void_p(self._row_ptr(W2, first)), first, count, px, pw, pt))
         return out[:12].copy(), out[12:].copy()
 
-    def step_begin_async(self, W2: np.ndarray, X2) -> None:
-        """Enqueue a step (W2 / X2 host buffers must stay alive until step_wait returns)."""
+    def step_begin_async(self, W2, X2) -> None:
+        """Enqueue a step (W2 / X2 host buffers must stay alive until step_wait returns).  W2: host array, or an int = device
+        address of a resident witness of num_vars rows."""
         s = self.shape
-        if not (type(W2) is np.ndarray and W2.dtype == np.uint64 and W2.ndim == 2 and W2.flags.c_contiguous):
-            W2 = as_fr(W2)
-        if W2.shape[0] != s.num_vars or W2.shape[1] != 4:
-            raise InvalidWitnessLength(_lib.VIMZ_ERR_LENGTH, "step_begin_async: witness length != num_vars")
+        if not isinstance(W2, int):
+            if not (type(W2) is np.ndarray and W2.dtype == np.uint64 and W2.ndim == 2 and W2.flags.c_contiguous):
+                W2 = as_fr(W2)
+            if W2.shape[0] != s.num_vars or W2.shape[1] != 4:
+                raise InvalidWitnessLength(_lib.VIMZ_ERR_LENGTH, "step_begin_async: witness length != num_vars")
         X2, px = self._fr_ptr(X2, s.num_io)
         self._pending = (W2, X2)
-        check(lib.vimz_acc_step_begin_async(self._h, C.c_void_p(W2.__array_interface__["data"][0]), px))
+        check(lib.vimz_acc_step_begin_async(self._h, C.c_void_p(self._row_ptr(W2, 0)), px))
 
     def step_wait(self) -> Tuple[np.ndarray, np.ndarray]:
         out, pw, pt = self._io()
