@@ -42,6 +42,7 @@ NUM_WITNESSES = 32             # distinct fresh witnesses (one image row each) c
 # bucket insertions and a few giant buckets: 0.89 ms/step before, 0.95 ms/step after (measured).  An HD
 # proof is 720 steps, so the timed window is placed around its median step (folds 263..463 with the default --steps 200),
 # not in the cheaper first 130 folds.
+SECONDARY_DIRECT_C = 14
 PREFOLD = int(os.environ.get("VIMZ_BENCH_PREFOLD", "260"))   # the ncu scripts under tools/ use 32 to keep their captures short
 IMAD_PER_MODMUL = 272          # 8-limb CIOS: 2*8^2 + 8 products x 2 IMAD
 MODMUL_PER_MADD = 10           # XYZZ mixed add 8M + 2S
@@ -303,6 +304,10 @@ class GpuFold:
             self.eng.set_option("cross_cache", int(os.environ["VIMZ_CROSS_CACHE"]))
         if os.environ.get("VIMZ_DIRECT_C"):
             self.eng.set_option("msm_direct_c", int(os.environ["VIMZ_DIRECT_C"]))
+        elif circuit == "secondary":
+            # the secondary curve's 10.5 k-point key keeps ALL multiples of 14-bit digits resident (19 windows instead of 26 at the
+            # library's default c = 10): 105 GB of the 180 GB that the prover has no other use for, -28 us per step (measured A/B)
+            self.eng.set_option("msm_direct_c", SECONDARY_DIRECT_C)
         if os.environ.get("VIMZ_DIRECT_BPS"):
             self.eng.set_option("msm_direct_bps", int(os.environ["VIMZ_DIRECT_BPS"]))
         if os.environ.get("VIMZ_DIRECT_MAX"):
@@ -317,7 +322,8 @@ class GpuFold:
         sh = self.sh
         self.shape = R1CSShape(self.eng, sh.num_cons, sh.num_vars, sh.num_io, sh.A, sh.B, sh.C)
         nck = max(sh.num_cons, sh.num_vars)
-        nck = 1 << (nck - 1).bit_length()
+        if circuit != "secondary":   # (nova-snark sizes ck to the next power of two; bases past max(m, n) are never read, and the
+            nck = 1 << (nck - 1).bit_length()   # secondary key's multiples table is 10 MB per point, so that one holds exactly what is used)
         d_bases = torch.empty(nck * 8, dtype=torch.int64, device=f"cuda:{device}")
         vimz_b200._lib.check(vimz_b200.lib.vimz_gen_bases_dev(self.eng._h, K0, DK, nck, d_bases.data_ptr()))
         self.ck = CommitmentKey.from_device(self.eng, d_bases.data_ptr(), nck)
@@ -364,10 +370,13 @@ class GpuFold:
         i = k % len(self.wits)
         self.acc.stage_fresh(self.dev_ptr[i] if resident else self.pin_np[i], 0, self.staged_split())
 
-    def step_staged(self, k: int, resident=False):
+    def step_staged(self, k: int, resident=False, wait=True):
         i = k % len(self.wits)
         e = self.staged_split()
-        cw, ct = self.acc.step_begin_staged(self.dev_ptr[i] if resident else self.pin_np[i], e, self.sh.num_vars - e, self.X2_bytes[i])
+        out = self.acc.step_begin_staged(self.dev_ptr[i] if resident else self.pin_np[i], e, self.sh.num_vars - e, self.X2_bytes[i], wait=wait)
+        if not wait:
+            return
+        cw, ct = out
         self.acc.step_end(((challenge_from(ct.tobytes(), k) << 256) % self.q).to_bytes(32, "little"))
 
     def begin_async(self, k: int, resident=False):
@@ -593,8 +602,43 @@ def run_configs(args, torch, dist, rank, world, local_rank, sec, peaks, comm):
     return out
 
 
-def timed_region(torch, engines, fn, steps, dist):
-    """barrier + sync; CUDA events on the primary context's stream around `steps` calls of fn; max over ranks."""
+class Overlapped:
+    """Host sequencing of one two-curve fold step.  The host needs each curve's challenge r to produce the OTHER curve's next
+    witness, not that curve's folded accumulator, so a curve's step_end (W += r W2 ... on its own streams) is issued while the
+    other curve's step_begin is already running instead of in front of it: the ~25 us of launches per step leave the critical
+    path.  Same calls, same order per accumulator (begin, end, begin, ...), same results."""
+
+    def __init__(self, prim, sec):
+        self.prim, self.sec, self.pend = prim, sec, None
+
+    def step(self, k: int, resident: bool, staged: bool):
+        prim, sec = self.prim, self.sec
+        sec.begin_async(k, resident)
+        if self.pend is not None:
+            prim.acc.step_end(self.pend)
+            self.pend = None
+        if staged:   # the fold-independent rows of the primary witness travel while the secondary curve is folded
+            prim.stage(k, resident)
+        cw, ct = sec.acc.step_wait()
+        r_s = ((challenge_from(ct.tobytes(), k) << 256) % sec.q).to_bytes(32, "little")
+        if staged:
+            prim.step_staged(k, resident, wait=False)
+        else:
+            prim.begin_async(k, resident)
+        sec.acc.step_end(r_s)
+        cw, ct = prim.acc.step_wait()
+        self.pend = ((challenge_from(ct.tobytes(), k) << 256) % prim.q).to_bytes(32, "little")
+        return ct
+
+    def flush(self):
+        if self.pend is not None:
+            self.prim.acc.step_end(self.pend)
+            self.pend = None
+
+
+def timed_region(torch, engines, fn, steps, dist, finish=None):
+    """barrier + sync; CUDA events on the primary context's stream around `steps` calls of fn (+ `finish`, the last deferred call of
+    an overlapped sequence); max over ranks."""
     stream = torch.cuda.ExternalStream(engines[0].stream)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for e in engines:
@@ -606,6 +650,8 @@ def timed_region(torch, engines, fn, steps, dist):
     t0 = time.perf_counter()
     for k in range(steps):
         fn(k)
+    if finish is not None:
+        finish()
     for e in engines:
         e.sync()
     e1.record(stream)
@@ -769,12 +815,17 @@ def main_gpu(args, rank, world, local_rank):
         step_resident(PREFOLD + k)
     for k in range(2):
         step_e2e(k)
+    ov = Overlapped(prim, sec)
+    for k in range(3):
+        ov.step(k, True, False)
+    ov.flush()
     launches0 = sum(e.launch_count for e in engines)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, wall = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + k), steps, dist)
+    ms, wall = timed_region(torch, engines, lambda k: ov.step(PREFOLD + warmup + k, True, False), steps, dist, finish=ov.flush)
     clocks = sampler.stop()
     launches = sum(e.launch_count for e in engines) - launches0
+    ms_serial, _ = timed_region(torch, engines, lambda k: step_resident(PREFOLD + warmup + 5 * steps + k), steps, dist)
     ms_e2e, wall_e2e = timed_region(torch, engines, lambda k: step_e2e(PREFOLD + warmup + steps + k), steps, dist)
 
     def step_staged(k):     # pipelined e2e: the Circom part of the primary witness travels while the secondary curve is folded
@@ -788,7 +839,11 @@ def main_gpu(args, rank, world, local_rank):
 
     for k in range(2):
         step_staged(k)
-    ms_staged, _ = timed_region(torch, engines, lambda k: step_staged(PREFOLD + warmup + 4 * steps + k), steps, dist)
+    ms_staged_serial, _ = timed_region(torch, engines, lambda k: step_staged(PREFOLD + warmup + 4 * steps + k), steps, dist)
+    for k in range(3):
+        ov.step(k, False, True)
+    ov.flush()
+    ms_staged, _ = timed_region(torch, engines, lambda k: ov.step(PREFOLD + warmup + 6 * steps + k, False, True), steps, dist, finish=ov.flush)
 
     def step_pageable(k):   # W2 in plain (pageable) host memory, as a Rust Vec<Scalar> would be
         sec.step(k, "pageable"); prim.step(k, "pageable")
@@ -932,14 +987,21 @@ def main_gpu(args, rank, world, local_rank):
         line = {"metric": "nova_fold_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
-                "config": workload_config(prim.sh, cycle=args.cycle, extra={"parallelism": f"replicas x{world} (one transformation per GPU)",
-                                                                   "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows}),
+                "config": workload_config(prim.sh, cycle=args.cycle, extra={
+                    "parallelism": f"replicas x{world} (one transformation per GPU)",
+                    "msm_window_bits": prim.ck.window_bits, "msm_windows": prim.ck.num_windows,
+                    "secondary_key": {"points": sec.ck.n if hasattr(sec.ck, "n") else None, "direct_digit_bits": sec.ck.window_bits, "windows": sec.ck.num_windows,
+                                      "note": "all multiples of every digit resident (msm_direct_c): 64 B << (bits - 1) per point and window"},
+                    "host_sequencing": "each curve's step_end is issued while the other curve's step_begin runs (class Overlapped); "
+                                       "value_serial_calls / e2e.serial_calls_value are the same steps with begin -> end -> begin strictly in turn"}),
+                "value_serial_calls": world * steps / (ms_serial * 1e-3),
                 "e2e": {"value": world * steps / (ms_staged * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
                         "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_staged / steps,
                         "api": "vimz_acc_stage_fresh + vimz_acc_step_begin_staged (primary), vimz_acc_step_begin_async / _wait (secondary), vimz_acc_step_end: every "
                                "step copies its whole fresh witness host -> device inside the timed region; the fold-independent rows of the "
                                f"primary witness ({prim.staged_split()} of {prim.sh.num_vars}: the Circom step circuit's variables) are enqueued before the "
                                "secondary curve's step so the copy overlaps it, the augmented circuit's ~10 k variables go up inside step_begin",
+                        "serial_calls_value": world * steps / (ms_staged_serial * 1e-3),
                         "plain_call_value": e2e_value, "plain_call_ms_per_step": ms_e2e / steps,
                         "plain_call_note": "same steps through vimz_acc_step_begin alone (whole W2 copied inside the call, nothing overlapped)",
                         "host_buffers": "pinned (cudaHostAlloc)", "pageable_value": world * steps / (ms_page * 1e-3),

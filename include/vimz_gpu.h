@@ -59,10 +59,11 @@ int vimz_ctx_create(int curve_id, int device, vimz_ctx** out);
 void vimz_ctx_destroy(vimz_ctx* ctx);
 int vimz_ctx_sync(vimz_ctx* ctx);
 /* Tunables: "msm_window" (c bits, 0 = auto), "msm_acc_blocks" (accumulation blocks per SM, 1..8), "msm_seg_min" (shortest accumulation segment, 1..4096),
- * "msm_direct_c" (digit width of that table, 0 = by key length: 10 up to 16 384 points, else 8),
+ * "msm_direct_c" (digit width of that table, 4 .. 14, 0 = by key length: 10 up to 16 384 points, else 8; 64 B << (c - 1) per point and window),
  * "msm_direct_max" (keys uploaded afterwards with at most this many points keep ALL digit multiples resident -- 256 KB per point at c = 8 --
  * and commit without buckets; default 32768, 0 = always the bucket pipeline; a forced msm_window also selects buckets), "msm_defer_giants" (0/1, default 1: buckets cut into hundreds of segments are summed beside
- * the bucket reduction instead of in front of it), "bitrow_fold" (0/1, default 1: accumulators created afterwards
+ * the bucket reduction instead of in front of it), "stage_commit" (0/1, default 0, see vimz_acc_stage_fresh), "acc_order" (0/1, default 0: commit(T)'s accumulation
+ * kernel starts when commit(W2)'s has finished instead of sharing the SMs with it), "bitrow_fold" (0/1, default 1: accumulators created afterwards
  * on shapes with many booleanity rows b*(b-1)=0 keep K_S = sum over those rows of (A z1)_i ck_i and commit T + [row] A z1 instead of T -- half
  * of those rows then insert nothing; same comm_T), "spin_wait" (0/1, default 1: step_begin polls its stream instead of a blocking wait), "cross_cache" (0/1, default 1:
  * accumulators created afterwards keep (Az1, Bz1, Cz1) of the running instance resident and fold them in step_end instead of
@@ -181,7 +182,12 @@ int vimz_acc_fresh_witness(vimz_acc* acc, vimz_fr* W2, vimz_fr* X2);
 /* Streaming upload of the fresh witness: vimz_acc_stage_fresh enqueues an H2D copy of W2[first .. first + count) behind the
  * previous step_end and returns at once (the host buffer must stay valid until the next step_begin* returns); the part of a
  * witness that does not depend on the previous fold (the Circom step circuit's variables) can so travel while the other curve
- * is being folded.  vimz_acc_step_begin_staged uploads the remaining range and runs the step. */
+ * is being folded.  vimz_acc_step_begin_staged uploads the remaining range and runs the step; with comm_W2 = comm_T = NULL it only
+ * enqueues the step and vimz_acc_step_wait collects the commitments.  The witness pointers of stage_fresh, step_begin_staged and
+ * step_begin_async may also be DEVICE memory (unified addressing tells): a resident witness is then copied on the GPU.  With the
+ * context option "stage_commit" = 1 a staged prefix / suffix of at least 1024 variables is also COMMITTED at once, on a lane of
+ * its own beside whatever the GPU does for the other curve; the step then commits only the rest and adds the two (same comm_W2;
+ * the staged rows must not change afterwards -- re-uploading them in step_begin_staged voids the early commitment). */
 int vimz_acc_stage_fresh(vimz_acc* acc, const vimz_fr* W2_part, size_t first, size_t count);
 /* vimz_acc_step_begin in two halves: _async copies W2 / X2 and enqueues the step (the host buffers must stay valid until _wait
  * returns), _wait blocks for the commitments.  Host-to-device copies of different accumulators share one copy engine in issue

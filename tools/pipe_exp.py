@@ -26,6 +26,27 @@ def piped(k, resident=True):
     prim.step_staged(k, resident)
 
 
+pend = [None]
+
+
+def overlapped(k, resident=True):
+    """step_end of each curve issued while the OTHER curve's step runs (the host needs r for the other curve's witness, not the fold)"""
+    sec.begin_async(k, resident)
+    if pend[0] is not None:
+        prim.acc.step_end(pend[0])
+    cw, ct = sec.acc.step_wait()
+    r_s = ((bench.challenge_from(ct.tobytes(), k) << 256) % sec.q).to_bytes(32, "little")
+    prim.begin_async(k, resident)
+    sec.acc.step_end(r_s)
+    cw, ct = prim.acc.step_wait()
+    pend[0] = ((bench.challenge_from(ct.tobytes(), k) << 256) % prim.q).to_bytes(32, "little")
+
+
+def flush():
+    if pend[0] is not None:
+        prim.acc.step_end(pend[0]); pend[0] = None
+
+
 for k in range(prefold):
     plain(k)
 # parity of the pipelined comm_W2 / comm_T against the plain path on a twin accumulator is covered by the GPU tests; here: comm_W2
@@ -38,25 +59,28 @@ for k in range(prefold, prefold + 3):
     prim.acc.step_end(((bench.challenge_from(ct.tobytes(), k) << 256) % prim.q).to_bytes(32, "little"))
 print("pipelined comm_W2 == stand-alone commit: ok")
 k0 = prefold + 3
-for name, fn in (("plain", plain), ("piped", piped), ("plain", plain), ("piped", piped)):
+for name, fn in (("plain", plain), ("overlapped", overlapped), ("plain", plain), ("overlapped", overlapped), ("piped", piped)):
     for k in range(k0, k0 + 5):
         fn(k)
     prim.eng.sync(); sec.eng.sync()
     t0 = time.perf_counter()
     for k in range(k0 + 5, k0 + 5 + N):
         fn(k)
+    flush()
     prim.eng.sync(); sec.eng.sync()
     dt = (time.perf_counter() - t0) / N
     print(f"{name}: {dt * 1e6:.1f} us/step = {1 / dt:.1f} steps/s")
     k0 += 5 + N
-for name, fn in (("piped-e2e(pinned)", lambda k: piped(k, False)),):
+for name, fn in (("overlapped-e2e(pinned)", lambda k: overlapped(k, False)), ("piped-e2e(pinned)", lambda k: piped(k, False)),):
     for k in range(k0, k0 + 5):
         fn(k)
     prim.eng.sync(); sec.eng.sync()
     t0 = time.perf_counter()
     for k in range(k0 + 5, k0 + 5 + N):
         fn(k)
+    flush()
     prim.eng.sync(); sec.eng.sync()
     dt = (time.perf_counter() - t0) / N
     print(f"{name}: {dt * 1e6:.1f} us/step = {1 / dt:.1f} steps/s")
+    k0 += 5 + N
 print("primary lanes:", prim.eng.lane_stats())

@@ -304,7 +304,7 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
     return VIMZ_OK;
   }
   if (strcmp(key, "msm_direct_c") == 0) {  // applies to keys uploaded afterwards; 0 = by key length
-    if (value != 0 && (value < 4 || value > 12)) return set_error(VIMZ_ERR_ARG, "msm_direct_c must be 0 or in [4, 12]");
+    if (value != 0 && (value < 4 || value > 14)) return set_error(VIMZ_ERR_ARG, "msm_direct_c must be 0 or in [4, 14]");
     ctx->opt_direct_c = value;
     return VIMZ_OK;
   }
@@ -1392,13 +1392,14 @@ int vimz_acc_stage_fresh(vimz_acc* a, const vimz_fr* W2_part, size_t first, size
 
 int vimz_acc_step_begin_staged(vimz_acc* a, const vimz_fr* W2_rest, size_t first, size_t count, const vimz_fr* X2, vimz_point* comm_W2,
                                vimz_point* comm_T) {
-  CHECK_ARG(a && comm_W2 && comm_T && (W2_rest || count == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_staged: null argument");
+  CHECK_ARG(a && ((comm_W2 && comm_T) || (!comm_W2 && !comm_T)) && (W2_rest || count == 0) && (X2 || a->shape->io == 0),
+            "vimz_acc_step_begin_staged: null argument");
   if (first > a->shape->n || count > a->shape->n - first) return set_error(VIMZ_ERR_LENGTH, "vimz_acc_step_begin_staged: range outside the witness");
   CtxGuard g(a->ctx);
   if (a->early_valid && count && first < a->early_first + a->early_count && a->early_first < first + count)
     a->early_valid = false;  // the range committed early is being overwritten: commit everything in the step
   VIMZ_TRY(copy_in(a->ctx, (char*)a->W2 + first * 32, W2_rest, count * 32));
-  return acc_step_begin_common(a, X2, comm_W2, comm_T);
+  return acc_step_begin_common(a, X2, comm_W2, comm_T, comm_W2 != nullptr);  // (no outputs: enqueue only, vimz_acc_step_wait follows)
 }
 
 // step_begin in two halves for a host that has something to enqueue in between (another accumulator's staged upload, its
@@ -1407,8 +1408,18 @@ int vimz_acc_step_begin_async(vimz_acc* a, const vimz_fr* W2, const vimz_fr* X2)
   CHECK_ARG(a && (W2 || a->shape->n == 0) && (X2 || a->shape->io == 0), "vimz_acc_step_begin_async: null argument");
   CtxGuard g(a->ctx);
   a->early_valid = false;
-  VIMZ_TRY(copy_in(a->ctx, a->W2, W2, a->shape->n * 32));
-  return acc_step_begin_common(a, X2, nullptr, nullptr, false);
+  cudaPointerAttributes at;
+  if (W2 && cudaPointerGetAttributes(&at, W2) == cudaSuccess && at.type == cudaMemoryTypeDevice && (reinterpret_cast<uintptr_t>(W2) & 15) == 0 &&
+      (const void*)W2 != a->W2) {  // a resident witness: its copy is the first node of the step's graph (as in vimz_acc_step_begin_dev)
+    a->w2_mailbox = true;
+    a->w2_src = W2;
+  } else {
+    cudaGetLastError();
+    VIMZ_TRY(copy_in(a->ctx, a->W2, W2, a->shape->n * 32));
+  }
+  int rc = acc_step_begin_common(a, X2, nullptr, nullptr, false);
+  a->w2_mailbox = false;
+  return rc;
 }
 
 int vimz_acc_step_wait(vimz_acc* a, vimz_point* comm_W2, vimz_point* comm_T) {

@@ -485,9 +485,14 @@ class FoldAccumulator:
         at once, beside whatever the GPU is doing for the other curve."""
         check(lib.vimz_acc_stage_fresh(self._h, C.c_void_p(self._row_ptr(W2, first)), first, count))
 
-    def step_begin_staged(self, W2: np.ndarray, first: int, count: int, X2: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        """Upload the remaining rows W2[first : first + count] and run the step on the staged witness -> (comm_W2, comm_T)."""
+    def step_begin_staged(self, W2, first: int, count: int, X2: np.ndarray, wait: bool = True):
+        """Upload the remaining rows W2[first : first + count] and run the step on the staged witness -> (comm_W2, comm_T);
+        wait = False: enqueue only (step_wait collects the commitments)."""
         X2, px = self._fr_ptr(X2, self.shape.num_io)
+        if not wait:
+            self._pending = (W2, X2)
+            check(lib.vimz_acc_step_begin_staged(self._h, C.c_void_p(self._row_ptr(W2, first)), first, count, px, None, None))
+            return None
         out, pw, pt = self._io()
         check(lib.vimz_acc_step_begin_staged(self._h, C.c_void_p(self._row_ptr(W2, first)), first, count, px, pw, pt))
         return out[:12].copy(), out[12:].copy()
