@@ -316,7 +316,8 @@ class GpuFold:
             self.eng.set_option("spin_wait", int(os.environ["VIMZ_SPIN_WAIT"]))
         if os.environ.get("VIMZ_ACC_BLOCKS"):
             self.eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
-        for kv in filter(None, os.environ.get("VIMZ_OPTS", "").split(",")):   # A/B experiments: VIMZ_OPTS=bitrow_fold=0,graph=1
+        opts = os.environ.get("VIMZ_OPTS", "") + "," + os.environ.get("VIMZ_OPTS_" + ("SECONDARY" if circuit == "secondary" else "PRIMARY"), "")
+        for kv in filter(None, opts.split(",")):   # A/B experiments: VIMZ_OPTS=bitrow_fold=0,graph=1 (VIMZ_OPTS_PRIMARY / _SECONDARY: one curve)
             key, val = kv.split("=")
             self.eng.set_option(key, int(val))
         sh = self.sh
@@ -331,10 +332,10 @@ class GpuFold:
         self.acc = FoldAccumulator(self.shape, self.ck)
         # resident copies (for `value`) and pinned host copies (for `e2e`) of the fresh witnesses
         self.dev_W = [torch.from_numpy(w.view(np.int64)).to(f"cuda:{device}") for w, _ in self.wits]
-        self.pin_W = []
-        for w, _ in self.wits:
-            t = torch.from_numpy(w.view(np.int64).copy()).pin_memory()
-            self.pin_W.append(t)
+        # (page-locked buffers from the library's own allocator, vimz_host_alloc: what a host keeps its witness vectors in)
+        from vimz_b200.nova import pinned_fr
+        self.pin_keep = [pinned_fr(w) for w, _ in self.wits]
+        self.pin_W = [torch.from_numpy(a.view(np.int64).reshape(-1)) for a in self.pin_keep]
         self.q = self.cv.scalar_modulus
         # host-side constants of the loop, prepared once: device addresses, host views of the pinned witnesses, X2 as raw bytes
         self.dev_ptr = [t.data_ptr() for t in self.dev_W]
@@ -406,7 +407,7 @@ class GpuFold:
         return recs, final
 
     def close(self):
-        self.dev_W = self.pin_W = self.pin_np = self.dev_ptr = None
+        self.dev_W = self.pin_W = self.pin_np = self.dev_ptr = self.pin_keep = None
         self.acc.close(); self.shape.close(); self.ck.close(); self.eng.close()
 
     def h2d_bytes(self):

@@ -52,6 +52,12 @@ enum vimz_status {
 const char* vimz_last_error(void);
 int vimz_version(void);
 int vimz_device_count(void);
+/* Page-locked host memory for witness buffers: a witness handed over from ordinary (pageable) memory -- a Rust Vec<Scalar> -- is
+ * staged by the driver at ~10 GB/s (0.4 ms for a grayscale-HD witness, measured: e2e.pageable_value of bench.py), from memory
+ * obtained here it travels at PCIe speed and may be read asynchronously (vimz_acc_stage_fresh, vimz_acc_step_begin_async).
+ * A host keeps two such buffers per curve and lets its witness generator write into them.  Returns NULL on failure. */
+void* vimz_host_alloc(size_t bytes);
+void vimz_host_free(void* p);
 
 /* ---- context -------------------------------------------------------------------------------- */
 /* Replaces the choice of provider made by `type G1/G2` (mod.rs:19-20): one context per curve. */

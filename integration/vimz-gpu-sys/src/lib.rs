@@ -39,6 +39,9 @@ pub struct Point { pub x: [u64; 4], pub y: [u64; 4], pub z: [u64; 4] }
 
 extern "C" {
     pub fn vimz_last_error() -> *const c_char;
+    /// page-locked host memory for witness buffers (a pageable Vec<Scalar> is staged by the driver at ~10 GB/s)
+    pub fn vimz_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn vimz_host_free(p: *mut c_void);
     pub fn vimz_ctx_create(curve_id: c_int, device: c_int, out: *mut *mut vimz_ctx) -> c_int;
     pub fn vimz_ctx_destroy(ctx: *mut vimz_ctx);
     pub fn vimz_ctx_set_option(ctx: *mut vimz_ctx, key: *const c_char, value: c_long) -> c_int;

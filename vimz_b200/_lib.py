@@ -50,6 +50,8 @@ def _load() -> C.CDLL:
         "vimz_last_error": (C.c_char_p, []),
         "vimz_version": (i32, []),
         "vimz_device_count": (i32, []),
+        "vimz_host_alloc": (vp, [sz]),
+        "vimz_host_free": (None, [vp]),
         "vimz_ctx_create": (i32, [i32, i32, pp]),
         "vimz_ctx_destroy": (None, [vp]),
         "vimz_ctx_sync": (i32, [vp]),

@@ -195,6 +195,19 @@ extern "C" {
 
 const char* vimz_last_error(void) { return g_last_error.c_str(); }
 int vimz_version(void) { return 100; }
+void* vimz_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    set_error(VIMZ_ERR_CUDA, "vimz_host_alloc: cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+void vimz_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int vimz_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -290,6 +303,12 @@ int vimz_ctx_set_option(vimz_ctx* ctx, const char* key, long value) {
   if (strcmp(key, "msm_seg_min") == 0) {
     if (value < 1 || value > 4096) return set_error(VIMZ_ERR_ARG, "msm_seg_min must be in [1, 4096]");
     ctx->opt_seg_min = value;
+    alloc_epoch()++;
+    return VIMZ_OK;
+  }
+  if (strcmp(key, "msm_seg_min_aux") == 0) {  // the same for the MSMs of lane 1 (a fold step's commit(W2)); 0 = msm_seg_min
+    if (value < 0 || value > 4096) return set_error(VIMZ_ERR_ARG, "msm_seg_min_aux must be in [0, 4096]");
+    ctx->opt_seg_min_aux = value;
     alloc_epoch()++;
     return VIMZ_OK;
   }

@@ -156,6 +156,7 @@ struct vimz_ctx {
   bool opt_bitrow_fold = true;  // accumulators created from now on keep K_S and commit T + [bit row] Az1 (r1cs.cuh, k_cross_finish)
   bool opt_spin_wait = true; // step_begin polls the stream for its result instead of a blocking synchronise
   long opt_acc_blocks = 4; // 128-thread accumulation blocks per SM (4 = register-file limit)
+  long opt_seg_min_aux = 0; // the same for lane 1 (0 = opt_seg_min)
   long opt_seg_min = 8;    // shortest accumulation segment (entries per thread): fewer => more threads busy on small MSMs
   bool opt_cross_stream = true; // cross term: chunked CSR streaming through shared memory (false: row-class kernel)
   bool opt_cross_cache = true;  // accumulators created from now on keep (Az1, Bz1, Cz1) resident instead of recomputing them

@@ -197,7 +197,7 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   const int G = (int)std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 2), 1), 64), g_fit);
   // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
   const uint32_t nthreads = msm_nthreads(ctx);
-  const uint32_t seg_min = (uint32_t)ctx->opt_seg_min;
+  const uint32_t seg_min = (uint32_t)(lane == 1 && ctx->opt_seg_min_aux ? ctx->opt_seg_min_aux : ctx->opt_seg_min);
   // capacity bounds: a bucket cut into p pieces overlaps p segments and every segment boundary cuts at most one
   // bucket, so sum(pieces) <= 2 * nthreads; a giant has > COMBINE_MID pieces and ceil(p / GIANT_CHUNK) chunks
   const uint32_t max_giants = msm_max_giants(ctx);

@@ -26,6 +26,22 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def pinned_fr(src: np.ndarray) -> np.ndarray:
+    """A copy of the (n, 4) uint64 field-element array `src` in page-locked host memory from `vimz_host_alloc` (what a host keeps
+    its witness buffers in: a pageable buffer is staged by the driver at ~10 GB/s).  Freed when the array is collected."""
+    import weakref
+    src = np.ascontiguousarray(src, dtype=np.uint64)
+    nbytes = max(src.nbytes, 32)
+    p = lib.vimz_host_alloc(nbytes)
+    if not p:
+        raise MemoryError("vimz_host_alloc failed")
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.uint64, count=src.size).reshape(src.shape)
+    arr[...] = src
+    weakref.finalize(buf, lib.vimz_host_free, C.c_void_p(p))
+    return arr
+
+
 class Engine:
     """One curve on one GPU (a `vimz_ctx`): plays the role of the `Group` type selected by
     `type G1` / `type G2` (mod.rs:19-20) together with its CommitmentEngine."""
