@@ -18,8 +18,8 @@ ncu -i gpurun_out/${TAG}_acc_step.ncu-rep --page raw --csv > gpurun_out/${TAG}_a
 python tools/ncu_summary.py < gpurun_out/${TAG}_acc_step.csv > gpurun_out/${TAG}_ncu_msm_accumulate_fold_step.txt
 ncu -i gpurun_out/${TAG}_acc_step.ncu-rep --page source --csv > gpurun_out/${TAG}_acc_step_source.csv 2>/dev/null
 python tools/ncu_hot.py k_msm_accumulate < gpurun_out/${TAG}_acc_step_source.csv > gpurun_out/${TAG}_ncu_msm_accumulate_hotspots.txt 2>/dev/null
-# per step: matvec x2, finish x2, direct x2, tail x2, combine x2, scatter x2, chunks x2 = 14 matching launches -> skip 14 * 264
-ncu --set full --clock-control none -k "regex:k_matvec_stream|k_cross_finish|k_msm_direct|k_reduce_tail|k_msm_combine_all|k_msm_scatter|k_reduce_chunks" -s 3696 -c 14 \
+# per step: matvec x2, finish x2, direct x2, tail x2, combine x2, scatter x2, chunks x2, masked sum, pow2 parts, scale-add parts = 17 matching launches -> skip 17 * 264
+ncu --set full --clock-control none -k "regex:k_matvec_stream|k_cross_finish|k_msm_direct|k_reduce_tail|k_msm_combine_all|k_msm_scatter|k_reduce_chunks|k_masked_base_sum|k_point_pow2_parts|k_point_scale_add_parts" -s 4488 -c 17 \
     -o gpurun_out/${TAG}_step_kernels $BENCH > /dev/null 2>&1
 ncu -i gpurun_out/${TAG}_step_kernels.ncu-rep --page raw --csv > gpurun_out/${TAG}_step_kernels.csv 2>/dev/null
 python tools/ncu_summary.py < gpurun_out/${TAG}_step_kernels.csv > gpurun_out/${TAG}_ncu_fold_step_kernels.txt
@@ -29,7 +29,7 @@ ncu -i gpurun_out/${TAG}_acc_2p20.ncu-rep --page raw --csv | python tools/ncu_su
 rm -f gpurun_out/${TAG}_step_kernels.ncu-rep gpurun_out/${TAG}_acc_step.ncu-rep gpurun_out/${TAG}_acc_2p20.ncu-rep gpurun_out/${TAG}_acc_step_source.csv
 # 4. compute-sanitizer over the kernels new or changed this round (TMA/cp.async mat-vec, cross finish, deferred giants, aggregated scatter,
 #    cached products, library-level sharded step)
-SEL='(cached_products or row_classes or skewed or big_bucket or library_level or (chain_vs_oracle and pallas)) and not direct'
+SEL='(cached_products or row_classes or skewed or big_bucket or library_level or (chain_vs_oracle and pallas) or booleanity or (staged_async and opts1)) and not direct'
 for tool in memcheck racecheck synccheck; do
   echo "== compute-sanitizer --tool $tool  pytest -k \"$SEL\""
   compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_msm.py tests/test_gpu_r1cs.py -m gpu -x -q -k "$SEL" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|rror" | head -8

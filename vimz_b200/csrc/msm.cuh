@@ -831,31 +831,60 @@ __global__ void __launch_bounds__(128, 4) k_msm_direct(const uint32_t* __restric
 // An entry equal to one is ONE mixed addition; any other non-zero value -- only an unsatisfying witness has them -- is multiplied
 // out bit by bit so that the result stays exact.  Same tree as k_msm_direct; the arrival counters reset themselves.
 template <class C>
-__global__ void __launch_bounds__(128, 4) k_masked_base_sum(const void* __restrict__ vals, const uint32_t* __restrict__ bitcol, uint32_t m,
+__global__ void __launch_bounds__(128, 2) k_masked_base_sum(const void* __restrict__ vals, const uint32_t* __restrict__ bitcol, uint32_t m,
                                                             const void* __restrict__ bases, void* __restrict__ partials,
                                                             uint32_t* __restrict__ ctrl, void* __restrict__ out_jac) {
   using Fs = Fp<typename C::Fs>;
   __shared__ __align__(16) uint32_t smem[4 * 32];
   __shared__ uint32_t flag;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
+  // Rows whose wire is 1 are ~43 % of a chunk, scattered: added where they are found, every lane of a warp would sit through an
+  // addition for every chunk.  Each warp queues the row numbers of its hits instead (ballot + prefix count) and adds 32 at a time,
+  // one per lane: ~6 dense additions per thread instead of ~14 sparse ones.
+  __shared__ uint32_t queue[4][64];
+  const uint32_t nthreads = gridDim.x * blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Xyzz<C> acc = Xyzz<C>::identity();
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += nthreads) {
-    const uint32_t col = __ldg(bitcol + i);
-    if (col == 0xffffffffu) continue;
-    const Fs v = Fs::load(reinterpret_cast<const char*>(vals) + (size_t)col * 32);
-    if (v.is_zero()) continue;
-    const Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
-    if (v == Fs::one()) {
-      xyzz_madd<C, VIMZ_DIRECT_MUL>(acc, p, false);
-    } else {  // rare, slow, exact: v * p by double-and-add
-      const Fs raw = fp_from_mont(v);
-      Xyzz<C> t = Xyzz<C>::identity();
-      for (int bit = 255; bit >= 0; bit--) {
-        xyzz_dbl_call<C>(t);
-        if ((raw.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd_call<C>(t, p, false);
+  uint32_t qn = 0;  // warp-uniform
+  const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
+#pragma unroll 1
+  for (uint32_t base = first; base < m; base += nthreads) {  // warp-uniform trip count
+    const uint32_t i = base + lane;
+    bool hit = false;
+    if (i < m) {
+      const uint32_t col = __ldg(bitcol + i);
+      if (col != 0xffffffffu) {
+        const Fs v = Fs::load(reinterpret_cast<const char*>(vals) + (size_t)col * 32);
+        if (v == Fs::one()) {
+          hit = true;
+        } else if (!v.is_zero()) {  // rare, slow, exact: v * p by double-and-add
+          const Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
+          const Fs raw = fp_from_mont(v);
+          Xyzz<C> t = Xyzz<C>::identity();
+          for (int bit = 255; bit >= 0; bit--) {
+            xyzz_dbl_call<C>(t);
+            if ((raw.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd_call<C>(t, p, false);
+          }
+          xyzz_add_call<C>(acc, t);
+        }
       }
-      xyzz_add_call<C>(acc, t);
     }
+    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (hit) queue[warp][qn + __popc(mask & ((1u << lane) - 1))] = i;
+    qn += __popc(mask);
+    __syncwarp();
+    if (qn >= 32) {
+      const uint32_t idx = queue[warp][lane];
+      const uint32_t spill = lane < qn - 32 ? queue[warp][32 + lane] : 0;
+      __syncwarp();
+      if (lane < qn - 32) queue[warp][lane] = spill;
+      qn -= 32;
+      __syncwarp();
+      const Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(bases) + (size_t)idx * 64);
+      xyzz_madd<C, VIMZ_DIRECT_MUL>(acc, p, false);
+    }
+  }
+  if (lane < qn) {
+    const Affine<C> p = Affine<C>::load_nc(reinterpret_cast<const char*>(bases) + (size_t)queue[warp][lane] * 64);
+    xyzz_madd_call<C>(acc, p, false);
   }
   direct_tree<C>(acc, smem, &flag, partials, ctrl, out_jac, nullptr, true);
 }
