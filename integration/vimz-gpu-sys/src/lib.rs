@@ -186,6 +186,21 @@ impl Accumulator {
         check(unsafe { vimz_acc_step_begin_staged(self.raw, rest.as_ptr(), first, rest.len(), x2.as_ptr(), &mut cw, &mut ct) })?;
         Ok((cw, ct))
     }
+    /// The same without waiting: the step is enqueued, `step_wait` collects the commitments (host sequencing of the two curves:
+    /// the other curve's `step_end` is issued in between).
+    /// # Safety: `rest` and `x2` must stay alive and unchanged until `step_wait` returns.
+    pub unsafe fn step_begin_staged_async(&mut self, rest: &[Scalar], first: usize, x2: &[Scalar]) -> Result<(), GpuError> {
+        check(vimz_acc_step_begin_staged(self.raw, rest.as_ptr(), first, rest.len(), x2.as_ptr(), std::ptr::null_mut(), std::ptr::null_mut()))
+    }
+    /// # Safety: `w2` and `x2` must stay alive and unchanged until `step_wait` returns.
+    pub unsafe fn step_begin_async(&mut self, w2: &[Scalar], x2: &[Scalar]) -> Result<(), GpuError> {
+        check(vimz_acc_step_begin_async(self.raw, w2.as_ptr(), x2.as_ptr()))
+    }
+    pub fn step_wait(&mut self) -> Result<(Point, Point), GpuError> {
+        let (mut cw, mut ct) = (Point::default(), Point::default());
+        check(unsafe { vimz_acc_step_wait(self.raw, &mut cw, &mut ct) })?;
+        Ok((cw, ct))
+    }
     pub fn raw(&self) -> *mut vimz_acc { self.raw }
 }
 impl Drop for Accumulator { fn drop(&mut self) { unsafe { vimz_acc_destroy(self.raw) } } }
