@@ -998,7 +998,8 @@ def main_gpu(args, rank, world, local_rank):
                 "value_serial_calls": world * steps / (ms_serial * 1e-3),
                 "e2e": {"value": world * steps / (ms_staged * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prim.h2d_bytes() + sec.h2d_bytes(),
                         "d2h_bytes_per_step": 4 * 96, "ms_per_step": ms_staged / steps,
-                        "api": "vimz_acc_stage_fresh + vimz_acc_step_begin_staged (primary), vimz_acc_step_begin_async / _wait (secondary), vimz_acc_step_end: every "
+                        "api": "vimz_acc_stage_fresh + vimz_acc_step_begin_staged / _wait (primary), vimz_acc_step_begin_async / _wait (secondary), vimz_acc_step_end of "
+                               "each curve issued while the other curve's step runs (class Overlapped): every "
                                "step copies its whole fresh witness host -> device inside the timed region; the fold-independent rows of the "
                                f"primary witness ({prim.staged_split()} of {prim.sh.num_vars}: the Circom step circuit's variables) are enqueued before the "
                                "secondary curve's step so the copy overlaps it, the augmented circuit's ~10 k variables go up inside step_begin",
