@@ -159,6 +159,66 @@ VIMZ_DI QPoint<C> q_add_inl(const QPoint<C>& p1, const QPoint<C>& p2) {
 template <class C>
 __device__ __noinline__ QPoint<C> q_add(QPoint<C> p1, QPoint<C> p2) { return q_add_inl<C>(p1, p2); }
 
+// TWO independent additions (p1 + p2, s1 + s2) with their product rounds interleaved (fp_mul2_call: two Montgomery chains in flight
+// in one warp -- a lone warp pays ~1.45x the time of one addition for both).  For the running-sum chains of the bucket reduction,
+// where "running += bucket" and "weighted += running" of consecutive steps are independent of each other.
+template <class C>
+struct QPair {
+  QPoint<C> a, b;
+};
+template <class C>
+__device__ __noinline__ QPair<C> q_add2(QPoint<C> p1, QPoint<C> p2, QPoint<C> s1, QPoint<C> s2) {
+  using F = Fp<typename C::Fb>;
+  using Fb = typename C::Fb;
+  const int role = threadIdx.x & 3;
+  const bool id1 = p1.is_identity(), id2 = p2.is_identity(), jd1 = s1.is_identity(), jd2 = s2.is_identity();
+  // round 1 (see q_add_inl for the lane roles)
+  FpPair<Fb> r1 = fp_mul2_call<Fb>(p1.c, q_fetch(p2.c, role ^ 2), s1.c, q_fetch(s2.c, role ^ 2));
+  F dA = fp_sub(q_fetch(r1.a, role | 2), q_fetch(r1.a, role & 1));
+  F dB = fp_sub(q_fetch(r1.b, role | 2), q_fetch(r1.b, role & 1));
+  const bool pzA = q_flag(dA.is_zero(), 0), rzA = q_flag(dA.is_zero(), 1);
+  const bool pzB = q_flag(dB.is_zero(), 0), rzB = q_flag(dB.is_zero(), 1);
+  // round 2
+  FpPair<Fb> r2 = fp_mul2_call<Fb>(role < 2 ? dA : p1.c, role < 2 ? dA : p2.c, role < 2 ? dB : s1.c, role < 2 ? dB : s2.c);
+  // round 3
+  F ppA = q_fetch(r2.a, 0), u1A = q_fetch(r1.a, 0);
+  F ppB = q_fetch(r2.b, 0), u1B = q_fetch(r1.b, 0);
+  FpPair<Fb> r3 = fp_mul2_call<Fb>(role == 0 ? dA : (role == 1 ? u1A : r2.a), ppA, role == 0 ? dB : (role == 1 ? u1B : r2.b), ppB);
+  // round 4
+  F pppA = q_fetch(r3.a, 0), s1A = q_fetch(r1.a, 1);
+  F pppB = q_fetch(r3.b, 0), s1B = q_fetch(r1.b, 1);
+  F x3A = fp_sub(fp_sub(r2.a, pppA), fp_dbl(r3.a));
+  F x3B = fp_sub(fp_sub(r2.b, pppB), fp_dbl(r3.b));
+  FpPair<Fb> r4 = fp_mul2_call<Fb>(role == 0 ? s1A : (role == 1 ? dA : r2.a), role == 1 ? fp_sub(r3.a, x3A) : pppA,
+                                   role == 0 ? s1B : (role == 1 ? dB : r2.b), role == 1 ? fp_sub(r3.b, x3B) : pppB);
+  QPair<C> out;
+  {
+    F t2 = q_fetch(r4.a, 0), x3b = q_fetch(x3A, 1);
+    out.a.c = role == 0 ? x3b : (role == 1 ? fp_sub(r4.a, t2) : (role == 2 ? r3.a : r4.a));
+  }
+  {
+    F t2 = q_fetch(r4.b, 0), x3b = q_fetch(x3B, 1);
+    out.b.c = role == 0 ? x3b : (role == 1 ? fp_sub(r4.b, t2) : (role == 2 ? r3.b : r4.b));
+  }
+  // exceptional cases, as in q_add_inl
+  const bool dblA = !id1 && !id2 && pzA && rzA, dblB = !jd1 && !jd2 && pzB && rzB;
+  if (__any_sync(FULL, dblA)) {
+    QPoint<C> dd = q_dbl<C>(p1);
+    if (dblA) out.a = dd;
+  }
+  if (__any_sync(FULL, dblB)) {
+    QPoint<C> dd = q_dbl<C>(s1);
+    if (dblB) out.b = dd;
+  }
+  if (!id1 && !id2 && pzA && !rzA) out.a.c = F::zero();
+  if (!jd1 && !jd2 && pzB && !rzB) out.b.c = F::zero();
+  if (id2) out.a = p1;
+  else if (id1) out.a = p2;
+  if (jd2) out.b = s1;
+  else if (jd1) out.b = s2;
+  return out;
+}
+
 // acc (quad) -> Jacobian {X*ZZ^4, Y*ZZZ^4, ZZ*ZZZ}; identity -> (0, R, 0).  Writes 96 bytes from the quad.
 template <class C>
 VIMZ_DI void q_store_jacobian(const QPoint<C>& p, void* out, bool do_store = true, void* out2 = nullptr) {

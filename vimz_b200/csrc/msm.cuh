@@ -566,13 +566,22 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
                                                        void* __restrict__ chunkA, void* __restrict__ chunkL) {
   uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const bool valid = t < T;  // whole quads are valid or not; invalid quads still run the shuffles
-  QPoint<C> running = QPoint<C>::identity(), acc = QPoint<C>::identity();
   const char* base = reinterpret_cast<const char*>(buckets) + (size_t)(valid ? t : 0) * K * 128;
+  auto bucket = [&](int j) { return valid ? QPoint<C>::load(base + (size_t)j * 128) : QPoint<C>::identity(); };
+  // running_j = running_{j+1} + B_j, acc_j = acc_{j+1} + running_j, from running_{K-1} = acc_{K-1} = B_{K-1} (no addition).  The
+  // weighted sum lags one step behind the running sum, so each step's two additions are independent and share their product
+  // rounds (q_add2): K - 2 paired steps + 2 single ones instead of 2 K sequential additions.
+  QPoint<C> running = bucket(K - 1), acc = running;  // running_{K-1}, acc_{K-1}
+  if (K >= 2) {
+    running = q_add<C>(running, bucket(K - 2));      // running_{K-2}
 #pragma unroll 1
-  for (int j = K - 1; j >= 0; j--) {
-    QPoint<C> b = valid ? QPoint<C>::load(base + (size_t)j * 128) : QPoint<C>::identity();
-    running = q_add<C>(running, b);
-    acc = q_add<C>(acc, running);
+    for (int j = K - 3; j >= 0; j--) {
+      // running_j = running_{j+1} + B_j   ||   acc_{j+1} = acc_{j+2} + running_{j+1}
+      QPair<C> r = q_add2<C>(running, bucket(j), acc, running);
+      running = r.a;
+      acc = r.b;
+    }
+    acc = q_add<C>(acc, running);                    // acc_0 = acc_1 + running_0
   }
   if (valid) {
     running.store(reinterpret_cast<char*>(chunkA) + (size_t)t * 128);
