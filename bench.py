@@ -868,7 +868,7 @@ def main_gpu(args, rank, world, local_rank):
     value = world * steps / (ms * 1e-3)
     e2e_value = world * steps / (ms_e2e * 1e-3)
     # what the e2e path pays for: the pinned-host -> HBM copy of one fresh primary witness, timed alone
-    probe_dst = torch.empty_like(prim.dev_W[0])
+    probe_dst = torch.empty_like(prim.dev_W[0]).reshape(-1)   # pin_W is flat (vimz_host_alloc buffer), dev_W is (n, 4)
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     probe_dst.copy_(prim.pin_W[0], non_blocking=True)
     torch.cuda.synchronize()

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 
 prefold = int(sys.argv[1]) if len(sys.argv) > 1 else 260
-prim = bench.GpuFold("pallas", "grayscale", bench.SEED, 0, torch)
+prim = bench.GpuFold("pallas", os.environ.get("VIMZ_TL_CIRCUIT", "grayscale"), bench.SEED, 0, torch)
 sec = bench.GpuFold("vesta", "secondary", bench.SEED + 1, 0, torch)
 for k in range(prefold):
     sec.step(k, True); prim.step(k, True)

@@ -25,7 +25,7 @@ def one(k):
         prim.step_staged(k)
     else:
         sec.step(k, resident); prim.step(k, resident)
-prim = bench.GpuFold("pallas", "grayscale", bench.SEED, 0, torch)
+prim = bench.GpuFold("pallas", os.environ.get("VIMZ_TL_CIRCUIT", "grayscale"), bench.SEED, 0, torch)
 sec = bench.GpuFold("vesta", "secondary", bench.SEED + 1, 0, torch)
 for k in range(prefold):
     sec.step(k, True); prim.step(k, True)
