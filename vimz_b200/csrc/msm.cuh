@@ -249,7 +249,10 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
 // into more than COMBINE_SPAN pieces go to k_msm_combine_big, one block of cooperating quads each).
 // Small bucket counts (M <= SCAN1_MAX_M, every fold-step MSM): ONE block scans the counts and writes the offsets and
 // the scatter cursors -- one launch instead of three on a latency-bound chain.
-constexpr uint32_t SCAN1_THREADS = 1024;
+#ifndef VIMZ_SCAN1_THREADS
+#define VIMZ_SCAN1_THREADS 1024
+#endif
+constexpr uint32_t SCAN1_THREADS = VIMZ_SCAN1_THREADS;  // a multiple of 32, at most 1024
 constexpr uint32_t SCAN1_MAX_M = 32768;
 static __global__ void __launch_bounds__(SCAN1_THREADS) k_scan_single(const uint32_t* __restrict__ counts, uint32_t M,
                                                                       uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
@@ -275,7 +278,7 @@ static __global__ void __launch_bounds__(SCAN1_THREADS) k_scan_single(const uint
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    uint32_t w = warp_tot[lane], wi = w;
+    uint32_t w = lane < SCAN1_THREADS / 32 ? warp_tot[lane] : 0u, wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
