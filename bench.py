@@ -676,6 +676,8 @@ def msm_bench(torch, device, rank, world, dist, log2n, iters, peaks, scalar_dist
     eng = vimz_b200.Engine("pallas", device)
     if os.environ.get("VIMZ_WINDOW_MSM"):
         eng.set_option("msm_window", int(os.environ["VIMZ_WINDOW_MSM"]))
+    if os.environ.get("VIMZ_ACC_BLOCKS"):   # A/B experiments only
+        eng.set_option("msm_acc_blocks", int(os.environ["VIMZ_ACC_BLOCKS"]))
     from vimz_b200.sharding import shard_range
     n = 1 << log2n
     first, per = shard_range(n, rank, world)   # point-range shard of this rank

@@ -242,7 +242,8 @@ int vimz_acc_step_begin_sharded(vimz_acc* acc, vimz_comm* comm, const vimz_fr* W
 /* bases[i] = (k0 + i*dk) * G written as n affine points to device memory d_out (64*n bytes). */
 int vimz_gen_bases_dev(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* d_out);
 /* Element-wise Montgomery product out[i] = a[i]*b[i] in the curve's BASE (which=0) or SCALAR (which=1)
- * field, plus sum/difference: op 0 = mul, 1 = add, 2 = sub.  Exercises fp.cuh directly for the parity tests. */
+ * field, plus sum/difference: op 0 = mul, 1 = add, 2 = sub, 3 = square of a (b is ignored).  Exercises fp.cuh directly for
+ * the parity tests. */
 int vimz_field_op(vimz_ctx* ctx, int which, int op, const vimz_fr* a, const vimz_fr* b, size_t n, vimz_fr* out);
 
 #ifdef __cplusplus

@@ -25,6 +25,30 @@ def test_field_ops_bit_exact(name, which, engines):
     assert mont_to_ints(eng.field_op(which, "sub", A, B), mod) == [(x - y) % mod for x, y in zip(a, b)]
 
 
+@pytest.mark.parametrize("name", list(P.CURVES))
+@pytest.mark.parametrize("which", ["base", "scalar"])
+def test_field_square_bit_exact(name, which, engines):
+    """fp_sqr (the dedicated squaring of fp_sqr.cuh on the Pasta fields: the two squarings of every mixed addition) equals the
+    big-integer square and, limb for limb in Montgomery form, the product a * a."""
+    import numpy as np
+    c = P.CURVES[name]
+    mod = c.p if which == "base" else c.q
+    rng = random.Random(hash((name, which, "sqr")) & 0xFFFF)
+    top = (1 << 254) - 1
+    edge = [0, 1, 2, mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1, (1 << 255) % mod, (1 << 256) % mod, (1 << 128) - 1, (1 << 64), 0xFFFFFFFF,
+            top % mod, (top - 0xFFFFFFFF) % mod, (1 << 253), sum(0xFFFFFFFF << (64 * i) for i in range(4)) % mod,
+            sum(0xFFFFFFFF << (64 * i + 32) for i in range(4)) % mod]
+    # values whose Montgomery FORM (x * 2^256 mod p) hits the carry-heavy patterns, not only the values themselves
+    rinv = pow(1 << 256, -1, mod)
+    edge += [e * rinv % mod for e in edge]
+    a = edge + [rng.randrange(mod) for _ in range(20000)]
+    A = ints_to_mont(a, mod)
+    eng = engines[name]
+    sq = eng.field_op(which, "sqr", A, A)
+    assert mont_to_ints(sq, mod) == [x * x % mod for x in a]
+    assert np.array_equal(sq, eng.field_op(which, "mul", A, A))
+
+
 def test_field_op_matches_c_oracle_limbs(engines, coracle):
     """Limb-for-limb (Montgomery representation) equality with the 4x64 CPU restatement."""
     import numpy as np

@@ -1614,7 +1614,7 @@ int vimz_gen_bases_dev(vimz_ctx* ctx, uint64_t k0, uint64_t dk, size_t n, void* 
 }
 
 int vimz_field_op(vimz_ctx* ctx, int which, int op, const vimz_fr* a, const vimz_fr* b, size_t n, vimz_fr* out) {
-  CHECK_ARG(ctx && (n == 0 || (a && b && out)) && which >= 0 && which <= 1 && op >= 0 && op <= 2, "vimz_field_op: bad argument");
+  CHECK_ARG(ctx && (n == 0 || (a && b && out)) && which >= 0 && which <= 1 && op >= 0 && op <= 3, "vimz_field_op: bad argument");
   CtxGuard g(ctx);
   size_t bytes = std::max<size_t>(n * 32, 32);
   VIMZ_TRY(ctx->tmp0.reserve(bytes));

@@ -89,8 +89,16 @@ __device__ __noinline__ FpPair<F> fp_mul2_call(Fp<F> a1, Fp<F> b1, Fp<F> a2, Fp<
 struct MulInline {
   template <class F> static VIMZ_DI Fp<F> mul(const Fp<F>& a, const Fp<F>& b) { return fp_mul(a, b); }
   template <class F> static VIMZ_DI void mul2(Fp<F>& r1, const Fp<F>& a1, const Fp<F>& b1, Fp<F>& r2, const Fp<F>& a2, const Fp<F>& b2) {
+#ifdef VIMZ_INLINE_MUL2_INTERLEAVED   // A/B: rows of the two products interleaved in program order (more registers live)
+    fp_mul2(r1, a1, b1, r2, a2, b2);
+#else
     r1 = fp_mul(a1, b1);
     r2 = fp_mul(a2, b2);
+#endif
+  }
+  template <class F> static VIMZ_DI void sqr2(Fp<F>& r1, const Fp<F>& a1, Fp<F>& r2, const Fp<F>& a2) {
+    r1 = fp_sqr(a1);
+    r2 = fp_sqr(a2);
   }
 };
 struct MulCall {
@@ -100,6 +108,7 @@ struct MulCall {
     r1 = r.a;
     r2 = r.b;
   }
+  template <class F> static VIMZ_DI void sqr2(Fp<F>& r1, const Fp<F>& a1, Fp<F>& r2, const Fp<F>& a2) { mul2(r1, a1, a1, r2, a2, a2); }
 };
 
 // 2 * (affine point) -> XYZZ   ("mdbl-2008-s-1", a = 0)
@@ -166,7 +175,7 @@ VIMZ_DI void xyzz_madd(Xyzz<C>& acc, const Affine<C>& q, bool neg) {
     return;
   }
   F pp, rr, ppp, qq, t1, t2;
-  M::mul2(pp, p, p, rr, r, r);
+  M::sqr2(pp, p, rr, r);
   M::mul2(ppp, p, pp, qq, acc.x, pp);
   F x3 = fp_sub(fp_sub(rr, ppp), fp_dbl(qq));
   M::mul2(t1, r, fp_sub(qq, x3), t2, acc.y, ppp);

@@ -416,8 +416,28 @@ VIMZ_DI void fp_mul2(Fp<F>& r1, const Fp<F>& a1, const Fp<F>& b1, Fp<F>& r2, con
   fp_final_sub(r2);
 }
 
+}  // namespace vimz
+#include "fp_sqr.cuh"
+namespace vimz {
+// Squaring.  Pasta base / scalar fields with -DVIMZ_FP_SQR=1: the dedicated routine of fp_sqr.cuh (generated by tools/gen_fp_sqr.py:
+// off-diagonal triangle once + doubling + diagonal, then reduction-only rows: 60 wide products instead of 88), bit-identical to
+// fp_mul(a, a) (tests/test_gpu_field.py); otherwise the plain product.
+#ifndef VIMZ_FP_SQR
+#define VIMZ_FP_SQR 1
+#endif
 template <class F>
-VIMZ_DI Fp<F> fp_sqr(const Fp<F>& a) { return fp_mul(a, a); }
+VIMZ_DI Fp<F> fp_sqr(const Fp<F>& a) {
+#if VIMZ_FP_SQR
+  constexpr bool PASTA = F::p(4) == 0 && F::p(5) == 0 && F::p(6) == 0 && F::p(0) == 1 && F::p(7) == 0x40000000u && F::INV == 0xffffffffu;
+  if constexpr (PASTA) {
+    Fp<F> r;
+    fp_sqr_pasta_limbs<F>(r.v, a.v);
+    fp_final_sub(r);  // the routine returns a value below 2p
+    return r;
+  }
+#endif
+  return fp_mul(a, a);
+}
 
 template <class F>
 VIMZ_DI Fp<F> fp_from_mont(const Fp<F>& a) {

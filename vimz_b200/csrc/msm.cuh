@@ -21,6 +21,9 @@
 
 namespace vimz {
 
+#ifndef VIMZ_ACC_MINBLOCKS
+#define VIMZ_ACC_MINBLOCKS 4  // resident blocks per SM the accumulation kernel is compiled for (128 registers at 4)
+#endif
 #ifndef VIMZ_ACC_MUL
 #define VIMZ_ACC_MUL MulInline  // multiplication policy of the accumulation hot loop (A/B: -DVIMZ_ACC_MUL=MulCall)
 #endif
@@ -310,7 +313,7 @@ static __global__ void __launch_bounds__(SCAN1_THREADS) k_scan_single(const uint
 }
 
 template <class C>
-__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128, VIMZ_ACC_MINBLOCKS) k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
                                                            const void* __restrict__ table, uint32_t M, uint32_t nthreads, uint32_t seg_min,
                                                            void* __restrict__ buckets, void* __restrict__ partials) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -436,7 +436,7 @@ __global__ void k_field_op(int op, const void* __restrict__ a, const void* __res
   if (i >= len) return;
   Fp<F> x = Fp<F>::load(reinterpret_cast<const char*>(a) + i * 32);
   Fp<F> y = Fp<F>::load(reinterpret_cast<const char*>(b) + i * 32);
-  Fp<F> r = op == 0 ? fp_mul(x, y) : (op == 1 ? fp_add(x, y) : fp_sub(x, y));
+  Fp<F> r = op == 0 ? fp_mul(x, y) : (op == 1 ? fp_add(x, y) : (op == 2 ? fp_sub(x, y) : fp_sqr(x)));  // 3: a^2 (b ignored)
   r.store(reinterpret_cast<char*>(out) + i * 32);
 }
 

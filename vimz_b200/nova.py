@@ -136,7 +136,7 @@ class Engine:
     def field_op(self, which: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a, b = as_fr(a), as_fr(b, None)
         out = np.zeros_like(a)
-        check(lib.vimz_field_op(self._h, {"base": 0, "scalar": 1}[which], {"mul": 0, "add": 1, "sub": 2}[op],
+        check(lib.vimz_field_op(self._h, {"base": 0, "scalar": 1}[which], {"mul": 0, "add": 1, "sub": 2, "sqr": 3}[op],
                                 _ptr(a), _ptr(b), a.shape[0], _ptr(out)))
         return out
 
