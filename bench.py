@@ -889,7 +889,7 @@ def main_gpu(args, rank, world, local_rank):
     imad = entries * MODMUL_PER_MADD * IMAD_PER_MODMUL
     achieved = imad / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
     traffic, traffic_src = None, None
-    for tname in ("r2f_traffic.json", "r2_traffic.json", "r1s3_traffic.json"):   # dram__bytes of one ncu --set full capture of this kernel, per launch
+    for tname in ("r2h_traffic.json", "r2f_traffic.json", "r2_traffic.json", "r1s3_traffic.json"):   # dram__bytes of one ncu --set full capture of this kernel, per launch
         tpath = os.path.join(ROOT, "profiles", tname)
         if os.path.exists(tpath):
             try:
