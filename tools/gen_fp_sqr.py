@@ -86,7 +86,7 @@ def program():
     c = t[:8]
     for i in range(8):
         m, mlo, mhi, z, c8 = f"m{i}", f"ml{i}", f"mh{i}", f"z{i}", f"c8_{i}"
-        S.append(("cxx", f"const uint32_t {m} = 0u - {c[0]}, {mlo} = {m} << 30, {mhi} = {m} >> 2;", None))
+        S.append(("cxx", f"const uint32_t {m} = 0u - {c[0]}, {mlo} = {m} << SH30, {mhi} = {m} >> SH2;", None))
         S.append(("model", lambda env, m=m, mlo=mlo, mhi=mhi, c0=c[0]: env.update({m: (-env[c0]) & M32, mlo: ((-env[c0]) << 30) & M32,
                                                                                     mhi: ((-env[c0]) & M32) >> 2})))
         ops = [("add", z, c[0], m, None, False, True),
@@ -171,7 +171,12 @@ def emit():
     w("__device__ __forceinline__ void fp_sqr_pasta_limbs(uint32_t (&r)[8], const uint32_t (&a)[8]) {")
     w("  const uint32_t " + ", ".join(f"a{i} = a[{i}]" for i in range(8)) + ";")
     w("  const uint32_t P1 = F::p(1), P2 = F::p(2), P3 = F::p(3);")
-    declared = set(f"a{i}" for i in range(8)) | {"P1", "P2", "P3", "0"}
+    w("#if VIMZ_OPAQUE_P  // shift counts ptxas cannot see: (m << 30, m >> 2) stays two shifts instead of a wide multiply by 2^30 (fp.cuh)")
+    w("  const uint32_t SH30 = red_const<F>[3], SH2 = red_const<F>[4];")
+    w("#else")
+    w("  const uint32_t SH30 = 30u, SH2 = 2u;")
+    w("#endif")
+    declared = set(f"a{i}" for i in range(8)) | {"P1", "P2", "P3", "0", "SH30", "SH2"}
     for st in S:
         if st[0] == "wide":
             _, lo, hi, x, y = st

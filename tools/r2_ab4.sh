@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B: dedicated squaring (-DVIMZ_FP_SQR=1, build/variants/sqr.so) against the default library; correctness first
-VIMZ_GPU_LIB=$PWD/build/variants/il2.so python -m pytest tests/test_gpu_field.py tests/test_gpu_msm.py -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests/test_gpu_field.py tests/test_gpu_msm.py -m gpu -x -q 2>&1 | tail -2
 python -m pytest tests/test_gpu_field.py -m gpu -x -q 2>&1 | tail -1
 run() {
   echo "== $1"
@@ -12,5 +12,5 @@ for m in d['msm']: print('  msm', m['log2_points'], round(m['mpts_per_s'],1), 'M
 "
 }
 run vimz_b200/libvimz_gpu.so
-run build/variants/il2.so
+run build/variants/noopaque.so
 python -m pytest tests/test_gpu_r1cs.py tests/test_gpu_msm.py -m gpu -x -q 2>&1 | tail -1

@@ -220,6 +220,17 @@ VIMZ_DI bool fp_gt_half(const Fp<F>& a) {
   return borrow != 0;
 }
 
+// A/B knob (default OFF, measured slower): reduction constants and shift counts of the Pasta fields read from CONSTANT MEMORY.
+// With the limbs of p as immediates ptxas splits every m * p[k] into a half-rate IMAD.HI plus an IMAD and turns the two shifts
+// of m * 2^254 back into a wide multiply by 2^30; opaque values remove 12 of the 227 multiplier-pipe issue units of a product
+// (IMAD.WIDE / IMAD.HI run at half rate, profiles/int_peak.json) but add 18 instructions: k_msm_accumulate 2.604 -> 2.654 ms at
+// 2^20 -- the kernel is bound by issue slots and dependent-issue stalls, not by the multiplier pipe alone.  {p[1], p[2], p[3], 30, 2}
+#ifndef VIMZ_OPAQUE_P
+#define VIMZ_OPAQUE_P 0
+#endif
+template <class F>
+__constant__ uint32_t red_const[5] = {F::p(1), F::p(2), F::p(3), 30u, 2u};
+
 // ---- Montgomery multiplication ----------------------------------------------------------------
 // One row: acc += a * bi ; m = acc[0] * INV ; acc += m * p ; acc >>= 32, with the accumulator split
 // into an even-aligned (ev) and an odd-aligned (od) set of 64-bit lanes.  The 32-bit right shift
@@ -268,7 +279,13 @@ VIMZ_DI void mont_row(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&a)[
     // (carry = acc0 != 0) and m*p[7] = m << 30 is two shifts -- only p[1], p[2], p[3] need the multiplier.
     // (Left to ptxas, the constants 1 and 2^30 break the lo/hi pairs into half-rate IMAD.HI plus carries.)
     m = 0u - ev[0];
+#if VIMZ_OPAQUE_P
+    const uint32_t P1 = red_const<F>[0], P2 = red_const<F>[1], P3 = red_const<F>[2];
+    uint32_t mlo = m << red_const<F>[3], mhi = m >> red_const<F>[4];
+#else
+    const uint32_t P1 = F::p(1), P2 = F::p(2), P3 = F::p(3);
     uint32_t mlo = m << 30, mhi = m >> 2;
+#endif
     asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
         "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
         "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
@@ -278,7 +295,7 @@ VIMZ_DI void mont_row(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&a)[
         "addc.cc.u32 %6, %6, %11;\n\t"
         "addc.u32 %7, %7, %12;"
         : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
-        : "r"(m), "r"(F::p(1)), "r"(F::p(3)), "r"(mlo), "r"(mhi));
+        : "r"(m), "r"(P1), "r"(P3), "r"(mlo), "r"(mhi));
     asm("add.cc.u32 %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, 0;\n\t"
         "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
@@ -289,7 +306,7 @@ VIMZ_DI void mont_row(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&a)[
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, %8, 0;"
         : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(od[7])
-        : "r"(m), "r"(F::p(2)));
+        : "r"(m), "r"(P2));
   } else if (SPARSE) {
     // odd lanes += m * p[1,3,-,7]; even lanes += m * p[0,2,-,-]; zero limbs only ripple the carry.
     asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
