@@ -1,6 +1,6 @@
 #!/bin/bash
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python -m pytest tests/test_gpu_field.py tests/test_gpu_msm.py -m gpu -x -q 2>&1 | tail -1
+python -m pytest tests/test_gpu_msm.py tests/test_gpu_r1cs.py -m gpu -x -q 2>&1 | tail -1
 python bench.py --steps 100 --warmup 5 --no-configs > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err; echo "bench rc $?"
 python -c "
 import json

@@ -11,6 +11,9 @@
 #define VIMZ_BIG_BLOCKS_PER_SM 1  // blocks of the giant-bucket role of k_msm_combine_all per SM
 #endif
 
+#ifndef VIMZ_TAIL_PER_QUAD
+#define VIMZ_TAIL_PER_QUAD 4  // chunk sums a quad of k_reduce_tail adds serially before the block tree (A/B at c = 15: 2 -> +9 us, 8 -> +40 us)
+#endif
 namespace vimz {
 
 struct CurveVTable {
@@ -190,11 +193,11 @@ int impl_msm(vimz_ctx* ctx, int lane, const vimz_ck* ck, size_t first, const voi
   const uint32_t T = M / K;
   int nb = 0;
   while ((1u << nb) < T) nb++;
-  // second level: 32 quads per block, ~2 chunk sums per quad: the tree depth, not the work, sets the time
+  // second level: 32 quads per block, ~VIMZ_TAIL_PER_QUAD chunk sums per quad: the tree depth, not the work, sets the time
   // (G * (nb + 1) blocks of 128 threads must stay resident together -- 4 per SM -- or the last-arriving hand-offs wait for a
   // second wave: with 32 768 buckets and G = 64 the tail took 1.5 waves and ~50 us longer)
   const uint32_t g_fit = std::max<uint32_t>(((uint32_t)ctx->sm_count * 4) / (uint32_t)(nb + 2), 1);
-  const int G = (int)std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * 2), 1), 64), g_fit);
+  const int G = (int)std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(ceil_div(std::max<uint32_t>(T / 2, 1), 32 * VIMZ_TAIL_PER_QUAD), 1), 64), g_fit);
   // accumulation geometry: a fixed number of threads (4 resident warps per scheduler) share the E insertions
   const uint32_t nthreads = msm_nthreads(ctx);
   const uint32_t seg_min = (uint32_t)(lane == 1 && ctx->opt_seg_min_aux ? ctx->opt_seg_min_aux : ctx->opt_seg_min);
