@@ -137,7 +137,6 @@ def model(a_limbs, p):
                     assert v >> 32 == 0, ("carry lost", kind, d)
                     carry = 0
                 env[d] = v & M32
-            assert carry == 0 or True
     R = sum(env[n] << (32 * k) for k, n in enumerate(res))
     assert R < 2 * p
     return R - p if R >= p else R
@@ -196,11 +195,6 @@ def emit():
         else:
             ops = st[1]
             # operand table: read-write (in place), write-only, read-only
-            names = []
-            def idx(n):
-                if n not in names:
-                    names.append(n)
-                return names.index(n)
             dsts = [op[1] for op in ops]
             rw, wo = [], []
             seen_written = set()
@@ -209,8 +203,6 @@ def emit():
                 for s_ in srcs:
                     if s_ in dsts and s_ not in seen_written and s_ not in rw and s_ != "0":
                         rw.append(s_)       # read before (or when) written in this chain: must be an in/out operand
-                if d not in rw and d not in wo and d not in seen_written:
-                    pass
                 seen_written.add(d)
             for d in dsts:
                 if d not in rw and d not in wo:
